@@ -1,0 +1,33 @@
+"""Shared helpers for the parity tests."""
+import dataclasses
+import os
+
+import numpy as np
+
+from opensc2_b200.problem import StepArrays
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load_golden(name):
+    """(topology, StepArrays inputs, dict of reference outputs) for a fixture."""
+    from cases import STEP_CASES
+
+    fac, fkw, _n, _skw = STEP_CASES[name]
+    topo = fac(**fkw)
+    z = np.load(os.path.join(GOLDEN_DIR, f"step_{name}.npz"))
+    kw = {}
+    for f in dataclasses.fields(StepArrays):
+        v = z["in_" + f.name]
+        kw[f.name] = v if v.ndim else v.item()
+    outs = {k[4:]: z[k] for k in z.files if k.startswith("out_")}
+    return topo, StepArrays(**kw), outs
+
+
+def assert_bits(a, b, what=""):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape, f"{what}: shape {a.shape} vs {b.shape}"
+    if not np.array_equal(a, b):
+        bad = np.argwhere(a != b)
+        rel = np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300))
+        raise AssertionError(f"{what}: {len(bad)} of {a.size} values differ, max rel {rel:.3e}, first at {bad[0]}")
