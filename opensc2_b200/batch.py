@@ -1,0 +1,148 @@
+"""Batched conductor step on one B200: Python face of the C ABI.
+
+`BatchedStep` is the batch counterpart of the reference's
+`step(conductor, environment, qsource, num_step)`
+(/root/reference/source_code/utility_functions/transient_solution_functions.py:186):
+one call advances B independent conductors that share a topology.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import numpy as np
+
+from . import _lib
+from ._abi import (KERNEL_NAMES, OSC2_K_COUNT, STEP_INPUT_FIELDS, Osc2StepInputs, as_f64, c_ip,
+                   dptr, topology_struct)
+from .problem import StepArrays, Topology
+
+
+class BatchedStep:
+    def __init__(self, topo: Topology, batch: int, n_nodes: int, device: int = 0):
+        self._L = _lib.load()
+        self.topo = topo
+        self.batch, self.n_nodes = int(batch), int(n_nodes)
+        self.ndf = topo.ndf
+        self.total = self.ndf * self.n_nodes
+        self._h = C.c_void_p()
+        self._tstruct = topology_struct(topo)
+        _lib.check(self._L.osc2_create(C.byref(self._tstruct), self.batch, self.n_nodes, int(device), C.byref(self._h)))
+
+    # -- lifetime -----------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._L.osc2_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- data movement ------------------------------------------------------
+    def _shape(self, a, shape, name):
+        a = as_f64(a)
+        if a.shape != shape:
+            raise ValueError(f"{name}: expected shape {shape}, got {a.shape}")
+        return a
+
+    def upload_state(self, sysvar=None, syslod=None):
+        sv = self._shape(sysvar, (self.batch, self.total), "sysvar") if sysvar is not None else None
+        sl = self._shape(syslod, (self.batch, self.total, 2), "syslod") if syslod is not None else None
+        _lib.check(self._L.osc2_upload_state(self._h, dptr(sv) if sv is not None else None,
+                                             dptr(sl) if sl is not None else None))
+
+    def upload_step_inputs(self, arr: StepArrays):
+        s = Osc2StepInputs()
+        keep = []
+        for name in STEP_INPUT_FIELDS:
+            a = as_f64(getattr(arr, name))
+            if a.shape[0] != self.batch:
+                raise ValueError(f"{name}: leading axis {a.shape[0]} is not the batch {self.batch}")
+            keep.append(a)
+            setattr(s, name, dptr(a) if a.size else None)
+        s.t_env = float(arr.t_env)
+        _lib.check(self._L.osc2_upload_step_inputs(self._h, C.byref(s)))
+
+    def step(self, dt: float, num_step: int):
+        _lib.check(self._L.osc2_step(self._h, float(dt), int(num_step)))
+
+    def synchronize(self):
+        _lib.check(self._L.osc2_synchronize(self._h))
+
+    def download_state(self, want_syslod: bool = True):
+        sv = np.empty((self.batch, self.total))
+        sl = np.empty((self.batch, self.total, 2)) if want_syslod else None
+        st = np.empty(self.batch, dtype=np.int32)
+        _lib.check(self._L.osc2_download_state(self._h, dptr(sv), dptr(sl) if sl is not None else None,
+                                               st.ctypes.data_as(c_ip)))
+        return sv, sl, st
+
+    def download_diagnostics(self) -> Dict[str, np.ndarray]:
+        d, E, nff = self.ndf, self.n_nodes - 1, len(self.topo.ff)
+        out = {"norm_solution": np.empty((self.batch, d)), "norm_change": np.empty((self.batch, d)),
+               "eqteig": np.empty((self.batch, d)), "k123": np.empty((self.batch, 3, nff, E))}
+        _lib.check(self._L.osc2_download_diagnostics(
+            self._h, dptr(out["norm_solution"]), dptr(out["norm_change"]), dptr(out["eqteig"]),
+            dptr(out["k123"]) if out["k123"].size else None))
+        return out
+
+    def set_capture(self, on: bool):
+        _lib.check(self._L.osc2_set_capture(self._h, int(on)))
+
+    def download_system(self):
+        d = self.ndf
+        sysmat = np.empty((self.batch, 4 * d - 1, self.total))
+        known = np.empty((self.batch, self.total))
+        _lib.check(self._L.osc2_download_system(self._h, dptr(sysmat), dptr(known)))
+        return sysmat, known
+
+    # -- timing -------------------------------------------------------------
+    def set_profiling(self, on: bool):
+        _lib.check(self._L.osc2_set_profiling(self._h, int(on)))
+
+    def kernel_ms(self, reset: bool = False):
+        ms = (C.c_double * OSC2_K_COUNT)()
+        n = (C.c_longlong * OSC2_K_COUNT)()
+        _lib.check(self._L.osc2_get_kernel_ms(self._h, C.byref(ms), C.byref(n)))
+        out = {KERNEL_NAMES[k]: (ms[k], n[k]) for k in range(OSC2_K_COUNT) if n[k]}
+        if reset:
+            _lib.check(self._L.osc2_reset_kernel_ms(self._h))
+        return out
+
+    def timer_start(self):
+        _lib.check(self._L.osc2_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_double()
+        _lib.check(self._L.osc2_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
+    @property
+    def device_bytes(self) -> int:
+        return int(self._L.osc2_device_bytes(self._h))
+
+    # -- convenience: one full reference-equivalent step on host arrays -------
+    def run(self, arr: StepArrays, capture: bool = False) -> Dict[str, np.ndarray]:
+        """upload -> step -> download; `arr` is batched.  Raises on a singular system."""
+        if capture:
+            self.set_capture(True)
+        self.upload_state(arr.sysvar, arr.syslod)
+        self.upload_step_inputs(arr)
+        self.step(arr.dt, arr.num_step)
+        self.synchronize()
+        sv, sl, st = self.download_state()
+        out = {"sysvar": sv, "syslod": sl, "status": st}
+        out.update(self.download_diagnostics())
+        if capture:
+            out["sysmat"], out["known"] = self.download_system()
+            self.set_capture(False)
+        return out

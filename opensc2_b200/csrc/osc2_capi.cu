@@ -1,0 +1,486 @@
+// C-ABI layer of libopensc2_b200.so (see include/opensc2_b200.h).
+// Host buffers in the reference's per-conductor layout go through one staging
+// buffer and a tiled transpose into the batch-innermost device layout.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "step_launch.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess)                                                               \
+            return fail(OSC2_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                        __FILE__, __LINE__);                                                  \
+    } while (0)
+
+struct EventPair { cudaEvent_t a, b; int kid; };
+
+}  // namespace
+
+struct osc2_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    osc2_topology topo;
+    osc2_topology *topo_dev = nullptr;
+    int B = 0, N = 0, E = 0, M = 0, S = 0, d = 0, NS = 0;
+    size_t total = 0;
+    StepDev p;                       // device pointers
+    std::vector<void *> allocs;
+    size_t bytes = 0;
+    double *staging = nullptr;       // [max array] for layout changes
+    size_t staging_doubles = 0;
+    double *sysvar_a = nullptr, *sysvar_b = nullptr;
+    bool have_state = false, have_inputs = false;
+    bool capture = false, profiling = false;
+    int max_smem = 0, sm_count = 0;
+    std::vector<EventPair> pending, pool;
+    double kernel_ms[OSC2_K_COUNT] = {0};
+    long long kernel_launches[OSC2_K_COUNT] = {0};
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    int *status_host = nullptr;
+    std::string launch_error;
+
+    // ---- Launcher policy for osc2_run_step --------------------------------
+    size_t get_max_smem() const { return (size_t)max_smem; }
+};
+
+namespace {
+
+struct CudaLauncher {
+    osc2_context *h;
+    size_t max_smem() const { return (size_t)h->max_smem; }
+    int sm_count() const { return h->sm_count; }
+
+    template <class K, class... A>
+    void launch(int kid, K kernel, unsigned grid, unsigned block, size_t smem, A... args)
+    {
+        if (!h->launch_error.empty()) return;
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) { h->launch_error = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return; }
+        }
+        EventPair ev{};
+        if (h->profiling) {
+            if (!h->pool.empty()) { ev = h->pool.back(); h->pool.pop_back(); }
+            else { cudaEventCreate(&ev.a); cudaEventCreate(&ev.b); }
+            ev.kid = kid;
+            cudaEventRecord(ev.a, h->stream);
+        }
+        kernel<<<grid, block, smem, h->stream>>>(args...);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) h->launch_error = std::string("kernel launch: ") + cudaGetErrorString(e);
+        if (h->profiling) { cudaEventRecord(ev.b, h->stream); h->pending.push_back(ev); }
+        h->kernel_launches[kid]++;
+    }
+};
+
+int dev_alloc(osc2_context *h, double **ptr, size_t n_doubles)
+{
+    if (n_doubles == 0) n_doubles = 1;
+    void *q = nullptr;
+    CK(cudaMalloc(&q, n_doubles * sizeof(double)));
+    h->allocs.push_back(q);
+    h->bytes += n_doubles * sizeof(double);
+    *ptr = (double *)q;
+    return OSC2_OK;
+}
+
+// host [B][K] -> device [K][B]
+int upload_transposed(osc2_context *h, const double *host, double *dev, size_t K)
+{
+    const size_t n = (size_t)h->B * K;
+    if (n == 0) return OSC2_OK;
+    if (n > h->staging_doubles) return fail(OSC2_ERR_STATE, "staging buffer too small");
+    CK(cudaMemcpyAsync(h->staging, host, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CudaLauncher L{h};
+    const long long tiles = (((long long)h->B + 31) / 32) * (((long long)K + 31) / 32);
+    L.launch(OSC2_K_TRANSPOSE, osc2_transpose_kernel, (unsigned)tiles, 256u, (size_t)0,
+             (const double *)h->staging, dev, (long long)h->B, (long long)K);
+    if (!h->launch_error.empty()) return fail(OSC2_ERR_CUDA, "%s", h->launch_error.c_str());
+    return OSC2_OK;
+}
+
+// device [K][B] -> host [B][K]
+int download_transposed(osc2_context *h, const double *dev, double *host, size_t K)
+{
+    const size_t n = (size_t)h->B * K;
+    if (n == 0) return OSC2_OK;
+    if (n > h->staging_doubles) return fail(OSC2_ERR_STATE, "staging buffer too small");
+    CudaLauncher L{h};
+    const long long tiles = (((long long)K + 31) / 32) * (((long long)h->B + 31) / 32);
+    L.launch(OSC2_K_TRANSPOSE, osc2_transpose_kernel, (unsigned)tiles, 256u, (size_t)0,
+             dev, h->staging, (long long)K, (long long)h->B);
+    if (!h->launch_error.empty()) return fail(OSC2_ERR_CUDA, "%s", h->launch_error.c_str());
+    CK(cudaMemcpyAsync(host, h->staging, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return OSC2_OK;
+}
+
+int drain_events(osc2_context *h)
+{
+    for (auto &ev : h->pending) {
+        CK(cudaEventSynchronize(ev.b));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, ev.a, ev.b));
+        h->kernel_ms[ev.kid] += ms;
+        h->pool.push_back(ev);
+    }
+    h->pending.clear();
+    return OSC2_OK;
+}
+
+int validate_topology(const osc2_topology *t)
+{
+    if (!t) return fail(OSC2_ERR_INVALID, "topology is NULL");
+    if (t->n_ch < 0 || t->n_ch > OSC2_MAX_CHANNELS || t->n_sol < 0 || t->n_sol > OSC2_MAX_SOLIDS)
+        return fail(OSC2_ERR_INVALID, "component counts out of range (%d channels, %d solids)", t->n_ch, t->n_sol);
+    if (3 * t->n_ch + t->n_sol < 1 || 3 * t->n_ch + t->n_sol > 64)
+        return fail(OSC2_ERR_INVALID, "NODOFS = %d outside 1..64", 3 * t->n_ch + t->n_sol);
+    const int counts[4] = {t->nff, t->nfs, t->nss, t->nes};
+    for (int c : counts)
+        if (c < 0 || c > OSC2_MAX_INTERFACES) return fail(OSC2_ERR_INVALID, "interface count out of range");
+    for (int j = 0; j < t->n_ch; ++j)
+        if (t->ch_intial[j] < 1 || t->ch_intial[j] > 3)
+            return fail(OSC2_ERR_INVALID, "abs(INTIAL) of channel %d must be 1, 2 or 3", j);
+    for (int k = 0; k < t->nff; ++k)
+        if (t->ff[k][0] < 0 || t->ff[k][0] >= t->n_ch || t->ff[k][1] < 0 || t->ff[k][1] >= t->n_ch)
+            return fail(OSC2_ERR_INVALID, "fluid-fluid interface %d names a missing channel", k);
+    for (int k = 0; k < t->nfs; ++k)
+        if (t->fs[k][0] < 0 || t->fs[k][0] >= t->n_ch || t->fs[k][1] < 0 || t->fs[k][1] >= t->n_sol)
+            return fail(OSC2_ERR_INVALID, "fluid-solid interface %d names a missing component", k);
+    for (int k = 0; k < t->nss; ++k)
+        if (t->ss[k][0] < 0 || t->ss[k][0] >= t->n_sol || t->ss[k][1] < 0 || t->ss[k][1] >= t->n_sol)
+            return fail(OSC2_ERR_INVALID, "solid-solid interface %d names a missing solid", k);
+    for (int k = 0; k < t->nes; ++k)
+        if (t->es[k] < 0 || t->es[k] >= t->n_sol)
+            return fail(OSC2_ERR_INVALID, "environment interface %d names a missing solid", k);
+    if (t->method != 0 && t->method != 1)
+        return fail(OSC2_ERR_INVALID, "METHOD must be BE (0) or CN (1); AM4 is not supported");
+    return OSC2_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *osc2_last_error(void) { return g_err.c_str(); }
+int osc2_version(void) { return 100; }
+
+int osc2_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int osc2_create(const osc2_topology *topo, int batch, int n_nodes, int device, osc2_handle *out)
+{
+    if (!out) return fail(OSC2_ERR_INVALID, "out handle is NULL");
+    *out = nullptr;
+    int rc = validate_topology(topo);
+    if (rc) return rc;
+    if (batch < 1) return fail(OSC2_ERR_INVALID, "batch must be >= 1");
+    if (n_nodes < 4)
+        return fail(OSC2_ERR_INVALID, "n_nodes = %d: the reference needs at least 4 nodes "
+                    "(build_known_therm_vector indexes out of bounds below that)", n_nodes);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(OSC2_ERR_NO_DEVICE, "no CUDA device visible; opensc2_b200 has no CPU fallback");
+    }
+    if (device < 0 || device >= ndev) return fail(OSC2_ERR_INVALID, "device %d of %d", device, ndev);
+    CK(cudaSetDevice(device));
+    osc2_context *h = new osc2_context();
+    h->device = device;
+    h->topo = *topo;
+    h->B = batch; h->N = n_nodes; h->E = n_nodes - 1;
+    h->M = topo->n_ch; h->S = topo->n_sol; h->d = 3 * h->M + h->S;
+    h->total = (size_t)h->d * h->N;
+    const GmSlots sl{h->d, h->M, h->S};
+    h->NS = sl.count();
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    h->max_smem = (int)prop.sharedMemPerBlockOptin;
+    h->sm_count = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&h->t0));
+    CK(cudaEventCreate(&h->t1));
+    CK(cudaMalloc((void **)&h->topo_dev, sizeof(osc2_topology)));
+    CK(cudaMemcpy(h->topo_dev, topo, sizeof(osc2_topology), cudaMemcpyHostToDevice));
+    CK(cudaMallocHost((void **)&h->status_host, sizeof(int) * (size_t)batch));
+
+    const size_t B = batch, E = h->E, N = h->N, M = h->M, S = h->S, d = h->d;
+    StepDev &p = h->p;
+    memset(&p, 0, sizeof p);
+    p.B = batch; p.N = h->N; p.E = h->E; p.M = h->M; p.S = h->S; p.d = h->d; p.NS = h->NS;
+    p.nff = topo->nff; p.nfs = topo->nfs; p.nss = topo->nss; p.nes = topo->nes;
+    struct { const double **dst; size_t k; } ins[] = {
+        {&p.dz, E}, {&p.fl_gauss, 9 * M * E}, {&p.fl_node, 4 * M}, {&p.fl_bc, 6 * M},
+        {&p.sol_gauss, 3 * S * E}, {&p.sol_q, 2 * S * E * 2},
+        {&p.peri_ff, 2 * (size_t)p.nff * E}, {&p.htc_ff, 2 * (size_t)p.nff * E},
+        {&p.peri_fs, (size_t)p.nfs * E}, {&p.htc_fs, (size_t)p.nfs * E},
+        {&p.peri_ss, (size_t)p.nss * E}, {&p.htc_ss, (size_t)p.nss * E},
+        {&p.peri_es, (size_t)p.nes * E}, {&p.htc_es, (size_t)p.nes * 3 * E}, {&p.qsource, N * S},
+    };
+    size_t kmax = h->total * 2;   // syslod
+    for (auto &in : ins) {
+        double *q = nullptr;
+        rc = dev_alloc(h, &q, in.k * B);
+        if (rc) { osc2_destroy(h); return rc; }
+        *in.dst = q;
+        if (in.k > kmax) kmax = in.k;
+    }
+    const size_t k123 = 3 * (size_t)p.nff * E;
+    if (k123 > kmax) kmax = k123;
+    rc = dev_alloc(h, &h->sysvar_a, h->total * B);
+    if (!rc) rc = dev_alloc(h, &h->sysvar_b, h->total * B);
+    if (!rc) rc = dev_alloc(h, &p.syslod, h->total * 2 * B);
+    if (!rc) rc = dev_alloc(h, &p.gm, E * (size_t)h->NS * B);
+    if (!rc) rc = dev_alloc(h, &p.k123, k123 * B);
+    if (!rc) rc = dev_alloc(h, &p.spill, N * d * (2 * d + 1) * B);
+    if (!rc) rc = dev_alloc(h, &p.norm_solution, d * B);
+    if (!rc) rc = dev_alloc(h, &p.norm_change, d * B);
+    if (!rc) rc = dev_alloc(h, &p.eqteig, d * B);
+    if (!rc) { double *q = nullptr; rc = dev_alloc(h, &q, (B + 1) / 2 + 1); p.status = (int *)q; }
+    h->staging_doubles = kmax * B;
+    if (!rc) rc = dev_alloc(h, &h->staging, h->staging_doubles);
+    if (rc) { osc2_destroy(h); return rc; }
+    p.sysvar = h->sysvar_a;
+    p.sysvar_new = h->sysvar_b;
+    cudaMemsetAsync(p.status, 0, sizeof(int) * B, h->stream);
+    cudaMemsetAsync(p.syslod, 0, h->total * 2 * B * sizeof(double), h->stream);
+    CK(cudaStreamSynchronize(h->stream));
+    *out = h;
+    return OSC2_OK;
+}
+
+int osc2_destroy(osc2_handle h)
+{
+    if (!h) return OSC2_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (void *q : h->allocs) cudaFree(q);
+    if (h->topo_dev) cudaFree(h->topo_dev);
+    if (h->status_host) cudaFreeHost(h->status_host);
+    for (auto &ev : h->pending) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
+    for (auto &ev : h->pool) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
+    if (h->t0) cudaEventDestroy(h->t0);
+    if (h->t1) cudaEventDestroy(h->t1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return OSC2_OK;
+}
+
+int osc2_upload_state(osc2_handle h, const double *sysvar, const double *syslod)
+{
+    if (!h) return fail(OSC2_ERR_INVALID, "handle is NULL");
+    CK(cudaSetDevice(h->device));
+    int rc = OSC2_OK;
+    if (sysvar) { rc = upload_transposed(h, sysvar, (double *)h->p.sysvar, h->total); if (rc) return rc; h->have_state = true; }
+    if (syslod) { rc = upload_transposed(h, syslod, h->p.syslod, h->total * 2); if (rc) return rc; }
+    return OSC2_OK;
+}
+
+int osc2_upload_step_inputs(osc2_handle h, const osc2_step_inputs *in)
+{
+    if (!h || !in) return fail(OSC2_ERR_INVALID, "NULL argument");
+    CK(cudaSetDevice(h->device));
+    const size_t E = h->E, N = h->N, M = h->M, S = h->S;
+    StepDev &p = h->p;
+    struct { const double *src; const double *dst; size_t k; const char *name; } a[] = {
+        {in->dz, p.dz, E, "dz"}, {in->fl_gauss, p.fl_gauss, 9 * M * E, "fl_gauss"},
+        {in->fl_node, p.fl_node, 4 * M, "fl_node"}, {in->fl_bc, p.fl_bc, 6 * M, "fl_bc"},
+        {in->sol_gauss, p.sol_gauss, 3 * S * E, "sol_gauss"}, {in->sol_q, p.sol_q, 2 * S * E * 2, "sol_q"},
+        {in->peri_ff, p.peri_ff, 2 * (size_t)p.nff * E, "peri_ff"}, {in->htc_ff, p.htc_ff, 2 * (size_t)p.nff * E, "htc_ff"},
+        {in->peri_fs, p.peri_fs, (size_t)p.nfs * E, "peri_fs"}, {in->htc_fs, p.htc_fs, (size_t)p.nfs * E, "htc_fs"},
+        {in->peri_ss, p.peri_ss, (size_t)p.nss * E, "peri_ss"}, {in->htc_ss, p.htc_ss, (size_t)p.nss * E, "htc_ss"},
+        {in->peri_es, p.peri_es, (size_t)p.nes * E, "peri_es"}, {in->htc_es, p.htc_es, (size_t)p.nes * 3 * E, "htc_es"},
+        {in->qsource, p.qsource, N * S, "qsource"},
+    };
+    for (auto &x : a) {
+        if (x.k == 0) continue;
+        if (!x.src) return fail(OSC2_ERR_INVALID, "step input %s is NULL", x.name);
+        int rc = upload_transposed(h, x.src, (double *)x.dst, x.k);
+        if (rc) return rc;
+    }
+    p.t_env = in->t_env;
+    h->have_inputs = true;
+    return OSC2_OK;
+}
+
+int osc2_step(osc2_handle h, double dt, int num_step)
+{
+    if (!h) return fail(OSC2_ERR_INVALID, "handle is NULL");
+    if (!h->have_state || !h->have_inputs)
+        return fail(OSC2_ERR_STATE, "osc2_step needs osc2_upload_state and osc2_upload_step_inputs first");
+    if (!(dt > 0.0)) return fail(OSC2_ERR_INVALID, "time step must be positive");
+    if (num_step < 1) return fail(OSC2_ERR_INVALID, "num_step must be >= 1");
+    CK(cudaSetDevice(h->device));
+    h->p.dt = dt;
+    h->p.num_step = num_step;
+    if (h->capture) {
+        const size_t full = 4 * (size_t)h->d - 1;
+        CK(cudaMemsetAsync(h->p.cap_sysmat, 0, full * h->total * h->B * sizeof(double), h->stream));
+    }
+    CudaLauncher L{h};
+    StepDev pp = h->p;
+    if (!h->capture) { pp.cap_sysmat = nullptr; pp.cap_known = nullptr; }
+    osc2_run_step(L, h->topo_dev, pp);
+    if (!h->launch_error.empty()) {
+        const int rc = fail(OSC2_ERR_CUDA, "%s", h->launch_error.c_str());
+        h->launch_error.clear();
+        return rc;
+    }
+    // the new solution becomes the state of the next step
+    const double *old = h->p.sysvar;
+    h->p.sysvar = h->p.sysvar_new;
+    h->p.sysvar_new = (double *)old;
+    return OSC2_OK;
+}
+
+int osc2_synchronize(osc2_handle h)
+{
+    if (!h) return fail(OSC2_ERR_INVALID, "handle is NULL");
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(h->status_host, h->p.status, sizeof(int) * (size_t)h->B, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int b = 0; b < h->B; ++b)
+        if (h->status_host[b] != 0)
+            return fail(OSC2_ERR_SINGULAR, "ERROR! Matrix is singular at line %d (conductor %d of the batch)",
+                        -h->status_host[b] - 1, b);
+    return OSC2_OK;
+}
+
+int osc2_download_state(osc2_handle h, double *sysvar, double *syslod, int *status)
+{
+    if (!h) return fail(OSC2_ERR_INVALID, "handle is NULL");
+    CK(cudaSetDevice(h->device));
+    int rc;
+    if (sysvar) { rc = download_transposed(h, h->p.sysvar, sysvar, h->total); if (rc) return rc; }
+    if (syslod) { rc = download_transposed(h, h->p.syslod, syslod, h->total * 2); if (rc) return rc; }
+    if (status) {
+        CK(cudaMemcpyAsync(status, h->p.status, sizeof(int) * (size_t)h->B, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    return OSC2_OK;
+}
+
+int osc2_download_diagnostics(osc2_handle h, double *norm_solution, double *norm_change, double *eqteig, double *k123)
+{
+    if (!h) return fail(OSC2_ERR_INVALID, "handle is NULL");
+    CK(cudaSetDevice(h->device));
+    int rc;
+    if (norm_solution) { rc = download_transposed(h, h->p.norm_solution, norm_solution, h->d); if (rc) return rc; }
+    if (norm_change) { rc = download_transposed(h, h->p.norm_change, norm_change, h->d); if (rc) return rc; }
+    if (eqteig) { rc = download_transposed(h, h->p.eqteig, eqteig, h->d); if (rc) return rc; }
+    if (k123) { rc = download_transposed(h, h->p.k123, k123, 3 * (size_t)h->p.nff * h->E); if (rc) return rc; }
+    return OSC2_OK;
+}
+
+int osc2_set_capture(osc2_handle h, int on)
+{
+    if (!h) return fail(OSC2_ERR_INVALID, "handle is NULL");
+    CK(cudaSetDevice(h->device));
+    if (on && !h->p.cap_sysmat) {
+        const size_t full = 4 * (size_t)h->d - 1;
+        int rc = dev_alloc(h, &h->p.cap_sysmat, full * h->total * h->B);
+        if (!rc) rc = dev_alloc(h, &h->p.cap_known, h->total * h->B);
+        if (rc) return rc;
+        if (full * h->total * h->B > h->staging_doubles) {
+            double *q = nullptr;
+            rc = dev_alloc(h, &q, full * h->total * h->B);
+            if (rc) return rc;
+            h->staging = q;
+            h->staging_doubles = full * h->total * h->B;
+        }
+    }
+    h->capture = on != 0;   // buffers are kept; osc2_step hides the pointers when off
+    return OSC2_OK;
+}
+
+int osc2_download_system(osc2_handle h, double *sysmat, double *known)
+{
+    if (!h) return fail(OSC2_ERR_INVALID, "handle is NULL");
+    if (!h->capture || !h->p.cap_sysmat) return fail(OSC2_ERR_STATE, "enable osc2_set_capture before the step");
+    CK(cudaSetDevice(h->device));
+    const size_t full = 4 * (size_t)h->d - 1;
+    int rc;
+    if (sysmat) { rc = download_transposed(h, h->p.cap_sysmat, sysmat, full * h->total); if (rc) return rc; }
+    if (known) { rc = download_transposed(h, h->p.cap_known, known, h->total); if (rc) return rc; }
+    return OSC2_OK;
+}
+
+int osc2_set_profiling(osc2_handle h, int on)
+{
+    if (!h) return fail(OSC2_ERR_INVALID, "handle is NULL");
+    h->profiling = on != 0;
+    return OSC2_OK;
+}
+
+int osc2_get_kernel_ms(osc2_handle h, double ms[OSC2_K_COUNT], long long launches[OSC2_K_COUNT])
+{
+    if (!h) return fail(OSC2_ERR_INVALID, "handle is NULL");
+    CK(cudaSetDevice(h->device));
+    int rc = drain_events(h);
+    if (rc) return rc;
+    for (int k = 0; k < OSC2_K_COUNT; ++k) {
+        if (ms) ms[k] = h->kernel_ms[k];
+        if (launches) launches[k] = h->kernel_launches[k];
+    }
+    return OSC2_OK;
+}
+
+int osc2_reset_kernel_ms(osc2_handle h)
+{
+    if (!h) return fail(OSC2_ERR_INVALID, "handle is NULL");
+    CK(cudaSetDevice(h->device));
+    int rc = drain_events(h);
+    if (rc) return rc;
+    for (int k = 0; k < OSC2_K_COUNT; ++k) { h->kernel_ms[k] = 0.0; h->kernel_launches[k] = 0; }
+    return OSC2_OK;
+}
+
+int osc2_timer_start(osc2_handle h)
+{
+    if (!h) return fail(OSC2_ERR_INVALID, "handle is NULL");
+    CK(cudaSetDevice(h->device));
+    CK(cudaEventRecord(h->t0, h->stream));
+    return OSC2_OK;
+}
+
+int osc2_timer_stop(osc2_handle h, double *elapsed_ms)
+{
+    if (!h) return fail(OSC2_ERR_INVALID, "handle is NULL");
+    CK(cudaSetDevice(h->device));
+    CK(cudaEventRecord(h->t1, h->stream));
+    CK(cudaEventSynchronize(h->t1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, h->t0, h->t1));
+    if (elapsed_ms) *elapsed_ms = ms;
+    return OSC2_OK;
+}
+
+size_t osc2_device_bytes(osc2_handle h) { return h ? h->bytes : 0; }
+
+}  // extern "C"

@@ -1,0 +1,63 @@
+// Device-side parameter blocks shared by the kernels and the C-ABI layer.
+//
+// Device layout is batch-innermost: an array the reference keeps as
+// x[...] per conductor is x[...][b] here, so a warp touching 32 consecutive
+// conductors issues one 256-byte FP64 transaction per value.
+#pragma once
+
+#include "../../include/opensc2_b200.h"
+
+#ifndef OSC2_EMU
+#include <cuda_runtime.h>
+#endif
+
+struct StepDev {
+    int B, N, E, M, S, d, NS;
+    int nff, nfs, nss, nes;
+    double dt, t_env;
+    int num_step;
+    // inputs ([...][B])
+    const double *dz;         // [E]
+    const double *fl_gauss;   // [9][M][E]
+    const double *fl_node;    // [4][M]
+    const double *fl_bc;      // [6][M]
+    const double *sol_gauss;  // [3][S][E]
+    const double *sol_q;      // [2][S][E][2]
+    const double *peri_ff, *htc_ff;   // [2][nff][E]
+    const double *peri_fs, *htc_fs;   // [nfs][E]
+    const double *peri_ss, *htc_ss;   // [nss][E]
+    const double *peri_es;            // [nes][E]
+    const double *htc_es;             // [nes][3][E]
+    const double *qsource;            // [N][S]
+    // state
+    const double *sysvar;     // [N][d]   old solution
+    double *sysvar_new;       // [N][d]   new solution
+    double *syslod;           // [N][d][2]
+    // work
+    double *gm;               // [E][NS]  Gauss-point matrices (see gm_slots)
+    double *k123;             // [3][nff][E]
+    double *spill;            // [N][d][2d+1]  U factors + forward-substituted rhs
+    // outputs
+    double *norm_solution, *norm_change, *eqteig;   // [d]
+    int *status;              // [B] 0 or -(row+1)
+    double *cap_sysmat;       // optional [Full][Total]
+    double *cap_known;        // optional [Total]
+};
+
+// Slot map of one element's Gauss-point record in `gm`:
+//   S      d*d   source Jacobian SMAT, row major
+//   Msol   S     MMAT diagonal of the solid equations (fluid rows are 1)
+//   K      d     KMAT diagonal
+//   A      4*M   per channel: v, 1/rho, rho*c0^2, Gruneisen*T (AMAT non-zeros)
+//   SV     2*S   SVEC present  [l][0|1]
+//   SVP    2*S   SVEC previous [l][0|1]  (first step only)
+struct GmSlots {
+    int d, M, S;
+    __host__ __device__ int s(int r, int c) const { return r * d + c; }
+    __host__ __device__ int msol(int l) const { return d * d + l; }
+    __host__ __device__ int k(int r) const { return d * d + S + r; }
+    __host__ __device__ int a(int j, int q) const { return d * d + S + d + 4 * j + q; }
+    __host__ __device__ int sv(int l, int t) const { return d * d + S + d + 4 * M + 2 * l + t; }
+    __host__ __device__ int svp(int l, int t) const { return d * d + S + d + 4 * M + 2 * S + 2 * l + t; }
+    __host__ __device__ int count() const { return d * d + S + d + 4 * M + 4 * S; }
+};

@@ -1,0 +1,75 @@
+// Minimal CPU thread emulator for the CUDA kernels' LOGIC tests (test
+// infrastructure only -- never loaded by the product).  Every CUDA thread of a
+// CTA becomes a host thread; CTAs run one after another; __syncthreads and
+// __syncwarp are std::barrier.  It exists because the build container has no
+// GPU: index arithmetic, synchronisation placement and operand order of the
+// kernels can be checked against the oracle before GPU time is spent.
+#pragma once
+#define OSC2_EMU 1
+
+#include <barrier>
+#include <cmath>
+#include <cstddef>
+#include <cstring>
+#include <memory>
+#include <thread>
+#include <vector>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __restrict__
+#define __shared__ static
+
+struct emu_dim3 { unsigned x = 1, y = 1, z = 1; };
+inline thread_local emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
+inline thread_local double *emu_dyn_smem = nullptr;
+inline thread_local std::barrier<> *emu_block_barrier = nullptr;
+inline thread_local std::barrier<> *emu_warp_barrier = nullptr;
+
+#define OSC2_DYN_SMEM(name) double *name = emu_dyn_smem
+
+inline void __syncthreads() { emu_block_barrier->arrive_and_wait(); }
+inline void __syncwarp() { emu_warp_barrier->arrive_and_wait(); }
+using std::fabs;
+using std::sqrt;
+
+struct EmuLauncher {
+    size_t max_smem() const { return 227 * 1024; }
+    int sm_count() const { return 148; }
+    long long launches = 0;
+
+    template <class K, class... A>
+    void launch(int /*kernel_id*/, K kernel, unsigned grid, unsigned block, size_t smem, A... args)
+    {
+        ++launches;
+        std::vector<double> dyn((smem + 7) / 8 + 1);
+        for (unsigned bid = 0; bid < grid; ++bid) {
+            std::barrier<> bb((std::ptrdiff_t)block);
+            const unsigned nwarps = (block + 31) / 32;
+            std::vector<std::unique_ptr<std::barrier<>>> wb;
+            for (unsigned w = 0; w < nwarps; ++w) {
+                const unsigned lanes = (w + 1) * 32 <= block ? 32 : block - w * 32;
+                wb.emplace_back(new std::barrier<>((std::ptrdiff_t)lanes));
+            }
+            // poison shared memory so that reads of unwritten slots show up
+            for (auto &v : dyn) v = std::nan("");
+            std::vector<std::thread> th;
+            th.reserve(block);
+            for (unsigned t = 0; t < block; ++t) {
+                th.emplace_back([&, t]() {
+                    threadIdx.x = t; blockIdx.x = bid; blockDim.x = block; gridDim.x = grid;
+                    emu_dyn_smem = dyn.data();
+                    emu_block_barrier = &bb;
+                    emu_warp_barrier = wb[t / 32].get();
+                    kernel(args...);
+                    // a thread that returns early must not block the others
+                    bb.arrive_and_drop();
+                    wb[t / 32]->arrive_and_drop();
+                });
+            }
+            for (auto &x : th) x.join();
+        }
+    }
+};

@@ -1,0 +1,96 @@
+"""Python driver of the CPU thread emulator (kernel LOGIC tests, CPU only)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from opensc2_b200._abi import Osc2Topology, c_dp, c_ip, topology_struct
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+
+
+class StepDev(C.Structure):
+    """Mirror of opensc2_b200/csrc/osc2_dev.h:StepDev."""
+    _fields_ = [(n, C.c_int) for n in ("B", "N", "E", "M", "S", "d", "NS", "nff", "nfs", "nss", "nes")] + [
+        ("dt", C.c_double), ("t_env", C.c_double), ("num_step", C.c_int)] + [
+        (n, c_dp) for n in ("dz", "fl_gauss", "fl_node", "fl_bc", "sol_gauss", "sol_q", "peri_ff", "htc_ff",
+                            "peri_fs", "htc_fs", "peri_ss", "htc_ss", "peri_es", "htc_es", "qsource",
+                            "sysvar", "sysvar_new", "syslod", "gm", "k123", "spill",
+                            "norm_solution", "norm_change", "eqteig")] + [
+        ("status", c_ip), ("cap_sysmat", c_dp), ("cap_known", c_dp)]
+
+
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(HERE, "libosc2_emu.so")
+        srcs = [os.path.join(HERE, f) for f in ("emu_step.cpp", "cuda_emu.h")]
+        srcs += [os.path.join(ROOT, "opensc2_b200", "csrc", f) for f in ("step_kernels.cuh", "step_launch.h", "osc2_dev.h")]
+        srcs += [os.path.join(ROOT, "include", "opensc2_b200.h")]
+        if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+            subprocess.run(["g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-ffp-contract=off", "-pthread",
+                            "-o", so, os.path.join(HERE, "emu_step.cpp")], check=True)
+        _LIB = C.CDLL(so)
+        assert _LIB.osc2_emu_sizeof_stepdev() == C.sizeof(StepDev)
+        assert _LIB.osc2_emu_sizeof_topology() == C.sizeof(Osc2Topology)
+    return _LIB
+
+
+def to_dev(a):
+    """[B][...] -> [...][B] contiguous (the device layout)."""
+    return np.ascontiguousarray(np.moveaxis(np.asarray(a, dtype=np.float64), 0, -1))
+
+
+def from_dev(a):
+    return np.ascontiguousarray(np.moveaxis(a, -1, 0))
+
+
+def emu_step(topo, arr, capture=False):
+    """Run K_G, K_F, K_B, K_N on a batched StepArrays through the emulator."""
+    L = lib()
+    B, E = arr.dz.shape
+    N, M, S, d = E + 1, topo.n_ch, topo.n_sol, topo.ndf
+    total = N * d
+    NS = d * d + S + d + 4 * M + 4 * S
+    t = topology_struct(topo)
+    p = StepDev()
+    p.B, p.N, p.E, p.M, p.S, p.d, p.NS = B, N, E, M, S, d, NS
+    p.nff, p.nfs, p.nss, p.nes = len(topo.ff), len(topo.fs), len(topo.ss), len(topo.es)
+    p.dt, p.t_env, p.num_step = arr.dt, arr.t_env, arr.num_step
+    keep = {}
+    for name in ("dz", "fl_gauss", "fl_node", "fl_bc", "sol_gauss", "sol_q", "peri_ff", "htc_ff",
+                 "peri_fs", "htc_fs", "peri_ss", "htc_ss", "peri_es", "htc_es", "qsource", "sysvar", "syslod"):
+        a = to_dev(getattr(arr, name))
+        if a.size == 0:
+            a = np.zeros(1)
+        keep[name] = a
+        setattr(p, name, a.ctypes.data_as(c_dp))
+    outs = {
+        "sysvar_new": np.full((total, B), np.nan), "gm": np.full((E, NS, B), np.nan),
+        "k123": np.zeros((3, max(p.nff, 1), E, B)), "spill": np.full((N, d, 2 * d + 1, B), np.nan),
+        "norm_solution": np.zeros((d, B)), "norm_change": np.zeros((d, B)), "eqteig": np.zeros((d, B)),
+    }
+    for k, a in outs.items():
+        setattr(p, k, a.ctypes.data_as(c_dp))
+    status = np.full(B, 12345, dtype=np.int32)
+    p.status = status.ctypes.data_as(c_ip)
+    if capture:
+        outs["cap_sysmat"] = np.zeros((4 * d - 1, total, B))
+        outs["cap_known"] = np.zeros((total, B))
+        p.cap_sysmat = outs["cap_sysmat"].ctypes.data_as(c_dp)
+        p.cap_known = outs["cap_known"].ctypes.data_as(c_dp)
+    L.osc2_emu_step(C.byref(t), C.byref(p))
+    res = {
+        "sysvar": from_dev(outs["sysvar_new"]), "syslod": from_dev(keep["syslod"]),
+        "k123": from_dev(outs["k123"])[:, :, :p.nff], "norm_solution": from_dev(outs["norm_solution"]),
+        "norm_change": from_dev(outs["norm_change"]), "eqteig": from_dev(outs["eqteig"]), "status": status,
+    }
+    if capture:
+        res["sysmat"] = from_dev(outs["cap_sysmat"])
+        res["known"] = from_dev(outs["cap_known"])
+    return res

@@ -1,0 +1,23 @@
+// Runs the CUDA step kernels through the CPU thread emulator on host arrays
+// that are already in the device (batch-innermost) layout.
+#include "cuda_emu.h"
+
+#include "../../opensc2_b200/csrc/step_launch.h"
+
+extern "C" int osc2_emu_step(const osc2_topology *tp, const StepDev *p)
+{
+    EmuLauncher L;
+    osc2_run_step(L, tp, *p);
+    return (int)L.launches;
+}
+
+extern "C" int osc2_emu_transpose(const double *in, double *out, long long rows, long long cols)
+{
+    EmuLauncher L;
+    const long long tiles = ((rows + 31) / 32) * ((cols + 31) / 32);
+    L.launch(0, osc2_transpose_kernel, (unsigned)tiles, 256u, (size_t)0, in, out, rows, cols);
+    return 0;
+}
+
+extern "C" int osc2_emu_sizeof_stepdev() { return (int)sizeof(StepDev); }
+extern "C" int osc2_emu_sizeof_topology() { return (int)sizeof(osc2_topology); }

@@ -31,3 +31,16 @@ def assert_bits(a, b, what=""):
         bad = np.argwhere(a != b)
         rel = np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300))
         raise AssertionError(f"{what}: {len(bad)} of {a.size} values differ, max rel {rel:.3e}, first at {bad[0]}")
+
+
+def singular_case():
+    """Two pure-solid conductors (d = 1); the second has no mass term, so its
+    Neumann diffusion matrix is singular: the reference raises at line 8."""
+    from opensc2_b200.problem import Topology, synthetic_step_arrays
+
+    topo = Topology(n_ch=0, n_sol=1, ch_area=(), ch_dh=(), ch_forward=(), ch_intial=(),
+                    sol_area=(1e-4,), sol_costeta=(1.0,))
+    arr = synthetic_step_arrays(topo, 9, batch=2, seed=2, heated=False)
+    arr.sol_gauss[1, 0] = 0.0
+    arr.sol_gauss[1, 2] = 100.0
+    return topo, arr

@@ -1,0 +1,132 @@
+"""GPU parity: the sm_100a kernels, called through the C ABI, against the
+reference fixtures and the CPU oracle.  Bit-exact (FP64, -fmad=false)."""
+import dataclasses
+
+import numpy as np
+import pytest
+
+from cases import STEP_CASES, WITH_SYSTEM
+from helpers import assert_bits, load_golden
+from opensc2_b200.problem import (case1_topology, case2_topology, case3_topology,
+                                  synthetic_step_arrays)
+
+pytestmark = pytest.mark.gpu
+
+KEYS = ("sysvar", "syslod", "k123", "norm_solution", "norm_change", "eqteig")
+
+
+def _batched(arr):
+    kw = {}
+    for f in dataclasses.fields(arr):
+        v = getattr(arr, f.name)
+        kw[f.name] = v[None].copy() if isinstance(v, np.ndarray) else v
+    return type(arr)(**kw)
+
+
+@pytest.mark.parametrize("name", sorted(STEP_CASES))
+def test_reference_fixture_bit_exact(name):
+    from opensc2_b200.batch import BatchedStep
+
+    topo, arr, ref = load_golden(name)
+    cap = name in WITH_SYSTEM
+    with BatchedStep(topo, 1, arr.n_nodes) as bs:
+        out = bs.run(_batched(arr), capture=cap)
+    assert out["status"][0] == 0
+    if cap:
+        assert_bits(out["sysmat"][0], ref["sysmat"], f"{name}:sysmat")
+        assert_bits(out["known"][0], ref["known"], f"{name}:known")
+    for key in KEYS:
+        assert_bits(out[key][0], ref[key], f"{name}:{key}")
+
+
+@pytest.mark.parametrize("label,topo,n,batch", [
+    ("case1", case1_topology(1), 65, 37),
+    ("case1_intial3", case1_topology(3), 130, 64),
+    ("case3", case3_topology(), 40, 9),
+    ("case2", case2_topology(), 7, 3),
+])
+def test_batch_matches_oracle(label, topo, n, batch):
+    from opensc2_b200.batch import BatchedStep
+    from oracle import oracle as O
+
+    arr = synthetic_step_arrays(topo, n, batch=batch, seed=17, exact_squares=False)
+    with BatchedStep(topo, batch, n) as bs:
+        out = bs.run(arr)
+    ref = O.step(topo, arr)
+    assert np.all(out["status"] == 0)
+    for key in KEYS:
+        assert_bits(out[key], ref[key], f"{label}:{key}")
+
+
+def test_chained_steps_match_oracle():
+    """Five consecutive steps (state and SYSLOD history carried on the device)."""
+    from opensc2_b200.batch import BatchedStep
+    from oracle import oracle as O
+
+    topo = case1_topology(1)
+    n, batch = 41, 12
+    arr = synthetic_step_arrays(topo, n, batch=batch, seed=23, num_step=1)
+    host = arr.copy()
+    with BatchedStep(topo, batch, n) as bs:
+        bs.upload_state(arr.sysvar, arr.syslod)
+        bs.upload_step_inputs(arr)
+        for k in range(1, 6):
+            bs.step(arr.dt, k)
+            host.num_step = k
+            ref = O.step(topo, host)
+            host.sysvar, host.syslod = ref["sysvar"], ref["syslod"]
+        bs.synchronize()
+        sv, sl, st = bs.download_state()
+    assert np.all(st == 0)
+    assert_bits(sv, host.sysvar, "sysvar after 5 steps")
+    assert_bits(sl, host.syslod, "syslod after 5 steps")
+
+
+def test_full_size_mesh_linearity_property():
+    """10k-node mesh (BASELINE size per conductor): solution of the captured system
+    satisfies SYSMAT x = Known to FP64 round-off (size-independent residual check)."""
+    from opensc2_b200.batch import BatchedStep
+
+    topo = case1_topology(1)
+    n, batch = 10001, 4
+    arr = synthetic_step_arrays(topo, n, batch=batch, seed=3)
+    with BatchedStep(topo, batch, n) as bs:
+        out = bs.run(arr, capture=True)
+    d = topo.ndf
+    total = d * n
+    main = 2 * d - 1
+    x = out["sysvar"]
+    for b in range(batch):
+        band, known = out["sysmat"][b], out["known"][b]
+        ax = np.zeros(total)
+        for k in range(4 * d - 1):
+            off = k - main
+            lo, hi = max(0, -off), min(total, total - off)
+            ax[lo:hi] += band[k, lo:hi] * x[b, lo + off:hi + off]
+        scale = np.abs(band).T @ np.ones(4 * d - 1) * np.max(np.abs(x[b]))
+        assert np.max(np.abs(ax - known) / scale) < 1e-9
+
+
+def test_too_few_nodes_is_rejected():
+    from opensc2_b200.batch import BatchedStep
+
+    with pytest.raises(ValueError):
+        BatchedStep(case1_topology(1), 2, 3)
+
+
+def test_singular_system_raises_like_reference():
+    """Pure-solid Neumann diffusion without a mass term: the reference raises
+    `ValueError: Matrix is singular at line 8` (tsf:763-786); here status = -(8+1)."""
+    from opensc2_b200 import _lib
+    from opensc2_b200.batch import BatchedStep
+    from helpers import singular_case
+
+    topo, arr = singular_case()
+    with BatchedStep(topo, 2, arr.n_nodes) as bs:
+        bs.upload_state(arr.sysvar, arr.syslod)
+        bs.upload_step_inputs(arr)
+        bs.step(arr.dt, arr.num_step)
+        with pytest.raises(_lib.SingularMatrixError):
+            bs.synchronize()
+        _sv, _sl, st = bs.download_state(want_syslod=False)
+    assert st[0] == 0 and st[1] == -9
