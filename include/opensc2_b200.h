@@ -133,6 +133,10 @@ int osc2_timer_stop(osc2_handle h, double *elapsed_ms);      /* synchronises */
 
 size_t osc2_device_bytes(osc2_handle h);
 
+/* Device self test: the shared-divisor division used by the fast kernels
+ * (csrc/osc2_div.cuh) against the compiler's a / b on n pseudo-random pairs. */
+int osc2_selftest_division(int device, long long n, unsigned long long seed, unsigned long long *mismatches);
+
 #ifdef __cplusplus
 }
 #endif

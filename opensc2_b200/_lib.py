@@ -53,6 +53,8 @@ def load() -> C.CDLL:
     L.osc2_reset_kernel_ms.argtypes = [H]
     L.osc2_timer_start.argtypes = [H]
     L.osc2_timer_stop.argtypes = [H, C.POINTER(C.c_double)]
+    L.osc2_selftest_division.argtypes = [C.c_int, C.c_longlong, C.c_ulonglong, C.POINTER(C.c_ulonglong)]
+    L.osc2_selftest_division.restype = C.c_int
     L.osc2_device_bytes.argtypes = [H]
     L.osc2_device_bytes.restype = C.c_size_t
     for name in ("osc2_create", "osc2_destroy", "osc2_upload_state", "osc2_upload_step_inputs", "osc2_step",
@@ -69,7 +71,7 @@ EXPORTED = (
     "osc2_upload_state", "osc2_upload_step_inputs", "osc2_step", "osc2_synchronize",
     "osc2_download_state", "osc2_download_diagnostics", "osc2_set_capture", "osc2_download_system",
     "osc2_set_profiling", "osc2_get_kernel_ms", "osc2_reset_kernel_ms", "osc2_timer_start",
-    "osc2_timer_stop", "osc2_device_bytes",
+    "osc2_timer_stop", "osc2_device_bytes", "osc2_selftest_division",
 )
 
 

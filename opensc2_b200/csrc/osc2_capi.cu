@@ -5,6 +5,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -53,6 +54,7 @@ struct osc2_context {
     double *sysvar_a = nullptr, *sysvar_b = nullptr;
     bool have_state = false, have_inputs = false;
     bool capture = false, profiling = false;
+    bool fast = false;               // register-resident kernels (step_kernels_fast.cuh)
     int max_smem = 0, sm_count = 0;
     std::vector<EventPair> pending, pool;
     double kernel_ms[OSC2_K_COUNT] = {0};
@@ -180,9 +182,67 @@ int validate_topology(const osc2_topology *t)
     return OSC2_OK;
 }
 
+// ---- self test of the shared-divisor division (osc2_div.cuh) ---------------
+__device__ inline unsigned long long splitmix64(unsigned long long &s)
+{
+    unsigned long long z = (s += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+__device__ inline double random_double(unsigned long long &s, int exp_span)
+{
+    const unsigned long long m = splitmix64(s);
+    const unsigned long long mant = m & 0xFFFFFFFFFFFFFull;
+    const int e = 1023 + (int)((m >> 52) % (unsigned)(2 * exp_span + 1)) - exp_span;
+    const unsigned long long sign = (m >> 63) << 63;
+    return __longlong_as_double((long long)(sign | ((unsigned long long)e << 52) | mant));
+}
+
+__global__ void osc2_div_selftest_kernel(unsigned long long seed, long long per_thread, unsigned long long *mismatch)
+{
+    unsigned long long s = seed + 0x1234567ull * (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x);
+    unsigned long long bad = 0;
+    for (long long i = 0; i < per_thread; ++i) {
+        const int mode = (int)(splitmix64(s) & 15);
+        double a, b;
+        if (mode < 8) { a = random_double(s, 40); b = random_double(s, 40); }
+        else if (mode < 11) { a = random_double(s, 1000); b = random_double(s, 1000); }
+        else if (mode == 11) { a = (splitmix64(s) & 1) ? 0.0 : -0.0; b = random_double(s, 300); }
+        else if (mode == 12) { a = random_double(s, 20) * 1e-300; b = random_double(s, 20); }
+        else if (mode == 13) { a = random_double(s, 20); b = random_double(s, 3) * 1e305; }
+        else if (mode == 14) { a = random_double(s, 3); b = 1.0 + (double)(splitmix64(s) & 0xFFFF) * 2.220446049250313e-16; }
+        else { a = random_double(s, 600); b = (double)(1 + (splitmix64(s) & 1023)); }
+        const Osc2Rcp r = osc2_rcp_prepare(b);
+        const double q = osc2_div(a, r);
+        const double ref = a / b;
+        if (__double_as_longlong(q) != __double_as_longlong(ref) && !(q != q && ref != ref)) ++bad;
+    }
+    if (bad) atomicAdd(mismatch, bad);
+}
+
 }  // namespace
 
 extern "C" {
+
+int osc2_selftest_division(int device, long long n, unsigned long long seed, unsigned long long *mismatches)
+{
+    if (!mismatches) return fail(OSC2_ERR_INVALID, "NULL argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(OSC2_ERR_NO_DEVICE, "no CUDA device visible"); }
+    CK(cudaSetDevice(device));
+    unsigned long long *d = nullptr;
+    CK(cudaMalloc((void **)&d, sizeof(unsigned long long)));
+    CK(cudaMemset(d, 0, sizeof(unsigned long long)));
+    const int threads = 148 * 8 * 128;
+    const long long per = (n + threads - 1) / threads;
+    osc2_div_selftest_kernel<<<148 * 8, 128>>>(seed, per, d);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(mismatches, d, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    CK(cudaFree(d));
+    return OSC2_OK;
+}
 
 const char *osc2_last_error(void) { return g_err.c_str(); }
 int osc2_version(void) { return 100; }
@@ -217,8 +277,11 @@ int osc2_create(const osc2_topology *topo, int batch, int n_nodes, int device, o
     h->B = batch; h->N = n_nodes; h->E = n_nodes - 1;
     h->M = topo->n_ch; h->S = topo->n_sol; h->d = 3 * h->M + h->S;
     h->total = (size_t)h->d * h->N;
-    const GmSlots sl{h->d, h->M, h->S};
-    h->NS = sl.count();
+    {
+        const char *force = getenv("OSC2_FORCE_GENERIC");
+        h->fast = osc2_has_fast_path(h->d) && !(force && force[0] == '1');
+    }
+    h->NS = osc2_gm_slots(h->d, h->M, h->S, h->fast);
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     h->max_smem = (int)prop.sharedMemPerBlockOptin;
@@ -258,7 +321,7 @@ int osc2_create(const osc2_topology *topo, int batch, int n_nodes, int device, o
     if (!rc) rc = dev_alloc(h, &p.syslod, h->total * 2 * B);
     if (!rc) rc = dev_alloc(h, &p.gm, E * (size_t)h->NS * B);
     if (!rc) rc = dev_alloc(h, &p.k123, k123 * B);
-    if (!rc) rc = dev_alloc(h, &p.spill, N * d * (2 * d + 1) * B);
+    if (!rc) rc = dev_alloc(h, &p.spill, N * d * (2 * d + 2) * B);
     if (!rc) rc = dev_alloc(h, &p.norm_solution, d * B);
     if (!rc) rc = dev_alloc(h, &p.norm_change, d * B);
     if (!rc) rc = dev_alloc(h, &p.eqteig, d * B);
@@ -346,7 +409,7 @@ int osc2_step(osc2_handle h, double dt, int num_step)
     CudaLauncher L{h};
     StepDev pp = h->p;
     if (!h->capture) { pp.cap_sysmat = nullptr; pp.cap_known = nullptr; }
-    osc2_run_step(L, h->topo_dev, pp);
+    osc2_run_step(L, h->topo_dev, pp, h->fast, h->topo.theta);
     if (!h->launch_error.empty()) {
         const int rc = fail(OSC2_ERR_CUDA, "%s", h->launch_error.c_str());
         h->launch_error.clear();

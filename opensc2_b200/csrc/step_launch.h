@@ -9,6 +9,7 @@
 #pragma once
 
 #include "step_kernels.cuh"
+#include "step_kernels_fast.cuh"
 
 struct Osc2LaunchPlan {
     int lpc;            // lanes per conductor (8, 16, 32, 64)
@@ -18,6 +19,17 @@ struct Osc2LaunchPlan {
     int gauss_block;
     size_t smem_gauss;  // 0: SMAT staged in the output record
 };
+
+// NODOFS values with a register-resident instantiation (CASE_1: 8, CASE_3: 13).
+inline bool osc2_has_fast_path(int d) { return d == 4 || d == 8 || d == 13; }
+
+// number of doubles of one element record in `gm` for the chosen path
+inline int osc2_gm_slots(int d, int M, int S, bool fast)
+{
+    if (fast) { const GmSlots2 s{d, M, S}; return s.count(); }
+    const GmSlots s{d, M, S};
+    return s.count();
+}
 
 inline int osc2_pick_lpc(int d)
 {
@@ -52,10 +64,40 @@ inline Osc2LaunchPlan osc2_make_plan(int d, int batch, size_t max_smem, int sm_c
     return pl;
 }
 
+template <int D, int LPC, class Launcher>
+void osc2_run_fast_sweeps(Launcher &L, const osc2_topology *tp_dev, const StepDev &p, double theta)
+{
+    // one warp per CTA: a batch of a few thousand conductors then still spreads
+    // over all SMs (4096 conductors x 8 lanes = 1024 warps on 148 SMs)
+    constexpr int cpb = 32 / LPC;
+    const unsigned grid = (unsigned)((p.B + cpb - 1) / cpb);
+    const size_t smem_f = (size_t)FastFwdSmem<D>::PER_COND * cpb * sizeof(double);
+    const size_t smem_b = (size_t)(2 * D + 2) * cpb * sizeof(double);
+    const bool be = (theta == 1.0), cap = (p.cap_sysmat != nullptr);
+    if (be && !cap) L.launch(OSC2_K_FORWARD, osc2_forward_fast_kernel<D, LPC, true, false>, grid, 32u, smem_f, tp_dev, p);
+    else if (be) L.launch(OSC2_K_FORWARD, osc2_forward_fast_kernel<D, LPC, true, true>, grid, 32u, smem_f, tp_dev, p);
+    else if (!cap) L.launch(OSC2_K_FORWARD, osc2_forward_fast_kernel<D, LPC, false, false>, grid, 32u, smem_f, tp_dev, p);
+    else L.launch(OSC2_K_FORWARD, osc2_forward_fast_kernel<D, LPC, false, true>, grid, 32u, smem_f, tp_dev, p);
+    L.launch(OSC2_K_BACKWARD, osc2_backward_fast_kernel<D, LPC>, grid, 32u, smem_b, p);
+}
+
 template <class Launcher>
-void osc2_run_step(Launcher &L, const osc2_topology *tp_dev, const StepDev &p)
+void osc2_run_step(Launcher &L, const osc2_topology *tp_dev, const StepDev &p, bool fast, double theta)
 {
     const Osc2LaunchPlan pl = osc2_make_plan(p.d, p.B, L.max_smem(), L.sm_count());
+    if (fast) {
+        const long long work = (long long)p.E * p.B;
+        const unsigned grid = (unsigned)((work + pl.gauss_block - 1) / pl.gauss_block);
+        L.launch(OSC2_K_GAUSS, osc2_gauss2_kernel<true>, grid, pl.gauss_block, pl.smem_gauss, tp_dev, p);
+        switch (p.d) {
+        case 4: osc2_run_fast_sweeps<4, 8>(L, tp_dev, p, theta); break;
+        case 8: osc2_run_fast_sweeps<8, 8>(L, tp_dev, p, theta); break;
+        default: osc2_run_fast_sweeps<13, 16>(L, tp_dev, p, theta); break;
+        }
+        const long long nw = (long long)p.d * p.B;
+        L.launch(OSC2_K_NORMS, osc2_norms_kernel, (unsigned)((nw + 127) / 128), 128u, (size_t)0, p);
+        return;
+    }
     // K_G
     {
         const long long work = (long long)p.E * p.B;

@@ -30,7 +30,7 @@ def lib():
     if _LIB is None:
         so = os.path.join(HERE, "libosc2_emu.so")
         srcs = [os.path.join(HERE, f) for f in ("emu_step.cpp", "cuda_emu.h")]
-        srcs += [os.path.join(ROOT, "opensc2_b200", "csrc", f) for f in ("step_kernels.cuh", "step_launch.h", "osc2_dev.h")]
+        srcs += [os.path.join(ROOT, "opensc2_b200", "csrc", f) for f in ("step_kernels.cuh", "step_kernels_fast.cuh", "step_launch.h", "osc2_dev.h")]
         srcs += [os.path.join(ROOT, "include", "opensc2_b200.h")]
         if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
             subprocess.run(["g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-ffp-contract=off", "-pthread",
@@ -50,13 +50,15 @@ def from_dev(a):
     return np.ascontiguousarray(np.moveaxis(a, -1, 0))
 
 
-def emu_step(topo, arr, capture=False):
+def emu_step(topo, arr, capture=False, fast=None):
     """Run K_G, K_F, K_B, K_N on a batched StepArrays through the emulator."""
     L = lib()
     B, E = arr.dz.shape
     N, M, S, d = E + 1, topo.n_ch, topo.n_sol, topo.ndf
     total = N * d
-    NS = d * d + S + d + 4 * M + 4 * S
+    if fast is None:
+        fast = bool(L.osc2_emu_has_fast(d))
+    NS = L.osc2_emu_gm_slots(d, M, S, int(fast))
     t = topology_struct(topo)
     p = StepDev()
     p.B, p.N, p.E, p.M, p.S, p.d, p.NS = B, N, E, M, S, d, NS
@@ -72,7 +74,7 @@ def emu_step(topo, arr, capture=False):
         setattr(p, name, a.ctypes.data_as(c_dp))
     outs = {
         "sysvar_new": np.full((total, B), np.nan), "gm": np.full((E, NS, B), np.nan),
-        "k123": np.zeros((3, max(p.nff, 1), E, B)), "spill": np.full((N, d, 2 * d + 1, B), np.nan),
+        "k123": np.zeros((3, max(p.nff, 1), E, B)), "spill": np.full((N, d, 2 * d + 2, B), np.nan),
         "norm_solution": np.zeros((d, B)), "norm_change": np.zeros((d, B)), "eqteig": np.zeros((d, B)),
     }
     for k, a in outs.items():
@@ -84,7 +86,7 @@ def emu_step(topo, arr, capture=False):
         outs["cap_known"] = np.zeros((total, B))
         p.cap_sysmat = outs["cap_sysmat"].ctypes.data_as(c_dp)
         p.cap_known = outs["cap_known"].ctypes.data_as(c_dp)
-    L.osc2_emu_step(C.byref(t), C.byref(p))
+    L.osc2_emu_step(C.byref(t), C.byref(p), int(fast))
     res = {
         "sysvar": from_dev(outs["sysvar_new"]), "syslod": from_dev(keep["syslod"]),
         "k123": from_dev(outs["k123"])[:, :, :p.nff], "norm_solution": from_dev(outs["norm_solution"]),

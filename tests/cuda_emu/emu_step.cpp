@@ -4,12 +4,14 @@
 
 #include "../../opensc2_b200/csrc/step_launch.h"
 
-extern "C" int osc2_emu_step(const osc2_topology *tp, const StepDev *p)
+extern "C" int osc2_emu_step(const osc2_topology *tp, const StepDev *p, int fast)
 {
     EmuLauncher L;
-    osc2_run_step(L, tp, *p);
+    osc2_run_step(L, tp, *p, fast != 0, tp->theta);
     return (int)L.launches;
 }
+extern "C" int osc2_emu_has_fast(int d) { return osc2_has_fast_path(d) ? 1 : 0; }
+extern "C" int osc2_emu_gm_slots(int d, int M, int S, int fast) { return osc2_gm_slots(d, M, S, fast != 0); }
 
 extern "C" int osc2_emu_transpose(const double *in, double *out, long long rows, long long cols)
 {

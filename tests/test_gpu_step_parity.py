@@ -130,3 +130,15 @@ def test_singular_system_raises_like_reference():
             bs.synchronize()
         _sv, _sl, st = bs.download_state(want_syslod=False)
     assert st[0] == 0 and st[1] == -9
+
+
+def test_shared_divisor_division_is_ieee():
+    """csrc/osc2_div.cuh returns exactly a / b (incl. signed zeros, tiny/huge operands)."""
+    import ctypes as C
+
+    from opensc2_b200 import _lib
+
+    L = _lib.load()
+    bad = C.c_ulonglong(123)
+    _lib.check(L.osc2_selftest_division(0, 400_000_000, 20261019, C.byref(bad)))
+    assert bad.value == 0

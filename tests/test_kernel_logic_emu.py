@@ -27,9 +27,10 @@ def _batched(arr):
 @pytest.mark.parametrize("name", ["case1_pdrop_n21", "case1_pinl_vout_first_step_n17",
                                   "case1_vinl_pout_cn_refined_n12", "case1_min_mesh_n4",
                                   "case3_backward_n15", "case3_rectangular_env_n9"])
-def test_emulated_kernels_match_reference_fixture(name):
+@pytest.mark.parametrize("fast", [False, True])
+def test_emulated_kernels_match_reference_fixture(name, fast):
     topo, arr, ref = load_golden(name)
-    out = emu.emu_step(topo, _batched(arr), capture=True)
+    out = emu.emu_step(topo, _batched(arr), capture=True, fast=fast)
     assert out["status"][0] == 0
     assert_bits(out["sysmat"][0], ref["sysmat"], f"{name}:sysmat")
     assert_bits(out["known"][0], ref["known"], f"{name}:known")
@@ -41,6 +42,7 @@ def test_emulated_batch_ragged_tail():
     """B not a multiple of the conductors-per-warp; every slot matches the oracle."""
     topo = case1_topology(2)
     arr = synthetic_step_arrays(topo, 7, batch=6, seed=5)
+    assert np.array_equal(emu.emu_step(topo, arr, fast=False)["sysvar"], emu.emu_step(topo, arr, fast=True)["sysvar"])
     out = emu.emu_step(topo, arr)
     ref = O.step(topo, arr)
     assert np.all(out["status"] == 0)
