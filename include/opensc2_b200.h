@@ -37,7 +37,9 @@ typedef enum {
     OSC2_ERR_CUDA = -2,        /* CUDA runtime failure, see osc2_last_error() */
     OSC2_ERR_NO_DEVICE = -3,   /* no usable CUDA device: there is no CPU fallback */
     OSC2_ERR_SINGULAR = -4,    /* at least one conductor hit abs(pivot) <= 1e-20 (gredub/gbacsb, tsf:676,763) */
-    OSC2_ERR_STATE = -5        /* call order violated (e.g. step before upload) */
+    OSC2_ERR_STATE = -5,       /* call order violated (e.g. step before upload) */
+    OSC2_ERR_RANGE = -6        /* a non-zero value below 2^-900 (or a divisor outside 2^+-100) met the fast
+                                  kernels' exactness guard; rerun with OSC2_FORCE_GENERIC=1 */
 } osc2_status;
 
 /* Uniform-across-the-batch description of the conductor; mirrors what step()

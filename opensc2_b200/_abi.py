@@ -17,6 +17,8 @@ OSC2_ERR_CUDA = -2
 OSC2_ERR_NO_DEVICE = -3
 OSC2_ERR_SINGULAR = -4
 OSC2_ERR_STATE = -5
+OSC2_ERR_RANGE = -6
+OSC2_STATUS_RANGE = -2000000000
 
 c_dp = C.POINTER(C.c_double)
 c_ip = C.POINTER(C.c_int)

@@ -429,6 +429,11 @@ int osc2_synchronize(osc2_handle h)
     CK(cudaMemcpyAsync(h->status_host, h->p.status, sizeof(int) * (size_t)h->B, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     for (int b = 0; b < h->B; ++b)
+        if (h->status_host[b] == OSC2_STATUS_RANGE)
+            return fail(OSC2_ERR_RANGE, "conductor %d of the batch: a value left the range in which the fast kernels' "
+                        "division is verified exact (0 < |x| < 2^-900 or a divisor outside 2^+-100); "
+                        "set OSC2_FORCE_GENERIC=1 to use the generic kernels", b);
+    for (int b = 0; b < h->B; ++b)
         if (h->status_host[b] != 0)
             return fail(OSC2_ERR_SINGULAR, "ERROR! Matrix is singular at line %d (conductor %d of the batch)",
                         -h->status_host[b] - 1, b);

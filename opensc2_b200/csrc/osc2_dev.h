@@ -11,6 +11,10 @@
 #include <cuda_runtime.h>
 #endif
 
+// status[b] value of a conductor whose numbers left the range in which the fast
+// kernels' division is verified exact (osc2_div.cuh); never produced by the generic path
+#define OSC2_STATUS_RANGE (-2000000000)
+
 struct StepDev {
     int B, N, E, M, S, d, NS;
     int nff, nfs, nss, nes;

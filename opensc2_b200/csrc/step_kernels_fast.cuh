@@ -15,6 +15,8 @@
 //     node's row, and exchanges the solved unknowns through shared memory.
 #pragma once
 
+#include <type_traits>
+
 #include "step_kernels.cuh"
 #include "osc2_div.cuh"
 
@@ -240,6 +242,8 @@ __global__ void osc2_forward_fast_kernel(const osc2_topology *__restrict__ tp, S
     const Osc2Rcp rdt = osc2_rcp_prepare(p.dt);
     const bool first = (p.num_step == 1);
     const bool shift = (p.num_step > 1);
+    int dt_flag = 0;
+    osc2_rcp_check(rdt, dt_flag);
 
     double *base = sm_dyn + (size_t)grp * SM::PER_COND;
     double *pub = base;                                  // [2][D][PW]
@@ -285,6 +289,7 @@ __global__ void osc2_forward_fast_kernel(const osc2_topology *__restrict__ tp, S
 #undef FND
     }
     long long bad_row = -1;
+    int range_flag = 0;     // set when a value leaves the exact range of osc2_div_flag
 
     // this lane's row record of one element
     struct Elem {
@@ -332,8 +337,11 @@ __global__ void osc2_forward_fast_kernel(const osc2_topology *__restrict__ tp, S
         double *t = xa; xa = xc; xc = xb; xb = t;                 // xb = slot0 (node 0), xc = slot1 (node 1)
     }
 
-    for (int n = 0; n < N; ++n) {
-        const bool hasL = n > 0, hasR = n < N - 1;
+    // One node of the sweep.  The first and the last node are compiled separately
+    // (no left / right element, boundary rows possible), so the interior loop has
+    // neither of those branches.
+    auto node = [&](auto HL, auto HR, const int n) {
+        constexpr bool hasL = decltype(HL)::value, hasR = decltype(HR)::value;
         double *pub_cur = pub + (size_t)(n & 1) * D * PW;
         const double *pub_prev = pub + (size_t)((n + 1) & 1) * D * PW;
         const long long i_row = (long long)n * D + r;
@@ -355,17 +363,17 @@ __global__ void osc2_forward_fast_kernel(const osc2_topology *__restrict__ tp, S
             lodptr[0] = sl0;
             lodptr[B] = sl1;
 
-            const bool is_bc = (n == 0 && bc_first) || (n == N - 1 && bc_last);
+            const bool is_bc = (!hasL && bc_first) || (!hasR && bc_last);
             if (is_bc) {
 #pragma unroll
                 for (int c = 0; c < D; ++c) { rowL[c] = 0.0; rowD[c] = (c == r) ? 1.0 : 0.0; rowU[c] = 0.0; }
-                rhs = (n == 0) ? val_first : val_last;
+                rhs = (!hasL) ? val_first : val_last;
             } else {
                 double mx = 0.0;
                 // MASMAT/dt is non-zero on the diagonal entry of each block only
-                const double masL = hasL ? osc2_div(eL.mo, rdt) : 0.0;
-                const double masD = osc2_div((hasL ? eL.md : 0.0) + (hasR ? eR.md : 0.0), rdt);
-                const double masU = hasR ? osc2_div(eR.mo, rdt) : 0.0;
+                const double masL = hasL ? osc2_div_flag(eL.mo, rdt, range_flag) : 0.0;
+                const double masD = osc2_div_flag((hasL ? eL.md : 0.0) + (hasR ? eR.md : 0.0), rdt, range_flag);
+                const double masU = hasR ? osc2_div_flag(eR.mo, rdt, range_flag) : 0.0;
 #pragma unroll
                 for (int c = 0; c < D; ++c) {
                     const bool dg = (c == r);
@@ -381,7 +389,7 @@ __global__ void osc2_forward_fast_kernel(const osc2_topology *__restrict__ tp, S
                             if (!CLOSED_KNOWN) strip[D + c] = (m - omt * fds) * xa[c];
                         } else if (!CLOSED_KNOWN) strip[D + c] = 0.0;
                         rowL[c] = sys;
-                        mx = fmax(mx, fabs(sys));
+                        { const double a_ = fabs(sys); if (a_ > mx) mx = a_; }
                     }
                     // D block: lower-right of element n-1 + upper-left of element n
                     {
@@ -393,7 +401,7 @@ __global__ void osc2_forward_fast_kernel(const osc2_topology *__restrict__ tp, S
                         const double sys = BE ? m + fds : m + theta * fds;
                         if (!CLOSED_KNOWN) strip[2 * D + c] = (m - omt * fds) * xb[c];
                         rowD[c] = sys;
-                        mx = fmax(mx, fabs(sys));
+                        { const double a_ = fabs(sys); if (a_ > mx) mx = a_; }
                     }
                     // U block: upper-right of element n
                     {
@@ -405,7 +413,7 @@ __global__ void osc2_forward_fast_kernel(const osc2_topology *__restrict__ tp, S
                             if (!CLOSED_KNOWN) strip[3 * D + c] = (m - omt * fds) * xc[c];
                         } else if (!CLOSED_KNOWN) strip[3 * D + c] = 0.0;
                         rowU[c] = sys;
-                        mx = fmax(mx, fabs(sys));
+                        { const double a_ = fabs(sys); if (a_ > mx) mx = a_; }
                     }
                 }
                 // Known (smc:1366-1443)
@@ -442,9 +450,14 @@ __global__ void osc2_forward_fast_kernel(const osc2_topology *__restrict__ tp, S
                 known += BE ? sl0 : (theta * sl0 + omt * sl1);
                 // row scaling (tsf:538-551)
                 const Osc2Rcp rmx = osc2_rcp_prepare(mx);
+                osc2_rcp_check(rmx, range_flag);
 #pragma unroll
-                for (int c = 0; c < D; ++c) { rowL[c] = osc2_div(rowL[c], rmx); rowD[c] = osc2_div(rowD[c], rmx); rowU[c] = osc2_div(rowU[c], rmx); }
-                rhs = osc2_div(known, rmx);
+                for (int c = 0; c < D; ++c) {
+                    rowL[c] = osc2_div_flag(rowL[c], rmx, range_flag);
+                    rowD[c] = osc2_div_flag(rowD[c], rmx, range_flag);
+                    rowU[c] = osc2_div_flag(rowU[c], rmx, range_flag);
+                }
+                rhs = osc2_div_flag(known, rmx, range_flag);
             }
             if (CAPTURE) {
 #pragma unroll
@@ -463,7 +476,7 @@ __global__ void osc2_forward_fast_kernel(const osc2_topology *__restrict__ tp, S
 #pragma unroll
                 for (int k = 0; k < D; ++k) {
                     const double *pk = pub_prev + k * PW;
-                    const double q = osc2_div(rowL[k], osc2_rcp_make(pk[k], pk[2 * D + 1]));
+                    const double q = osc2_div_flag(rowL[k], osc2_rcp_make(pk[k], pk[2 * D + 1]), range_flag);
 #pragma unroll
                     for (int c = k + 1; c < D; ++c) rowL[c] = rowL[c] - pk[c] * q;
 #pragma unroll
@@ -488,12 +501,13 @@ __global__ void osc2_forward_fast_kernel(const osc2_topology *__restrict__ tp, S
                 pk[2 * D] = rhs;
                 my_rcp = osc2_rcp_prepare(rowD[k]);
                 pk[2 * D + 1] = my_rcp.y;
-                if (fabs(rowD[k]) <= OSC2_TINY_PIVOT && bad_row < 0) bad_row = i_row;
+                if (fabs(rowD[k]) <= OSC2_TINY_PIVOT) { if (bad_row < 0) bad_row = i_row; }
+                else osc2_rcp_check(my_rcp, range_flag);
             }
             __syncwarp();
             if (act && r > k) {
                 const double *pk = pub_cur + k * PW;
-                const double q = osc2_div(rowD[k], osc2_rcp_make(pk[k], pk[2 * D + 1]));
+                const double q = osc2_div_flag(rowD[k], osc2_rcp_make(pk[k], pk[2 * D + 1]), range_flag);
 #pragma unroll
                 for (int c = k + 1; c < D; ++c) rowD[c] = rowD[c] - pk[c] * q;
 #pragma unroll
@@ -518,18 +532,24 @@ __global__ void osc2_forward_fast_kernel(const osc2_topology *__restrict__ tp, S
         xptr += xstep;
         lodptr += 2 * xstep;
         spptr += (size_t)D * (2 * D + 2) * B;
-    }
+    };
+    node(std::false_type(), std::true_type(), 0);
+    for (int n = 1; n < N - 1; ++n) node(std::true_type(), std::true_type(), n);
+    node(std::true_type(), std::false_type(), N - 1);
     __syncwarp();
     double *scratch = base;
-    if (r < D) scratch[r] = (double)bad_row;
+    if (r < D) { scratch[r] = (double)bad_row; scratch[D + r] = (double)(range_flag | dt_flag); }
     __syncwarp();
     if (act && r == 0) {
         long long worst = -1;
+        bool range = false;
         for (int q = 0; q < D; ++q) {
             const long long v = (long long)scratch[q];
             if (v >= 0 && (worst < 0 || v < worst)) worst = v;
+            range = range || (scratch[D + q] != 0.0);
         }
-        p.status[b] = (worst < 0) ? 0 : -(int)(worst + 1);
+        // a singular pivot wins (the reference raises there); otherwise report the range problem
+        p.status[b] = (worst >= 0) ? -(int)(worst + 1) : (range ? OSC2_STATUS_RANGE : 0);
     }
 }
 
@@ -551,6 +571,7 @@ __global__ void osc2_backward_fast_kernel(StepDev p)
     double *xnxt = xcur + D;                              // [D]
 
     constexpr int W = 2 * D + 2;      // D' | U | rhs | 1/pivot
+    int range_flag = 0;
     double f[W], fn[W];
 #pragma unroll
     for (int c = 0; c < W; ++c) { f[c] = 0.0; fn[c] = 0.0; }
@@ -582,7 +603,7 @@ __global__ void osc2_backward_fast_kernel(StepDev p)
 #pragma unroll
                     for (int c = 0; c < D; ++c) q = q - pu[c];
                 }
-                const double x = osc2_div(q, osc2_rcp_make(f[rr], f[2 * D + 1]));
+                const double x = osc2_div_flag(q, osc2_rcp_make(f[rr], f[2 * D + 1]), range_flag);
                 xcur[rr] = x;
                 p.sysvar_new[((size_t)n * D + r) * B + b] = x;
             }
@@ -591,4 +612,5 @@ __global__ void osc2_backward_fast_kernel(StepDev p)
         if (act) xnxt[r] = xcur[r];
         __syncwarp();
     }
+    if (act && range_flag && p.status[b] == 0) p.status[b] = OSC2_STATUS_RANGE;
 }
