@@ -326,6 +326,22 @@ int osc2_create(const osc2_topology *topo, int batch, int n_nodes, int device, o
     if (!rc) rc = dev_alloc(h, &p.norm_change, d * B);
     if (!rc) rc = dev_alloc(h, &p.eqteig, d * B);
     if (!rc) { double *q = nullptr; rc = dev_alloc(h, &q, (B + 1) / 2 + 1); p.status = (int *)q; }
+    if (!rc) {   // numpy pairwise-sum tree of the N nodal values of one equation (norms)
+        std::vector<int> leaves, prog;
+        osc2_build_norm_plan(0, h->N, leaves, prog);
+        p.n_leaves = (int)(leaves.size() / 2);
+        p.n_prog = (int)prog.size();
+        double *ql = nullptr, *qp = nullptr;
+        rc = dev_alloc(h, &ql, leaves.size() / 2 + 1);
+        if (!rc) rc = dev_alloc(h, &qp, prog.size() / 2 + 1);
+        if (!rc) rc = dev_alloc(h, &p.norm_part, (size_t)p.n_leaves * 3 * d * B);
+        if (!rc) {
+            CK(cudaMemcpy(ql, leaves.data(), leaves.size() * sizeof(int), cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(qp, prog.data(), prog.size() * sizeof(int), cudaMemcpyHostToDevice));
+            p.norm_leaf = (const int *)ql;
+            p.norm_prog = (const int *)qp;
+        }
+    }
     h->staging_doubles = kmax * B;
     if (!rc) rc = dev_alloc(h, &h->staging, h->staging_doubles);
     if (rc) { osc2_destroy(h); return rc; }

@@ -46,6 +46,11 @@ struct StepDev {
     int *status;              // [B] 0 or -(row+1)
     double *cap_sysmat;       // optional [Full][Total]
     double *cap_known;        // optional [Total]
+    // norms: numpy pairwise-sum tree of N values (osc2_build_norm_plan)
+    const int *norm_leaf;     // [n_leaves][2]  start node, length
+    const int *norm_prog;     // [n_prog]       >= 0: push leaf, -1: add the two on top
+    double *norm_part;        // [n_leaves][3][d][B]
+    int n_leaves, n_prog;
 };
 
 // Slot map of one element's Gauss-point record in `gm`:

@@ -624,7 +624,39 @@ __device__ double osc2_pairwise(const double *a, long long n, size_t stride, F f
     }
 }
 
-__global__ void osc2_norms_kernel(StepDev p)
+// numpy's pairwise sum of N values is a fixed binary tree whose leaves are runs
+// of at most 128 values (8 running accumulators + sequential tail).  The tree
+// only depends on N, so the leaves are summed by independent threads
+// (K_N1: one thread per leaf, equation and conductor -- coalesced over the
+// batch) and K_N2 replays the tree's additions in numpy's order from a postfix
+// program built on the host (osc2_build_norm_plan in step_launch.h).
+// part: [leaf][3: solution, change, eig max][d][B].
+__global__ void osc2_norm_leaves_kernel(StepDev p)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long per_leaf = (long long)p.d * p.B;
+    if (idx >= per_leaf * p.n_leaves) return;
+    const size_t B = (size_t)p.B;
+    const int leaf = (int)(idx / per_leaf);
+    const size_t qb = (size_t)(idx % per_leaf);          // q * B + b
+    const int d = p.d;
+    const size_t stride = (size_t)d * B;
+    const int start = p.norm_leaf[2 * leaf], len = p.norm_leaf[2 * leaf + 1];
+    const double *x = p.sysvar_new + (size_t)start * stride + qb;
+    double *out = p.norm_part + ((size_t)leaf * 3) * stride + qb;
+    out[0] = osc2_pairwise(x, len, stride, Osc2NormSolution(), p.dt);
+    out[stride] = osc2_pairwise(x, len, stride, Osc2NormChange(), p.dt);
+    double mxe = 0.0;
+    for (int n = 0; n < len; ++n) {
+        const double v = x[(size_t)n * stride];
+        const double sq = v * v;
+        const double eig = fabs((sq - v) / p.dt) / (fabs(sq) + 1.0e-5);
+        if (n == 0 || eig > mxe) mxe = eig;
+    }
+    out[2 * stride] = mxe;
+}
+
+__global__ void osc2_norm_combine_kernel(StepDev p)
 {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)p.d * p.B) return;
@@ -633,17 +665,23 @@ __global__ void osc2_norms_kernel(StepDev p)
     const int q = (int)(idx / p.B);
     const int d = p.d, M = p.M;
     const size_t stride = (size_t)d * B;
-    const double *x = p.sysvar_new + (size_t)q * B + b;
-    p.norm_solution[(size_t)q * B + b] = sqrt(osc2_pairwise(x, p.N, stride, Osc2NormSolution(), p.dt));
-    p.norm_change[(size_t)q * B + b] = sqrt(osc2_pairwise(x, p.N, stride, Osc2NormChange(), p.dt));
+    const double *part = p.norm_part + (size_t)q * B + b;
+    for (int which = 0; which < 2; ++which) {
+        double st[24];
+        int sp = 0;
+        for (int i = 0; i < p.n_prog; ++i) {
+            const int op = p.norm_prog[i];
+            if (op >= 0) st[sp++] = part[((size_t)op * 3 + which) * stride];
+            else { st[sp - 2] = st[sp - 2] + st[sp - 1]; --sp; }
+        }
+        (which ? p.norm_change : p.norm_solution)[(size_t)q * B + b] = sqrt(st[0]);
+    }
     const int src = (q >= M && q < 2 * M) ? q - M : q;   // pressure <- velocity (tsf:886-888)
-    const double *xe = p.sysvar_new + (size_t)src * B + b;
+    const double *pe = p.norm_part + (size_t)src * B + b + 2 * stride;
     double mxe = 0.0;
-    for (int n = 0; n < p.N; ++n) {
-        const double v = xe[(size_t)n * stride];
-        const double sq = v * v;
-        const double eig = fabs((sq - v) / p.dt) / (fabs(sq) + 1.0e-5);
-        if (n == 0 || eig > mxe) mxe = eig;
+    for (int leaf = 0; leaf < p.n_leaves; ++leaf) {
+        const double eig = pe[(size_t)leaf * 3 * stride];
+        if (leaf == 0 || eig > mxe) mxe = eig;
     }
     p.eqteig[(size_t)q * B + b] = mxe;
 }

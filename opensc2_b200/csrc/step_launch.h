@@ -11,6 +11,25 @@
 #include "step_kernels.cuh"
 #include "step_kernels_fast.cuh"
 
+#include <vector>
+
+// numpy pairwise summation (loops_utils.h.src, PW_BLOCKSIZE = 128) of n values:
+// leaves (start, length) in order and the postfix program of its additions.
+inline void osc2_build_norm_plan(long long start, long long n, std::vector<int> &leaves, std::vector<int> &prog)
+{
+    if (n <= 128) {
+        prog.push_back((int)(leaves.size() / 2));
+        leaves.push_back((int)start);
+        leaves.push_back((int)n);
+        return;
+    }
+    long long n2 = n / 2;
+    n2 -= n2 % 8;
+    osc2_build_norm_plan(start, n2, leaves, prog);
+    osc2_build_norm_plan(start + n2, n - n2, leaves, prog);
+    prog.push_back(-1);
+}
+
 struct Osc2LaunchPlan {
     int lpc;            // lanes per conductor (8, 16, 32, 64)
     int cpb_fwd;        // conductors per CTA, forward sweep
@@ -94,8 +113,11 @@ void osc2_run_step(Launcher &L, const osc2_topology *tp_dev, const StepDev &p, b
         case 8: osc2_run_fast_sweeps<8, 8>(L, tp_dev, p, theta); break;
         default: osc2_run_fast_sweeps<13, 16>(L, tp_dev, p, theta); break;
         }
-        const long long nw = (long long)p.d * p.B;
-        L.launch(OSC2_K_NORMS, osc2_norms_kernel, (unsigned)((nw + 127) / 128), 128u, (size_t)0, p);
+        {
+            const long long nl = (long long)p.d * p.B * p.n_leaves, nw = (long long)p.d * p.B;
+            L.launch(OSC2_K_NORMS, osc2_norm_leaves_kernel, (unsigned)((nl + 127) / 128), 128u, (size_t)0, p);
+            L.launch(OSC2_K_NORMS, osc2_norm_combine_kernel, (unsigned)((nw + 127) / 128), 128u, (size_t)0, p);
+        }
         return;
     }
     // K_G
@@ -130,7 +152,8 @@ void osc2_run_step(Launcher &L, const osc2_topology *tp_dev, const StepDev &p, b
     }
     // K_N
     {
-        const long long work = (long long)p.d * p.B;
-        L.launch(OSC2_K_NORMS, osc2_norms_kernel, (unsigned)((work + 127) / 128), 128u, (size_t)0, p);
+        const long long nl = (long long)p.d * p.B * p.n_leaves, nw = (long long)p.d * p.B;
+        L.launch(OSC2_K_NORMS, osc2_norm_leaves_kernel, (unsigned)((nl + 127) / 128), 128u, (size_t)0, p);
+        L.launch(OSC2_K_NORMS, osc2_norm_combine_kernel, (unsigned)((nw + 127) / 128), 128u, (size_t)0, p);
     }
 }

@@ -19,7 +19,8 @@ class StepDev(C.Structure):
                             "peri_fs", "htc_fs", "peri_ss", "htc_ss", "peri_es", "htc_es", "qsource",
                             "sysvar", "sysvar_new", "syslod", "gm", "k123", "spill",
                             "norm_solution", "norm_change", "eqteig")] + [
-        ("status", c_ip), ("cap_sysmat", c_dp), ("cap_known", c_dp)]
+        ("status", c_ip), ("cap_sysmat", c_dp), ("cap_known", c_dp),
+        ("norm_leaf", c_ip), ("norm_prog", c_ip), ("norm_part", c_dp), ("n_leaves", C.c_int), ("n_prog", C.c_int)]
 
 
 _LIB = None

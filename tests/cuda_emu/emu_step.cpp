@@ -7,7 +7,13 @@
 extern "C" int osc2_emu_step(const osc2_topology *tp, const StepDev *p, int fast)
 {
     EmuLauncher L;
-    osc2_run_step(L, tp, *p, fast != 0, tp->theta);
+    StepDev q = *p;
+    std::vector<int> leaves, prog;
+    osc2_build_norm_plan(0, q.N, leaves, prog);
+    std::vector<double> part(leaves.size() / 2 * 3 * (size_t)q.d * q.B, std::nan(""));
+    q.norm_leaf = leaves.data(); q.norm_prog = prog.data(); q.norm_part = part.data();
+    q.n_leaves = (int)(leaves.size() / 2); q.n_prog = (int)prog.size();
+    osc2_run_step(L, tp, q, fast != 0, tp->theta);
     return (int)L.launches;
 }
 extern "C" int osc2_emu_has_fast(int d) { return osc2_has_fast_path(d) ? 1 : 0; }

@@ -63,3 +63,14 @@ def test_emulated_singular_status():
     topo, arr = singular_case()
     out = emu.emu_step(topo, arr)
     assert list(out["status"]) == [0, -9]
+
+
+@pytest.mark.parametrize("n", [129, 201, 300, 1100])
+def test_emulated_norm_tree_matches_numpy_pairwise(n):
+    """Leaf-parallel norms (K_N1/K_N2) replay numpy's pairwise-sum tree for N > 128."""
+    topo = case1_topology(1)
+    arr = synthetic_step_arrays(topo, n, batch=2, seed=n)
+    out = emu.emu_step(topo, arr)
+    ref = O.step(topo, arr)
+    for key in KEYS:
+        assert_bits(out[key], ref[key], key)
