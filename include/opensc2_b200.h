@@ -88,6 +88,61 @@ typedef struct {
     double t_env;             /* environment.inputs["Temperature"] */
 } osc2_step_inputs;
 
+/* ---- Operating conditions at the Gauss points (what the reference evaluates every
+ * time step BEFORE step(): Conductor.operating_conditions_em / _th, conductor.py:4591-4744,
+ * eval_transp_coeff conductor.py:4822-5406, build_heat_source conductor.py:4423-4581).
+ * osc2_model is uniform across the batch; osc2_sweep holds the swept per-conductor scalars. */
+#define OSC2_MAX_MATERIALS 5
+#define OSC2_MAX_FLUIDS 4
+#define OSC2_N_FLUID_PROPS 10
+/* property order of a fluid table = the reference's alias table (simulation.py:89-100) */
+enum { OSC2_FP_BETA = 0,   /* isobaric_expansion_coefficient */
+       OSC2_FP_KAPPA,      /* isothermal_compressibility */
+       OSC2_FP_PRANDTL, OSC2_FP_RHO, OSC2_FP_MU, OSC2_FP_H, OSC2_FP_CP, OSC2_FP_CV,
+       OSC2_FP_SOUND, OSC2_FP_K };
+/* materials (the fits of properties_of_materials/) */
+enum { OSC2_MAT_CU_NIST = 0, OSC2_MAT_NB3SN = 1, OSC2_MAT_SS = 2, OSC2_MAT_GE = 3, OSC2_MAT_COUNT };
+/* solid kinds: StrandMixedComponent, StrandStabilizerComponent, JacketComponent */
+enum { OSC2_SOLID_STRAND_MIXED = 0, OSC2_SOLID_STRAND_STAB = 1, OSC2_SOLID_JACKET = 2 };
+
+typedef struct {
+    /* channels (channel.py:43-169) */
+    int ch_fluid[OSC2_MAX_CHANNELS];            /* which fluid table */
+    int ch_ifriction[OSC2_MAX_CHANNELS];        /* IFRICTION: -99 or 124 */
+    double ch_friction_mult[OSC2_MAX_CHANNELS]; /* FRICTION_MULTIPLIER */
+    int ch_htc_corr[OSC2_MAX_CHANNELS];         /* Flag_htc_steady_corr: 1 or 212 */
+    /* solids */
+    int sol_kind[OSC2_MAX_SOLIDS];
+    int sol_nmat[OSC2_MAX_SOLIDS];
+    int sol_mat[OSC2_MAX_SOLIDS][OSC2_MAX_MATERIALS];
+    double sol_weight[OSC2_MAX_SOLIDS][OSC2_MAX_MATERIALS]; /* homogenization_cefficients | cross_sections */
+    double sol_weight_sum[OSC2_MAX_SOLIDS];     /* homogenization_cefficients_sum | inputs["CROSSECTION"] */
+    double sol_rrr[OSC2_MAX_SOLIDS];
+    double sol_tc0m[OSC2_MAX_SOLIDS], sol_bc20m[OSC2_MAX_SOLIDS];
+    int sol_heated[OSC2_MAX_SOLIDS];            /* IQFUN == 1 (square wave, solid_component.py:415-576) */
+    /* interfaces, in the order of the topology lists.  choice = HTC_choice; htc = contact_HTC;
+     * mlt = HTC_multiplier (conductor.py:4867-5160) */
+    int fs_choice[OSC2_MAX_INTERFACES];         /* 2 or -2 */
+    double fs_htc[OSC2_MAX_INTERFACES], fs_mlt[OSC2_MAX_INTERFACES];
+    int ff_choice[OSC2_MAX_INTERFACES];         /* 2 or -2 */
+    double ff_htc[OSC2_MAX_INTERFACES], ff_mlt[OSC2_MAX_INTERFACES], ff_thick[OSC2_MAX_INTERFACES];
+    int ss_choice[OSC2_MAX_INTERFACES];         /* 1 or -1 */
+    double ss_htc[OSC2_MAX_INTERFACES], ss_mlt[OSC2_MAX_INTERFACES];
+    double ss_thick_rc[OSC2_MAX_INTERFACES], ss_thick_cr[OSC2_MAX_INTERFACES], ss_rcontact[OSC2_MAX_INTERFACES];
+    double es_htc[OSC2_MAX_INTERFACES];         /* constant convective HTC (choices -2, -4), Phi_conv and multiplier applied */
+} osc2_model;
+
+/* Swept per-conductor scalars, batch leading. */
+typedef struct {
+    const double *b_field;   /* [B][S][2]  BISS, BOSS (IBIFUN == 0: linspace, solid_component.py:383-388) */
+    const double *eps;       /* [B][S]     strain (IEPS 0/1, strand_component.py:353-399) */
+    const double *q0;        /* [B][S]     Q0, W/m */
+    const double *q_window;  /* [B][S][4]  first node, last node (heat0_where), TQBEG, TQEND */
+    const double *tcs;       /* [B][S][E]  T_cur_sharing_min at the Gauss points (evaluated once at
+                                           step 0 by the caller, conductor.py:4615-4619); may be NULL
+                                           when no solid holds a superconductor */
+} osc2_sweep;
+
 typedef struct osc2_context *osc2_handle;
 
 /* Kernel ids for osc2_get_kernel_ms. */
@@ -107,6 +162,22 @@ int osc2_destroy(osc2_handle h);
 /* dict_Step["SYSVAR"][:,0] ([B][Total]) and dict_Step["SYSLOD"] ([B][Total][2]). */
 int osc2_upload_state(osc2_handle h, const double *sysvar, const double *syslod);
 int osc2_upload_step_inputs(osc2_handle h, const osc2_step_inputs *in);
+
+/* Device-side operating conditions.  osc2_set_model + osc2_set_fluid_table + osc2_upload_sweep
+ * once; then osc2_eval_operating_conditions(h, t) computes, from the device-resident state, every
+ * per-step array osc2_step consumes except the geometry (dz, contact perimeters, qsource) and the
+ * boundary values fl_bc, which stay as uploaded by osc2_upload_step_inputs (NULL members of
+ * osc2_step_inputs are then allowed for the computed arrays).
+ * Fluid table: regular grid, props[OSC2_N_FLUID_PROPS][n_p][n_t], bilinear in (p, T). */
+int osc2_set_model(osc2_handle h, const osc2_model *model);
+int osc2_set_fluid_table(osc2_handle h, int fluid, int n_p, int n_t, double p_min, double p_step,
+                         double t_min, double t_step, const double *props);
+int osc2_upload_sweep(osc2_handle h, const osc2_sweep *sweep);
+/* `time` = conductor.cond_time[-1] of the step about to be taken. */
+int osc2_eval_operating_conditions(osc2_handle h, double time);
+/* Device -> host copy of the computed step inputs (parity tests); any member may be NULL. */
+int osc2_download_step_inputs(osc2_handle h, double *fl_gauss, double *fl_node, double *sol_gauss,
+                              double *sol_q, double *htc_ff, double *htc_fs, double *htc_ss, double *htc_es);
 
 /* One reference step() for every conductor of the batch, on device-resident
  * inputs: Gauss matrices -> block rows + BC + row scaling -> no-pivot banded

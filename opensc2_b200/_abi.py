@@ -53,6 +53,35 @@ class Osc2StepInputs(C.Structure):
         "peri_fs", "htc_fs", "peri_ss", "htc_ss", "peri_es", "htc_es", "qsource")] + [("t_env", C.c_double)]
 
 
+OSC2_MAX_MATERIALS = 5
+OSC2_MAX_FLUIDS = 4
+OSC2_N_FLUID_PROPS = 10
+_CH, _SO, _IF = OSC2_MAX_CHANNELS, OSC2_MAX_SOLIDS, OSC2_MAX_INTERFACES
+
+
+class Osc2Model(C.Structure):
+    """Mirror of `osc2_model` (include/opensc2_b200.h)."""
+    _fields_ = [
+        ("ch_fluid", C.c_int * _CH), ("ch_ifriction", C.c_int * _CH), ("ch_friction_mult", C.c_double * _CH),
+        ("ch_htc_corr", C.c_int * _CH),
+        ("sol_kind", C.c_int * _SO), ("sol_nmat", C.c_int * _SO),
+        ("sol_mat", (C.c_int * OSC2_MAX_MATERIALS) * _SO),
+        ("sol_weight", (C.c_double * OSC2_MAX_MATERIALS) * _SO), ("sol_weight_sum", C.c_double * _SO),
+        ("sol_rrr", C.c_double * _SO), ("sol_tc0m", C.c_double * _SO), ("sol_bc20m", C.c_double * _SO),
+        ("sol_heated", C.c_int * _SO),
+        ("fs_choice", C.c_int * _IF), ("fs_htc", C.c_double * _IF), ("fs_mlt", C.c_double * _IF),
+        ("ff_choice", C.c_int * _IF), ("ff_htc", C.c_double * _IF), ("ff_mlt", C.c_double * _IF),
+        ("ff_thick", C.c_double * _IF),
+        ("ss_choice", C.c_int * _IF), ("ss_htc", C.c_double * _IF), ("ss_mlt", C.c_double * _IF),
+        ("ss_thick_rc", C.c_double * _IF), ("ss_thick_cr", C.c_double * _IF), ("ss_rcontact", C.c_double * _IF),
+        ("es_htc", C.c_double * _IF),
+    ]
+
+
+class Osc2Sweep(C.Structure):
+    _fields_ = [(n, c_dp) for n in ("b_field", "eps", "q0", "q_window", "tcs")]
+
+
 STEP_INPUT_FIELDS = tuple(n for n, _ in Osc2StepInputs._fields_[:-1])
 
 

@@ -7,7 +7,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-from ._abi import OSC2_K_COUNT, Osc2StepInputs, Osc2Topology, c_dp, c_ip
+from ._abi import OSC2_K_COUNT, Osc2Model, Osc2StepInputs, Osc2Sweep, Osc2Topology, c_dp, c_ip
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libopensc2_b200.so")
@@ -43,6 +43,11 @@ def load() -> C.CDLL:
     L.osc2_upload_state.argtypes = [H, c_dp, c_dp]
     L.osc2_upload_step_inputs.argtypes = [H, C.POINTER(Osc2StepInputs)]
     L.osc2_step.argtypes = [H, C.c_double, C.c_int]
+    L.osc2_set_model.argtypes = [H, C.POINTER(Osc2Model)]
+    L.osc2_set_fluid_table.argtypes = [H, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, c_dp]
+    L.osc2_upload_sweep.argtypes = [H, C.POINTER(Osc2Sweep)]
+    L.osc2_eval_operating_conditions.argtypes = [H, C.c_double]
+    L.osc2_download_step_inputs.argtypes = [H] + [c_dp] * 8
     L.osc2_synchronize.argtypes = [H]
     L.osc2_download_state.argtypes = [H, c_dp, c_dp, c_ip]
     L.osc2_download_diagnostics.argtypes = [H, c_dp, c_dp, c_dp, c_dp]
@@ -60,7 +65,8 @@ def load() -> C.CDLL:
     for name in ("osc2_create", "osc2_destroy", "osc2_upload_state", "osc2_upload_step_inputs", "osc2_step",
                  "osc2_synchronize", "osc2_download_state", "osc2_download_diagnostics", "osc2_set_capture",
                  "osc2_download_system", "osc2_set_profiling", "osc2_get_kernel_ms", "osc2_reset_kernel_ms",
-                 "osc2_timer_start", "osc2_timer_stop"):
+                 "osc2_timer_start", "osc2_timer_stop", "osc2_set_model", "osc2_set_fluid_table", "osc2_upload_sweep",
+                 "osc2_eval_operating_conditions", "osc2_download_step_inputs"):
         getattr(L, name).restype = C.c_int
     _LIB = L
     return L
@@ -71,7 +77,8 @@ EXPORTED = (
     "osc2_upload_state", "osc2_upload_step_inputs", "osc2_step", "osc2_synchronize",
     "osc2_download_state", "osc2_download_diagnostics", "osc2_set_capture", "osc2_download_system",
     "osc2_set_profiling", "osc2_get_kernel_ms", "osc2_reset_kernel_ms", "osc2_timer_start",
-    "osc2_timer_stop", "osc2_device_bytes", "osc2_selftest_division",
+    "osc2_timer_stop", "osc2_device_bytes", "osc2_selftest_division", "osc2_set_model", "osc2_set_fluid_table",
+    "osc2_upload_sweep", "osc2_eval_operating_conditions", "osc2_download_step_inputs",
 )
 
 

@@ -72,6 +72,46 @@ class BatchedStep:
         s.t_env = float(arr.t_env)
         _lib.check(self._L.osc2_upload_step_inputs(self._h, C.byref(s)))
 
+    # -- device-side operating conditions (K_P) ---------------------------------
+    def set_model(self, model, tables=()):
+        """`model`: opensc2_b200.model.Model; `tables`: FluidTable per fluid index."""
+        self._model_struct = model.struct(self.topo)
+        _lib.check(self._L.osc2_set_model(self._h, C.byref(self._model_struct)))
+        for i, t in enumerate(tables):
+            _lib.check(self._L.osc2_set_fluid_table(self._h, i, t.props.shape[1], t.props.shape[2], t.p_min, t.p_step,
+                                                    t.t_min, t.t_step, dptr(t.props)))
+
+    def upload_sweep(self, sweep):
+        s, keep = sweep.struct()
+        _lib.check(self._L.osc2_upload_sweep(self._h, C.byref(s)))
+        del keep
+
+    def upload_geometry(self, arr: StepArrays):
+        """Only what K_P does not compute: dz, contact perimeters, qsource, boundary values."""
+        s = Osc2StepInputs()
+        keep = []
+        for name in ("dz", "fl_bc", "peri_ff", "peri_fs", "peri_ss", "peri_es", "qsource"):
+            a = as_f64(getattr(arr, name))
+            keep.append(a)
+            setattr(s, name, dptr(a) if a.size else None)
+        s.t_env = float(arr.t_env)
+        _lib.check(self._L.osc2_upload_step_inputs(self._h, C.byref(s)))
+
+    def eval_operating_conditions(self, time: float):
+        _lib.check(self._L.osc2_eval_operating_conditions(self._h, float(time)))
+
+    def download_step_inputs(self) -> Dict[str, np.ndarray]:
+        B, E, M, S = self.batch, self.n_nodes - 1, self.topo.n_ch, self.topo.n_sol
+        t = self.topo
+        out = {"fl_gauss": np.empty((B, 9, M, E)), "fl_node": np.empty((B, 4, M)), "sol_gauss": np.empty((B, 3, S, E)),
+               "sol_q": np.empty((B, 2, S, E, 2)), "htc_ff": np.empty((B, 2, len(t.ff), E)),
+               "htc_fs": np.empty((B, len(t.fs), E)), "htc_ss": np.empty((B, len(t.ss), E)),
+               "htc_es": np.empty((B, len(t.es), 3, E))}
+        ptrs = [dptr(out[k]) if out[k].size else None for k in
+                ("fl_gauss", "fl_node", "sol_gauss", "sol_q", "htc_ff", "htc_fs", "htc_ss", "htc_es")]
+        _lib.check(self._L.osc2_download_step_inputs(self._h, *ptrs))
+        return out
+
     def step(self, dt: float, num_step: int):
         _lib.check(self._L.osc2_step(self._h, float(dt), int(num_step)))
 

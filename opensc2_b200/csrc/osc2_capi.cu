@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "step_launch.h"
+#include "props_kernels.cuh"
 
 namespace {
 
@@ -62,6 +63,12 @@ struct osc2_context {
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     int *status_host = nullptr;
     std::string launch_error;
+    // device-side operating conditions (props_kernels.cuh)
+    osc2_model *model_dev = nullptr;
+    PropsDev q;
+    bool have_model = false, have_sweep = false;
+    bool have_table[OSC2_MAX_FLUIDS] = {false, false, false, false};
+    int n_fluids_used = 0;
 
     // ---- Launcher policy for osc2_run_step --------------------------------
     size_t get_max_smem() const { return (size_t)max_smem; }
@@ -361,6 +368,7 @@ int osc2_destroy(osc2_handle h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (void *q : h->allocs) cudaFree(q);
     if (h->topo_dev) cudaFree(h->topo_dev);
+    if (h->model_dev) cudaFree(h->model_dev);
     if (h->status_host) cudaFreeHost(h->status_host);
     for (auto &ev : h->pending) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
     for (auto &ev : h->pool) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
@@ -399,12 +407,153 @@ int osc2_upload_step_inputs(osc2_handle h, const osc2_step_inputs *in)
     };
     for (auto &x : a) {
         if (x.k == 0) continue;
+        if (!x.src && h->have_model) continue;   // computed on the device by osc2_eval_operating_conditions
         if (!x.src) return fail(OSC2_ERR_INVALID, "step input %s is NULL", x.name);
         int rc = upload_transposed(h, x.src, (double *)x.dst, x.k);
         if (rc) return rc;
     }
     p.t_env = in->t_env;
     h->have_inputs = true;
+    return OSC2_OK;
+}
+
+int osc2_set_model(osc2_handle h, const osc2_model *model)
+{
+    if (!h || !model) return fail(OSC2_ERR_INVALID, "NULL argument");
+    CK(cudaSetDevice(h->device));
+    int nf = 0;
+    for (int j = 0; j < h->M; ++j) {
+        if (model->ch_fluid[j] < 0 || model->ch_fluid[j] >= OSC2_MAX_FLUIDS)
+            return fail(OSC2_ERR_INVALID, "channel %d: fluid table index %d", j, model->ch_fluid[j]);
+        if (model->ch_fluid[j] + 1 > nf) nf = model->ch_fluid[j] + 1;
+        if (model->ch_ifriction[j] != -99 && model->ch_ifriction[j] != 124)
+            return fail(OSC2_ERR_INVALID, "channel %d: IFRICTION %d is not implemented on the device (-99, 124)", j, model->ch_ifriction[j]);
+        if (model->ch_htc_corr[j] != 1 && model->ch_htc_corr[j] != 212)
+            return fail(OSC2_ERR_INVALID, "channel %d: Flag_htc_steady_corr %d is not implemented on the device (1, 212)", j, model->ch_htc_corr[j]);
+    }
+    for (int l = 0; l < h->S; ++l) {
+        if (model->sol_nmat[l] < 1 || model->sol_nmat[l] > OSC2_MAX_MATERIALS)
+            return fail(OSC2_ERR_INVALID, "solid %d: %d materials", l, model->sol_nmat[l]);
+        if (model->sol_kind[l] < OSC2_SOLID_STRAND_MIXED || model->sol_kind[l] > OSC2_SOLID_JACKET)
+            return fail(OSC2_ERR_INVALID, "solid %d: unknown kind %d", l, model->sol_kind[l]);
+        for (int i = 0; i < model->sol_nmat[l]; ++i)
+            if (model->sol_mat[l][i] < 0 || model->sol_mat[l][i] >= OSC2_MAT_COUNT)
+                return fail(OSC2_ERR_INVALID, "solid %d: material id %d is not implemented on the device", l, model->sol_mat[l][i]);
+    }
+    for (int k = 0; k < h->p.nfs; ++k)
+        if (model->fs_choice[k] != 2 && model->fs_choice[k] != -2)
+            return fail(OSC2_ERR_INVALID, "channel-solid interface %d: HTC_choice %d is not implemented on the device (2, -2)", k, model->fs_choice[k]);
+    for (int k = 0; k < h->p.nff; ++k)
+        if (model->ff_choice[k] != 2 && model->ff_choice[k] != -2)
+            return fail(OSC2_ERR_INVALID, "channel-channel interface %d: HTC_choice %d is not implemented on the device (2, -2)", k, model->ff_choice[k]);
+    for (int k = 0; k < h->p.nss; ++k)
+        if (model->ss_choice[k] != 1 && model->ss_choice[k] != -1)
+            return fail(OSC2_ERR_INVALID, "solid-solid interface %d: HTC_choice %d is not implemented on the device (1, -1)", k, model->ss_choice[k]);
+    if (!h->model_dev) CK(cudaMalloc((void **)&h->model_dev, sizeof(osc2_model)));
+    CK(cudaMemcpy(h->model_dev, model, sizeof(osc2_model), cudaMemcpyHostToDevice));
+    if (!h->have_model) {
+        memset(&h->q, 0, sizeof h->q);
+        double *t = nullptr;
+        int rc = dev_alloc(h, &t, (size_t)h->S * h->B);
+        if (rc) return rc;
+        h->q.tmax = t;
+    }
+    h->q.model = h->model_dev;
+    h->n_fluids_used = nf;
+    h->have_model = true;
+    return OSC2_OK;
+}
+
+int osc2_set_fluid_table(osc2_handle h, int fluid, int n_p, int n_t, double p_min, double p_step,
+                         double t_min, double t_step, const double *props)
+{
+    if (!h || !props) return fail(OSC2_ERR_INVALID, "NULL argument");
+    if (!h->have_model) return fail(OSC2_ERR_STATE, "osc2_set_model first");
+    if (fluid < 0 || fluid >= OSC2_MAX_FLUIDS) return fail(OSC2_ERR_INVALID, "fluid index %d", fluid);
+    if (n_p < 2 || n_t < 2 || !(p_step > 0.0) || !(t_step > 0.0)) return fail(OSC2_ERR_INVALID, "table needs >= 2 x 2 points and positive steps");
+    CK(cudaSetDevice(h->device));
+    double *dev = nullptr;
+    const size_t n = (size_t)OSC2_N_FLUID_PROPS * n_p * n_t;
+    int rc = dev_alloc(h, &dev, n);
+    if (rc) return rc;
+    CK(cudaMemcpy(dev, props, n * sizeof(double), cudaMemcpyHostToDevice));
+    FluidTableDev &t = h->q.fluid[fluid];
+    t.n_p = n_p; t.n_t = n_t; t.p_min = p_min; t.p_step = p_step; t.t_min = t_min; t.t_step = t_step; t.props = dev;
+    h->have_table[fluid] = true;
+    return OSC2_OK;
+}
+
+// host [B][K] int-free doubles -> device [K][B]; allocates on first use
+static int upload_sweep_array(osc2_context *h, const double *host, const double **dev, size_t K)
+{
+    if (K == 0) return OSC2_OK;
+    if (!*dev) { double *t = nullptr; int rc = dev_alloc(h, &t, K * h->B); if (rc) return rc; *dev = t; }
+    if (K * h->B > h->staging_doubles) return fail(OSC2_ERR_STATE, "staging buffer too small");
+    return upload_transposed(h, host, (double *)*dev, K);
+}
+
+int osc2_upload_sweep(osc2_handle h, const osc2_sweep *sw)
+{
+    if (!h || !sw) return fail(OSC2_ERR_INVALID, "NULL argument");
+    if (!h->have_model) return fail(OSC2_ERR_STATE, "osc2_set_model first");
+    if (h->S > 0 && (!sw->b_field || !sw->eps || !sw->q0 || !sw->q_window))
+        return fail(OSC2_ERR_INVALID, "b_field, eps, q0 and q_window are required");
+    CK(cudaSetDevice(h->device));
+    const size_t S = h->S, E = h->E;
+    int rc = upload_sweep_array(h, sw->b_field, &h->q.b_field, S * 2);
+    if (!rc) rc = upload_sweep_array(h, sw->eps, &h->q.eps, S);
+    if (!rc) rc = upload_sweep_array(h, sw->q0, &h->q.q0, S);
+    if (!rc) rc = upload_sweep_array(h, sw->q_window, &h->q.q_window, S * 4);
+    if (!rc && sw->tcs) rc = upload_sweep_array(h, sw->tcs, &h->q.tcs, S * E);
+    if (rc) return rc;
+    h->have_sweep = true;
+    return OSC2_OK;
+}
+
+int osc2_eval_operating_conditions(osc2_handle h, double time)
+{
+    if (!h) return fail(OSC2_ERR_INVALID, "handle is NULL");
+    if (!h->have_model || !h->have_sweep || !h->have_state)
+        return fail(OSC2_ERR_STATE, "osc2_eval_operating_conditions needs osc2_set_model, osc2_upload_sweep and osc2_upload_state first");
+    for (int f = 0; f < h->n_fluids_used; ++f)
+        if (!h->have_table[f]) return fail(OSC2_ERR_STATE, "fluid table %d was not set", f);
+    CK(cudaSetDevice(h->device));
+    h->q.time = time;
+    CudaLauncher L{h};
+    if (h->S > 0) {
+        CK(cudaMemsetAsync(h->q.tmax, 0, sizeof(double) * (size_t)h->S * h->B, h->stream));
+        const long long w = (long long)((h->E + 63) / 64) * h->B;
+        L.launch(OSC2_K_PROPS, osc2_solid_tmax_kernel, (unsigned)((w + 127) / 128), 128u, (size_t)0, h->p, h->q);
+    }
+    const long long work = (long long)h->E * h->B;
+    L.launch(OSC2_K_PROPS, osc2_opcond_kernel, (unsigned)((work + 127) / 128), 128u, (size_t)0,
+             (const osc2_topology *)h->topo_dev, h->p, h->q);
+    if (!h->launch_error.empty()) {
+        const int rc = fail(OSC2_ERR_CUDA, "%s", h->launch_error.c_str());
+        h->launch_error.clear();
+        return rc;
+    }
+    h->have_inputs = true;
+    return OSC2_OK;
+}
+
+int osc2_download_step_inputs(osc2_handle h, double *fl_gauss, double *fl_node, double *sol_gauss, double *sol_q,
+                              double *htc_ff, double *htc_fs, double *htc_ss, double *htc_es)
+{
+    if (!h) return fail(OSC2_ERR_INVALID, "handle is NULL");
+    CK(cudaSetDevice(h->device));
+    const size_t E = h->E, M = h->M, S = h->S;
+    const StepDev &p = h->p;
+    struct { double *dst; const double *src; size_t k; } a[] = {
+        {fl_gauss, p.fl_gauss, 9 * M * E}, {fl_node, p.fl_node, 4 * M}, {sol_gauss, p.sol_gauss, 3 * S * E},
+        {sol_q, p.sol_q, 2 * S * E * 2}, {htc_ff, p.htc_ff, 2 * (size_t)p.nff * E}, {htc_fs, p.htc_fs, (size_t)p.nfs * E},
+        {htc_ss, p.htc_ss, (size_t)p.nss * E}, {htc_es, p.htc_es, (size_t)p.nes * 3 * E},
+    };
+    for (auto &x : a) {
+        if (!x.dst || x.k == 0) continue;
+        int rc = download_transposed(h, x.src, x.dst, x.k);
+        if (rc) return rc;
+    }
     return OSC2_OK;
 }
 

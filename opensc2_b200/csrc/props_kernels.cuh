@@ -1,0 +1,428 @@
+// K_P: operating conditions at the Gauss points, evaluated on the device from the
+// device-resident state -- what the reference does on the host before every step():
+//   Conductor.operating_conditions_em / _th   conductor.py:4591-4744
+//   Conductor.eval_transp_coeff               conductor.py:4822-5406 (choices +-2, +-1, env constants)
+//   Conductor.build_heat_source               conductor.py:4423-4581, solid_component.py:415-576
+//   Coolant Gauss p, T, v / Reynolds / Gruneisen  coolant.py:134-180
+//   Channel friction (-99, 124) and Nusselt (1, 212)  channel.py:392-401, 782-795, 1104-1273
+//   material fits  properties_of_materials/{copper,niobium3_tin,stainless_steel,glass_epoxy}.py
+// Coolant properties come from (p, T) tables by bilinear interpolation (the reference calls
+// CoolProp.PropsSI, coolant.py:209-217).  One thread per (element, conductor); every array is
+// batch-innermost, so a warp reads and writes 256 contiguous bytes per value.
+#pragma once
+
+#include "osc2_dev.h"
+
+struct FluidTableDev {
+    int n_p, n_t;
+    double p_min, p_step, t_min, t_step;
+    const double *props;   // [10][n_p][n_t]
+};
+
+struct PropsDev {
+    const osc2_model *model;
+    FluidTableDev fluid[OSC2_MAX_FLUIDS];
+    // sweep, batch-innermost
+    const double *b_field;   // [S][2][B]
+    const double *eps;       // [S][B]
+    const double *q0;        // [S][B]
+    const double *q_window;  // [S][4][B]
+    const double *tcs;       // [S][E][B] or nullptr
+    double *tmax;            // [S][B] max Gauss temperature of each solid (whole-array branches)
+    double time;
+};
+
+namespace osc2p {
+
+__device__ __forceinline__ double sq(double x) { return x * x; }
+
+// copper.py:221-275
+__device__ inline double rhoecu0(double t, double rrr)
+{
+    const double P0 = 1.553e-8, P1 = 1.171e-17, P2 = 4.49, P3 = 3.841e10, P4 = 1.14, P5 = 50, P6 = 6.428, P7 = 0.4531;
+    const double rho0 = P0 / rrr;
+    const double rhoi = (P1 * pow(t, P2)) / (1.0 + P1 * P3 * pow(t, P2 - P4) * exp(-pow(P5 / t, P6)));
+    const double rhoi0 = P7 * rhoi * rho0 / (rhoi + rho0);
+    return rho0 + rhoi + rhoi0;
+}
+// copper.py:140-217
+__device__ inline double rhoecu(double t, double b, double rrr)
+{
+    if (!(rrr > 1.0 && b >= 0 && t > 0)) return 0.0;
+    const double rhoN = rhoecu0(t, rrr);
+    double ccc = 0.0;
+    if (b > 0) {
+        const double xxx = rhoecu0(273.0, rrr) / rhoecu0(t, rrr) * b;
+        const double L = log10(xxx);
+        double aaa = 0.0;
+        aaa = aaa + -2.662 * 1.0;
+        aaa = aaa + 0.3168 * L;
+        aaa = aaa + 0.6229 * sq(L);
+        aaa = aaa + -0.1839 * pow(L, 3.0);
+        aaa = aaa + 0.01827 * pow(L, 4.0);
+        ccc = pow(10.0, aaa);
+    }
+    return rhoN * (1.0 + ccc);
+}
+// copper.py:5-71
+__device__ inline double k_cu(double t, double b, double rrr)
+{
+    const double beta = 0.634 / rrr, betat = beta / 0.0003;
+    const double P1 = 1.754e-8, P2 = 2.763, P3 = 1102, P4 = -0.165, P5 = 70, P6 = 1.756;
+    const double P7 = 0.838 / pow(betat, 0.1661);
+    const double W0 = beta / t;
+    const double Wi = (P1 * pow(t, P2)) / (1 + (P1 * P3 * pow(t, P2 + P4) * exp(-pow(P5 / t, P6))));
+    const double Wi0 = P7 * Wi * W0 / (Wi + W0);
+    return 1.0 / (Wi + W0 + Wi0) * rhoecu0(t, rrr) / rhoecu(t, b, rrr);
+}
+// copper.py:75-136
+__device__ inline double cp_cu(double t)
+{
+    if (!(t >= 4 && t <= 300)) return 0.0;
+    const double L = log10(t);
+    return pow(10.0, -1.91844 + -0.15973 * L + 8.61013 * sq(L) + -18.996 * pow(L, 3.0) + 21.9661 * pow(L, 4.0)
+                         + -12.7328 * pow(L, 5.0) + 3.54322 * pow(L, 6.0) + -0.3797 * pow(L, 7.0));
+}
+// niobium3_tin.py:371-434
+__device__ inline double snbsn(double eps)
+{
+    const double Ca1 = 47.02, Ca2 = 11.76, EPS0a = 2.31e-3;
+    const double EPSsh = Ca2 * EPS0a / sqrt(Ca1 * Ca1 - Ca2 * Ca2);
+    return 1.0 + 1.0 / (1.0 - Ca1 * EPS0a)
+                     * (Ca1 * (sqrt(EPSsh * EPSsh + EPS0a * EPS0a) - sqrt(sq(eps - EPSsh) + EPS0a * EPS0a)) - Ca2 * eps);
+}
+// niobium3_tin.py:437-490
+__device__ inline double tc_nb3sn(double b, double eps, double tc0m, double bc20m)
+{
+    const double blim = fmax(b, 0.01);
+    const double s = snbsn(eps);
+    const double blcase = blim / (bc20m * s);
+    if (!(blcase < 1.0)) return 0.0;
+    return tc0m * pow(s, 1.0 / 3.0) * pow(1.0 - blcase, 1.0 / 1.52);
+}
+// niobium3_tin.py:62-124
+__device__ inline double k_nb3sn(double tt)
+{
+    const double T0 = 21.9620369;
+    tt = fmin(tt, 750.0);
+    tt = fmax(tt, 4.0);
+    if (tt <= T0) return 1.3905e14 * pow(tt, 3.66343961) / pow(76.6127237 + tt, 9.3220843);
+    if (tt > T0) return -7.1614565e-1 * log(tt) + 5.40229689;
+    return 0.0;
+}
+// niobium3_tin.py:127-262
+__device__ inline double cp_nb3sn(double T, double TCS, double TC, double TC0)
+{
+    const double AA = 38.2226877, BB = -848.364226, CC = 1415.13808, DD = -346.837966;
+    const double a = 6.80458608, b = 59.9209182, c = 25.8286334, d = 8.77918335;
+    T = fmin(T, 1000.0);
+    double CPN = 0.0;
+    if (T <= 10.0) CPN = 7.5475e-3 * sq(T);
+    else if (T > 10.0 && T <= 20.0) CPN = (-0.3 + 0.00375 * sq(T)) / 0.09937;
+    else if (T > 20.0)
+        CPN = AA * T / (a + T) + BB * sq(T) / sq(b + T) + CC * pow(T, 3.0) / pow(c + T, 3.0)
+              + DD * pow(T, 4.0) / pow(d + T, 4.0);
+    double CPNTC = 0.0;
+    if (TC <= 10.0) CPNTC = 7.5475e-3 * sq(TC);
+    else if (TC > 10.0 && TC <= 20.0) CPNTC = (-0.3 + 0.00375 * sq(TC)) / 0.09937;
+    double CPS = 0.0;
+    if (T <= TC) {
+        const double TC_norm = TC / TC0;
+        const double DBC2DT = -0.46306 - 0.067830 * TC;
+        const double DELCP = 1500.0 * sq(DBC2DT) / (2.0 * sq(27.2 / (1.0 + (0.34 * TC_norm))) - 1.0);
+        CPS = (CPNTC + DELCP) * pow(T / TC, 3.0);
+    }
+    double CP = 0.0;
+    if (T <= TCS) CP = CPS;
+    if (T > TCS && T <= TC) {
+        double F = 1.0;
+        if (TCS < TC) F = (T - TCS) / (TC - TCS);
+        CP = F * CPN + (1.0 - F) * CPS;
+    }
+    if (T > TC) CP = CPN;
+    return CP;
+}
+// the four-term rational form shared by the SS and glass-epoxy fits
+__device__ inline double four_term(double T, double C0, double C1, double C2, double C3, double s0, double s1,
+                                   double s2, double s3, double n0, double n1, double n2, double n3)
+{
+    return C0 * T / pow(s0 + T, n0) + C1 * sq(T) / pow(s1 + T, n1) + C2 * pow(T, 3.0) / pow(s2 + T, n2)
+           + C3 * pow(T, 4.0) / pow(s3 + T, n3);
+}
+// stainless_steel.py:5-38
+__device__ inline double k_ss(double t)
+{
+    return four_term(t, 21224.0426, 103.007623, 135.870511, 0.07942859, 10844822.8, 6800262.44, 34.4411414,
+                     0.23194142, 1.07801291, 1.88806818, 3.44233222, 3.20629457);
+}
+// stainless_steel.py:41-88 -- branch on max(T) of the whole array
+__device__ inline double cp_ss(double T, double tmax)
+{
+    if (tmax <= 1.0) return 0.498 * T + 3.71e-4 * pow(T, 3.0);
+    if (tmax < 12.8973011) {
+        T = fmin(T, 1253.0);
+        return 0.46437387 * T + 0.00035157 * pow(T, 3.0);
+    }
+    T = fmin(T, 1253.0);
+    return four_term(T, -468.772387, -81.2353649, 827.209072, 29.9811823, 422.117262, 1235598.51, 51.2732976,
+                     0.44591988, 0.57149148, 2.0006633, 2.79384889, 3.25864797);
+}
+// glass_epoxy.py:5-42, 45-84
+__device__ inline double k_ge(double t)
+{
+    t = fmin(t, 1000.0);
+    t = fmax(t, 1.0);
+    return four_term(t, 0.106635834, 4.254937095, 0.369710568, -0.220612963, 4.374557267, 78.36483015,
+                     0.896107679, 0.261916360, 0.551227580, 2.274402853, 2.979875183, 3.644905343);
+}
+__device__ inline double cp_ge(double t)
+{
+    t = fmin(t, 1000.0);
+    t = fmax(t, 1.0);
+    return four_term(t, 0.309399374, -1387.509141, 283.0320589, 1.822153805, 113.1687618, 80.88333136,
+                     26.27075203, 1.104229335, 0.254475819, 1.938523579, 2.603466143, 3.522809815);
+}
+__device__ inline double mat_density(int mat)
+{
+    return mat == OSC2_MAT_CU_NIST ? 8900.0 : mat == OSC2_MAT_NB3SN ? 8950.0 : mat == OSC2_MAT_SS ? 7800.0 : 2000.0;
+}
+// channel.py:392-401, 782-795, 1104-1115
+__device__ inline double friction_124(double re)
+{
+    re = fabs(re);
+    double f = (0.316 * pow(re, -0.25)) / 4.0;
+    if (re > 1e4) f = 2.21 * pow(re, -0.4) / 4.0;
+    return fmax(0.0, f);
+}
+// channel.py:1156-1192
+__device__ inline double nusselt_1(double re, double pr)
+{
+    double nu = 0.023 * pow(re, 0.8) * pow(pr, 0.3);
+    if (nu < 8.235) nu = 8.235;
+    return nu;
+}
+// channel.py:1245-1273: the exponent really used is eval_steady_state_htc's nn = 0.3
+__device__ inline double nusselt_212(double re) { return 0.42 * pow(re, 0.3); }
+
+// bilinear (p, T) table lookup: cell index and weights once per point, then one
+// 4-value stencil per property
+struct Cell { int off; double a, b; int n_t; };
+__device__ inline Cell locate(const FluidTableDev &tab, double p, double t)
+{
+    double fp = floor((p - tab.p_min) / tab.p_step), ft = floor((t - tab.t_min) / tab.t_step);
+    if (!(fp >= 0.0)) fp = 0.0;
+    if (fp > (double)(tab.n_p - 2)) fp = (double)(tab.n_p - 2);
+    if (!(ft >= 0.0)) ft = 0.0;
+    if (ft > (double)(tab.n_t - 2)) ft = (double)(tab.n_t - 2);
+    Cell c;
+    c.off = (int)fp * tab.n_t + (int)ft;
+    c.a = (p - (tab.p_min + fp * tab.p_step)) / tab.p_step;
+    c.b = (t - (tab.t_min + ft * tab.t_step)) / tab.t_step;
+    c.n_t = tab.n_t;
+    return c;
+}
+__device__ inline double lookup(const FluidTableDev &tab, const Cell &c, int prop)
+{
+    const double *f = tab.props + (size_t)prop * tab.n_p * tab.n_t + c.off;
+    const double f00 = __ldg(f), f01 = __ldg(f + 1), f10 = __ldg(f + c.n_t), f11 = __ldg(f + c.n_t + 1);
+    const double lo = f00 + c.b * (f01 - f00);
+    const double hi = f10 + c.b * (f11 - f10);
+    return lo + c.a * (hi - lo);
+}
+// np.linspace(start, stop, N)[i]
+__device__ inline double linspace_at(double start, double stop, int N, int i)
+{
+    if (i == N - 1 && N > 1) return stop;
+    const double div = (double)(N - 1), delta = stop - start;
+    const double step = delta / div;
+    if (step == 0.0) return ((double)i / div) * delta + start;
+    return (double)i * step + start;
+}
+
+}  // namespace osc2p
+
+// max over the Gauss points of |T_i + T_i+1| / 2 for every solid (isobaric_specific_heat_ss picks
+// its formula from it).  One thread per (chunk of 64 elements, conductor); temperatures are >= 0 so
+// the IEEE bit pattern orders like an unsigned integer.
+__global__ void osc2_solid_tmax_kernel(StepDev p, PropsDev q)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int chunks = (p.E + 63) / 64;
+    if (idx >= (long long)chunks * p.B) return;
+    const size_t B = (size_t)p.B;
+    const size_t b = (size_t)(idx % p.B);
+    const int c = (int)(idx / p.B);
+    const int e0 = c * 64, e1 = min(p.E, e0 + 64);
+    for (int l = 0; l < p.S; ++l) {
+        const int is = 3 * p.M + l;
+        double prev = p.sysvar[((size_t)e0 * p.d + is) * B + b];
+        double mx = 0.0;
+        for (int e = e0; e < e1; ++e) {
+            const double nxt = p.sysvar[((size_t)(e + 1) * p.d + is) * B + b];
+            const double tg = fabs(prev + nxt) / 2.0;
+            if (tg > mx) mx = tg;
+            prev = nxt;
+        }
+        atomicMax((unsigned long long *)(q.tmax + (size_t)l * B + b), (unsigned long long)__double_as_longlong(mx));
+    }
+}
+
+__global__ void __launch_bounds__(128) osc2_opcond_kernel(const osc2_topology *__restrict__ tp, StepDev p, PropsDev q)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)p.E * p.B) return;
+    const size_t B = (size_t)p.B;
+    const size_t b = (size_t)(idx % p.B);
+    const int e = (int)(idx / p.B);
+    const int M = p.M, S = p.S, d = p.d, E = p.E, N = p.N;
+    const osc2_model *md = q.model;
+    const double *x0 = p.sysvar + ((size_t)e * d) * B + b;          // node e
+    const double *x1 = x0 + (size_t)d * B;                          // node e + 1
+    double *fg = const_cast<double *>(p.fl_gauss);
+    double *sg = const_cast<double *>(p.sol_gauss);
+    double tf[OSC2_MAX_CHANNELS], hst[OSC2_MAX_CHANNELS], rcp[OSC2_MAX_CHANNELS];
+
+    for (int j = 0; j < M; ++j) {
+        const FluidTableDev &tab = q.fluid[md->ch_fluid[j]];
+        const double v = (x0[(size_t)j * B] + x1[(size_t)j * B]) / 2.0;
+        const double pr = (x0[(size_t)(M + j) * B] + x1[(size_t)(M + j) * B]) / 2.0;
+        const double T = (x0[(size_t)(2 * M + j) * B] + x1[(size_t)(2 * M + j) * B]) / 2.0;
+        const osc2p::Cell c = osc2p::locate(tab, pr, T);
+        const double rho = osc2p::lookup(tab, c, OSC2_FP_RHO), mu = osc2p::lookup(tab, c, OSC2_FP_MU);
+        const double cv = osc2p::lookup(tab, c, OSC2_FP_CV), kk = osc2p::lookup(tab, c, OSC2_FP_K);
+        const double re = fabs(tp->ch_dh[j] * v * rho / mu);
+        const double grun = osc2p::lookup(tab, c, OSC2_FP_BETA) / osc2p::lookup(tab, c, OSC2_FP_KAPPA) / cv / rho;
+        const double nu = (md->ch_htc_corr[j] == 212) ? osc2p::nusselt_212(re)
+                                                      : osc2p::nusselt_1(re, osc2p::lookup(tab, c, OSC2_FP_PRANDTL));
+        const double ftot = ((md->ch_ifriction[j] == 124) ? osc2p::friction_124(re) : 1.0) * md->ch_friction_mult[j];
+#define FGW(qq) fg[((((size_t)(qq) * M + j) * E) + e) * B + b]
+        FGW(0) = v; FGW(1) = pr; FGW(2) = T; FGW(3) = rho;
+        FGW(4) = osc2p::lookup(tab, c, OSC2_FP_SOUND);
+        FGW(5) = grun;
+        FGW(6) = osc2p::lookup(tab, c, OSC2_FP_H);
+        FGW(7) = cv;
+        FGW(8) = ftot;
+#undef FGW
+        tf[j] = T;
+        hst[j] = nu * kk / tp->ch_dh[j];
+        rcp[j] = kk * rho * osc2p::lookup(tab, c, OSC2_FP_CP);     // k * rho * cp of the transient HTC
+        if (e == 0) {   // nodal values the boundary rows look at
+            double *fn = const_cast<double *>(p.fl_node);
+            const double *xl = p.sysvar + ((size_t)(N - 1) * d) * B + b;
+            fn[((size_t)0 * M + j) * B + b] = x0[(size_t)j * B];
+            fn[((size_t)1 * M + j) * B + b] = xl[(size_t)j * B];
+            const osc2p::Cell cf = osc2p::locate(tab, x0[(size_t)(M + j) * B], x0[(size_t)(2 * M + j) * B]);
+            const osc2p::Cell cl = osc2p::locate(tab, xl[(size_t)(M + j) * B], xl[(size_t)(2 * M + j) * B]);
+            fn[((size_t)2 * M + j) * B + b] = osc2p::lookup(tab, cf, OSC2_FP_RHO);
+            fn[((size_t)3 * M + j) * B + b] = osc2p::lookup(tab, cl, OSC2_FP_RHO);
+        }
+    }
+
+    double *sqv = const_cast<double *>(p.sol_q);
+    for (int l = 0; l < S; ++l) {
+        const int is = 3 * M + l;
+        const double T = fabs(x0[(size_t)is * B] + x1[(size_t)is * B]) / 2.0;
+        const double biss = q.b_field[((size_t)l * 2 + 0) * B + b], boss = q.b_field[((size_t)l * 2 + 1) * B + b];
+        const double bg = fabs(osc2p::linspace_at(biss, boss, N, e) + osc2p::linspace_at(biss, boss, N, e + 1)) / 2.0;
+        const int nmat = md->sol_nmat[l];
+        const int kind = md->sol_kind[l];
+        double tc = 0.0, tcs = 0.0;
+        if (kind == OSC2_SOLID_STRAND_MIXED) {
+            const double eps = q.eps[(size_t)l * B + b];
+            tc = osc2p::tc_nb3sn(bg, (eps + eps) / 2.0, md->sol_tc0m[l], md->sol_bc20m[l]);
+            tcs = q.tcs ? q.tcs[((size_t)l * E + e) * B + b] : 0.0;
+        }
+        const double tmax = q.tmax[(size_t)l * B + b];
+        double nsum = 0.0, cps = 0.0, ksum = 0.0, rho1 = 0.0, cp1 = 0.0, k1 = 0.0;
+        for (int i = 0; i < nmat; ++i) {
+            const int mat = md->sol_mat[l][i];
+            const double w = md->sol_weight[l][i];
+            const double rho_i = osc2p::mat_density(mat);
+            double cp_i, k_i;
+            if (mat == OSC2_MAT_CU_NIST) { cp_i = osc2p::cp_cu(T); k_i = osc2p::k_cu(T, bg, md->sol_rrr[l]); }
+            else if (mat == OSC2_MAT_NB3SN) { cp_i = osc2p::cp_nb3sn(T, tcs, tc, md->sol_tc0m[l]); k_i = osc2p::k_nb3sn(T); }
+            else if (mat == OSC2_MAT_SS) { cp_i = osc2p::cp_ss(T, tmax); k_i = osc2p::k_ss(T); }
+            else { cp_i = osc2p::cp_ge(T); k_i = osc2p::k_ge(T); }
+            const double num = rho_i * w;
+            if (i == 0) { nsum = num; cps = cp_i * num; ksum = k_i * w; rho1 = rho_i; cp1 = cp_i; k1 = k_i; }
+            else { nsum = nsum + num; cps = cps + cp_i * num; ksum = ksum + k_i * w; }
+        }
+        double rho, cp, kk;
+        if (kind == OSC2_SOLID_JACKET && nmat == 1) { rho = rho1; cp = cp1; kk = k1; }
+        else { rho = nsum / md->sol_weight_sum[l]; cp = cps / nsum; kk = ksum / md->sol_weight_sum[l]; }
+        sg[(((size_t)0 * S + l) * E + e) * B + b] = rho;
+        sg[(((size_t)1 * S + l) * E + e) * B + b] = cp;
+        sg[(((size_t)2 * S + l) * E + e) * B + b] = kk;
+        // square-wave external heating
+        const double n0 = q.q_window[((size_t)l * 4 + 0) * B + b], n1 = q.q_window[((size_t)l * 4 + 1) * B + b];
+        const double tb = q.q_window[((size_t)l * 4 + 2) * B + b], te = q.q_window[((size_t)l * 4 + 3) * B + b];
+        const double q0 = q.q0[(size_t)l * B + b];
+        const bool on_now = md->sol_heated[l] && q.time >= tb && q.time <= te;
+        const bool on_t0 = md->sol_heated[l] && 0.0 >= tb && 0.0 <= te;
+        for (int side = 0; side < 2; ++side) {
+            const int node = e + side;
+            const bool in = node >= (int)n0 && node <= (int)n1;
+            sqv[(((((size_t)side * S + l) * E + e) * 2) + 0) * B + b] = (on_now && in) ? q0 : 0.0;
+            sqv[(((((size_t)side * S + l) * E + e) * 2) + 1) * B + b] = (on_t0 && in) ? q0 : 0.0;
+        }
+    }
+
+    // interface heat transfer coefficients
+    double *hfs = const_cast<double *>(p.htc_fs);
+    for (int k = 0; k < p.nfs; ++k) {
+        const int j = tp->fs[k][0], l = tp->fs[k][1];
+        double h;
+        if (md->fs_choice[k] == 2) {
+            const int is = 3 * M + l;
+            const double Ts = fabs(x0[(size_t)is * B] + x1[(size_t)is * B]) / 2.0, Tf = tf[j];
+            const double hK = 200.0 * (Ts + Tf) * (osc2p::sq(Ts) + osc2p::sq(Tf));
+            const double tqbeg = q.q_window[((size_t)l * 4 + 2) * B + b];
+            double full = 0.0;
+            if (q.time > tqbeg) {
+                const double htr = sqrt(rcp[j] / (3.141592653589793 * (q.time - tqbeg)));
+                full = (hK * htr) / (hK + htr);
+            }
+            h = fmax(hst[j] * md->fs_mlt[k], full);
+        } else {
+            h = md->fs_htc[k] * md->fs_mlt[k];
+        }
+        hfs[((size_t)k * E + e) * B + b] = h;
+    }
+    double *hff = const_cast<double *>(p.htc_ff);
+    for (int k = 0; k < p.nff; ++k) {
+        const int ja = tp->ff[k][0], jb = tp->ff[k][1];
+        double ho, hc;
+        if (md->ff_choice[k] == 2) {
+            const double h1 = hst[ja], h2 = hst[jb];
+            ho = md->ff_mlt[k] * h1 * h2 / (h1 + h2);
+            const double cond = osc2p::k_ss((tf[ja] + tf[jb]) / 2);
+            const double rwall = md->ff_thick[k] / cond;
+            hc = md->ff_mlt[k] / (1 / h1 + 1 / h2 + rwall);
+        } else {
+            ho = md->ff_htc[k] * md->ff_mlt[k];
+            hc = ho;
+        }
+        hff[(((size_t)0 * p.nff + k) * E + e) * B + b] = ho;
+        hff[(((size_t)1 * p.nff + k) * E + e) * B + b] = hc;
+    }
+    double *hss = const_cast<double *>(p.htc_ss);
+    for (int k = 0; k < p.nss; ++k) {
+        double h;
+        if (md->ss_choice[k] == 1) {
+            const double ka = sg[(((size_t)2 * S + tp->ss[k][0]) * E + e) * B + b];
+            const double kb = sg[(((size_t)2 * S + tp->ss[k][1]) * E + e) * B + b];
+            const double rr = md->ss_thick_rc[k] / ka;
+            const double rc = md->ss_thick_cr[k] / kb;
+            h = md->ss_mlt[k] * (1.0 / (rr + md->ss_rcontact[k] + rc));
+        } else {
+            h = md->ss_htc[k] * md->ss_mlt[k];
+        }
+        hss[((size_t)k * E + e) * B + b] = h;
+    }
+    double *hes = const_cast<double *>(p.htc_es);
+    for (int k = 0; k < p.nes; ++k) {
+        hes[(((size_t)k * 3 + 0) * E + e) * B + b] = md->es_htc[k];
+        hes[(((size_t)k * 3 + 1) * E + e) * B + b] = 0.0;
+        hes[(((size_t)k * 3 + 2) * E + e) * B + b] = 0.0;
+    }
+}

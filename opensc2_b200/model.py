@@ -1,0 +1,194 @@
+"""Operating-condition model of a conductor batch: what the reference evaluates on the
+host before every `step()` (`Conductor.operating_conditions_em/_th`,
+/root/reference/source_code/conductor.py:4591-4744; `eval_transp_coeff` :4822-5406;
+`build_heat_source` :4423-4581), described as flat data for the device kernel K_P.
+
+* `Model`   -- uniform across the batch (materials, correlations, HTC models): `osc2_model`.
+* `Sweep`   -- swept per-conductor scalars (field, strain, heat slug, Tcs): `osc2_sweep`.
+* `FluidTable` -- coolant properties on a regular (p, T) grid; the reference calls
+  `CoolProp.PropsSI` (coolant.py:209-217), which is absent from this image: tables are
+  an INPUT of the library (to be generated with CoolProp where it exists).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Optional, Tuple
+
+import numpy as np
+
+from ._abi import OSC2_N_FLUID_PROPS, Osc2Model, Osc2Sweep, c_dp
+
+# fluid-table property order = the reference's alias table (simulation.py:89-100)
+FP_BETA, FP_KAPPA, FP_PRANDTL, FP_RHO, FP_MU, FP_H, FP_CP, FP_CV, FP_SOUND, FP_K = range(10)
+MAT_CU_NIST, MAT_NB3SN, MAT_SS, MAT_GE = range(4)
+SOLID_STRAND_MIXED, SOLID_STRAND_STAB, SOLID_JACKET = range(3)
+
+
+@dataclass(frozen=True)
+class SolidModel:
+    kind: int                               # SOLID_*
+    materials: Tuple[int, ...]              # MAT_*, in the order of the reference's *_function arrays
+    weights: Tuple[float, ...]              # homogenization_cefficients | cross_sections
+    weight_sum: float                       # homogenization_cefficients_sum | inputs["CROSSECTION"]
+    rrr: float = 100.0
+    tc0m: float = 0.0
+    bc20m: float = 0.0
+    heated: bool = False                    # IQFUN == 1
+
+
+@dataclass(frozen=True)
+class Model:
+    ch_fluid: Tuple[int, ...]
+    ch_ifriction: Tuple[int, ...]           # -99 | 124
+    ch_friction_mult: Tuple[float, ...]
+    ch_htc_corr: Tuple[int, ...]            # 1 | 212
+    solids: Tuple[SolidModel, ...]
+    fs: Tuple[Tuple[int, float, float], ...] = ()                        # (HTC_choice, contact_HTC, multiplier)
+    ff: Tuple[Tuple[int, float, float, float], ...] = ()                 # (+ interf_thickness)
+    ss: Tuple[Tuple[int, float, float, float, float, float], ...] = ()   # (+ thick_rc, thick_cr, R_contact)
+    es_htc: Tuple[float, ...] = ()          # constant convective HTC incl. Phi_conv and multiplier
+
+    def struct(self, topo) -> Osc2Model:
+        assert len(self.ch_fluid) == topo.n_ch and len(self.solids) == topo.n_sol
+        assert len(self.fs) == len(topo.fs) and len(self.ff) == len(topo.ff)
+        assert len(self.ss) == len(topo.ss) and len(self.es_htc) == len(topo.es)
+        m = Osc2Model()
+        for j in range(topo.n_ch):
+            m.ch_fluid[j], m.ch_ifriction[j] = self.ch_fluid[j], self.ch_ifriction[j]
+            m.ch_friction_mult[j], m.ch_htc_corr[j] = self.ch_friction_mult[j], self.ch_htc_corr[j]
+        for l, s in enumerate(self.solids):
+            m.sol_kind[l], m.sol_nmat[l] = s.kind, len(s.materials)
+            for i, (mat, w) in enumerate(zip(s.materials, s.weights)):
+                m.sol_mat[l][i], m.sol_weight[l][i] = mat, w
+            m.sol_weight_sum[l], m.sol_rrr[l] = s.weight_sum, s.rrr
+            m.sol_tc0m[l], m.sol_bc20m[l], m.sol_heated[l] = s.tc0m, s.bc20m, int(s.heated)
+        for k, (c, h, mlt) in enumerate(self.fs):
+            m.fs_choice[k], m.fs_htc[k], m.fs_mlt[k] = c, h, mlt
+        for k, (c, h, mlt, th) in enumerate(self.ff):
+            m.ff_choice[k], m.ff_htc[k], m.ff_mlt[k], m.ff_thick[k] = c, h, mlt, th
+        for k, (c, h, mlt, t1, t2, rc) in enumerate(self.ss):
+            m.ss_choice[k], m.ss_htc[k], m.ss_mlt[k] = c, h, mlt
+            m.ss_thick_rc[k], m.ss_thick_cr[k], m.ss_rcontact[k] = t1, t2, rc
+        for k, h in enumerate(self.es_htc):
+            m.es_htc[k] = h
+        return m
+
+
+@dataclass
+class FluidTable:
+    p_min: float
+    p_step: float
+    t_min: float
+    t_step: float
+    props: np.ndarray            # (10, n_p, n_t)
+
+    def __post_init__(self):
+        self.props = np.ascontiguousarray(self.props, dtype=np.float64)
+        assert self.props.ndim == 3 and self.props.shape[0] == OSC2_N_FLUID_PROPS
+
+
+@dataclass
+class Sweep:
+    """Batch-leading arrays; S = number of solids, E = elements."""
+    b_field: np.ndarray          # (B, S, 2)  BISS, BOSS
+    eps: np.ndarray              # (B, S)
+    q0: np.ndarray               # (B, S)     W/m
+    q_window: np.ndarray         # (B, S, 4)  first node, last node, TQBEG, TQEND
+    tcs: Optional[np.ndarray] = None   # (B, S, E)
+
+    def struct(self):
+        keep = []
+        s = Osc2Sweep()
+        for name in ("b_field", "eps", "q0", "q_window", "tcs"):
+            a = getattr(self, name)
+            if a is None or a.size == 0:
+                setattr(s, name, None)
+                continue
+            a = np.ascontiguousarray(a, dtype=np.float64)
+            keep.append(a)
+            setattr(s, name, a.ctypes.data_as(c_dp))
+        return s, keep
+
+
+def heat_window(zcoord: np.ndarray, xq_beg: float, xq_end: float) -> Tuple[int, int]:
+    """`SolidComponent.heat0_where` (solid_component.py:523-531): inclusive node window."""
+    lo = int(np.min(np.nonzero(zcoord >= xq_beg)))
+    hi = int(np.max(np.nonzero(zcoord <= xq_end)))
+    return lo, hi
+
+
+# ----------------------------------------------------------------------------------------
+# Shipped-deck shaped models
+# ----------------------------------------------------------------------------------------
+
+def case1_model(correlations: bool = False) -> Model:
+    """CASE_1 ITER-like LTS: 2 He channels (f = 0.02), STR_MIX_1 (Cu RRR 197.71 + Nb3Sn,
+    Cu:nonCu 2.0846), Z_JACKET_1 (SS 3.0699e-4 + glass-epoxy 2.7966e-4 m^2); the deck's
+    interfaces are all constant (HTC_choice -2 / -1: 1000, 1000, 1000, 500, 0 W/m^2K).
+    `correlations=True` switches the interfaces to the correlation-driven models
+    (choice 2 / 1) to exercise them."""
+    stab = 2.0846
+    solids = (
+        SolidModel(SOLID_STRAND_MIXED, (MAT_CU_NIST, MAT_NB3SN), (stab, 1.0), float(np.array([stab, 1.0]).sum()),
+                   rrr=197.71, tc0m=16.22, bc20m=32.35, heated=True),
+        SolidModel(SOLID_JACKET, (MAT_SS, MAT_GE), (3.0699e-4, 2.7966e-4), 3.0699e-4 + 2.7966e-4),
+    )
+    if correlations:
+        fs = ((2, 0.0, 1.0), (2, 0.0, 0.8))
+        ff = ((2, 0.0, 1.0, 1.0e-3),)
+        ss = ((1, 0.0, 1.0, 1.0e-3, 2.0e-3, 5.0e-4),)
+    else:
+        fs = ((-2, 1000.0, 1.0), (-2, 1000.0, 1.0))
+        ff = ((-2, 1000.0, 1.0, 1.0e-3),)
+        ss = ((-1, 500.0, 1.0, 0.0, 0.0, 0.0),)
+    return Model(ch_fluid=(0, 0), ch_ifriction=(-99, 124 if correlations else -99), ch_friction_mult=(0.02, 0.02),
+                 ch_htc_corr=(1, 212 if correlations else 1), solids=solids, fs=fs, ff=ff, ss=ss, es_htc=(0.0,))
+
+
+def synthetic_helium_table(n_p: int = 65, n_t: int = 129) -> FluidTable:
+    """Smooth stand-in for supercritical helium near 4.5 K / 6 bar (CoolProp is absent here;
+    magnitudes follow SURVEY.md Appendix A).  NOT physical data: benchmarks and parity tests
+    only need the same table on both sides."""
+    p = np.linspace(4.0e5, 8.0e5, n_p)
+    t = np.linspace(3.5, 12.0, n_t)
+    P, T = np.meshgrid(p, t, indexing="ij")
+    dp, dt = (P - 6.0e5) / 1.0e5, T - 4.5
+    rho = 140.0 - 8.0 * dt + 0.35 * dt ** 2 + 2.0 * dp
+    cv = 2.5e3 + 200.0 * dt - 6.0 * dt ** 2 + 30.0 * dp
+    cp = 3.9e3 + 500.0 * dt - 25.0 * dt ** 2 - 60.0 * dp
+    props = np.empty((OSC2_N_FLUID_PROPS, n_p, n_t))
+    props[FP_BETA] = 0.06 + 0.02 * dt - 0.002 * dp
+    props[FP_KAPPA] = 2.0e-7 * (1.0 + 0.15 * dt - 0.05 * dp)
+    props[FP_PRANDTL] = 0.75 + 0.03 * dt
+    props[FP_RHO] = rho
+    props[FP_MU] = 3.5e-6 * (1.0 - 0.03 * dt + 0.02 * dp)
+    props[FP_H] = 1.2e4 + 4.0e3 * dt + 300.0 * dp
+    props[FP_CP] = cp
+    props[FP_CV] = cv
+    props[FP_SOUND] = 220.0 + 15.0 * dt + 8.0 * dp
+    props[FP_K] = 0.02 * (1.0 + 0.02 * dt)
+    return FluidTable(float(p[0]), float(p[1] - p[0]), float(t[0]), float(t[1] - t[0]), props)
+
+
+def synthetic_sweep(topo, model: Model, n_nodes: int, batch: int, seed: int = 20261019, length: float = 10.0,
+                    with_tcs: bool = True) -> Sweep:
+    """Swept scalars of SURVEY.md 8(d): Q0 ~ U[50, 1000] W/m on x in [1, 3] m for t in [10, 20] s,
+    background field ~ U[0, 12] T.  Tcs here is a smooth synthetic profile (the real one is the
+    reference's bisection, evaluated once at step 0 on the host)."""
+    rng = np.random.default_rng(seed)
+    S, E = topo.n_sol, n_nodes - 1
+    z = np.linspace(0.0, length, n_nodes)
+    lo, hi = heat_window(z, 0.1 * length, 0.3 * length)
+    b_field = np.zeros((batch, S, 2))
+    b0 = rng.uniform(0.0, 12.0, (batch, 1))
+    b_field[:, :, 0] = b0
+    b_field[:, :, 1] = b0 * rng.uniform(0.9, 1.1, (batch, 1))
+    eps = np.tile(rng.uniform(-0.006, 0.0, (batch, 1)), (1, S))
+    q0 = rng.uniform(50.0, 1000.0, (batch, S))
+    q_window = np.empty((batch, S, 4))
+    q_window[..., 0], q_window[..., 1], q_window[..., 2], q_window[..., 3] = lo, hi, 10.0, 20.0
+    tcs = None
+    if with_tcs:
+        tcs = 6.0 + 2.0 * rng.uniform(0.0, 1.0, (batch, S, 1)) + 0.5 * np.sin(np.linspace(0.0, 3.0, E))[None, None, :]
+    return Sweep(b_field=b_field, eps=eps, q0=q0, q_window=q_window, tcs=tcs)

@@ -67,6 +67,8 @@ def lib() -> C.CDLL:
         _LIB.osc2o_step_batch.restype = C.c_int
         _LIB.osc2o_pairwise_sum.argtypes = [c_dp, C.c_long, C.c_long]
         _LIB.osc2o_pairwise_sum.restype = C.c_double
+        _LIB.osc2o_fit.argtypes = [C.c_int, C.c_long, c_dp, c_dp, c_dp, C.c_double, C.c_double, c_dp]
+        _LIB.osc2o_fit.restype = C.c_int
     return _LIB
 
 
@@ -162,3 +164,73 @@ def pairwise_sum(a, stride: int = 1) -> float:
     a = np.ascontiguousarray(a, dtype=np.float64)
     n = (a.size + stride - 1) // stride
     return lib().osc2o_pairwise_sum(a.ctypes.data_as(c_dp), n, stride)
+
+
+FITS = {"k_cu": 0, "cp_cu": 1, "k_nb3sn": 2, "cp_nb3sn": 3, "tc_nb3sn": 4, "k_ss": 5, "cp_ss": 6, "k_ge": 7,
+        "cp_ge": 8, "friction_124": 9, "nusselt_1": 10, "nusselt_212": 11, "rhoe_cu": 12}
+
+
+def fit(name, x, y=None, z=None, p1=0.0, p2=0.0):
+    """Element-wise material / correlation fit of oracle/props_oracle.c (see props_oracle.h)."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.ascontiguousarray(x if y is None else y, dtype=np.float64)
+    z = np.ascontiguousarray(x if z is None else z, dtype=np.float64)
+    out = np.empty_like(x)
+    rc = lib().osc2o_fit(FITS[name], x.size, x.ctypes.data_as(c_dp), y.ctypes.data_as(c_dp), z.ctypes.data_as(c_dp),
+                         float(p1), float(p2), out.ctypes.data_as(c_dp))
+    assert rc == 0
+    return out
+
+
+# ---- operating conditions at the Gauss points (oracle/props_oracle.c) -----------------
+class _FluidTab(C.Structure):
+    _fields_ = [("n_p", C.c_int), ("n_t", C.c_int), ("p_min", C.c_double), ("p_step", C.c_double),
+                ("t_min", C.c_double), ("t_step", C.c_double), ("props", c_dp)]
+
+
+class _OpcondIO(C.Structure):
+    _fields_ = [("batch", C.c_int), ("n_nodes", C.c_int), ("time", C.c_double), ("sysvar", c_dp),
+                ("fluid", _FluidTab * 4)] + [(n, c_dp) for n in (
+        "b_field", "eps", "q0", "q_window", "tcs",
+        "fl_gauss", "fl_node", "sol_gauss", "sol_q", "htc_ff", "htc_fs", "htc_ss", "htc_es")]
+
+
+def operating_conditions(topo, model, tables, sweep, sysvar, n_nodes, time, n_threads=1):
+    """CPU restatement of what K_P computes.  `sysvar`: (B, N*d); returns the dict of
+    step-input arrays (batch leading) that `osc2_download_step_inputs` returns."""
+    from opensc2_b200._abi import topology_struct      # struct definitions only (the C header's mirror)
+
+    L = lib()
+    L.osc2o_operating_conditions.restype = C.c_int
+    sysvar = np.ascontiguousarray(sysvar, dtype=np.float64)
+    B = sysvar.shape[0]
+    E, M, S = n_nodes - 1, topo.n_ch, topo.n_sol
+    t = topology_struct(topo)
+    m = model.struct(topo)
+    io = _OpcondIO()
+    io.batch, io.n_nodes, io.time = B, n_nodes, float(time)
+    io.sysvar = sysvar.ctypes.data_as(c_dp)
+    keep = [sysvar]
+    for i, tab in enumerate(tables):
+        io.fluid[i].n_p, io.fluid[i].n_t = tab.props.shape[1], tab.props.shape[2]
+        io.fluid[i].p_min, io.fluid[i].p_step = tab.p_min, tab.p_step
+        io.fluid[i].t_min, io.fluid[i].t_step = tab.t_min, tab.t_step
+        io.fluid[i].props = tab.props.ctypes.data_as(c_dp)
+    for name in ("b_field", "eps", "q0", "q_window", "tcs"):
+        a = getattr(sweep, name)
+        if a is None or a.size == 0:
+            setattr(io, name, None)
+            continue
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        keep.append(a)
+        setattr(io, name, a.ctypes.data_as(c_dp))
+    out = {"fl_gauss": np.zeros((B, 9, M, E)), "fl_node": np.zeros((B, 4, M)), "sol_gauss": np.zeros((B, 3, S, E)),
+           "sol_q": np.zeros((B, 2, S, E, 2)), "htc_ff": np.zeros((B, 2, len(topo.ff), E)),
+           "htc_fs": np.zeros((B, len(topo.fs), E)), "htc_ss": np.zeros((B, len(topo.ss), E)),
+           "htc_es": np.zeros((B, len(topo.es), 3, E))}
+    dummy = np.zeros(1)
+    for k, a in out.items():
+        setattr(io, k, (a if a.size else dummy).ctypes.data_as(c_dp))
+    rc = L.osc2o_operating_conditions(C.byref(t), C.byref(m), C.byref(io), int(n_threads))
+    assert rc == 0
+    return out

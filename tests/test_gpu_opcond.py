@@ -1,0 +1,123 @@
+"""GPU parity of K_P (device-side operating conditions: Gauss averaging, coolant tables,
+friction / Nusselt correlations, HTC models, material fits + homogenisation, heat source)
+against the CPU oracle (oracle/props_oracle.c, itself pinned to the reference's fits in
+tests/test_props_oracle_golden.py).
+
+Tolerances (stated FP64 relative tolerance of north_star):
+  * everything without a transcendental (Gauss means, table interpolation, Gruneisen, heat
+    source, constant HTCs): bit-exact;
+  * fits and correlations (chains of pow / exp / log10, CUDA libm vs glibc): RTOL_FIT = 2e-12;
+  * five chained time steps (K_P + step on the device vs oracle + oracle): the fit differences
+    are amplified by the conditioning of the system (cond ~ 2e8 after row scaling):
+    RTOL_CHAIN_V = 1e-6 on velocities, RTOL_CHAIN = 1e-8 on pressures and temperatures."""
+import numpy as np
+import pytest
+
+from helpers import assert_bits
+from opensc2_b200.model import case1_model, synthetic_helium_table, synthetic_sweep
+from opensc2_b200.problem import case1_topology, synthetic_step_arrays
+
+pytestmark = pytest.mark.gpu
+RTOL_FIT = 2e-12
+RTOL_CHAIN_V, RTOL_CHAIN = 1e-6, 1e-8
+
+
+def rel(a, b):
+    return np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)) if a.size else 0.0
+
+
+def _setup(correlations, n, batch, seed=5, cold_jacket=False):
+    topo = case1_topology(1)
+    model = case1_model(correlations)
+    tab = synthetic_helium_table()
+    arr = synthetic_step_arrays(topo, n, batch=batch, seed=seed)
+    if cold_jacket:      # conductor 0: jacket below 12.897 K everywhere except one node above it in conductor 1
+        sv = arr.sysvar.reshape(batch, n, topo.ndf)
+        sv[1, n // 2, topo.ndf - 1] = 30.0
+    sweep = synthetic_sweep(topo, model, n, batch, seed=seed)
+    return topo, model, tab, arr, sweep
+
+
+@pytest.mark.parametrize("correlations", [False, True])
+@pytest.mark.parametrize("time", [5.0, 12.0])
+def test_operating_conditions_match_oracle(correlations, time):
+    from opensc2_b200.batch import BatchedStep
+    from oracle import oracle as O
+
+    n, batch = 65, 37
+    topo, model, tab, arr, sweep = _setup(correlations, n, batch, cold_jacket=True)
+    with BatchedStep(topo, batch, n) as bs:
+        bs.set_model(model, [tab])
+        bs.upload_sweep(sweep)
+        bs.upload_state(arr.sysvar, arr.syslod)
+        bs.upload_geometry(arr)
+        bs.eval_operating_conditions(time)
+        bs.synchronize()
+        out = bs.download_step_inputs()
+    ref = O.operating_conditions(topo, model, [tab], sweep, arr.sysvar, n, time)
+    # exact parts
+    for q in (0, 1, 2, 3, 4, 5, 6, 7):
+        assert_bits(out["fl_gauss"][:, q], ref["fl_gauss"][:, q], f"fl_gauss[{q}]")
+    assert_bits(out["fl_node"], ref["fl_node"], "fl_node")
+    assert_bits(out["sol_q"], ref["sol_q"], "sol_q")
+    assert_bits(out["sol_gauss"][:, 0], ref["sol_gauss"][:, 0], "solid density")
+    assert_bits(out["htc_es"], ref["htc_es"], "htc_es")
+    if not correlations:
+        for key in ("htc_ff", "htc_fs", "htc_ss"):
+            assert_bits(out[key], ref[key], key)
+    # fits
+    for key in ("fl_gauss", "sol_gauss", "htc_ff", "htc_fs", "htc_ss"):
+        assert rel(out[key], ref[key]) <= RTOL_FIT, f"{key}: {rel(out[key], ref[key]):.3e}"
+    # the heat slug is on at t = 12 s and off at t = 5 s
+    assert (ref["sol_q"][..., 0].max() > 0.0) == (time == 12.0)
+    # the whole-array SS branch differs between conductor 0 (cold jacket) and 1 (one warm node)
+    assert np.max(np.abs(ref["sol_gauss"][0, 1, 1] - ref["sol_gauss"][1, 1, 1])) > 0.0
+
+
+@pytest.mark.parametrize("correlations", [False, True])
+def test_chained_steps_with_device_side_properties(correlations):
+    """State stays on the device: [K_P -> step] x 5 vs [oracle K_P -> oracle step] x 5."""
+    from opensc2_b200.batch import BatchedStep
+    from oracle import oracle as O
+
+    n, batch, dt = 41, 9, 0.1
+    topo, model, tab, arr, sweep = _setup(correlations, n, batch, seed=11)
+    host = arr.copy()
+    with BatchedStep(topo, batch, n) as bs:
+        bs.set_model(model, [tab])
+        bs.upload_sweep(sweep)
+        bs.upload_state(arr.sysvar, arr.syslod)
+        bs.upload_geometry(arr)
+        for k in range(1, 6):
+            t = 9.8 + k * dt                     # crosses TQBEG = 10 s
+            bs.eval_operating_conditions(t)
+            bs.step(dt, k)
+            ref_in = O.operating_conditions(topo, model, [tab], sweep, host.sysvar, n, t)
+            for key, v in ref_in.items():
+                setattr(host, key, v)
+            host.num_step, host.dt = k, dt
+            ref = O.step(topo, host)
+            assert np.all(ref["status"] == 0)
+            host.sysvar, host.syslod = ref["sysvar"], ref["syslod"]
+        bs.synchronize()
+        sv, sl, st = bs.download_state()
+    assert np.all(st == 0)
+    d, M = topo.ndf, topo.n_ch
+    a, b = sv.reshape(batch, n, d), host.sysvar.reshape(batch, n, d)
+    assert rel(a[..., :M], b[..., :M]) <= RTOL_CHAIN_V
+    assert rel(a[..., M:], b[..., M:]) <= RTOL_CHAIN
+    if not correlations:
+        # f = const, constant HTCs: only the solid fits differ in the last ulp
+        assert rel(a[..., M:], b[..., M:]) <= 1e-10
+
+
+def test_model_validation_rejects_unimplemented_flags():
+    import dataclasses
+
+    from opensc2_b200.batch import BatchedStep
+
+    topo = case1_topology(1)
+    bad = dataclasses.replace(case1_model(), ch_ifriction=(-99, 122))
+    with BatchedStep(topo, 2, 9) as bs:
+        with pytest.raises(ValueError):
+            bs.set_model(bad, [synthetic_helium_table()])

@@ -1,0 +1,66 @@
+"""The props oracle (oracle/props_oracle.c) against fixtures produced by the UNMODIFIED
+reference fits (tests/golden/make_golden_props.py -> props_fits.npz).
+
+Tolerance: the fits are chains of pow/exp/log10; numpy's SIMD loops and glibc's libm differ
+in the last ulp, and the 10**(polynomial) forms amplify that by |exponent| * ln(10).
+RTOL = 2e-12 is the stated FP64 relative tolerance of every transcendental fit."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import GOLDEN_DIR
+from oracle import oracle as O
+
+RTOL = 2e-12
+
+
+@pytest.fixture(scope="module")
+def g():
+    return np.load(os.path.join(GOLDEN_DIR, "props_fits.npz"))
+
+
+def close(a, b, what):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape
+    err = np.abs(a - b) / np.maximum(np.abs(b), 1e-300)
+    err[(a == b)] = 0.0
+    assert np.all(err <= RTOL), f"{what}: max rel err {err.max():.3e} at {err.argmax()}"
+
+
+@pytest.mark.parametrize("rrr", [197.71, 100.0])
+def test_copper_conductivity_and_resistivity(g, rrr):
+    close(O.fit("k_cu", g["t"], g["b"], p1=rrr), g[f"k_cu_{rrr}"], "k_cu")
+    close(O.fit("rhoe_cu", g["t"], g["b"], p1=rrr), g[f"rhoe_cu_{rrr}"], "rhoe_cu")
+
+
+def test_copper_specific_heat_including_out_of_range_zero(g):
+    out = O.fit("cp_cu", g["t"])
+    close(out, g["cp_cu"], "cp_cu")
+    assert np.count_nonzero(g["cp_cu"] == 0.0) > 0 and np.array_equal(out == 0.0, g["cp_cu"] == 0.0)
+
+
+def test_nb3sn(g):
+    close(O.fit("k_nb3sn", g["tw"]), g["k_nb3sn"], "k_nb3sn")
+    tc = O.fit("tc_nb3sn", g["bb"], g["eps"], p1=16.22, p2=32.35)
+    close(tc, g["tc_nb3sn"], "tc_nb3sn")
+    assert np.count_nonzero(g["tc_nb3sn"] == 0.0) > 0          # B above Bc2: Tc = 0 branch
+    close(O.fit("cp_nb3sn", g["tt"], g["tcs"], g["tc_nb3sn"], p1=16.22), g["cp_nb3sn"], "cp_nb3sn")
+
+
+def test_stainless_steel_whole_array_branches(g):
+    close(O.fit("k_ss", g["tw"]), g["k_ss"], "k_ss")
+    for name in ("cold", "mid", "warm"):
+        close(O.fit("cp_ss", g[f"t_ss_{name}"]), g[f"cp_ss_{name}"], f"cp_ss_{name}")
+
+
+def test_glass_epoxy(g):
+    close(O.fit("k_ge", g["tw"]), g["k_ge"], "k_ge")
+    close(O.fit("cp_ge", g["tw"]), g["cp_ge"], "cp_ge")
+
+
+def test_channel_correlations(g):
+    close(O.fit("friction_124", g["re"]) * 0.02, g["f124_total"], "friction 124")
+    dh = float(g["hydiameter"])
+    close(O.fit("nusselt_1", g["re"], g["pr"]) * g["kf"] / dh, g["htc_1"], "htc corr 1")
+    close(O.fit("nusselt_212", g["re"]) * g["kf"] / dh, g["htc_212"], "htc corr 212")
