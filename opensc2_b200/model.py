@@ -192,3 +192,55 @@ def synthetic_sweep(topo, model: Model, n_nodes: int, batch: int, seed: int = 20
     if with_tcs:
         tcs = 6.0 + 2.0 * rng.uniform(0.0, 1.0, (batch, S, 1)) + 0.5 * np.sin(np.linspace(0.0, 3.0, E))[None, None, :]
     return Sweep(b_field=b_field, eps=eps, q0=q0, q_window=q_window, tcs=tcs)
+
+
+def table_lookup(tab: FluidTable, prop: int, p, t):
+    """Host-side bilinear lookup with the arithmetic of the device kernel (initial states only)."""
+    p, t = np.asarray(p, dtype=np.float64), np.asarray(t, dtype=np.float64)
+    n_p, n_t = tab.props.shape[1:]
+    fp = np.clip(np.floor((p - tab.p_min) / tab.p_step), 0, n_p - 2)
+    ft = np.clip(np.floor((t - tab.t_min) / tab.t_step), 0, n_t - 2)
+    a = (p - (tab.p_min + fp * tab.p_step)) / tab.p_step
+    b = (t - (tab.t_min + ft * tab.t_step)) / tab.t_step
+    ip, it = fp.astype(int), ft.astype(int)
+    f = tab.props[prop]
+    lo = f[ip, it] + b * (f[ip, it + 1] - f[ip, it])
+    hi = f[ip + 1, it] + b * (f[ip + 1, it + 1] - f[ip + 1, it])
+    return lo + a * (hi - lo)
+
+
+def consistent_initial_state(topo, model: Model, tab: FluidTable, n_nodes: int, batch: int, seed: int = 20261019,
+                             length: float = 10.0, dt: float = 0.1, p_in: float = 6.0e5, p_out: float = 5.9e5):
+    """A physically consistent start of a CASE_1-like transient, in the spirit of the reference's
+    initialisation (coolant.py:87-130, solid_components_initialization.py:24-52): linear pressure,
+    uniform temperature (swept inlet T ~ U[4.3, 4.7] K), velocities at the friction/pressure-drop
+    balance, solids at the coolant temperature.  Returns a StepArrays whose geometry, boundary values
+    and state are filled; the coefficient arrays are placeholders K_P overwrites."""
+    from .problem import (BC_MDTIN, BC_MDTOUT, BC_PINL, BC_POUT, BC_TINL, BC_TOUT, synthetic_step_arrays)
+
+    arr = synthetic_step_arrays(topo, n_nodes, batch=batch, seed=seed, length=length, dt=dt, heated=False)
+    rng = np.random.default_rng(seed + 1)
+    M, S, d, N = topo.n_ch, topo.n_sol, topo.ndf, n_nodes
+    xi = np.linspace(0.0, 1.0, N)
+    t_in = rng.uniform(4.3, 4.7, (batch, 1))
+    sv = np.empty((batch, N, d))
+    sgn = np.where(np.array(topo.ch_forward), 1.0, -1.0)
+    for j in range(M):
+        pj = (p_in + (p_out - p_in) * xi)[None, :] if sgn[j] > 0 else (p_out + (p_in - p_out) * xi)[None, :]
+        pj = np.broadcast_to(pj, (batch, N))
+        tj = np.broadcast_to(t_in, (batch, N))
+        rho = table_lookup(tab, FP_RHO, pj, tj)
+        f = model.ch_friction_mult[j]                      # IFRICTION -99: f = 1 * multiplier
+        v = sgn[j] * np.sqrt(abs(p_in - p_out) / length * topo.ch_dh[j] / (2.0 * f * rho))
+        sv[:, :, j], sv[:, :, M + j], sv[:, :, 2 * M + j] = v, pj, tj
+        arr.fl_bc[:, BC_PINL, j], arr.fl_bc[:, BC_POUT, j] = p_in, p_out
+        arr.fl_bc[:, BC_TINL, j], arr.fl_bc[:, BC_TOUT, j] = t_in[:, 0], t_in[:, 0]
+        mdot = topo.ch_area[j] * v[:, 0] * rho[:, 0]
+        arr.fl_bc[:, BC_MDTIN, j], arr.fl_bc[:, BC_MDTOUT, j] = mdot, mdot
+    for l in range(S):
+        sv[:, :, 3 * M + l] = t_in
+    arr.sysvar = sv.reshape(batch, N * d)
+    arr.syslod = np.zeros((batch, N * d, 2))
+    arr.qsource = np.zeros((batch, N, S))
+    arr.num_step = 1
+    return arr
