@@ -4,15 +4,20 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 Metric: node-timesteps/s = conductors x nodes x steps / device time, whole job.
-Workload (BASELINE.json configs[3]): 4096 CASE_1 variants on a 10 001-node mesh
-per GPU (weak scaling for N > 1: every rank owns its own 4096 conductors, no
-data-path collective).  `--impl reference` times the CPU oracle port of the
-reference's step() (oracle/step_oracle.c) on all host threads, rank 0 only.
+Workload (BASELINE.json configs[3]): 4096 CASE_1 variants (swept heat-slug power, background
+field, inlet temperature) on a 10 001-node mesh per GPU.  One "step" = one full transient time
+step: operating conditions at the Gauss points (coolant tables, correlations, material fits,
+heat source; kernel K_P) + step() (assembly, boundary rows, scaling, banded LU, substitution,
+norms; kernels K_G, K_F, K_B, K_N).  N > 1: every rank owns its own 4096 conductors (weak
+scaling, no collective on the data path).
+
+`--impl reference` times the CPU oracle port of the same work (oracle/props_oracle.c +
+oracle/step_oracle.c) on all host threads, rank 0 only: the reference itself is Python and
+cannot travel to the GPU box.
 """
 from __future__ import annotations
 
 import argparse
-import dataclasses
 import json
 import os
 import subprocess
@@ -25,12 +30,15 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-from opensc2_b200.problem import case1_topology, synthetic_step_arrays  # noqa: E402
+from opensc2_b200.model import (case1_model, consistent_initial_state, synthetic_helium_table,  # noqa: E402
+                                synthetic_sweep)
+from opensc2_b200.problem import case1_topology  # noqa: E402
 
 BATCH = int(os.environ.get("OSC2_BENCH_BATCH", 4096))
 NODES = int(os.environ.get("OSC2_BENCH_NODES", 10001))
 TILE = 64            # distinct synthetic conductors generated on the host, tiled to the batch
 DT = 0.1
+T_START = 9.5        # s: the timed steps run through the start of the heat slug (TQBEG = 10 s)
 
 
 def peaks():
@@ -46,14 +54,19 @@ def b_alg(d: int) -> int:
     return 8 * (3 * d * (4 * d - 1) + 6 * d)
 
 
-def kernel_alg_bytes(d: int, M: int, S: int, n_coef: int):
-    """Per-unit algorithmic bytes of each kernel of the fast path."""
+def kernel_alg_bytes(topo):
+    """Per-unit algorithmic bytes of each kernel."""
+    d, M, S = topo.ndf, topo.n_ch, topo.n_sol
+    nff, nfs, nss, nes = len(topo.ff), len(topo.fs), len(topo.ss), len(topo.es)
     rec = d * (d + 9)
+    coef = 1 + 9 * M + 3 * S + 4 * S + 4 * nff + 2 * nfs + 2 * nss + 4 * nes     # per element, K_G inputs
+    computed = 9 * M + 3 * S + 4 * S + 2 * nff + nfs + nss + 3 * nes              # per element, K_P outputs
     return {
-        "gauss": 8 * (n_coef + rec),                       # per element: coefficients in, row records out
+        "props": 8 * (d + S + computed),                    # per element: state, Tcs in; coefficients out
+        "gauss": 8 * (coef + S + rec + 3 * nff),            # per element: coefficients, qsource in; row records, K1..K3 out
         "forward": 8 * (rec + d + 4 * d + d * (2 * d + 2)),  # per node: record, x_old, SYSLOD in/out, factors out
-        "backward": 8 * (d * (2 * d + 2) + d),             # per node: factors in, x out
-        "norms": 8 * d,                                     # per node: x in
+        "backward": 8 * (d * (2 * d + 2) + d),              # per node: factors in, x out
+        "norms": 8 * d,                                      # per node: x in
     }
 
 
@@ -70,7 +83,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.gpu)],
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -102,69 +115,84 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def tiled_inputs(topo, batch, nodes, seed, pinned=False):
-    """`TILE` distinct synthetic conductors repeated up to `batch`; optionally written
-    straight into page-locked host buffers (torch is used as the allocator only)."""
-    small = synthetic_step_arrays(topo, nodes, batch=min(TILE, batch), seed=seed, dt=DT)
-    nt = small.dz.shape[0]
-    keep, kw = [], {}
+def tile(a, batch):
+    """Repeat the leading axis of `a` up to `batch`."""
+    reps = (batch + a.shape[0] - 1) // a.shape[0]
+    return np.ascontiguousarray(np.concatenate([a] * reps, axis=0)[:batch])
+
+
+def make_workload(batch, nodes, seed):
+    """(topology, model, table, StepArrays with geometry/state/boundary values, Sweep), `batch` conductors."""
+    import dataclasses
+
+    topo, model, tab = case1_topology(1), case1_model(False), synthetic_helium_table()
+    nt = min(TILE, batch)
+    small = consistent_initial_state(topo, model, tab, nodes, nt, seed=seed, dt=DT)
+    sw = synthetic_sweep(topo, model, nodes, nt, seed=seed)
+    keep = ("dz", "fl_bc", "peri_ff", "peri_fs", "peri_ss", "peri_es", "qsource", "sysvar")
+    kw = {}
     for f in dataclasses.fields(small):
         v = getattr(small, f.name)
-        if not isinstance(v, np.ndarray):
-            kw[f.name] = v
-            continue
-        shape = (batch,) + v.shape[1:]
-        if pinned:
-            import torch
-            t = torch.empty(shape, dtype=torch.float64, pin_memory=True)
-            keep.append(t)
-            out = t.numpy()
+        if isinstance(v, np.ndarray):
+            kw[f.name] = tile(v, batch) if f.name in keep else v[:1]      # coefficient arrays are computed on the device
         else:
-            out = np.empty(shape)
-        for lo in range(0, batch, nt):
-            hi = min(batch, lo + nt)
-            out[lo:hi] = v[:hi - lo]
-        kw[f.name] = out
+            kw[f.name] = v
     arr = type(small)(**kw)
-    arr.__dict__["_pins"] = keep
-    return arr
+    sweep = type(sw)(**{f.name: (tile(getattr(sw, f.name), batch) if getattr(sw, f.name) is not None else None)
+                        for f in dataclasses.fields(sw)})
+    return topo, model, tab, arr, sweep
 
 
-def cpu_sample(topo, arr, n_cond, threads, steps=1):
-    """Oracle port of the reference step() on `n_cond` conductors of the workload."""
+def cpu_sample(topo, model, tab, arr, sweep, n_cond, threads, steps=1):
+    """Oracle port of one full time step (operating conditions + step()) on `n_cond` conductors."""
+    import dataclasses
+
     from oracle import oracle as O
 
-    kw = {}
-    for f in dataclasses.fields(arr):
-        v = getattr(arr, f.name)
-        kw[f.name] = np.ascontiguousarray(v[:n_cond]) if isinstance(v, np.ndarray) else v
-    sub = type(arr)(**kw)
     O.lib()
+    n = arr.n_nodes
+    sub = {f.name: getattr(arr, f.name) for f in dataclasses.fields(arr)}
+    for k in ("dz", "fl_bc", "peri_ff", "peri_fs", "peri_ss", "peri_es", "qsource", "sysvar"):
+        sub[k] = np.ascontiguousarray(sub[k][:n_cond])
+    sub["syslod"] = np.zeros((n_cond, n * topo.ndf, 2))
+    host = type(arr)(**sub)
+    sw = type(sweep)(**{f.name: (getattr(sweep, f.name)[:n_cond] if getattr(sweep, f.name) is not None else None)
+                        for f in dataclasses.fields(sweep)})
     t0 = time.perf_counter()
     for k in range(steps):
-        sub.num_step = 2 + k
-        out = O.step(topo, sub, n_threads=threads)
-        sub.sysvar, sub.syslod = out["sysvar"], out["syslod"]
+        ins = O.operating_conditions(topo, model, [tab], sw, host.sysvar, n, T_START + (k + 1) * DT, n_threads=threads)
+        for key, v in ins.items():
+            setattr(host, key, v)
+        host.num_step, host.dt = 2 + k, DT
+        out = O.step(topo, host, n_threads=threads)
+        host.sysvar, host.syslod = out["sysvar"], out["syslod"]
     dt = time.perf_counter() - t0
-    return n_cond * arr.n_nodes * steps / dt, dt
+    return n_cond * n * steps / dt, dt
+
+
+def workload_config(topo):
+    return {"workload": f"{BATCH} CASE_1 variants per GPU (d={topo.ndf}: 2 He channels + Cu/Nb3Sn strand + SS/glass-epoxy jacket, "
+                        f"5 interfaces; swept slug power, field, inlet T), {NODES}-node mesh, Backward Euler dt={DT} s; "
+                        "one step = operating conditions at the Gauss points (tables, fits, heat source) + step()",
+            "batch_per_gpu": BATCH, "nodes": NODES, "ndf": topo.ndf,
+            "l2": "state, coefficients and factors (>100 GB per step) exceed the 126 MB L2, no flush needed"}
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    topo = case1_topology(1)
     threads = os.cpu_count() or 1
-    n_cond = max(threads, 16)
-    arr = tiled_inputs(topo, n_cond, NODES, seed=20261019)
+    n_cond = max(4 * threads, 16)
+    topo, model, tab, arr, sweep = make_workload(n_cond, NODES, seed=20261019)
     if args.warmup > 0:
-        cpu_sample(topo, arr, n_cond, threads)      # one untimed pass warms caches and the allocator
-    times = []
+        cpu_sample(topo, model, tab, arr, sweep, n_cond, threads)      # one untimed pass warms caches and the allocator
+    total = 0.0
     for _ in range(args.steps):
-        v, dt = cpu_sample(topo, arr, n_cond, threads)
-        times.append(dt)
-    total = sum(times)
+        _v, dt = cpu_sample(topo, model, tab, arr, sweep, n_cond, threads)
+        total += dt
     value = n_cond * NODES * args.steps / total
-    sample = f"{n_cond} conductors x {NODES} nodes per step, {threads} threads (oracle/step_oracle.c)"
+    sample = (f"{n_cond} conductors x {NODES} nodes per step, {threads} threads "
+              "(oracle/props_oracle.c + oracle/step_oracle.c: C port of the reference's Python step path)")
     line = {
         "impl": "reference", "metric": "node_timesteps_per_s", "value": value, "unit": "node-timesteps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
@@ -174,13 +202,6 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": "node-timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
-
-
-def workload_config(topo):
-    return {"workload": f"{BATCH} CASE_1 variants per GPU (d={topo.ndf}: 2 He channels + strand + jacket, 5 interfaces), "
-                        f"{NODES}-node mesh, Backward Euler dt={DT} s, step() on Gauss-point coefficients",
-            "batch_per_gpu": BATCH, "nodes": NODES, "ndf": topo.ndf,
-            "l2": "inputs and factors (>100 GB per step) exceed the 126 MB L2, no flush needed"}
 
 
 def run_ours(args, rank, world, local_rank):
@@ -194,16 +215,24 @@ def run_ours(args, rank, world, local_rank):
         dist = dist_
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    topo = case1_topology(1)
+    topo, model, tab, arr, sweep = make_workload(BATCH, NODES, seed=20261019 + rank)
     d = topo.ndf
-    arr = tiled_inputs(topo, BATCH, NODES, seed=20261019 + rank, pinned=True)
-    h2d = sum(getattr(arr, n).nbytes for n in ("dz", "fl_gauss", "fl_node", "fl_bc", "sol_gauss", "sol_q", "peri_ff",
-                                                "htc_ff", "peri_fs", "htc_fs", "peri_ss", "htc_ss", "peri_es", "htc_es", "qsource"))
-    n_coef = h2d // (8 * BATCH * (NODES - 1))
     bs = BatchedStep(topo, BATCH, NODES, device=local_rank)
-    bs.upload_state(arr.sysvar, arr.syslod)
-    bs.upload_step_inputs(arr)
+    bs.set_model(model, [tab])
+    bs.upload_sweep(sweep)
+    bs.upload_state(arr.sysvar, None)           # SYSLOD starts at zero on the device
+    bs.upload_geometry(arr)
     bs.synchronize()
+
+    def pinned(shape, dtype):
+        t = torch.empty(shape, dtype=dtype, pin_memory=True)
+        return t, t.numpy()
+
+    keep_bc, bc_host = pinned(arr.fl_bc.shape, torch.float64)
+    bc_host[...] = arr.fl_bc
+    keep_diag = [pinned((BATCH, d), torch.float64) for _ in range(3)]
+    diag = {"norm_solution": keep_diag[0][1], "norm_change": keep_diag[1][1], "eqteig": keep_diag[2][1]}
+    keep_st, status = pinned((BATCH,), torch.int32)
 
     def barrier():
         bs.synchronize()
@@ -211,37 +240,48 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
             torch.cuda.synchronize()
 
-    # ---- resident: inputs already in HBM -----------------------------------
-    for k in range(args.warmup):
-        bs.step(DT, 2 + k)
+    def one_step(k):
+        bs.eval_operating_conditions(T_START + k * DT)
+        bs.step(DT, 1 + k)
+
+    # ---- resident: state and parameters already in HBM -------------------------
+    n = 0
+    for _ in range(args.warmup):
+        n += 1
+        one_step(n)
     barrier()
     bs.set_profiling(True)
     bs.kernel_ms(reset=True)
     clocks = ClockSampler(local_rank)
     clocks.start()
     bs.timer_start()
-    for k in range(args.steps):
-        bs.step(DT, 2 + args.warmup + k)
+    for _ in range(args.steps):
+        n += 1
+        one_step(n)
     ms = bs.timer_stop()
     barrier()
-    clk = clocks.stop()
     km = bs.kernel_ms(reset=True)
     bs.set_profiling(False)
     launches = int(sum(v[1] for v in km.values()))
 
-    # ---- end to end: host buffers in, diagnostics out, every step ----------
-    diag_bytes = 3 * BATCH * d * 8 + 4 * BATCH
-    bs.upload_step_inputs(arr); bs.step(DT, 2); bs.download_diagnostics()      # warm
+    # ---- end to end through the C ABI: every step uploads that step's boundary values from
+    # pinned host memory and reads the step's diagnostics (norms, EQTEIG, status) back ---------
+    n += 1
+    bs.upload_boundary_values(bc_host); one_step(n); bs.download_diagnostics(diag); bs.download_status(status)   # warm
     barrier()
     bs.timer_start()
-    for k in range(args.steps):
-        bs.upload_step_inputs(arr)
-        bs.step(DT, 3 + k)
-        bs.download_diagnostics()
-        bs.download_state(want_syslod=False)[2]
+    for _ in range(args.steps):
+        n += 1
+        bs.upload_boundary_values(bc_host)
+        one_step(n)
+        bs.download_diagnostics(diag)
+        bs.download_status(status)
     ms_e2e = bs.timer_stop()
     barrier()
-    d2h = diag_bytes + BATCH * d * NODES * 8
+    clk = clocks.stop()
+    h2d = bc_host.nbytes
+    d2h = sum(v.nbytes for v in diag.values()) + status.nbytes
+    healthy = bool(np.all(status == 0) and np.all(np.isfinite(diag["norm_solution"])))
 
     if dist is not None:
         t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=f"cuda:{local_rank}")
@@ -253,15 +293,18 @@ def run_ours(args, rank, world, local_rank):
 
     if rank == 0:
         peak, peak_src = peaks()
-        alg = kernel_alg_bytes(d, topo.n_ch, topo.n_sol, n_coef)
-        per_launch = {k: (v[0] / max(v[1], 1)) for k, v in km.items()}
-        dom = max((k for k in per_launch if k in alg), key=lambda k: per_launch[k])
-        dom_units = BATCH * (NODES - 1 if dom == "gauss" else NODES)
-        achieved = alg[dom] * dom_units / (per_launch[dom] * 1e-3) / 1e9
-        step_ms_kernels = sum(per_launch[k] for k in per_launch if k in alg)
+        alg = kernel_alg_bytes(topo)
+        per_step = {k: v[0] / args.steps for k, v in km.items()}          # ms of each kernel family per step
+        dom = max((k for k in per_step if k in alg), key=lambda k: per_step[k])
+        dom_units = BATCH * (NODES if dom in ("forward", "backward", "norms") else NODES - 1)
+        achieved = alg[dom] * dom_units / (per_step[dom] * 1e-3) / 1e9
+        step_ms_kernels = sum(per_step[k] for k in per_step if k in alg)
+        fracs = {k: alg[k] * BATCH * NODES / (per_step[k] * 1e-3) / 1e9 / peak for k in per_step if k in alg}
         # measured DRAM traffic per node of the forward sweep (profiles/): read + write, ncu --set full
-        traffic_per_unit = {"forward": 2162.0}.get(dom)
-        cpu_val, cpu_dt = cpu_sample(topo, arr, max(os.cpu_count() or 1, 16), os.cpu_count() or 1)
+        traffic_per_unit = {"forward": 2384.0, "gauss": 1379.0, "backward": 1215.0}.get(dom)
+        cpu_threads = os.cpu_count() or 1
+        n_cpu = max(8 * cpu_threads, 16)
+        cpu_val, cpu_dt = cpu_sample(topo, model, tab, arr, sweep, n_cpu, cpu_threads)
         line = {
             "metric": "node_timesteps_per_s", "value": value, "unit": "node-timesteps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -270,22 +313,25 @@ def run_ours(args, rank, world, local_rank):
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": "node-timesteps/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / args.steps,
-                    "call": "BatchedStep.upload_step_inputs + step + download_diagnostics + download_state (C ABI, pinned host buffers)"},
+                    "call": "BatchedStep.upload_boundary_values + eval_operating_conditions + step + download_diagnostics "
+                            "+ download_status (C ABI, pinned host buffers; state and coefficients stay in HBM)",
+                    "solution_finite_and_nonsingular": healthy},
             "gpu_launches": launches,
             "roofline": {
                 "bound": "hbm", "kernel": f"osc2_{dom}", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "peak_source": peak_src,
-                "alg_bytes_per_unit": alg[dom], "units_per_launch": dom_units, "launch_ms": per_launch[dom],
+                "alg_bytes_per_unit": alg[dom], "units_per_launch": dom_units, "launch_ms": per_step[dom],
                 "traffic": (traffic_per_unit * dom_units) if traffic_per_unit else None,
                 "traffic_source": "ncu dram__bytes_read+write per node at N=201 (profiles/), scaled to this launch" if traffic_per_unit else None,
-                "step": {"alg_bytes_per_node_timestep": b_alg(d), "model": "SURVEY.md 8(d) two-kernel model",
+                "per_kernel_frac": fracs,
+                "step": {"alg_bytes_per_node_timestep": b_alg(d), "model": "SURVEY.md 8(d) two-kernel model (assembly + solve)",
                          "achieved": b_alg(d) * BATCH * NODES / (step_ms_kernels * 1e-3) / 1e9,
                          "frac": b_alg(d) * BATCH * NODES / (step_ms_kernels * 1e-3) / 1e9 / peak,
-                         "kernel_ms": per_launch},
+                         "kernel_ms": per_step},
             },
-            "cpu_baseline": {"value": cpu_val, "unit": "node-timesteps/s", "cores": os.cpu_count() or 1, "kind": "port",
-                             "sample": f"{max(os.cpu_count() or 1, 16)} conductors x {NODES} nodes x 1 step of this workload, "
-                                       f"oracle/step_oracle.c on {os.cpu_count()} threads ({cpu_dt:.2f} s)"},
+            "cpu_baseline": {"value": cpu_val, "unit": "node-timesteps/s", "cores": cpu_threads, "kind": "port",
+                             "sample": f"{n_cpu} conductors x {NODES} nodes x 1 full step of this workload, "
+                                       f"oracle/props_oracle.c + oracle/step_oracle.c on {cpu_threads} threads ({cpu_dt:.2f} s)"},
         }
         print(json.dumps(line), flush=True)
     bs.close()

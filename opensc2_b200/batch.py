@@ -26,6 +26,7 @@ class BatchedStep:
         self.ndf = topo.ndf
         self.total = self.ndf * self.n_nodes
         self._h = C.c_void_p()
+        self._t_env = 300.0
         self._tstruct = topology_struct(topo)
         _lib.check(self._L.osc2_create(C.byref(self._tstruct), self.batch, self.n_nodes, int(device), C.byref(self._h)))
 
@@ -69,7 +70,7 @@ class BatchedStep:
                 raise ValueError(f"{name}: leading axis {a.shape[0]} is not the batch {self.batch}")
             keep.append(a)
             setattr(s, name, dptr(a) if a.size else None)
-        s.t_env = float(arr.t_env)
+        s.t_env = self._t_env = float(arr.t_env)
         _lib.check(self._L.osc2_upload_step_inputs(self._h, C.byref(s)))
 
     # -- device-side operating conditions (K_P) ---------------------------------
@@ -94,7 +95,7 @@ class BatchedStep:
             a = as_f64(getattr(arr, name))
             keep.append(a)
             setattr(s, name, dptr(a) if a.size else None)
-        s.t_env = float(arr.t_env)
+        s.t_env = self._t_env = float(arr.t_env)
         _lib.check(self._L.osc2_upload_step_inputs(self._h, C.byref(s)))
 
     def eval_operating_conditions(self, time: float):
@@ -126,14 +127,32 @@ class BatchedStep:
                                                st.ctypes.data_as(c_ip)))
         return sv, sl, st
 
-    def download_diagnostics(self) -> Dict[str, np.ndarray]:
+    def download_diagnostics(self, out: Optional[Dict[str, np.ndarray]] = None, want_k123: bool = True) -> Dict[str, np.ndarray]:
+        """`out`: optional preallocated (e.g. page-locked) arrays to fill."""
         d, E, nff = self.ndf, self.n_nodes - 1, len(self.topo.ff)
-        out = {"norm_solution": np.empty((self.batch, d)), "norm_change": np.empty((self.batch, d)),
-               "eqteig": np.empty((self.batch, d)), "k123": np.empty((self.batch, 3, nff, E))}
+        if out is None:
+            out = {"norm_solution": np.empty((self.batch, d)), "norm_change": np.empty((self.batch, d)),
+                   "eqteig": np.empty((self.batch, d))}
+            if want_k123:
+                out["k123"] = np.empty((self.batch, 3, nff, E))
+        k123 = out.get("k123")
         _lib.check(self._L.osc2_download_diagnostics(
             self._h, dptr(out["norm_solution"]), dptr(out["norm_change"]), dptr(out["eqteig"]),
-            dptr(out["k123"]) if out["k123"].size else None))
+            dptr(k123) if k123 is not None and k123.size else None))
         return out
+
+    def upload_boundary_values(self, fl_bc):
+        """Per-step boundary values only (PREINL, PREOUT, TEMINL, TEMOUT, MDTIN, MDTOUT): [B][6][M]."""
+        a = self._shape(fl_bc, (self.batch, 6, self.topo.n_ch), "fl_bc")
+        s = Osc2StepInputs()
+        s.fl_bc = dptr(a)
+        s.t_env = self._t_env          # the struct carries the environment temperature too
+        _lib.check(self._L.osc2_upload_step_inputs(self._h, C.byref(s)))
+
+    def download_status(self, out: Optional[np.ndarray] = None) -> np.ndarray:
+        st = out if out is not None else np.empty(self.batch, dtype=np.int32)
+        _lib.check(self._L.osc2_download_state(self._h, None, None, st.ctypes.data_as(c_ip)))
+        return st
 
     def set_capture(self, on: bool):
         _lib.check(self._L.osc2_set_capture(self._h, int(on)))

@@ -457,6 +457,15 @@ int osc2_set_model(osc2_handle h, const osc2_model *model)
         int rc = dev_alloc(h, &t, (size_t)h->S * h->B);
         if (rc) return rc;
         h->q.tmax = t;
+        double *c = nullptr;
+        rc = dev_alloc(h, &c, 2 * (size_t)h->S);
+        if (rc) return rc;
+        h->q.sol_const = c;
+    }
+    if (h->S > 0) {
+        osc2_model_consts_kernel<<<(h->S + 63) / 64, 64, 0, h->stream>>>(h->model_dev, h->S, h->q.sol_const);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(h->stream));
     }
     h->q.model = h->model_dev;
     h->n_fluids_used = nf;

@@ -29,12 +29,17 @@ struct PropsDev {
     const double *q_window;  // [S][4][B]
     const double *tcs;       // [S][E][B] or nullptr
     double *tmax;            // [S][B] max Gauss temperature of each solid (whole-array branches)
+    double *sol_const;       // [S][2] RRR-only constants of the copper fit: p7, rhoecu0(273 K)
     double time;
 };
 
 namespace osc2p {
 
 __device__ __forceinline__ double sq(double x) { return x * x; }
+// x ** 3, x ** 4 ...: numpy calls pow(); repeated multiplication differs from the correctly
+// rounded power by at most a few 1e-16 relative -- inside the stated tolerance of the fits
+__device__ __forceinline__ double cube(double x) { return x * x * x; }
+__device__ __forceinline__ double quart(double x) { const double y = x * x; return y * y; }
 
 // copper.py:221-275
 __device__ inline double rhoecu0(double t, double rrr)
@@ -45,43 +50,44 @@ __device__ inline double rhoecu0(double t, double rrr)
     const double rhoi0 = P7 * rhoi * rho0 / (rhoi + rho0);
     return rho0 + rhoi + rhoi0;
 }
-// copper.py:140-217
-__device__ inline double rhoecu(double t, double b, double rrr)
+// copper.py:140-217, with rhoecu0(t, rrr) and rhoecu0(273, rrr) passed in (evaluated once)
+__device__ inline double rhoecu(double t, double b, double rrr, double rho_t, double rho_273)
 {
     if (!(rrr > 1.0 && b >= 0 && t > 0)) return 0.0;
-    const double rhoN = rhoecu0(t, rrr);
     double ccc = 0.0;
     if (b > 0) {
-        const double xxx = rhoecu0(273.0, rrr) / rhoecu0(t, rrr) * b;
+        const double xxx = rho_273 / rho_t * b;
         const double L = log10(xxx);
         double aaa = 0.0;
         aaa = aaa + -2.662 * 1.0;
         aaa = aaa + 0.3168 * L;
         aaa = aaa + 0.6229 * sq(L);
-        aaa = aaa + -0.1839 * pow(L, 3.0);
-        aaa = aaa + 0.01827 * pow(L, 4.0);
+        aaa = aaa + -0.1839 * cube(L);
+        aaa = aaa + 0.01827 * quart(L);
         ccc = pow(10.0, aaa);
     }
-    return rhoN * (1.0 + ccc);
+    return rho_t * (1.0 + ccc);
 }
-// copper.py:5-71
-__device__ inline double k_cu(double t, double b, double rrr)
+// copper.py:5-71.  p7 = 0.838 / (beta / 0.0003) ** 0.1661 and rho_273 = rhoecu0(273, rrr) depend on
+// RRR only and are computed once per model (osc2_model_consts_kernel)
+__device__ inline double k_cu(double t, double b, double rrr, double p7, double rho_273)
 {
-    const double beta = 0.634 / rrr, betat = beta / 0.0003;
+    const double beta = 0.634 / rrr;
     const double P1 = 1.754e-8, P2 = 2.763, P3 = 1102, P4 = -0.165, P5 = 70, P6 = 1.756;
-    const double P7 = 0.838 / pow(betat, 0.1661);
     const double W0 = beta / t;
     const double Wi = (P1 * pow(t, P2)) / (1 + (P1 * P3 * pow(t, P2 + P4) * exp(-pow(P5 / t, P6))));
-    const double Wi0 = P7 * Wi * W0 / (Wi + W0);
-    return 1.0 / (Wi + W0 + Wi0) * rhoecu0(t, rrr) / rhoecu(t, b, rrr);
+    const double Wi0 = p7 * Wi * W0 / (Wi + W0);
+    const double rho_t = rhoecu0(t, rrr);
+    return 1.0 / (Wi + W0 + Wi0) * rho_t / rhoecu(t, b, rrr, rho_t, rho_273);
 }
 // copper.py:75-136
 __device__ inline double cp_cu(double t)
 {
     if (!(t >= 4 && t <= 300)) return 0.0;
     const double L = log10(t);
-    return pow(10.0, -1.91844 + -0.15973 * L + 8.61013 * sq(L) + -18.996 * pow(L, 3.0) + 21.9661 * pow(L, 4.0)
-                         + -12.7328 * pow(L, 5.0) + 3.54322 * pow(L, 6.0) + -0.3797 * pow(L, 7.0));
+    const double L2 = sq(L), L3 = L2 * L, L4 = L2 * L2;
+    return pow(10.0, -1.91844 + -0.15973 * L + 8.61013 * L2 + -18.996 * L3 + 21.9661 * L4
+                         + -12.7328 * (L4 * L) + 3.54322 * (L3 * L3) + -0.3797 * (L4 * L3));
 }
 // niobium3_tin.py:371-434
 __device__ inline double snbsn(double eps)
@@ -120,8 +126,8 @@ __device__ inline double cp_nb3sn(double T, double TCS, double TC, double TC0)
     if (T <= 10.0) CPN = 7.5475e-3 * sq(T);
     else if (T > 10.0 && T <= 20.0) CPN = (-0.3 + 0.00375 * sq(T)) / 0.09937;
     else if (T > 20.0)
-        CPN = AA * T / (a + T) + BB * sq(T) / sq(b + T) + CC * pow(T, 3.0) / pow(c + T, 3.0)
-              + DD * pow(T, 4.0) / pow(d + T, 4.0);
+        CPN = AA * T / (a + T) + BB * sq(T) / sq(b + T) + CC * cube(T) / cube(c + T)
+              + DD * quart(T) / quart(d + T);
     double CPNTC = 0.0;
     if (TC <= 10.0) CPNTC = 7.5475e-3 * sq(TC);
     else if (TC > 10.0 && TC <= 20.0) CPNTC = (-0.3 + 0.00375 * sq(TC)) / 0.09937;
@@ -130,7 +136,7 @@ __device__ inline double cp_nb3sn(double T, double TCS, double TC, double TC0)
         const double TC_norm = TC / TC0;
         const double DBC2DT = -0.46306 - 0.067830 * TC;
         const double DELCP = 1500.0 * sq(DBC2DT) / (2.0 * sq(27.2 / (1.0 + (0.34 * TC_norm))) - 1.0);
-        CPS = (CPNTC + DELCP) * pow(T / TC, 3.0);
+        CPS = (CPNTC + DELCP) * cube(T / TC);
     }
     double CP = 0.0;
     if (T <= TCS) CP = CPS;
@@ -146,8 +152,8 @@ __device__ inline double cp_nb3sn(double T, double TCS, double TC, double TC0)
 __device__ inline double four_term(double T, double C0, double C1, double C2, double C3, double s0, double s1,
                                    double s2, double s3, double n0, double n1, double n2, double n3)
 {
-    return C0 * T / pow(s0 + T, n0) + C1 * sq(T) / pow(s1 + T, n1) + C2 * pow(T, 3.0) / pow(s2 + T, n2)
-           + C3 * pow(T, 4.0) / pow(s3 + T, n3);
+    return C0 * T / pow(s0 + T, n0) + C1 * sq(T) / pow(s1 + T, n1) + C2 * cube(T) / pow(s2 + T, n2)
+           + C3 * quart(T) / pow(s3 + T, n3);
 }
 // stainless_steel.py:5-38
 __device__ inline double k_ss(double t)
@@ -158,10 +164,10 @@ __device__ inline double k_ss(double t)
 // stainless_steel.py:41-88 -- branch on max(T) of the whole array
 __device__ inline double cp_ss(double T, double tmax)
 {
-    if (tmax <= 1.0) return 0.498 * T + 3.71e-4 * pow(T, 3.0);
+    if (tmax <= 1.0) return 0.498 * T + 3.71e-4 * cube(T);
     if (tmax < 12.8973011) {
         T = fmin(T, 1253.0);
-        return 0.46437387 * T + 0.00035157 * pow(T, 3.0);
+        return 0.46437387 * T + 0.00035157 * cube(T);
     }
     T = fmin(T, 1253.0);
     return four_term(T, -468.772387, -81.2353649, 827.209072, 29.9811823, 422.117262, 1235598.51, 51.2732976,
@@ -240,6 +246,16 @@ __device__ inline double linspace_at(double start, double stop, int N, int i)
 }
 
 }  // namespace osc2p
+
+__global__ void osc2_model_consts_kernel(const osc2_model *md, int S, double *sol_const)
+{
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= S) return;
+    const double rrr = md->sol_rrr[l];
+    const double beta = 0.634 / rrr, betat = beta / 0.0003;
+    sol_const[2 * l] = 0.838 / pow(betat, 0.1661);
+    sol_const[2 * l + 1] = osc2p::rhoecu0(273.0, rrr);
+}
 
 // max over the Gauss points of |T_i + T_i+1| / 2 for every solid (isobaric_specific_heat_ss picks
 // its formula from it).  One thread per (chunk of 64 elements, conductor); temperatures are >= 0 so
@@ -339,7 +355,7 @@ __global__ void __launch_bounds__(128) osc2_opcond_kernel(const osc2_topology *_
             const double w = md->sol_weight[l][i];
             const double rho_i = osc2p::mat_density(mat);
             double cp_i, k_i;
-            if (mat == OSC2_MAT_CU_NIST) { cp_i = osc2p::cp_cu(T); k_i = osc2p::k_cu(T, bg, md->sol_rrr[l]); }
+            if (mat == OSC2_MAT_CU_NIST) { cp_i = osc2p::cp_cu(T); k_i = osc2p::k_cu(T, bg, md->sol_rrr[l], q.sol_const[2 * l], q.sol_const[2 * l + 1]); }
             else if (mat == OSC2_MAT_NB3SN) { cp_i = osc2p::cp_nb3sn(T, tcs, tc, md->sol_tc0m[l]); k_i = osc2p::k_nb3sn(T); }
             else if (mat == OSC2_MAT_SS) { cp_i = osc2p::cp_ss(T, tmax); k_i = osc2p::k_ss(T); }
             else { cp_i = osc2p::cp_ge(T); k_i = osc2p::k_ge(T); }
