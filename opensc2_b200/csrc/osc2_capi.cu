@@ -56,6 +56,7 @@ struct osc2_context {
     bool have_state = false, have_inputs = false;
     bool capture = false, profiling = false;
     bool fast = false;               // register-resident kernels (step_kernels_fast.cuh)
+    bool fwd_split = false;          // K_F as two specialised warps (step_kernels_split.cuh), experimental
     int max_smem = 0, sm_count = 0;
     std::vector<EventPair> pending, pool;
     double kernel_ms[OSC2_K_COUNT] = {0};
@@ -89,6 +90,8 @@ struct CudaLauncher {
             cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) { h->launch_error = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return; }
         }
+        if (kid == OSC2_K_FORWARD && block == 64)   // split K_F: 7 CTAs of ~26 KB per SM need a >= 180 KB carve-out
+            cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 80);
         EventPair ev{};
         if (h->profiling) {
             if (!h->pool.empty()) { ev = h->pool.back(); h->pool.pop_back(); }
@@ -289,6 +292,8 @@ int osc2_create(const osc2_topology *topo, int batch, int n_nodes, int device, o
         h->fast = osc2_has_fast_path(h->d) && !(force && force[0] == '1');
     }
     h->NS = osc2_gm_slots(h->d, h->M, h->S, h->fast);
+    // experimental: slower than the single-warp sweep today, off unless OSC2_FWD_SPLIT=1
+    { const char *sp = getenv("OSC2_FWD_SPLIT"); h->fwd_split = (sp && sp[0] == '1'); }
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     h->max_smem = (int)prop.sharedMemPerBlockOptin;
@@ -303,6 +308,7 @@ int osc2_create(const osc2_topology *topo, int batch, int n_nodes, int device, o
     const size_t B = batch, E = h->E, N = h->N, M = h->M, S = h->S, d = h->d;
     StepDev &p = h->p;
     memset(&p, 0, sizeof p);
+    p.fwd_split = h->fwd_split ? 1 : 0;
     p.B = batch; p.N = h->N; p.E = h->E; p.M = h->M; p.S = h->S; p.d = h->d; p.NS = h->NS;
     p.nff = topo->nff; p.nfs = topo->nfs; p.nss = topo->nss; p.nes = topo->nes;
     struct { const double **dst; size_t k; } ins[] = {

@@ -51,6 +51,7 @@ struct StepDev {
     const int *norm_prog;     // [n_prog]       >= 0: push leaf, -1: add the two on top
     double *norm_part;        // [n_leaves][3][d][B]
     int n_leaves, n_prog;
+    int fwd_split;            // 1: K_F as assembler + eliminator warps (step_kernels_split.cuh)
 };
 
 // Slot map of one element's Gauss-point record in `gm`:

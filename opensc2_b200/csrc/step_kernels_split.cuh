@@ -8,7 +8,8 @@
 //                        (SYSMAT/Known smc:1320-1474, boundary rows fc:255-565, scaling tsf:538-551)
 //   warp 1 (eliminator): gredub/gbacsb forward part (tsf:602-761) on the handed-over rows, spill.
 // Rows travel through a two-stage shared-memory ring guarded by named barriers (bar.sync /
-// bar.arrive with 64 participants), so each warp only ever waits for the other one.
+// bar.arrive with 64 participants; ids 0/1 = stage full, 2/3 = stage empty), so each warp only
+// ever waits for the other one.
 // Every floating-point operation and its operand order is that of the single-warp kernel.
 #pragma once
 
@@ -19,14 +20,16 @@
 #define OSC2_BAR_ARRIVE(id, n) (void)emu_named_barrier(id)->arrive()
 #define OSC2_FENCE_BLOCK() std::atomic_thread_fence(std::memory_order_seq_cst)
 #else
-#define OSC2_BAR_SYNC(id, n) asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory")
-#define OSC2_BAR_ARRIVE(id, n) asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory")
+// barrier ids are immediates so that ptxas reserves exactly the four named barriers in use
+// (a register id makes it reserve all 16, which caps the SM at two CTAs)
+#define OSC2_BAR_SYNC(id, n) asm volatile("bar.sync %0, %1;" ::"n"(id), "n"(n) : "memory")
+#define OSC2_BAR_ARRIVE(id, n) asm volatile("bar.arrive %0, %1;" ::"n"(id), "n"(n) : "memory")
 #define OSC2_FENCE_BLOCK() __threadfence_block()
 #endif
 
 template <int D>
 struct SplitFwdSmem {
-    static constexpr int RWS = (3 * D + 2) & ~1;          // handed-over row: L | D | U | rhs (+pad), 16-byte rows
+    static constexpr int RWS = (3 * D + 5) & ~1;          // handed-over row: L | D | U | Known | max|row| | its reciprocal | range flag; 16-byte rows
     static constexpr int PW = 2 * D + 2;                   // published pivot row: D' | U | rhs | 1/pivot
     static constexpr int STAGE = D * RWS;                  // one node of one conductor
     static constexpr int PUB = 2 * D * PW;
@@ -41,7 +44,7 @@ struct SplitFwdSmem {
 };
 
 template <int D, int LPC, bool BE, bool CAPTURE>
-__global__ void __launch_bounds__(64) osc2_forward_split_kernel(const osc2_topology *__restrict__ tp, StepDev p)
+__global__ void __maxnreg__(128) osc2_forward_split_kernel(const osc2_topology *__restrict__ tp, StepDev p)
 {
     OSC2_DYN_SMEM(sm_dyn);
     using SM = SplitFwdSmem<D>;
@@ -141,8 +144,8 @@ __global__ void __launch_bounds__(64) osc2_forward_split_kernel(const osc2_topol
             for (int c = 0; c < D; ++c) el.sd[c] = 0.0;
             el.md = el.mo = el.kb = el.ahd = el.aho = el.lodu = el.lodl = el.lodup = el.lodlp = 0.0;
         };
-        Elem eL, eR, eN;
-        zero_elem(eL); zero_elem(eR); zero_elem(eN);
+        Elem eL, eR;       // eL is refilled with element n+1 as soon as node n no longer needs element n-1
+        zero_elem(eL); zero_elem(eR);
         const size_t xstep = (size_t)D * B;
         const double *xptr = p.sysvar + (size_t)rr_ * B + b;
         double *lodptr = p.syslod + (size_t)rr_ * 2 * B + b;
@@ -165,14 +168,15 @@ __global__ void __launch_bounds__(64) osc2_forward_split_kernel(const osc2_topol
             const long long i_row = (long long)n * D + r;
             double sl0 = sl0_next, sl1 = sl1_next;
             if (act) {
-                if (n + 1 < N - 1) load_elem(gptr + gstep, eN);
                 if (n + 2 < N) x_pre = xptr[2 * xstep];
                 if (n + 1 < N) { sl0_next = lodptr[2 * xstep]; sl1_next = lodptr[2 * xstep + B]; }
             }
             if (!CLOSED_KNOWN) __syncwarp();
+            // the stage of node n-2 must have been drained by the eliminator before it is refilled
+            if (s) OSC2_BAR_SYNC(3, 64); else OSC2_BAR_SYNC(2, 64);
 
-            double rowL[D], rowD[D], rowU[D], rhs = 0.0;
             if (act) {
+                double *dst = stage + ((size_t)s * D + r) * RWS;
                 if (shift) { sl1 = sl0; sl0 = 0.0; }
                 if (hasL) { sl0 += eL.lodl; if (first) sl1 += eL.lodlp; }
                 if (hasR) { sl0 += eR.lodu; if (first) sl1 += eR.lodup; }
@@ -182,8 +186,11 @@ __global__ void __launch_bounds__(64) osc2_forward_split_kernel(const osc2_topol
                 const bool is_bc = (!hasL && bc_first) || (!hasR && bc_last);
                 if (is_bc) {
 #pragma unroll
-                    for (int c = 0; c < D; ++c) { rowL[c] = 0.0; rowD[c] = (c == r) ? 1.0 : 0.0; rowU[c] = 0.0; }
-                    rhs = (!hasL) ? val_first : val_last;
+                    for (int c = 0; c < D; ++c) { dst[c] = 0.0; dst[D + c] = (c == r) ? 1.0 : 0.0; dst[2 * D + c] = 0.0; }
+                    dst[3 * D] = (!hasL) ? val_first : val_last;
+                    dst[3 * D + 1] = 1.0;
+                    dst[3 * D + 2] = 1.0;
+                    if (n + 1 < N - 1) load_elem(gptr + gstep, eL);
                 } else {
                     double mx = 0.0;
                     const double masL = hasL ? osc2_div_flag(eL.mo, rdt, range_flag) : 0.0;
@@ -202,7 +209,7 @@ __global__ void __launch_bounds__(64) osc2_forward_split_kernel(const osc2_topol
                                 sys = BE ? m + fds : m + theta * fds;
                                 if (!CLOSED_KNOWN) strip[D + c] = (m - omt * fds) * xa[c];
                             } else if (!CLOSED_KNOWN) strip[D + c] = 0.0;
-                            rowL[c] = sys;
+                            dst[c] = sys;
                             { const double a_ = fabs(sys); if (a_ > mx) mx = a_; }
                         }
                         {
@@ -213,7 +220,7 @@ __global__ void __launch_bounds__(64) osc2_forward_split_kernel(const osc2_topol
                             const double m = dg ? masD : 0.0;
                             const double sys = BE ? m + fds : m + theta * fds;
                             if (!CLOSED_KNOWN) strip[2 * D + c] = (m - omt * fds) * xb[c];
-                            rowD[c] = sys;
+                            dst[D + c] = sys;
                             { const double a_ = fabs(sys); if (a_ > mx) mx = a_; }
                         }
                         {
@@ -224,7 +231,7 @@ __global__ void __launch_bounds__(64) osc2_forward_split_kernel(const osc2_topol
                                 sys = BE ? m + fds : m + theta * fds;
                                 if (!CLOSED_KNOWN) strip[3 * D + c] = (m - omt * fds) * xc[c];
                             } else if (!CLOSED_KNOWN) strip[3 * D + c] = 0.0;
-                            rowU[c] = sys;
+                            dst[2 * D + c] = sys;
                             { const double a_ = fabs(sys); if (a_ > mx) mx = a_; }
                         }
                     }
@@ -256,41 +263,22 @@ __global__ void __launch_bounds__(64) osc2_forward_split_kernel(const osc2_topol
                         }
                     }
                     known += BE ? sl0 : (theta * sl0 + omt * sl1);
+                    // element n-1 is dead: fetch element n+1 into its registers (used one node later)
+                    if (n + 1 < N - 1) load_elem(gptr + gstep, eL);
+                    // row scaling (tsf:538-551) is done by the eliminator with this reciprocal
                     const Osc2Rcp rmx = osc2_rcp_prepare(mx);
-                    osc2_rcp_check(rmx, range_flag);
-#pragma unroll
-                    for (int c = 0; c < D; ++c) {
-                        rowL[c] = osc2_div_flag(rowL[c], rmx, range_flag);
-                        rowD[c] = osc2_div_flag(rowD[c], rmx, range_flag);
-                        rowU[c] = osc2_div_flag(rowU[c], rmx, range_flag);
-                    }
-                    rhs = osc2_div_flag(known, rmx, range_flag);
+                    dst[3 * D] = known;
+                    dst[3 * D + 1] = mx;
+                    dst[3 * D + 2] = rmx.y;
                 }
-                if (CAPTURE) {
-#pragma unroll
-                    for (int c = 0; c < 3 * D; ++c) {
-                        const long long col = (long long)(n - 1) * D + c;
-                        if (col < 0 || col >= Total) continue;
-                        const long long kb_ = (2 * D - 1) + (col - i_row);
-                        const double v = (c < D) ? rowL[c % D] : (c < 2 * D ? rowD[c % D] : rowU[c % D]);
-                        p.cap_sysmat[((size_t)kb_ * Total + i_row) * B + b] = v;
-                    }
-                    p.cap_known[(size_t)i_row * B + b] = rhs;
-                }
-            }
-            // hand the row over: wait until the eliminator has drained this stage (node n-2)
-            OSC2_BAR_SYNC(3 + s, 64);
-            if (act) {
-                double *dst = stage + ((size_t)s * D + r) * RWS;
-#pragma unroll
-                for (int c = 0; c < D; ++c) { dst[c] = rowL[c]; dst[D + c] = rowD[c]; dst[2 * D + c] = rowU[c]; }
-                dst[3 * D] = rhs;
+                // flags ride along: bit 0 = the assembler's cumulative range guard, bit 1 = boundary row (not scaled)
+                dst[3 * D + 3] = (double)((range_flag ? 1 : 0) | (is_bc ? 2 : 0));
             }
             OSC2_FENCE_BLOCK();
-            OSC2_BAR_ARRIVE(1 + s, 64);
+            if (s) OSC2_BAR_ARRIVE(1, 64); else OSC2_BAR_ARRIVE(0, 64);
+            if (!CLOSED_KNOWN) __syncwarp();      // every lane is done reading the old-solution ring of this node
             if (act) {
-                eL = eR;
-                eR = eN;
+                { const Elem t = eL; eL = eR; eR = t; }     // eL <- element n, eR <- element n+1
                 x_prev = x_cur; x_cur = x_nxt; x_nxt = x_pre;
                 if (!CLOSED_KNOWN && n + 2 < N) xa[r] = x_pre;      // slot of node n-1 now holds node n+2
             }
@@ -305,8 +293,8 @@ __global__ void __launch_bounds__(64) osc2_forward_split_kernel(const osc2_topol
     } else {
         // ------------------------------------------------------------------ eliminator
         double *spptr = p.spill + (size_t)rr_ * (2 * D + 2) * B + b;
-        OSC2_BAR_ARRIVE(3, 64);          // both stages start empty
-        OSC2_BAR_ARRIVE(4, 64);
+        OSC2_BAR_ARRIVE(2, 64);          // both stages start empty
+        OSC2_BAR_ARRIVE(3, 64);
         for (int n = 0; n < N; ++n) {
             const int s = n & 1;
             const bool hasL = n > 0;
@@ -314,17 +302,53 @@ __global__ void __launch_bounds__(64) osc2_forward_split_kernel(const osc2_topol
             const double *pub_prev = pub + (size_t)((n + 1) & 1) * D * PW;
             const long long i_row = (long long)n * D + r;
             double rowL[D], rowD[D], rowU[D], rhs = 0.0;
-            OSC2_BAR_SYNC(1 + s, 64);
+            if (s) OSC2_BAR_SYNC(1, 64); else OSC2_BAR_SYNC(0, 64);
+            double kn = 0.0, mxv = 1.0, mxy = 1.0;
+            int rowflags = 2;
             if (act) {
                 const double *src = stage + ((size_t)s * D + r) * RWS;
 #pragma unroll
                 for (int c = 0; c < D; ++c) { rowL[c] = src[c]; rowD[c] = src[D + c]; rowU[c] = src[2 * D + c]; }
-                rhs = src[3 * D];
+                kn = src[3 * D];
+                mxv = src[3 * D + 1];
+                mxy = src[3 * D + 2];
+                rowflags = (int)src[3 * D + 3];
+                if (rowflags & 1) range_flag = 1;
             } else {
 #pragma unroll
                 for (int c = 0; c < D; ++c) { rowL[c] = 0.0; rowD[c] = 0.0; rowU[c] = 0.0; }
             }
-            if (n + 2 < N) { OSC2_FENCE_BLOCK(); OSC2_BAR_ARRIVE(3 + s, 64); }
+            if (n + 2 < N) {
+                OSC2_FENCE_BLOCK();
+                if (s) OSC2_BAR_ARRIVE(3, 64); else OSC2_BAR_ARRIVE(2, 64);
+            }
+            if (act) {
+                // row scaling (tsf:538-551); boundary rows stay as they are
+                if (!(rowflags & 2)) {
+                    const Osc2Rcp rmx = osc2_rcp_make(mxv, mxy);
+                    osc2_rcp_check(rmx, range_flag);
+#pragma unroll
+                    for (int c = 0; c < D; ++c) {
+                        rowL[c] = osc2_div_flag(rowL[c], rmx, range_flag);
+                        rowD[c] = osc2_div_flag(rowD[c], rmx, range_flag);
+                        rowU[c] = osc2_div_flag(rowU[c], rmx, range_flag);
+                    }
+                    rhs = osc2_div_flag(kn, rmx, range_flag);
+                } else {
+                    rhs = kn;
+                }
+                if (CAPTURE) {
+#pragma unroll
+                    for (int c = 0; c < 3 * D; ++c) {
+                        const long long col = (long long)(n - 1) * D + c;
+                        if (col < 0 || col >= Total) continue;
+                        const long long kb_ = (2 * D - 1) + (col - i_row);
+                        const double v = (c < D) ? rowL[c % D] : (c < 2 * D ? rowD[c % D] : rowU[c % D]);
+                        p.cap_sysmat[((size_t)kb_ * Total + i_row) * B + b] = v;
+                    }
+                    p.cap_known[(size_t)i_row * B + b] = rhs;
+                }
+            }
             // pivots of node n-1 (their rows were published by this warp one iteration ago)
             if (act && hasL) {
 #pragma unroll
@@ -376,20 +400,23 @@ __global__ void __launch_bounds__(64) osc2_forward_split_kernel(const osc2_topol
             __syncwarp();      // pub_prev of the next node is this node's pub_cur: all lanes done reading the older one
         }
     }
-    // status: first singular row wins (the reference raises there), else the range guard
-    flags[((size_t)role * 32 + lane) * 2 + 0] = (double)bad_row;
-    flags[((size_t)role * 32 + lane) * 2 + 1] = (double)range_flag;
-    __syncthreads();
-    if (role == 1 && act && r == 0) {
-        long long worst = -1;
-        bool range = false;
-        for (int ro = 0; ro < 2; ++ro)
+    // status: first singular row wins (the reference raises there), else the range guard.  Only the
+    // eliminator holds state here (the assembler's guard arrived with the rows), so a warp-level
+    // exchange suffices -- no CTA barrier: the named barriers may still hold the assembler's arrivals.
+    if (role == 1) {
+        flags[(size_t)lane * 2 + 0] = (double)bad_row;
+        flags[(size_t)lane * 2 + 1] = (double)range_flag;
+        __syncwarp();
+        if (act && r == 0) {
+            long long worst = -1;
+            bool range = false;
             for (int q = 0; q < LPC; ++q) {
-                const double *f = flags + ((size_t)ro * 32 + grp * LPC + q) * 2;
+                const double *f = flags + ((size_t)grp * LPC + q) * 2;
                 const long long v = (long long)f[0];
                 if (v >= 0 && (worst < 0 || v < worst)) worst = v;
                 range = range || (f[1] != 0.0);
             }
-        p.status[b] = (worst >= 0) ? -(int)(worst + 1) : (range ? OSC2_STATUS_RANGE : 0);
+            p.status[b] = (worst >= 0) ? -(int)(worst + 1) : (range ? OSC2_STATUS_RANGE : 0);
+        }
     }
 }

@@ -10,6 +10,7 @@
 
 #include "step_kernels.cuh"
 #include "step_kernels_fast.cuh"
+#include "step_kernels_split.cuh"
 
 #include <vector>
 
@@ -93,6 +94,16 @@ void osc2_run_fast_sweeps(Launcher &L, const osc2_topology *tp_dev, const StepDe
     const size_t smem_f = (size_t)FastFwdSmem<D>::PER_COND * cpb * sizeof(double);
     const size_t smem_b = (size_t)(2 * D + 2) * cpb * sizeof(double);
     const bool be = (theta == 1.0), cap = (p.cap_sysmat != nullptr);
+    if (p.fwd_split) {
+        const bool closed = be && (D % 8 == 0);
+        const size_t smem_s = ((size_t)SplitFwdSmem<D>::per_cond(closed) * cpb + 2 * 32 * 2) * sizeof(double);
+        if (be && !cap) L.launch(OSC2_K_FORWARD, osc2_forward_split_kernel<D, LPC, true, false>, grid, 64u, smem_s, tp_dev, p);
+        else if (be) L.launch(OSC2_K_FORWARD, osc2_forward_split_kernel<D, LPC, true, true>, grid, 64u, smem_s, tp_dev, p);
+        else if (!cap) L.launch(OSC2_K_FORWARD, osc2_forward_split_kernel<D, LPC, false, false>, grid, 64u, smem_s, tp_dev, p);
+        else L.launch(OSC2_K_FORWARD, osc2_forward_split_kernel<D, LPC, false, true>, grid, 64u, smem_s, tp_dev, p);
+        L.launch(OSC2_K_BACKWARD, osc2_backward_fast_kernel<D, LPC>, grid, 32u, smem_b, p);
+        return;
+    }
     if (be && !cap) L.launch(OSC2_K_FORWARD, osc2_forward_fast_kernel<D, LPC, true, false>, grid, 32u, smem_f, tp_dev, p);
     else if (be) L.launch(OSC2_K_FORWARD, osc2_forward_fast_kernel<D, LPC, true, true>, grid, 32u, smem_f, tp_dev, p);
     else if (!cap) L.launch(OSC2_K_FORWARD, osc2_forward_fast_kernel<D, LPC, false, false>, grid, 32u, smem_f, tp_dev, p);

@@ -7,6 +7,7 @@
 #pragma once
 #define OSC2_EMU 1
 
+#include <atomic>
 #include <barrier>
 #include <cmath>
 #include <cstddef>
@@ -20,6 +21,8 @@
 #define __host__
 #define __forceinline__ inline
 #define __restrict__
+#define __launch_bounds__(...)
+#define __maxnreg__(...)
 #define __shared__ static
 
 struct emu_dim3 { unsigned x = 1, y = 1, z = 1; };
@@ -27,6 +30,8 @@ inline thread_local emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
 inline thread_local double *emu_dyn_smem = nullptr;
 inline thread_local std::barrier<> *emu_block_barrier = nullptr;
 inline thread_local std::barrier<> *emu_warp_barrier = nullptr;
+inline thread_local std::vector<std::unique_ptr<std::barrier<>>> *emu_named = nullptr;
+inline std::barrier<> *emu_named_barrier(int id) { return (*emu_named)[id].get(); }
 
 #define OSC2_DYN_SMEM(name) double *name = emu_dyn_smem
 
@@ -53,6 +58,8 @@ struct EmuLauncher {
                 const unsigned lanes = (w + 1) * 32 <= block ? 32 : block - w * 32;
                 wb.emplace_back(new std::barrier<>((std::ptrdiff_t)lanes));
             }
+            std::vector<std::unique_ptr<std::barrier<>>> named;     // bar.sync / bar.arrive ids 0..15, all CTA-wide
+            for (int i = 0; i < 16; ++i) named.emplace_back(new std::barrier<>((std::ptrdiff_t)block));
             // poison shared memory so that reads of unwritten slots show up
             for (auto &v : dyn) v = std::nan("");
             std::vector<std::thread> th;
@@ -63,6 +70,7 @@ struct EmuLauncher {
                     emu_dyn_smem = dyn.data();
                     emu_block_barrier = &bb;
                     emu_warp_barrier = wb[t / 32].get();
+                    emu_named = &named;
                     kernel(args...);
                     // a thread that returns early must not block the others
                     bb.arrive_and_drop();

@@ -20,7 +20,7 @@ class StepDev(C.Structure):
                             "sysvar", "sysvar_new", "syslod", "gm", "k123", "spill",
                             "norm_solution", "norm_change", "eqteig")] + [
         ("status", c_ip), ("cap_sysmat", c_dp), ("cap_known", c_dp),
-        ("norm_leaf", c_ip), ("norm_prog", c_ip), ("norm_part", c_dp), ("n_leaves", C.c_int), ("n_prog", C.c_int)]
+        ("norm_leaf", c_ip), ("norm_prog", c_ip), ("norm_part", c_dp), ("n_leaves", C.c_int), ("n_prog", C.c_int), ("fwd_split", C.c_int)]
 
 
 _LIB = None
@@ -31,7 +31,7 @@ def lib():
     if _LIB is None:
         so = os.path.join(HERE, "libosc2_emu.so")
         srcs = [os.path.join(HERE, f) for f in ("emu_step.cpp", "cuda_emu.h")]
-        srcs += [os.path.join(ROOT, "opensc2_b200", "csrc", f) for f in ("step_kernels.cuh", "step_kernels_fast.cuh", "step_launch.h", "osc2_dev.h")]
+        srcs += [os.path.join(ROOT, "opensc2_b200", "csrc", f) for f in ("step_kernels.cuh", "step_kernels_fast.cuh", "step_kernels_split.cuh", "step_launch.h", "osc2_dev.h")]
         srcs += [os.path.join(ROOT, "include", "opensc2_b200.h")]
         if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
             subprocess.run(["g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-ffp-contract=off", "-pthread",
@@ -51,7 +51,7 @@ def from_dev(a):
     return np.ascontiguousarray(np.moveaxis(a, -1, 0))
 
 
-def emu_step(topo, arr, capture=False, fast=None):
+def emu_step(topo, arr, capture=False, fast=None, split=True):
     """Run K_G, K_F, K_B, K_N on a batched StepArrays through the emulator."""
     L = lib()
     B, E = arr.dz.shape
@@ -87,7 +87,7 @@ def emu_step(topo, arr, capture=False, fast=None):
         outs["cap_known"] = np.zeros((total, B))
         p.cap_sysmat = outs["cap_sysmat"].ctypes.data_as(c_dp)
         p.cap_known = outs["cap_known"].ctypes.data_as(c_dp)
-    L.osc2_emu_step(C.byref(t), C.byref(p), int(fast))
+    L.osc2_emu_step(C.byref(t), C.byref(p), int(fast), int(split))
     res = {
         "sysvar": from_dev(outs["sysvar_new"]), "syslod": from_dev(keep["syslod"]),
         "k123": from_dev(outs["k123"])[:, :, :p.nff], "norm_solution": from_dev(outs["norm_solution"]),

@@ -4,7 +4,7 @@
 
 #include "../../opensc2_b200/csrc/step_launch.h"
 
-extern "C" int osc2_emu_step(const osc2_topology *tp, const StepDev *p, int fast)
+extern "C" int osc2_emu_step(const osc2_topology *tp, const StepDev *p, int fast, int split)
 {
     EmuLauncher L;
     StepDev q = *p;
@@ -13,6 +13,7 @@ extern "C" int osc2_emu_step(const osc2_topology *tp, const StepDev *p, int fast
     std::vector<double> part(leaves.size() / 2 * 3 * (size_t)q.d * q.B, std::nan(""));
     q.norm_leaf = leaves.data(); q.norm_prog = prog.data(); q.norm_part = part.data();
     q.n_leaves = (int)(leaves.size() / 2); q.n_prog = (int)prog.size();
+    q.fwd_split = split;
     osc2_run_step(L, tp, q, fast != 0, tp->theta);
     return (int)L.launches;
 }
