@@ -42,7 +42,7 @@ __device__ __forceinline__ double cube(double x) { return x * x * x; }
 __device__ __forceinline__ double quart(double x) { const double y = x * x; return y * y; }
 
 // copper.py:221-275
-__device__ inline double rhoecu0(double t, double rrr)
+__device__ __noinline__ double rhoecu0(double t, double rrr)
 {
     const double P0 = 1.553e-8, P1 = 1.171e-17, P2 = 4.49, P3 = 3.841e10, P4 = 1.14, P5 = 50, P6 = 6.428, P7 = 0.4531;
     const double rho0 = P0 / rrr;
@@ -70,7 +70,7 @@ __device__ inline double rhoecu(double t, double b, double rrr, double rho_t, do
 }
 // copper.py:5-71.  p7 = 0.838 / (beta / 0.0003) ** 0.1661 and rho_273 = rhoecu0(273, rrr) depend on
 // RRR only and are computed once per model (osc2_model_consts_kernel)
-__device__ inline double k_cu(double t, double b, double rrr, double p7, double rho_273)
+__device__ __noinline__ double k_cu(double t, double b, double rrr, double p7, double rho_273)
 {
     const double beta = 0.634 / rrr;
     const double P1 = 1.754e-8, P2 = 2.763, P3 = 1102, P4 = -0.165, P5 = 70, P6 = 1.756;
@@ -81,7 +81,7 @@ __device__ inline double k_cu(double t, double b, double rrr, double p7, double 
     return 1.0 / (Wi + W0 + Wi0) * rho_t / rhoecu(t, b, rrr, rho_t, rho_273);
 }
 // copper.py:75-136
-__device__ inline double cp_cu(double t)
+__device__ __noinline__ double cp_cu(double t)
 {
     if (!(t >= 4 && t <= 300)) return 0.0;
     const double L = log10(t);
@@ -98,7 +98,7 @@ __device__ inline double snbsn(double eps)
                      * (Ca1 * (sqrt(EPSsh * EPSsh + EPS0a * EPS0a) - sqrt(sq(eps - EPSsh) + EPS0a * EPS0a)) - Ca2 * eps);
 }
 // niobium3_tin.py:437-490
-__device__ inline double tc_nb3sn(double b, double eps, double tc0m, double bc20m)
+__device__ __noinline__ double tc_nb3sn(double b, double eps, double tc0m, double bc20m)
 {
     const double blim = fmax(b, 0.01);
     const double s = snbsn(eps);
@@ -107,7 +107,7 @@ __device__ inline double tc_nb3sn(double b, double eps, double tc0m, double bc20
     return tc0m * pow(s, 1.0 / 3.0) * pow(1.0 - blcase, 1.0 / 1.52);
 }
 // niobium3_tin.py:62-124
-__device__ inline double k_nb3sn(double tt)
+__device__ __noinline__ double k_nb3sn(double tt)
 {
     const double T0 = 21.9620369;
     tt = fmin(tt, 750.0);
@@ -117,7 +117,7 @@ __device__ inline double k_nb3sn(double tt)
     return 0.0;
 }
 // niobium3_tin.py:127-262
-__device__ inline double cp_nb3sn(double T, double TCS, double TC, double TC0)
+__device__ __noinline__ double cp_nb3sn(double T, double TCS, double TC, double TC0)
 {
     const double AA = 38.2226877, BB = -848.364226, CC = 1415.13808, DD = -346.837966;
     const double a = 6.80458608, b = 59.9209182, c = 25.8286334, d = 8.77918335;
@@ -149,7 +149,7 @@ __device__ inline double cp_nb3sn(double T, double TCS, double TC, double TC0)
     return CP;
 }
 // the four-term rational form shared by the SS and glass-epoxy fits
-__device__ inline double four_term(double T, double C0, double C1, double C2, double C3, double s0, double s1,
+__device__ __noinline__ double four_term(double T, double C0, double C1, double C2, double C3, double s0, double s1,
                                    double s2, double s3, double n0, double n1, double n2, double n3)
 {
     return C0 * T / pow(s0 + T, n0) + C1 * sq(T) / pow(s1 + T, n1) + C2 * cube(T) / pow(s2 + T, n2)
@@ -283,7 +283,7 @@ __global__ void osc2_solid_tmax_kernel(StepDev p, PropsDev q)
     }
 }
 
-__global__ void __launch_bounds__(128) osc2_opcond_kernel(const osc2_topology *__restrict__ tp, StepDev p, PropsDev q)
+__global__ void __launch_bounds__(128, 6) osc2_opcond_kernel(const osc2_topology *__restrict__ tp, StepDev p, PropsDev q)
 {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)p.E * p.B) return;

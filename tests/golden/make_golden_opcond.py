@@ -1,0 +1,258 @@
+"""Generate tests/golden/opcond_case1_*.npz: the operating conditions at the Gauss points as the
+UNMODIFIED reference computes them, for a CASE_1-shaped conductor.
+
+Build-container only (needs /root/reference):  python tests/golden/make_golden_opcond.py
+
+The reference objects are created with `object.__new__` (their constructors parse xlsx sheets,
+and openpyxl is absent) and given exactly the attributes the called methods read; every number
+is then produced by the reference's own code:
+  * Conductor.eval_transp_coeff (conductor.py:4822-5406) incl. Coolant._eval_properties_nodal_gauss,
+    Channel.eval_steady_state_htc / eval_friction_factor, all HTC models;
+  * Conductor.__eval_gauss_point_em (conductor.py:4667-4744): solid Gauss temperature, B field,
+    critical temperature, homogenised rho / cp / k through the component classes;
+  * SolidComponent.get_heat + Conductor.__build_heat_source_gauss_pt (conductor.py:4519-4581).
+CoolProp is absent: `PropsSI` is replaced by the bilinear table lookup that defines the device's
+coolant properties (opensc2_b200.model.table_lookup), so the fixture pins everything EXCEPT the
+table values themselves.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import pandas as pd
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+import ref_harness as H  # noqa: E402
+from opensc2_b200.model import (FP_BETA, FP_CP, FP_CV, FP_H, FP_K, FP_KAPPA, FP_MU, FP_PRANDTL, FP_RHO, FP_SOUND,  # noqa: E402
+                                case1_model, consistent_initial_state, heat_window, synthetic_helium_table,
+                                synthetic_sweep, table_lookup)
+from opensc2_b200.problem import case1_topology  # noqa: E402
+
+ALIAS_TO_PROP = {"isobaric_expansion_coefficient": FP_BETA, "isothermal_compressibility": FP_KAPPA,
+                 "Prandtl": FP_PRANDTL, "Dmass": FP_RHO, "viscosity": FP_MU, "Hmass": FP_H, "Cpmass": FP_CP,
+                 "Cvmass": FP_CV, "speed_of_sound": FP_SOUND, "conductivity": FP_K}
+
+
+def reference_operating_conditions(topo, model, tab, sweep, sysvar, n_nodes, time, b=0, length=10.0):
+    H._import_reference()
+    import coolant as coolant_mod
+    from channel import Channel
+    from conductor import Conductor
+    from coolant import Coolant
+    from jacket_component import JacketComponent
+    from strand_mixed_component import StrandMixedComponent
+
+    def props_si(alias, _t, temperature, _p, pressure, _fluid):
+        return table_lookup(tab, ALIAS_TO_PROP[alias], pressure, temperature)
+
+    coolant_mod.PropsSI = props_si
+    # the reference's alias table (simulation.py:89-100)
+    aliases = dict(isobaric_expansion_coefficient="isobaric_expansion_coefficient",
+                   isothermal_compressibility="isothermal_compressibility", Prandtl="Prandtl",
+                   total_density="Dmass", total_dynamic_viscosity="viscosity", total_enthalpy="Hmass",
+                   total_isobaric_specific_heat="Cpmass", total_isochoric_specific_heat="Cvmass",
+                   total_speed_of_sound="speed_of_sound", total_thermal_conductivity="conductivity")
+    M, S, d, N = topo.n_ch, topo.n_sol, topo.ndf, n_nodes
+    x = sysvar[b].reshape(N, d)
+    zcoord = np.linspace(0.0, length, N)
+
+    cond = object.__new__(Conductor)
+    cond.identifier = "CONDUCTOR_1"
+    cond.grid_features = {"N_nod": N, "zcoord": zcoord}
+    cond.cond_time = [0.0, time]
+    cond.cond_num_step = 5
+    cond.cond_el_num_step = 0
+    cond.inputs = {"METHOD": "BE", "Phi_conv": 1.0, "Phi_rad": 0.0, "Is_rectangular": False, "I0_OP_TOT": 0.0,
+                   "I0_OP_MODE": None}
+    cond.dict_Gauss_pt, cond.dict_node_pt = {}, {}
+    sim = types.SimpleNamespace(fluid_prop_aliases=aliases, environment=types.SimpleNamespace(KIND="Environment"))
+
+    fluids = []
+    for j in range(M):
+        f = types.SimpleNamespace(identifier=f"CHAN_{j + 1}")
+        co = object.__new__(Coolant)
+        co.type = "He"
+        co.inputs = {"CROSSECTION": topo.ch_area[j], "HYDIAMETER": topo.ch_dh[j]}
+        co.dict_node_pt = {"velocity": x[:, j].copy(), "pressure": x[:, M + j].copy(), "temperature": x[:, 2 * M + j].copy()}
+        co.dict_Gauss_pt = {}
+        ch = object.__new__(Channel)
+        ch.inputs = {"HYDIAMETER": topo.ch_dh[j], "IFRICTION": model.ch_ifriction[j],
+                     "FRICTION_MULTIPLIER": model.ch_friction_mult[j], "Flag_htc_steady_corr": model.ch_htc_corr[j],
+                     "Roughness": 0.0, "Side": 1e-3, "Base": 1e-3, "Height": 1e-3}
+        kv = [("laminar", None), ("turbulent", None), ("total", 0.0)]
+        ch.dict_friction_factor = {None: dict(kv), True: dict(kv), False: dict(kv)}
+        ch.dict_htc_steady, ch.dict_nusselt = {True: None, False: None}, {True: None, False: None}
+        # the dispatch of Channel.__init__ (channel.py:43-169) for the flags in use
+        if model.ch_ifriction[j] == -99:
+            ch.turbulent_friction_factor_correlation = ch.user_defined_turbulent_friction_factor
+            ch.laminar_friction_factor_correlation = ch.user_defined_laminar_friction_factor
+            ch.total_friction_factor_correlation = ch.user_defined_friction_factor
+        else:
+            ch.turbulent_friction_factor_correlation = ch.rectangular_duct_enea_hts_cicc_trubulent_flow_hole
+            ch.laminar_friction_factor_correlation = ch.rectangular_duct_enea_hts_cicc_trubulent_flow_hole
+            ch.total_friction_factor_correlation = ch._eval_total_friction_factor_max
+        ch.nusselt_correlation = (ch.dittus_boelter_nusselt_lower_limit if model.ch_htc_corr[j] == 1
+                                  else ch.rectangular_duct_enea_hts_cicc_htc)
+        f.coolant, f.channel = co, ch
+        fluids.append(f)
+
+    solids = []
+    names = {0: "STR_MIX", 1: "STR_STAB", 2: "Z_JACKET"}
+    mat_name = {0: "Cu", 1: "Nb3Sn", 2: "ss", 3: "ge"}
+    for l, sm in enumerate(model.solids):
+        if sm.kind == 0:
+            s = object.__new__(StrandMixedComponent)
+            s.inputs = {"stabilizer_material": mat_name[sm.materials[0]], "superconducting_material": mat_name[sm.materials[1]],
+                        "STAB_NON_STAB": sm.weights[0], "NUM_MATERIAL_TYPES": 2, "RRR": sm.rrr, "Tc0m": sm.tc0m,
+                        "Bc20m": sm.bc20m, "c0": 1.21508e11, "CROSSECTION": topo.sol_area[l], "COSTETA": topo.sol_costeta[l]}
+            s._StrandMixedComponent__reorganize_input()
+            s._StrandMixedComponent__strand_density_flag = False
+        else:
+            s = object.__new__(JacketComponent)
+            s.inputs = {"jacket_material": mat_name[sm.materials[0]],
+                        "insulation_material": mat_name[sm.materials[1]] if len(sm.materials) > 1 else "none",
+                        "jacket_cross_section": sm.weights[0],
+                        "insulation_cross_section": sm.weights[1] if len(sm.materials) > 1 else 0.0,
+                        "NUM_MATERIAL_TYPES": len(sm.materials), "CROSSECTION": topo.sol_area[l],
+                        "COSTETA": topo.sol_costeta[l], "Jacket_kind": "whole_enclosure", "Emissivity": 0.0}
+            s._JacketComponent__reorganize_input()
+            s._JacketComponent__jacket_density_flag = False
+        s.name = names[sm.kind]
+        s.identifier = f"{names[sm.kind]}_{l + 1}"
+        win = sweep.q_window[b, l]
+        s.operations = {"IBIFUN": 0, "BISS": sweep.b_field[b, l, 0], "BOSS": sweep.b_field[b, l, 1], "IALPHAB": 0,
+                        "IEPS": 1, "EPS": sweep.eps[b, l], "TCS_EVALUATION": False,
+                        "IQFUN": 1 if sm.heated else 0, "Q0": sweep.q0[b, l], "TQBEG": win[2], "TQEND": win[3],
+                        "XQBEG": zcoord[int(win[0])], "XQEND": zcoord[int(win[1])]}
+        s.flag_heating = "On"
+        s.dict_node_pt = {"temperature": x[:, 3 * M + l].copy(), "EXTFLX": np.zeros((N, 2)), "JHTFLX": np.zeros((N, 2)),
+                          "total_linear_power_el_cond": np.zeros((N, 2))}
+        s.dict_Gauss_pt = {"linear_power_el_resistance": np.zeros((N - 1, 2))}
+        if sm.kind == 0:
+            s.dict_Gauss_pt["T_cur_sharing_min"] = sweep.tcs[b, l].copy()
+        s.radiative_heat_env = np.zeros((N, 2))
+        s.radiative_heat_inn = {}
+        solids.append(s)
+
+    coll = lambda items, name: types.SimpleNamespace(collection=items, number=len(items), name=name)
+    strands = [s for s in solids if s.name != "Z_JACKET"]
+    jackets = [s for s in solids if s.name == "Z_JACKET"]
+    cond.inventory = {
+        "FluidComponent": coll(fluids, "CHAN"), "SolidComponent": coll(solids, "SOLID"),
+        "StrandComponent": coll(strands, "STRAND"), "JacketComponent": coll(jackets, "Z_JACKET"),
+        "StrandMixedComponent": coll([s for s in solids if s.name == "STR_MIX"], "STR_MIX"),
+        "StrandStabilizerComponent": coll([s for s in solids if s.name == "STR_STAB"], "STR_STAB"),
+        "StackComponent": coll([], "STACK"),
+    }
+    ids = [f.identifier for f in fluids] + [s.identifier for s in solids]
+    frame = lambda fill, dtype=float: pd.DataFrame(fill, index=["Environment"] + ids, columns=["Environment"] + ids, dtype=dtype)
+    flag, choice = frame(0, int), frame(0, int)
+    htc, mlt, thick, rcont = frame(0.0), frame(1.0), frame(0.0), frame(0.0)
+    view = frame(0.0)
+    topo_names = {"ch_sol": {}, "sol_sol": {}, "ch_ch": {}}
+
+    def link(a, b, c, h, m):
+        flag.at[a, b] = 1
+        choice.at[a, b] = c
+        htc.at[a, b] = h
+        mlt.at[a, b] = m
+
+    for k, (j, l) in enumerate(topo.fs):
+        a, bb = fluids[j].identifier, solids[l].identifier
+        link(a, bb, *model.fs[k])
+        topo_names["ch_sol"].setdefault(a, {})[bb] = f"{a}_{bb}"
+    for k, (ja, jb) in enumerate(topo.ff):
+        a, bb = fluids[ja].identifier, fluids[jb].identifier
+        c, h, m, th = model.ff[k]
+        link(a, bb, c, h, m)
+        thick.at[a, bb] = th
+    for k, (la, lb) in enumerate(topo.ss):
+        a, bb = solids[la].identifier, solids[lb].identifier
+        c, h, m, t1, t2, rc = model.ss[k]
+        link(a, bb, c, h, m)
+        thick.at[a, bb], thick.at[bb, a], rcont.at[a, bb] = t1, t2, rc
+        topo_names["sol_sol"].setdefault(a, {})[bb] = f"{a}_{bb}"
+    for k, l in enumerate(topo.es):
+        link("Environment", solids[l].identifier, -4, model.es_htc[k], 1.0)
+    cond.dict_df_coupling = {"contact_perimeter_flag": flag, "HTC_choice": choice, "contact_HTC": htc,
+                             "HTC_multiplier": mlt, "interf_thickness": thick, "thermal_contact_resistance": rcont,
+                             "view_factors": view}
+    cond.dict_topology = topo_names
+
+    # ---- the reference's own sequence (simulation.py:375-405 with no current defined) ----------
+    for s in solids:                                     # nodal B field first (operating_conditions_em)
+        s.get_magnetic_field(cond)
+        if s.name != "Z_JACKET":
+            s.get_magnetic_field_gradient(cond)
+            s.get_eps(cond)
+    Conductor._Conductor__eval_gauss_point_em(cond)
+    cond.dict_Gauss_pt = Conductor.eval_transp_coeff(cond, sim, cond.dict_Gauss_pt, flag_nodal=False)
+    # nodal coolant density at both ends (what the boundary rows read): nodal pass of the coolant properties
+    for f in fluids:
+        f.coolant._eval_properties_nodal_gauss(cond, aliases, True)
+    for s in solids:
+        if s.operations["IQFUN"] != 0:
+            s.get_heat(cond)
+    Conductor._Conductor__build_heat_source_gauss_pt(cond)
+
+    E = N - 1
+    out = {"fl_gauss": np.zeros((9, M, E)), "fl_node": np.zeros((4, M)), "sol_gauss": np.zeros((3, S, E)),
+           "sol_q": np.zeros((2, S, E, 2)), "htc_ff": np.zeros((2, len(topo.ff), E)), "htc_fs": np.zeros((len(topo.fs), E)),
+           "htc_ss": np.zeros((len(topo.ss), E)), "htc_es": np.zeros((len(topo.es), 3, E))}
+    keys = ("velocity", "pressure", "temperature", "total_density", "total_speed_of_sound", "Gruneisen",
+            "total_enthalpy", "total_isochoric_specific_heat")
+    for j, f in enumerate(fluids):
+        for q, key in enumerate(keys):
+            out["fl_gauss"][q, j] = f.coolant.dict_Gauss_pt[key]
+        out["fl_gauss"][8, j] = f.channel.dict_friction_factor[False]["total"]
+        nd = f.coolant.dict_node_pt
+        out["fl_node"][:, j] = nd["velocity"][0], nd["velocity"][-1], nd["total_density"][0], nd["total_density"][-1]
+    for l, s in enumerate(solids):
+        g = s.dict_Gauss_pt
+        out["sol_gauss"][0, l], out["sol_gauss"][1, l] = g["total_density"], g["total_isobaric_specific_heat"]
+        out["sol_gauss"][2, l] = g["total_thermal_conductivity"]
+        out["sol_q"][0, l], out["sol_q"][1, l] = g["Q1"], g["Q2"]
+    H_ = cond.dict_Gauss_pt["HTC"]
+    for k, (ja, jb) in enumerate(topo.ff):
+        name = f"{fluids[ja].identifier}_{fluids[jb].identifier}"
+        out["htc_ff"][0, k], out["htc_ff"][1, k] = H_["ch_ch"]["Open"][name], H_["ch_ch"]["Close"][name]
+    for k, (j, l) in enumerate(topo.fs):
+        out["htc_fs"][k] = H_["ch_sol"][f"{fluids[j].identifier}_{solids[l].identifier}"]
+    for k, (la, lb) in enumerate(topo.ss):
+        out["htc_ss"][k] = H_["sol_sol"]["cond"][f"{solids[la].identifier}_{solids[lb].identifier}"]
+    for k, l in enumerate(topo.es):
+        out["htc_es"][k, 0] = H_["env_sol"][f"Environment_{solids[l].identifier}"]["conv"]
+    return out
+
+
+def main():
+    assert H.reference_available()
+    topo = case1_topology(1)
+    tab = synthetic_helium_table()
+    n, batch = 41, 3
+    for tag, corr, time in (("const_t12", False, 12.0), ("corr_t12", True, 12.0), ("corr_t5", True, 5.0)):
+        model = case1_model(corr)
+        arr = consistent_initial_state(topo, model, tab, n, batch, seed=3)
+        # a warmer, non-uniform state so that every branch of the fits is exercised
+        rng = np.random.default_rng(7)
+        sv = arr.sysvar.reshape(batch, n, topo.ndf)
+        sv[:, :, 4:] += rng.uniform(0.0, 1.0, (batch, 1, 4)) * np.exp(-((np.linspace(0, 1, n) - 0.2) / 0.1) ** 2)[None, :, None] * 6.0
+        sv[2, :, 7] += 20.0                                   # conductor 2: warm jacket (third SS cp branch)
+        sweep = synthetic_sweep(topo, model, n, batch, seed=3)
+        payload = {"sysvar": arr.sysvar, "time": np.array(time), "n_nodes": np.array(n), "correlations": np.array(corr),
+                   "b_field": sweep.b_field, "eps": sweep.eps, "q0": sweep.q0, "q_window": sweep.q_window, "tcs": sweep.tcs}
+        outs = [reference_operating_conditions(topo, model, tab, sweep, arr.sysvar, n, time, b=b) for b in range(batch)]
+        for key in outs[0]:
+            payload["out_" + key] = np.stack([o[key] for o in outs])
+        path = os.path.join(HERE, f"opcond_case1_{tag}.npz")
+        np.savez_compressed(path, **payload)
+        print(tag, os.path.getsize(path) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()
