@@ -241,8 +241,7 @@ def run_ours(args, rank, world, local_rank):
             torch.cuda.synchronize()
 
     def one_step(k):
-        bs.eval_operating_conditions(T_START + k * DT)
-        bs.step(DT, 1 + k)
+        bs.advance(T_START + k * DT, DT, 1 + k)
 
     # ---- resident: state and parameters already in HBM -------------------------
     n = 0
@@ -313,7 +312,7 @@ def run_ours(args, rank, world, local_rank):
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": "node-timesteps/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / args.steps,
-                    "call": "BatchedStep.upload_boundary_values + eval_operating_conditions + step + download_diagnostics "
+                    "call": "BatchedStep.upload_boundary_values + advance + download_diagnostics "
                             "+ download_status (C ABI, pinned host buffers; state and coefficients stay in HBM)",
                     "solution_finite_and_nonsingular": healthy},
             "gpu_launches": launches,

@@ -175,6 +175,10 @@ int osc2_set_fluid_table(osc2_handle h, int fluid, int n_p, int n_t, double p_mi
 int osc2_upload_sweep(osc2_handle h, const osc2_sweep *sweep);
 /* `time` = conductor.cond_time[-1] of the step about to be taken. */
 int osc2_eval_operating_conditions(osc2_handle h, double time);
+/* One full time step: osc2_eval_operating_conditions(time) + osc2_step(dt, num_step).
+ * (OSC2_FUSED_OPCOND=1 selects an experimental kernel that fuses the property evaluation with the
+ * element row records; it is bit-identical and, today, slower.) */
+int osc2_advance(osc2_handle h, double time, double dt, int num_step);
 /* Device -> host copy of the computed step inputs (parity tests); any member may be NULL. */
 int osc2_download_step_inputs(osc2_handle h, double *fl_gauss, double *fl_node, double *sol_gauss,
                               double *sol_q, double *htc_ff, double *htc_fs, double *htc_ss, double *htc_es);

@@ -47,6 +47,7 @@ def load() -> C.CDLL:
     L.osc2_set_fluid_table.argtypes = [H, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, c_dp]
     L.osc2_upload_sweep.argtypes = [H, C.POINTER(Osc2Sweep)]
     L.osc2_eval_operating_conditions.argtypes = [H, C.c_double]
+    L.osc2_advance.argtypes = [H, C.c_double, C.c_double, C.c_int]
     L.osc2_download_step_inputs.argtypes = [H] + [c_dp] * 8
     L.osc2_synchronize.argtypes = [H]
     L.osc2_download_state.argtypes = [H, c_dp, c_dp, c_ip]
@@ -66,7 +67,7 @@ def load() -> C.CDLL:
                  "osc2_synchronize", "osc2_download_state", "osc2_download_diagnostics", "osc2_set_capture",
                  "osc2_download_system", "osc2_set_profiling", "osc2_get_kernel_ms", "osc2_reset_kernel_ms",
                  "osc2_timer_start", "osc2_timer_stop", "osc2_set_model", "osc2_set_fluid_table", "osc2_upload_sweep",
-                 "osc2_eval_operating_conditions", "osc2_download_step_inputs"):
+                 "osc2_eval_operating_conditions", "osc2_download_step_inputs", "osc2_advance"):
         getattr(L, name).restype = C.c_int
     _LIB = L
     return L
@@ -78,7 +79,7 @@ EXPORTED = (
     "osc2_download_state", "osc2_download_diagnostics", "osc2_set_capture", "osc2_download_system",
     "osc2_set_profiling", "osc2_get_kernel_ms", "osc2_reset_kernel_ms", "osc2_timer_start",
     "osc2_timer_stop", "osc2_device_bytes", "osc2_selftest_division", "osc2_set_model", "osc2_set_fluid_table",
-    "osc2_upload_sweep", "osc2_eval_operating_conditions", "osc2_download_step_inputs",
+    "osc2_upload_sweep", "osc2_eval_operating_conditions", "osc2_download_step_inputs", "osc2_advance",
 )
 
 

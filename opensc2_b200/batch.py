@@ -101,6 +101,10 @@ class BatchedStep:
     def eval_operating_conditions(self, time: float):
         _lib.check(self._L.osc2_eval_operating_conditions(self._h, float(time)))
 
+    def advance(self, time: float, dt: float, num_step: int):
+        """Operating conditions at `time` + one step(); fused on the device where it fits."""
+        _lib.check(self._L.osc2_advance(self._h, float(time), float(dt), int(num_step)))
+
     def download_step_inputs(self) -> Dict[str, np.ndarray]:
         B, E, M, S = self.batch, self.n_nodes - 1, self.topo.n_ch, self.topo.n_sol
         t = self.topo

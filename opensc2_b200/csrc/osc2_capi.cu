@@ -7,11 +7,14 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "step_launch.h"
 #include "props_kernels.cuh"
+#include "opcond_gauss_fused.cuh"
 
 namespace {
 
@@ -56,6 +59,8 @@ struct osc2_context {
     bool have_state = false, have_inputs = false;
     bool capture = false, profiling = false;
     bool fast = false;               // register-resident kernels (step_kernels_fast.cuh)
+    bool fused_opcond = false;       // K_P + K_G in one kernel (opcond_gauss_fused.cuh), experimental
+    int fused_warps = 2;             // warps per CTA of the fused kernel
     bool fwd_split = false;          // K_F as two specialised warps (step_kernels_split.cuh), experimental
     int max_smem = 0, sm_count = 0;
     std::vector<EventPair> pending, pool;
@@ -292,6 +297,9 @@ int osc2_create(const osc2_topology *topo, int batch, int n_nodes, int device, o
         h->fast = osc2_has_fast_path(h->d) && !(force && force[0] == '1');
     }
     h->NS = osc2_gm_slots(h->d, h->M, h->S, h->fast);
+    // experimental: bit-identical to K_P + K_G but slower today, off unless OSC2_FUSED_OPCOND=1
+    { const char *fo = getenv("OSC2_FUSED_OPCOND"); h->fused_opcond = (fo && fo[0] == '1'); }
+    { const char *fw = getenv("OSC2_FUSED_WARPS"); if (fw && atoi(fw) >= 1 && atoi(fw) <= 4) h->fused_warps = atoi(fw); }
     // experimental: slower than the single-warp sweep today, off unless OSC2_FWD_SPLIT=1
     { const char *sp = getenv("OSC2_FWD_SPLIT"); h->fwd_split = (sp && sp[0] == '1'); }
     cudaDeviceProp prop;
@@ -474,6 +482,26 @@ int osc2_set_model(osc2_handle h, const osc2_model *model)
         CK(cudaStreamSynchronize(h->stream));
     }
     h->q.model = h->model_dev;
+    {   // greedy balance of the component items over the warps of the fused kernel by pow() count
+        static const int mat_cost[OSC2_MAT_COUNT] = {14, 9, 8, 8};   // Cu, Nb3Sn, SS, glass-epoxy
+        const int n_items = h->M + h->S + 1;
+        std::vector<std::pair<int, int>> items;     // (cost, item)
+        for (int j = 0; j < h->M; ++j) items.push_back({2 + (model->ch_ifriction[j] == 124 ? 2 : 0), j});
+        for (int l = 0; l < h->S; ++l) {
+            int c = 1;
+            for (int i = 0; i < model->sol_nmat[l]; ++i) c += mat_cost[model->sol_mat[l][i]];
+            items.push_back({c, h->M + l});
+        }
+        items.push_back({1, n_items - 1});
+        std::sort(items.begin(), items.end(), [](const std::pair<int, int> &a, const std::pair<int, int> &b) { return a.first > b.first; });
+        std::vector<int> load(h->fused_warps, 0);
+        for (auto &it : items) {
+            int best = 0;
+            for (int w = 1; w < h->fused_warps; ++w) if (load[w] < load[best]) best = w;
+            load[best] += it.first;
+            h->q.item_owner[it.second] = (unsigned char)best;
+        }
+    }
     h->n_fluids_used = nf;
     h->have_model = true;
     return OSC2_OK;
@@ -525,6 +553,8 @@ int osc2_upload_sweep(osc2_handle h, const osc2_sweep *sw)
     return OSC2_OK;
 }
 
+static int launch_tmax(osc2_context *h);
+
 int osc2_eval_operating_conditions(osc2_handle h, double time)
 {
     if (!h) return fail(OSC2_ERR_INVALID, "handle is NULL");
@@ -534,12 +564,8 @@ int osc2_eval_operating_conditions(osc2_handle h, double time)
         if (!h->have_table[f]) return fail(OSC2_ERR_STATE, "fluid table %d was not set", f);
     CK(cudaSetDevice(h->device));
     h->q.time = time;
+    { int rc = launch_tmax(h); if (rc) return rc; }
     CudaLauncher L{h};
-    if (h->S > 0) {
-        CK(cudaMemsetAsync(h->q.tmax, 0, sizeof(double) * (size_t)h->S * h->B, h->stream));
-        const long long w = (long long)((h->E + 63) / 64) * h->B;
-        L.launch(OSC2_K_PROPS, osc2_solid_tmax_kernel, (unsigned)((w + 127) / 128), 128u, (size_t)0, h->p, h->q);
-    }
     const long long work = (long long)h->E * h->B;
     L.launch(OSC2_K_PROPS, osc2_opcond_kernel, (unsigned)((work + 127) / 128), 128u, (size_t)0,
              (const osc2_topology *)h->topo_dev, h->p, h->q);
@@ -572,7 +598,55 @@ int osc2_download_step_inputs(osc2_handle h, double *fl_gauss, double *fl_node, 
     return OSC2_OK;
 }
 
+static int run_step(osc2_handle h, double dt, int num_step, bool records_ready);
+
 int osc2_step(osc2_handle h, double dt, int num_step)
+{
+    return run_step(h, dt, num_step, false);
+}
+
+static int launch_tmax(osc2_context *h)
+{
+    if (h->S == 0) return OSC2_OK;
+    CudaLauncher L{h};
+    CK(cudaMemsetAsync(h->q.tmax, 0, sizeof(double) * (size_t)h->S * h->B, h->stream));
+    const long long w = (long long)((h->E + 63) / 64) * h->B;
+    L.launch(OSC2_K_PROPS, osc2_solid_tmax_kernel, (unsigned)((w + 127) / 128), 128u, (size_t)0, h->p, h->q);
+    return OSC2_OK;
+}
+
+int osc2_advance(osc2_handle h, double time, double dt, int num_step)
+{
+    if (!h) return fail(OSC2_ERR_INVALID, "handle is NULL");
+    if (!h->have_model || !h->have_sweep || !h->have_state)
+        return fail(OSC2_ERR_STATE, "osc2_advance needs osc2_set_model, osc2_upload_sweep and osc2_upload_state first");
+    const FusedSlots sl{h->M, h->S, h->p.nff, h->p.nfs, h->p.nss, h->p.nes, h->d};
+    const int n_warps = h->fused_warps;
+    const size_t smem = sl.smem_doubles(n_warps) * sizeof(double);
+    if (!h->fused_opcond || !h->fast || smem > 48 * 1024) {
+        int rc = osc2_eval_operating_conditions(h, time);
+        if (rc) return rc;
+        return run_step(h, dt, num_step, false);
+    }
+    for (int f = 0; f < h->n_fluids_used; ++f)
+        if (!h->have_table[f]) return fail(OSC2_ERR_STATE, "fluid table %d was not set", f);
+    if (!(dt > 0.0)) return fail(OSC2_ERR_INVALID, "time step must be positive");
+    if (num_step < 1) return fail(OSC2_ERR_INVALID, "num_step must be >= 1");
+    CK(cudaSetDevice(h->device));
+    h->q.time = time;
+    h->p.dt = dt;
+    h->p.num_step = num_step;
+    int rc = launch_tmax(h);
+    if (rc) return rc;
+    CudaLauncher L{h};
+    const long long blocks = (long long)h->E * ((h->B + 31) / 32);
+    L.launch(OSC2_K_GAUSS, osc2_opcond_gauss_kernel, (unsigned)blocks, (unsigned)(32 * n_warps), smem, (const osc2_topology *)h->topo_dev,
+             h->p, h->q, h->capture ? 1 : 0);
+    h->have_inputs = true;
+    return run_step(h, dt, num_step, true);
+}
+
+static int run_step(osc2_handle h, double dt, int num_step, bool records_ready)
 {
     if (!h) return fail(OSC2_ERR_INVALID, "handle is NULL");
     if (!h->have_state || !h->have_inputs)
@@ -589,7 +663,7 @@ int osc2_step(osc2_handle h, double dt, int num_step)
     CudaLauncher L{h};
     StepDev pp = h->p;
     if (!h->capture) { pp.cap_sysmat = nullptr; pp.cap_known = nullptr; }
-    osc2_run_step(L, h->topo_dev, pp, h->fast, h->topo.theta);
+    osc2_run_step(L, h->topo_dev, pp, h->fast, h->topo.theta, records_ready);
     if (!h->launch_error.empty()) {
         const int rc = fail(OSC2_ERR_CUDA, "%s", h->launch_error.c_str());
         h->launch_error.clear();

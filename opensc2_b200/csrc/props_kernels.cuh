@@ -31,6 +31,8 @@ struct PropsDev {
     double *tmax;            // [S][B] max Gauss temperature of each solid (whole-array branches)
     double *sol_const;       // [S][2] RRR-only constants of the copper fit: p7, rhoecu0(273 K)
     double time;
+    // fused K_PG: which warp of the CTA evaluates component item i (channels, then solids, then geometry)
+    unsigned char item_owner[OSC2_MAX_CHANNELS + OSC2_MAX_SOLIDS + 1];
 };
 
 namespace osc2p {

@@ -111,14 +111,17 @@ void osc2_run_fast_sweeps(Launcher &L, const osc2_topology *tp_dev, const StepDe
     L.launch(OSC2_K_BACKWARD, osc2_backward_fast_kernel<D, LPC>, grid, 32u, smem_b, p);
 }
 
+// `records_ready`: the element row records were already produced by the fused K_PG kernel
 template <class Launcher>
-void osc2_run_step(Launcher &L, const osc2_topology *tp_dev, const StepDev &p, bool fast, double theta)
+void osc2_run_step(Launcher &L, const osc2_topology *tp_dev, const StepDev &p, bool fast, double theta,
+                   bool records_ready = false)
 {
     const Osc2LaunchPlan pl = osc2_make_plan(p.d, p.B, L.max_smem(), L.sm_count());
     if (fast) {
         const long long work = (long long)p.E * p.B;
         const unsigned grid = (unsigned)((work + pl.gauss_block - 1) / pl.gauss_block);
-        L.launch(OSC2_K_GAUSS, osc2_gauss2_kernel<true>, grid, pl.gauss_block, pl.smem_gauss, tp_dev, p);
+        if (!records_ready)
+            L.launch(OSC2_K_GAUSS, osc2_gauss2_kernel<true>, grid, pl.gauss_block, pl.smem_gauss, tp_dev, p);
         switch (p.d) {
         case 4: osc2_run_fast_sweeps<4, 8>(L, tp_dev, p, theta); break;
         case 8: osc2_run_fast_sweeps<8, 8>(L, tp_dev, p, theta); break;

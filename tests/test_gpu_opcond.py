@@ -139,3 +139,33 @@ def test_model_validation_rejects_unimplemented_flags():
     with BatchedStep(topo, 2, 9) as bs:
         with pytest.raises(ValueError):
             bs.set_model(bad, [synthetic_helium_table()])
+
+
+@pytest.mark.parametrize("correlations", [False, True])
+@pytest.mark.parametrize("batch", [9, 70])
+def test_fused_advance_is_bit_identical_to_separate_kernels(correlations, batch, monkeypatch):
+    """osc2_advance: the fused K_PG kernel (properties -> row records in shared memory) against the
+    separate K_P + K_G launches.  Same device arithmetic, so states, SYSLOD history, norms and the
+    materialised coefficient arrays must agree bit for bit (ragged last tile of 32 included)."""
+    from opensc2_b200.batch import BatchedStep
+
+    n, dt = 37, 0.1
+    topo, model, tab, _arr, sweep = _setup(correlations, n, batch, seed=21)
+    arr = consistent_initial_state(topo, model, tab, n, batch, seed=21, dt=dt)
+    results = {}
+    for fused in ("0", "1"):
+        monkeypatch.setenv("OSC2_FUSED_OPCOND", fused)
+        with BatchedStep(topo, batch, n) as bs:
+            bs.set_model(model, [tab])
+            bs.upload_sweep(sweep)
+            bs.upload_state(arr.sysvar, arr.syslod)
+            bs.upload_geometry(arr)
+            bs.set_capture(True)                         # also materialises the coefficient arrays
+            for k in range(1, 5):
+                bs.advance(9.8 + k * dt, dt, k)
+            bs.synchronize()
+            sv, sl, st = bs.download_state()
+            results[fused] = dict(sysvar=sv, syslod=sl, status=st, **bs.download_diagnostics(), **bs.download_step_inputs())
+    for key, v in results["0"].items():
+        assert_bits(results["1"][key], v, key)
+    assert np.all(results["1"]["status"] == 0)
