@@ -282,10 +282,18 @@ def run_ours(args, rank, world, local_rank):
     d2h = sum(v.nbytes for v in diag.values()) + status.nbytes
     healthy = bool(np.all(status == 0) and np.all(np.isfinite(diag["norm_solution"])))
 
+    gather = None
     if dist is not None:
         t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=f"cuda:{local_rank}")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e = float(t[0]), float(t[1])
+        # the only collective of the job: final gather of the results (here the solution norms), untimed
+        from opensc2_b200.shard import any_rank_failed, gather_to_all
+        t0 = time.perf_counter()
+        full = gather_to_all(np.ascontiguousarray(diag["norm_solution"]), world * BATCH, device=f"cuda:{local_rank}")
+        healthy = healthy and not any_rank_failed(status, device=f"cuda:{local_rank}")
+        gather = {"what": "norm_solution of every conductor to every rank (NCCL all_gather), outside the timed region",
+                  "bytes": int(full.nbytes), "ms": 1e3 * (time.perf_counter() - t0), "finite": bool(np.all(np.isfinite(full)))}
     units = world * BATCH * NODES * args.steps
     value = units / (ms * 1e-3)
     e2e_value = units / (ms_e2e * 1e-3)
@@ -316,6 +324,7 @@ def run_ours(args, rank, world, local_rank):
                             "+ download_status (C ABI, pinned host buffers; state and coefficients stay in HBM)",
                     "solution_finite_and_nonsingular": healthy},
             "gpu_launches": launches,
+            "final_gather": gather,
             "roofline": {
                 "bound": "hbm", "kernel": f"osc2_{dom}", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "peak_source": peak_src,
