@@ -347,6 +347,18 @@ int osc2_create(const osc2_topology *topo, int batch, int n_nodes, int device, o
     if (!rc) rc = dev_alloc(h, &p.norm_change, d * B);
     if (!rc) rc = dev_alloc(h, &p.eqteig, d * B);
     if (!rc) { double *q = nullptr; rc = dev_alloc(h, &q, (B + 1) / 2 + 1); p.status = (int *)q; }
+    if (!rc) {   // sparsity pattern of SMAT (K_G stages only the entries the topology can touch)
+        std::vector<unsigned char> map;
+        int slots = osc2_build_smap(*topo, map);
+        double *qm = nullptr;
+        // large systems (d > 15) can exceed a byte; they use the generic kernels with dense staging
+        if (slots > 0) rc = dev_alloc(h, &qm, map.size() / 8 + 1);
+        if (!rc && slots > 0) {
+            CK(cudaMemcpy(qm, map.data(), map.size(), cudaMemcpyHostToDevice));
+            p.smap = (const unsigned char *)qm;
+            p.s_slots = slots;
+        }
+    }
     if (!rc) {   // numpy pairwise-sum tree of the N nodal values of one equation (norms)
         std::vector<int> leaves, prog;
         osc2_build_norm_plan(0, h->N, leaves, prog);

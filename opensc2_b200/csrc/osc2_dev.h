@@ -52,6 +52,10 @@ struct StepDev {
     double *norm_part;        // [n_leaves][3][d][B]
     int n_leaves, n_prog;
     int fwd_split;            // 1: K_F as assembler + eliminator warps (step_kernels_split.cuh)
+    // K_G: SMAT is staged per thread in shared memory; only the entries the topology can touch get a
+    // slot (osc2_build_smap), every other (row, col) maps to one shared all-zero slot
+    const unsigned char *smap; // [d*d] -> slot
+    int s_slots;              // number of slots incl. the zero slot
 };
 
 // Slot map of one element's Gauss-point record in `gm`:

@@ -54,10 +54,11 @@ __global__ void osc2_gauss2_kernel(const osc2_topology *__restrict__ tp, StepDev
     static_assert(SMEM_S, "the fast path always stages SMAT in shared memory");
     double *Sb = sm_dyn + threadIdx.x;
     const size_t Ss = blockDim.x;
-#define SM_(r, c) Sb[(size_t)((r) * d + (c)) * Ss]
+    const unsigned char *__restrict__ smap = p.smap;
+#define SM_(r, c) Sb[(size_t)smap[(r) * d + (c)] * Ss]
 #define FG(q, j) p.fl_gauss[((((size_t)(q) * M + (j)) * E) + e) * B + b]
 #define GOUT(slot) g[(size_t)(slot) * B]
-    for (int i = 0; i < d * d; ++i) Sb[(size_t)i * Ss] = 0.0;
+    for (int i = 0; i < p.s_slots; ++i) Sb[(size_t)i * Ss] = 0.0;
     const double dz = p.dz[(size_t)e * B + b];
     const double alpha = 0.0;
     const double cdiag = dz * (1. / 3. + alpha), coff = dz * (1. / 6. - alpha);

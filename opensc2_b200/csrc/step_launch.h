@@ -31,6 +31,37 @@ inline void osc2_build_norm_plan(long long start, long long n, std::vector<int> 
     prog.push_back(-1);
 }
 
+// Sparsity pattern of the source Jacobian SMAT for a topology: exactly the (row, col) pairs the
+// statements of K_G can write (smc:262-311, 440-555, 596-668, 786-886).  Slot 0 is the shared zero.
+inline int osc2_build_smap(const osc2_topology &t, std::vector<unsigned char> &map)
+{
+    const int M = t.n_ch, d = 3 * M + t.n_sol;
+    std::vector<int> slot((size_t)d * d, 0);
+    int next = 1;
+    auto add = [&](int r, int c) { if (!slot[(size_t)r * d + c]) slot[(size_t)r * d + c] = next++; };
+    for (int j = 0; j < M; ++j) { add(j, j); add(M + j, j); add(2 * M + j, j); }
+    for (int k = 0; k < t.nff; ++k)
+        for (int side = 0; side < 2; ++side) {
+            const int c1 = t.ff[k][side], c2 = t.ff[k][1 - side];
+            const int v1 = c1, p1 = M + c1, t1 = 2 * M + c1, p2 = M + c2, t2 = 2 * M + c2;
+            add(v1, p1); add(v1, p2); add(p1, p1); add(p1, p2); add(p1, t1); add(p1, t2);
+            add(t1, p1); add(t1, p2); add(t1, t1); add(t1, t2);
+        }
+    for (int k = 0; k < t.nfs; ++k) {
+        const int j = t.fs[k][0], ip = M + j, it = 2 * M + j, is = 3 * M + t.fs[k][1];
+        add(ip, it); add(ip, is); add(it, it); add(it, is); add(is, is); add(is, it);
+    }
+    for (int k = 0; k < t.nss; ++k) {
+        const int a = 3 * M + t.ss[k][0], c = 3 * M + t.ss[k][1];
+        add(a, a); add(a, c); add(c, c); add(c, a);
+    }
+    for (int k = 0; k < t.nes; ++k) add(3 * M + t.es[k], 3 * M + t.es[k]);
+    if (next > 255) return -1;                 // does not fit a byte: the caller keeps the dense staging
+    map.resize((size_t)d * d);
+    for (size_t i = 0; i < map.size(); ++i) map[i] = (unsigned char)slot[i];
+    return next;
+}
+
 struct Osc2LaunchPlan {
     int lpc;            // lanes per conductor (8, 16, 32, 64)
     int cpb_fwd;        // conductors per CTA, forward sweep
@@ -121,7 +152,8 @@ void osc2_run_step(Launcher &L, const osc2_topology *tp_dev, const StepDev &p, b
         const long long work = (long long)p.E * p.B;
         const unsigned grid = (unsigned)((work + pl.gauss_block - 1) / pl.gauss_block);
         if (!records_ready)
-            L.launch(OSC2_K_GAUSS, osc2_gauss2_kernel<true>, grid, pl.gauss_block, pl.smem_gauss, tp_dev, p);
+            L.launch(OSC2_K_GAUSS, osc2_gauss2_kernel<true>, grid, pl.gauss_block,
+                     (size_t)p.s_slots * sizeof(double) * pl.gauss_block, tp_dev, p);
         switch (p.d) {
         case 4: osc2_run_fast_sweeps<4, 8>(L, tp_dev, p, theta); break;
         case 8: osc2_run_fast_sweeps<8, 8>(L, tp_dev, p, theta); break;

@@ -14,6 +14,9 @@ extern "C" int osc2_emu_step(const osc2_topology *tp, const StepDev *p, int fast
     q.norm_leaf = leaves.data(); q.norm_prog = prog.data(); q.norm_part = part.data();
     q.n_leaves = (int)(leaves.size() / 2); q.n_prog = (int)prog.size();
     q.fwd_split = split;
+    std::vector<unsigned char> smap;
+    q.s_slots = osc2_build_smap(*tp, smap);
+    q.smap = smap.data();
     osc2_run_step(L, tp, q, fast != 0, tp->theta);
     return (int)L.launches;
 }
