@@ -101,14 +101,15 @@ enum { OSC2_FP_BETA = 0,   /* isobaric_expansion_coefficient */
        OSC2_FP_PRANDTL, OSC2_FP_RHO, OSC2_FP_MU, OSC2_FP_H, OSC2_FP_CP, OSC2_FP_CV,
        OSC2_FP_SOUND, OSC2_FP_K };
 /* materials (the fits of properties_of_materials/) */
-enum { OSC2_MAT_CU_NIST = 0, OSC2_MAT_NB3SN = 1, OSC2_MAT_SS = 2, OSC2_MAT_GE = 3, OSC2_MAT_COUNT };
+enum { OSC2_MAT_CU_NIST = 0, OSC2_MAT_NB3SN = 1, OSC2_MAT_SS = 2, OSC2_MAT_GE = 3, OSC2_MAT_AL = 4,
+       OSC2_MAT_RE123 = 5, OSC2_MAT_COUNT };
 /* solid kinds: StrandMixedComponent, StrandStabilizerComponent, JacketComponent */
 enum { OSC2_SOLID_STRAND_MIXED = 0, OSC2_SOLID_STRAND_STAB = 1, OSC2_SOLID_JACKET = 2 };
 
 typedef struct {
     /* channels (channel.py:43-169) */
     int ch_fluid[OSC2_MAX_CHANNELS];            /* which fluid table */
-    int ch_ifriction[OSC2_MAX_CHANNELS];        /* IFRICTION: -99 or 124 */
+    int ch_ifriction[OSC2_MAX_CHANNELS];        /* IFRICTION: -99, 122 (Colebrook) or 124 */
     double ch_friction_mult[OSC2_MAX_CHANNELS]; /* FRICTION_MULTIPLIER */
     int ch_htc_corr[OSC2_MAX_CHANNELS];         /* Flag_htc_steady_corr: 1 or 212 */
     /* solids */
@@ -130,6 +131,7 @@ typedef struct {
     double ss_htc[OSC2_MAX_INTERFACES], ss_mlt[OSC2_MAX_INTERFACES];
     double ss_thick_rc[OSC2_MAX_INTERFACES], ss_thick_cr[OSC2_MAX_INTERFACES], ss_rcontact[OSC2_MAX_INTERFACES];
     double es_htc[OSC2_MAX_INTERFACES];         /* constant convective HTC (choices -2, -4), Phi_conv and multiplier applied */
+    double ch_roughness[OSC2_MAX_CHANNELS];     /* Channel.inputs["Roughness"] (IFRICTION 122) */
 } osc2_model;
 
 /* Swept per-conductor scalars, batch leading. */

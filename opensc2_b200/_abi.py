@@ -75,6 +75,7 @@ class Osc2Model(C.Structure):
         ("ss_choice", C.c_int * _IF), ("ss_htc", C.c_double * _IF), ("ss_mlt", C.c_double * _IF),
         ("ss_thick_rc", C.c_double * _IF), ("ss_thick_cr", C.c_double * _IF), ("ss_rcontact", C.c_double * _IF),
         ("es_htc", C.c_double * _IF),
+        ("ch_roughness", C.c_double * _CH),
     ]
 
 

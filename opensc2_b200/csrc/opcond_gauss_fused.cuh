@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(128, 6) osc2_opcond_gauss_kernel(const osc2_to
             const double grun = osc2p::lookup(tab, c, OSC2_FP_BETA) / osc2p::lookup(tab, c, OSC2_FP_KAPPA) / cv / rho;
             const double nu = (md->ch_htc_corr[j] == 212) ? osc2p::nusselt_212(re)
                                                           : osc2p::nusselt_1(re, osc2p::lookup(tab, c, OSC2_FP_PRANDTL));
-            const double ftot = ((md->ch_ifriction[j] == 124) ? osc2p::friction_124(re) : 1.0) * md->ch_friction_mult[j];
+            const double ftot = osc2p::friction_total(md, tp, j, re, q.cb_iters[(size_t)j * B + b]);
             IN(sl.fg(0, j)) = v; IN(sl.fg(1, j)) = pr; IN(sl.fg(2, j)) = T; IN(sl.fg(3, j)) = rho;
             IN(sl.fg(4, j)) = osc2p::lookup(tab, c, OSC2_FP_SOUND);
             IN(sl.fg(5, j)) = grun;
@@ -113,23 +113,21 @@ __global__ void __launch_bounds__(128, 6) osc2_opcond_gauss_kernel(const osc2_to
                 tc = osc2p::tc_nb3sn(bg, (eps + eps) / 2.0, md->sol_tc0m[l], md->sol_bc20m[l]);
                 tcs = q.tcs ? q.tcs[((size_t)l * E + e) * B + b] : 0.0;
             }
-            const double tmax = q.tmax[(size_t)l * B + b];
+            const double tmax = q.tmax[(size_t)l * B + b], tmin = q.tmin[(size_t)l * B + b];
             double nsum = 0.0, cps = 0.0, ksum = 0.0, rho1 = 0.0, cp1 = 0.0, k1 = 0.0;
             for (int i = 0; i < nmat; ++i) {
                 const int mat = md->sol_mat[l][i];
                 const double wgt = md->sol_weight[l][i];
                 const double rho_i = osc2p::mat_density(mat);
                 double cp_i, k_i;
-                if (mat == OSC2_MAT_CU_NIST) { cp_i = osc2p::cp_cu(T); k_i = osc2p::k_cu(T, bg, md->sol_rrr[l], q.sol_const[2 * l], q.sol_const[2 * l + 1]); }
-                else if (mat == OSC2_MAT_NB3SN) { cp_i = osc2p::cp_nb3sn(T, tcs, tc, md->sol_tc0m[l]); k_i = osc2p::k_nb3sn(T); }
-                else if (mat == OSC2_MAT_SS) { cp_i = osc2p::cp_ss(T, tmax); k_i = osc2p::k_ss(T); }
-                else { cp_i = osc2p::cp_ge(T); k_i = osc2p::k_ge(T); }
+                osc2p::material_cp_k(mat, T, bg, tcs, tc, tmin, tmax, md->sol_rrr[l], md->sol_tc0m[l], q.sol_const[2 * l],
+                                     q.sol_const[2 * l + 1], cp_i, k_i);
                 const double num = rho_i * wgt;
                 if (i == 0) { nsum = num; cps = cp_i * num; ksum = k_i * wgt; rho1 = rho_i; cp1 = cp_i; k1 = k_i; }
                 else { nsum = nsum + num; cps = cps + cp_i * num; ksum = ksum + k_i * wgt; }
             }
             double rho, cp, kk;
-            if (kind == OSC2_SOLID_JACKET && nmat == 1) { rho = rho1; cp = cp1; kk = k1; }
+            if ((kind == OSC2_SOLID_JACKET && nmat == 1) || kind == OSC2_SOLID_STRAND_STAB) { rho = rho1; cp = cp1; kk = k1; }
             else { rho = nsum / md->sol_weight_sum[l]; cp = cps / nsum; kk = ksum / md->sol_weight_sum[l]; }
             IN(sl.sg(0, l)) = rho; IN(sl.sg(1, l)) = cp; IN(sl.sg(2, l)) = kk;
             IN(sl.ts(l)) = T;

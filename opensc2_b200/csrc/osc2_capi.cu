@@ -452,8 +452,8 @@ int osc2_set_model(osc2_handle h, const osc2_model *model)
         if (model->ch_fluid[j] < 0 || model->ch_fluid[j] >= OSC2_MAX_FLUIDS)
             return fail(OSC2_ERR_INVALID, "channel %d: fluid table index %d", j, model->ch_fluid[j]);
         if (model->ch_fluid[j] + 1 > nf) nf = model->ch_fluid[j] + 1;
-        if (model->ch_ifriction[j] != -99 && model->ch_ifriction[j] != 124)
-            return fail(OSC2_ERR_INVALID, "channel %d: IFRICTION %d is not implemented on the device (-99, 124)", j, model->ch_ifriction[j]);
+        if (model->ch_ifriction[j] != -99 && model->ch_ifriction[j] != 124 && model->ch_ifriction[j] != 122)
+            return fail(OSC2_ERR_INVALID, "channel %d: IFRICTION %d is not implemented on the device (-99, 122, 124)", j, model->ch_ifriction[j]);
         if (model->ch_htc_corr[j] != 1 && model->ch_htc_corr[j] != 212)
             return fail(OSC2_ERR_INVALID, "channel %d: Flag_htc_steady_corr %d is not implemented on the device (1, 212)", j, model->ch_htc_corr[j]);
     }
@@ -483,6 +483,14 @@ int osc2_set_model(osc2_handle h, const osc2_model *model)
         int rc = dev_alloc(h, &t, (size_t)h->S * h->B);
         if (rc) return rc;
         h->q.tmax = t;
+        t = nullptr;
+        rc = dev_alloc(h, &t, (size_t)h->S * h->B);
+        if (rc) return rc;
+        h->q.tmin = t;
+        t = nullptr;
+        rc = dev_alloc(h, &t, ((size_t)h->M * h->B + 1) / 2 + 1);
+        if (rc) return rc;
+        h->q.cb_iters = (int *)t;
         double *c = nullptr;
         rc = dev_alloc(h, &c, 2 * (size_t)h->S);
         if (rc) return rc;
@@ -619,11 +627,14 @@ int osc2_step(osc2_handle h, double dt, int num_step)
 
 static int launch_tmax(osc2_context *h)
 {
-    if (h->S == 0) return OSC2_OK;
+    if (h->S == 0 && h->M == 0) return OSC2_OK;
     CudaLauncher L{h};
     CK(cudaMemsetAsync(h->q.tmax, 0, sizeof(double) * (size_t)h->S * h->B, h->stream));
+    CK(cudaMemsetAsync(h->q.tmin, 0x7f, sizeof(double) * (size_t)h->S * h->B, h->stream));   // a huge positive double
+    CK(cudaMemsetAsync(h->q.cb_iters, 0, sizeof(int) * (size_t)(h->M > 0 ? h->M : 1) * h->B, h->stream));
     const long long w = (long long)((h->E + 63) / 64) * h->B;
-    L.launch(OSC2_K_PROPS, osc2_solid_tmax_kernel, (unsigned)((w + 127) / 128), 128u, (size_t)0, h->p, h->q);
+    L.launch(OSC2_K_PROPS, osc2_solid_tmax_kernel, (unsigned)((w + 127) / 128), 128u, (size_t)0,
+             (const osc2_topology *)h->topo_dev, h->p, h->q);
     return OSC2_OK;
 }
 

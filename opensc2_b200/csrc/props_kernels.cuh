@@ -29,6 +29,8 @@ struct PropsDev {
     const double *q_window;  // [S][4][B]
     const double *tcs;       // [S][E][B] or nullptr
     double *tmax;            // [S][B] max Gauss temperature of each solid (whole-array branches)
+    double *tmin;            // [S][B] min Gauss temperature (aluminium's whole-array range check)
+    int *cb_iters;           // [M][B] array-wide Colebrook iteration count (IFRICTION 122)
     double *sol_const;       // [S][2] RRR-only constants of the copper fit: p7, rhoecu0(273 K)
     double time;
     // fused K_PG: which warp of the CTA evaluates component item i (channels, then solids, then geometry)
@@ -190,9 +192,112 @@ __device__ inline double cp_ge(double t)
     return four_term(t, 0.309399374, -1387.509141, 283.0320589, 1.822153805, 113.1687618, 80.88333136,
                      26.27075203, 1.104229335, 0.254475819, 1.938523579, 2.603466143, 3.522809815);
 }
+// aluminium.py:5-77 -- zeros when any element of the array is outside [2, 1000] K
+__device__ __noinline__ double k_al(double T, double tmin, double tmax)
+{
+    if (tmin < 2.0 || tmax > 1000.0) return 0.0;
+    if (T >= 2.0 && T <= 4.0) return 4.2345 * (T - 2.0) + 6.6510;
+    if (T > 4.0 && T <= 6.0) return 4.2000 * (T - 4.0) + 15.1200;
+    if (T > 6.0 && T <= 8.0) return 4.3650 * (T - 6.0) + 23.5200;
+    if (T > 8.0 && T <= 10.0) return 4.8550 * (T - 8.0) + 32.2500;
+    if (T > 10.0 && T <= 20.0) return 4.3430 * (T - 10.0) + 41.9600;
+    if (T > 20.0 && T <= 40.0) return 3.8805 * (T - 20.0) + 85.3900;
+    if (T > 40.0 && T <= 60.0) return 2.0375 * (T - 40.0) + 163.000;
+    if (T > 60.0 && T <= 80.0) return 0.5360 * (T - 60.0) + 203.75;
+    if (T > 80.0 && T <= 100.0) return 0.1145 * (T - 80.0) + 214.47;
+    if (T > 100.0 && T <= 200.0) return -0.0452 * (T - 100.0) + 216.76;
+    if (T > 200.0 && T <= 300.0) return -0.0291 * (T - 200.0) + 212.24;
+    if (T > 300.0 && T <= 1000.0) return 209.3300;
+    return 0.0;
+}
+// aluminium.py:80-164
+__device__ __noinline__ double cp_al(double T, double tmin, double tmax)
+{
+    if (tmin < 2.0 || tmax > 1000.0) return 0.0;
+    if (T >= 2.0 && T <= 11.0578562) return 0.04257809 * T + 0.00340313 * sq(T) + 0.00063472 * cube(T);
+    if (T > 11.0578562 && T <= 53.2685055)
+        return -2.50413265 + 0.71747923 * T + -0.06270275 * sq(T) + 0.0031683 * cube(T) + -2.0154e-05 * quart(T);
+    if (T > 53.2685055 && T <= 1000.0)
+        return four_term(T, 11458.0127, -438.603857, 331.057118, -10001.7006, -7.12302329, -34.6373149, -29.4649313,
+                         -3.30673113, 0.9531781, 2.00135991, 2.974805, 3.94384164);
+    return 0.0;
+}
+// rare_earth_123.py:65-135, 138-190
+__device__ inline double k_re123(double T)
+{
+    T = fmin(T, 300.0);
+    T = fmax(T, 4.0);
+    const double T2 = sq(T), T3 = T2 * T, T4 = T2 * T2, T5 = T4 * T;
+    if (T <= 70.0)
+        return -1.266103106492942e-5 * T5 + 0.002670105477219 * T4 + -0.197035302542769 * T3 + 4.933962659604384 * T2
+               + 29.651536939501670 * T + 66.578192505447330;
+    return -1.316704893540544e-9 * T5 + 2.636151594117440e-06 * T4 + -0.001601689632073 * T3 + 0.428760641312538 * T2
+           + -53.306643333287260 * T + 3.682252343338599e03;
+}
+__device__ inline double cp_re123(double T)
+{
+    T = fmin(T, 300.0);
+    T = fmax(T, 4.0);
+    const double T2 = sq(T), T3 = T2 * T, T4 = T2 * T2, T5 = T4 * T;
+    return -7.567485538209158e-10 * T5 + 6.351452642016898e-07 * T4 + -1.947975786547597e-04 * T3 + 0.023616673974415 * T2
+           + 0.239331954284042 * T + -1.096191721280114;
+}
 __device__ inline double mat_density(int mat)
 {
-    return mat == OSC2_MAT_CU_NIST ? 8900.0 : mat == OSC2_MAT_NB3SN ? 8950.0 : mat == OSC2_MAT_SS ? 7800.0 : 2000.0;
+    return mat == OSC2_MAT_CU_NIST ? 8900.0 : mat == OSC2_MAT_NB3SN ? 8950.0 : mat == OSC2_MAT_SS ? 7800.0
+           : mat == OSC2_MAT_AL ? 2700.0 : mat == OSC2_MAT_RE123 ? 6380.0 : 2000.0;
+}
+__device__ inline double friction_124(double re);
+// IFRICTION 122: haaland_equation channel.py:700-717 as the start, colebrook_formula channel.py:721-756
+__device__ inline double haaland(double re, double rough, double dh)
+{
+    const double x = -1.8 * log10(pow(rough / dh / 3.7, 1.11) + (6.9 / re));
+    return (1.0 / (x * x)) / 4.0;
+}
+__device__ inline double colebrook_step(double re, double f, double rough, double dh)
+{
+    const double x = -2.0 * log10((rough / dh / 3.7) + (2.51 / re / sqrt(f)));
+    return (1.0 / (x * x)) / 4.0;
+}
+// number of iterations THIS element needs (the reference iterates the whole array until the largest
+// error is <= 1e-5; each element's fixed-point iteration contracts, so the array-wide count is the max)
+__device__ inline int colebrook_count(double re, double rough, double dh)
+{
+    double f = haaland(re, rough, dh);
+    int it = 0;
+    double err = 10.0;
+    while (err > 1e-5 && it < 100) {
+        const double fn = colebrook_step(re, f, rough, dh);
+        err = fabs(f - fn);
+        if (err != err) err = 10.0;
+        f = fn;
+        ++it;
+    }
+    return it;
+}
+// total friction factor of channel j (channel.py:1119-1138)
+__device__ inline double friction_total(const osc2_model *md, const osc2_topology *tp, int j, double re, int cb_iters)
+{
+    double f = 1.0;
+    if (md->ch_ifriction[j] == 124) f = friction_124(re);
+    else if (md->ch_ifriction[j] == 122) {
+        const double rough = md->ch_roughness[j], dh = tp->ch_dh[j];
+        f = haaland(fabs(re), rough, dh);
+        for (int it = 0; it < cb_iters; ++it) f = colebrook_step(fabs(re), f, rough, dh);
+        f = fmax(0.0, f);
+    }
+    return f * md->ch_friction_mult[j];
+}
+// cp and k of one constituent material at a Gauss point
+__device__ inline void material_cp_k(int mat, double T, double bg, double tcs, double tc, double tmin, double tmax,
+                                     double rrr, double tc0m, double p7, double rho273, double &cp, double &k)
+{
+    if (mat == OSC2_MAT_CU_NIST) { cp = cp_cu(T); k = k_cu(T, bg, rrr, p7, rho273); }
+    else if (mat == OSC2_MAT_NB3SN) { cp = cp_nb3sn(T, tcs, tc, tc0m); k = k_nb3sn(T); }
+    else if (mat == OSC2_MAT_SS) { cp = cp_ss(T, tmax); k = k_ss(T); }
+    else if (mat == OSC2_MAT_AL) { cp = cp_al(T, tmin, tmax); k = k_al(T, tmin, tmax); }
+    else if (mat == OSC2_MAT_RE123) { cp = cp_re123(T); k = k_re123(T); }
+    else { cp = cp_ge(T); k = k_ge(T); }
 }
 // channel.py:392-401, 782-795, 1104-1115
 __device__ inline double friction_124(double re)
@@ -259,10 +364,11 @@ __global__ void osc2_model_consts_kernel(const osc2_model *md, int S, double *so
     sol_const[2 * l + 1] = osc2p::rhoecu0(273.0, rrr);
 }
 
-// max over the Gauss points of |T_i + T_i+1| / 2 for every solid (isobaric_specific_heat_ss picks
-// its formula from it).  One thread per (chunk of 64 elements, conductor); temperatures are >= 0 so
-// the IEEE bit pattern orders like an unsigned integer.
-__global__ void osc2_solid_tmax_kernel(StepDev p, PropsDev q)
+// Array-wide quantities the element-wise fits branch on, one thread per (chunk of 64 elements, conductor):
+//   max / min over the Gauss points of |T_i + T_i+1| / 2 for every solid (isobaric_specific_heat_ss,
+//   the aluminium fits); temperatures are >= 0 so the IEEE bit pattern orders like an unsigned integer;
+//   the iteration count of the Colebrook loop for channels with IFRICTION 122.
+__global__ void osc2_solid_tmax_kernel(const osc2_topology *__restrict__ tp, StepDev p, PropsDev q)
 {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int chunks = (p.E + 63) / 64;
@@ -271,17 +377,37 @@ __global__ void osc2_solid_tmax_kernel(StepDev p, PropsDev q)
     const size_t b = (size_t)(idx % p.B);
     const int c = (int)(idx / p.B);
     const int e0 = c * 64, e1 = min(p.E, e0 + 64);
+    const int M = p.M, d = p.d;
     for (int l = 0; l < p.S; ++l) {
-        const int is = 3 * p.M + l;
-        double prev = p.sysvar[((size_t)e0 * p.d + is) * B + b];
-        double mx = 0.0;
+        const int is = 3 * M + l;
+        double prev = p.sysvar[((size_t)e0 * d + is) * B + b];
+        double mx = 0.0, mn = __longlong_as_double(0x7ff0000000000000ll);
         for (int e = e0; e < e1; ++e) {
-            const double nxt = p.sysvar[((size_t)(e + 1) * p.d + is) * B + b];
+            const double nxt = p.sysvar[((size_t)(e + 1) * d + is) * B + b];
             const double tg = fabs(prev + nxt) / 2.0;
             if (tg > mx) mx = tg;
+            if (tg < mn) mn = tg;
             prev = nxt;
         }
         atomicMax((unsigned long long *)(q.tmax + (size_t)l * B + b), (unsigned long long)__double_as_longlong(mx));
+        atomicMin((unsigned long long *)(q.tmin + (size_t)l * B + b), (unsigned long long)__double_as_longlong(mn));
+    }
+    const osc2_model *md = q.model;
+    for (int j = 0; j < M; ++j) {
+        if (md->ch_ifriction[j] != 122) continue;
+        const FluidTableDev &tab = q.fluid[md->ch_fluid[j]];
+        int worst = 0;
+        for (int e = e0; e < e1; ++e) {
+            const double *x0 = p.sysvar + ((size_t)e * d) * B + b, *x1 = x0 + (size_t)d * B;
+            const double v = (x0[(size_t)j * B] + x1[(size_t)j * B]) / 2.0;
+            const double pr = (x0[(size_t)(M + j) * B] + x1[(size_t)(M + j) * B]) / 2.0;
+            const double T = (x0[(size_t)(2 * M + j) * B] + x1[(size_t)(2 * M + j) * B]) / 2.0;
+            const osc2p::Cell cl = osc2p::locate(tab, pr, T);
+            const double re = fabs(tp->ch_dh[j] * v * osc2p::lookup(tab, cl, OSC2_FP_RHO) / osc2p::lookup(tab, cl, OSC2_FP_MU));
+            const int it = osc2p::colebrook_count(re, md->ch_roughness[j], tp->ch_dh[j]);
+            if (it > worst) worst = it;
+        }
+        atomicMax(q.cb_iters + (size_t)j * B + b, worst);
     }
 }
 
@@ -312,7 +438,7 @@ __global__ void __launch_bounds__(128, 6) osc2_opcond_kernel(const osc2_topology
         const double grun = osc2p::lookup(tab, c, OSC2_FP_BETA) / osc2p::lookup(tab, c, OSC2_FP_KAPPA) / cv / rho;
         const double nu = (md->ch_htc_corr[j] == 212) ? osc2p::nusselt_212(re)
                                                       : osc2p::nusselt_1(re, osc2p::lookup(tab, c, OSC2_FP_PRANDTL));
-        const double ftot = ((md->ch_ifriction[j] == 124) ? osc2p::friction_124(re) : 1.0) * md->ch_friction_mult[j];
+        const double ftot = osc2p::friction_total(md, tp, j, re, q.cb_iters[(size_t)j * B + b]);
 #define FGW(qq) fg[((((size_t)(qq) * M + j) * E) + e) * B + b]
         FGW(0) = v; FGW(1) = pr; FGW(2) = T; FGW(3) = rho;
         FGW(4) = osc2p::lookup(tab, c, OSC2_FP_SOUND);
@@ -350,23 +476,21 @@ __global__ void __launch_bounds__(128, 6) osc2_opcond_kernel(const osc2_topology
             tc = osc2p::tc_nb3sn(bg, (eps + eps) / 2.0, md->sol_tc0m[l], md->sol_bc20m[l]);
             tcs = q.tcs ? q.tcs[((size_t)l * E + e) * B + b] : 0.0;
         }
-        const double tmax = q.tmax[(size_t)l * B + b];
+        const double tmax = q.tmax[(size_t)l * B + b], tmin = q.tmin[(size_t)l * B + b];
         double nsum = 0.0, cps = 0.0, ksum = 0.0, rho1 = 0.0, cp1 = 0.0, k1 = 0.0;
         for (int i = 0; i < nmat; ++i) {
             const int mat = md->sol_mat[l][i];
             const double w = md->sol_weight[l][i];
             const double rho_i = osc2p::mat_density(mat);
             double cp_i, k_i;
-            if (mat == OSC2_MAT_CU_NIST) { cp_i = osc2p::cp_cu(T); k_i = osc2p::k_cu(T, bg, md->sol_rrr[l], q.sol_const[2 * l], q.sol_const[2 * l + 1]); }
-            else if (mat == OSC2_MAT_NB3SN) { cp_i = osc2p::cp_nb3sn(T, tcs, tc, md->sol_tc0m[l]); k_i = osc2p::k_nb3sn(T); }
-            else if (mat == OSC2_MAT_SS) { cp_i = osc2p::cp_ss(T, tmax); k_i = osc2p::k_ss(T); }
-            else { cp_i = osc2p::cp_ge(T); k_i = osc2p::k_ge(T); }
+            osc2p::material_cp_k(mat, T, bg, tcs, tc, tmin, tmax, md->sol_rrr[l], md->sol_tc0m[l], q.sol_const[2 * l],
+                                 q.sol_const[2 * l + 1], cp_i, k_i);
             const double num = rho_i * w;
             if (i == 0) { nsum = num; cps = cp_i * num; ksum = k_i * w; rho1 = rho_i; cp1 = cp_i; k1 = k_i; }
             else { nsum = nsum + num; cps = cps + cp_i * num; ksum = ksum + k_i * w; }
         }
         double rho, cp, kk;
-        if (kind == OSC2_SOLID_JACKET && nmat == 1) { rho = rho1; cp = cp1; kk = k1; }
+        if ((kind == OSC2_SOLID_JACKET && nmat == 1) || kind == OSC2_SOLID_STRAND_STAB) { rho = rho1; cp = cp1; kk = k1; }
         else { rho = nsum / md->sol_weight_sum[l]; cp = cps / nsum; kk = ksum / md->sol_weight_sum[l]; }
         sg[(((size_t)0 * S + l) * E + e) * B + b] = rho;
         sg[(((size_t)1 * S + l) * E + e) * B + b] = cp;

@@ -21,7 +21,7 @@ from ._abi import OSC2_N_FLUID_PROPS, Osc2Model, Osc2Sweep, c_dp
 
 # fluid-table property order = the reference's alias table (simulation.py:89-100)
 FP_BETA, FP_KAPPA, FP_PRANDTL, FP_RHO, FP_MU, FP_H, FP_CP, FP_CV, FP_SOUND, FP_K = range(10)
-MAT_CU_NIST, MAT_NB3SN, MAT_SS, MAT_GE = range(4)
+MAT_CU_NIST, MAT_NB3SN, MAT_SS, MAT_GE, MAT_AL, MAT_RE123 = range(6)
 SOLID_STRAND_MIXED, SOLID_STRAND_STAB, SOLID_JACKET = range(3)
 
 
@@ -40,7 +40,7 @@ class SolidModel:
 @dataclass(frozen=True)
 class Model:
     ch_fluid: Tuple[int, ...]
-    ch_ifriction: Tuple[int, ...]           # -99 | 124
+    ch_ifriction: Tuple[int, ...]           # -99 | 122 | 124
     ch_friction_mult: Tuple[float, ...]
     ch_htc_corr: Tuple[int, ...]            # 1 | 212
     solids: Tuple[SolidModel, ...]
@@ -48,6 +48,7 @@ class Model:
     ff: Tuple[Tuple[int, float, float, float], ...] = ()                 # (+ interf_thickness)
     ss: Tuple[Tuple[int, float, float, float, float, float], ...] = ()   # (+ thick_rc, thick_cr, R_contact)
     es_htc: Tuple[float, ...] = ()          # constant convective HTC incl. Phi_conv and multiplier
+    ch_roughness: Tuple[float, ...] = ()    # Channel.inputs["Roughness"], used by IFRICTION 122
 
     def struct(self, topo) -> Osc2Model:
         assert len(self.ch_fluid) == topo.n_ch and len(self.solids) == topo.n_sol
@@ -57,6 +58,7 @@ class Model:
         for j in range(topo.n_ch):
             m.ch_fluid[j], m.ch_ifriction[j] = self.ch_fluid[j], self.ch_ifriction[j]
             m.ch_friction_mult[j], m.ch_htc_corr[j] = self.ch_friction_mult[j], self.ch_htc_corr[j]
+            m.ch_roughness[j] = self.ch_roughness[j] if self.ch_roughness else 0.0
         for l, s in enumerate(self.solids):
             m.sol_kind[l], m.sol_nmat[l] = s.kind, len(s.materials)
             for i, (mat, w) in enumerate(zip(s.materials, s.weights)):
@@ -144,6 +146,20 @@ def case1_model(correlations: bool = False) -> Model:
         ss = ((-1, 500.0, 1.0, 0.0, 0.0, 0.0),)
     return Model(ch_fluid=(0, 0), ch_ifriction=(-99, 124 if correlations else -99), ch_friction_mult=(0.02, 0.02),
                  ch_htc_corr=(1, 212 if correlations else 1), solids=solids, fs=fs, ff=ff, ss=ss, es_htc=(0.0,))
+
+
+def case2_mini_model() -> Model:
+    """Model of `problem.case2_mini_topology`: IFRICTION 122 / 124, Nusselt 1 / 212, Kapitza-limited
+    channel-solid HTCs (choice 2), one conductive and one constant solid-solid contact."""
+    solids = (
+        SolidModel(SOLID_STRAND_STAB, (MAT_AL,), (1.0,), 1.0, heated=True),
+        SolidModel(SOLID_STRAND_STAB, (MAT_CU_NIST,), (1.0,), 1.0, rrr=100.0),
+        SolidModel(SOLID_JACKET, (MAT_SS,), (1.3972e-4,), 1.3972e-4),
+    )
+    return Model(ch_fluid=(0, 0), ch_ifriction=(122, 124), ch_friction_mult=(0.02, 0.02), ch_htc_corr=(1, 212),
+                 ch_roughness=(2.0e-6, 0.0), solids=solids,
+                 fs=((2, 0.0, 1.0), (2, 0.0, 1.0), (2, 0.0, 1.0), (-2, 0.0, 1.0)),
+                 ss=((-1, 2.0e5, 1.0, 0.0, 0.0, 0.0), (1, 0.0, 1.0, 5.0e-4, 1.0e-3, 2.0e-4)), es_htc=(0.0,))
 
 
 def synthetic_helium_table(n_p: int = 65, n_t: int = 129) -> FluidTable:

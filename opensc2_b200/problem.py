@@ -162,6 +162,20 @@ def case3_topology(**kw) -> Topology:
     return replace(t, **kw)
 
 
+def case2_mini_topology(**kw) -> Topology:
+    """A small CASE_2-flavoured conductor (d = 9, generic kernels): two He channels with correlation
+    driven friction (122, 124) and Nusselt (1, 212), an aluminium and a copper stabiliser, a
+    stainless-steel jacket; no channel-channel interface (like CASE_2)."""
+    t = Topology(
+        n_ch=2, n_sol=3,
+        ch_area=(1.963e-5, 6.5e-7), ch_dh=(2.499e-3, 2.9115e-4),
+        ch_forward=(True, True), ch_intial=(3, 3),
+        sol_area=(2.10568e-5, 1.13187e-5, 1.3972e-4), sol_costeta=(1.0, 1.0, 1.0),
+        ff=(), fs=((0, 0), (0, 1), (1, 1), (1, 2)), ss=((0, 1), (1, 2)), es=(2,), es_choice2=(False,),
+    )
+    return replace(t, **kw)
+
+
 def case2_topology(**kw) -> Topology:
     """CASE_2 ENEA HTS CICC: 13 channels, 6 SC + 18 stabiliser + 1 jacket; d = 64.
 

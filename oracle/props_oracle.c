@@ -177,12 +177,65 @@ static double cp_ge(double t)
     return four_term(t, C, s, n);
 }
 
+/* ---- aluminium: properties_of_materials/aluminium.py --------------------------------- */
+/* thermal_conductivity_al, aluminium.py:5-77: all zeros when ANY element of the array is outside
+ * [2, 1000] K (the function prints an error and returns its zero initialisation) */
+static double k_al(double T, double tmin, double tmax)
+{
+    static const double t0[12] = {2., 4., 6., 8., 10., 20., 40., 60., 80., 100., 200., 300.};
+    static const double sl[12] = {4.2345, 4.2000, 4.3650, 4.8550, 4.3430, 3.8805, 2.0375, 0.5360, 0.1145, -0.0452, -0.0291, 0.0};
+    static const double of[12] = {6.6510, 15.1200, 23.5200, 32.2500, 41.9600, 85.3900, 163.000, 203.75, 214.47, 216.76, 212.24, 209.3300};
+    static const double hi[12] = {4., 6., 8., 10., 20., 40., 60., 80., 100., 200., 300., 1000.};
+    if (tmin < 2.0 || tmax > 1000.0) return 0.0;
+    for (int i = 0; i < 12; ++i) {
+        const int in = (i == 0) ? (T >= 2 && T <= hi[0]) : (T > t0[i] && T <= hi[i]);
+        if (in) return (i == 11) ? of[11] : sl[i] * (T - t0[i]) + of[i];
+    }
+    return 0.0;
+}
+/* isobaric_specific_heat_al, aluminium.py:80-164 */
+static double cp_al(double T, double tmin, double tmax)
+{
+    const double T0 = 11.0578562, T1 = 53.2685055, a1 = 0.04257809, a2 = 0.00340313, a3 = 0.00063472;
+    const double b0 = -2.50413265, b1 = 0.71747923, b2 = -0.06270275, b3 = 0.0031683, b4 = -2.0154e-05;
+    static const double C[4] = {11458.0127, -438.603857, 331.057118, -10001.7006};
+    static const double sh[4] = {-7.12302329, -34.6373149, -29.4649313, -3.30673113};
+    static const double n[4] = {0.9531781, 2.00135991, 2.974805, 3.94384164};
+    if (tmin < 2.0 || tmax > 1000.0) return 0.0;
+    if (T >= 2.0 && T <= T0) return a1 * T + a2 * sq(T) + a3 * pow(T, 3.0);
+    if (T > T0 && T <= T1) return b0 + b1 * T + b2 * sq(T) + b3 * pow(T, 3.0) + b4 * pow(T, 4.0);
+    if (T > T1 && T <= 1000.0) return four_term(T, C, sh, n);
+    return 0.0;
+}
+/* ---- RE123: properties_of_materials/rare_earth_123.py ---------------------------------- */
+/* thermal_conductivity_re123, rare_earth_123.py:65-135 */
+static double k_re123(double T)
+{
+    static const double A[2] = {-1.266103106492942e-5, -1.316704893540544e-9}, B[2] = {0.002670105477219, 2.636151594117440e-06};
+    static const double C[2] = {-0.197035302542769, -0.001601689632073}, D[2] = {4.933962659604384, 0.428760641312538};
+    static const double E[2] = {29.651536939501670, -53.306643333287260}, F[2] = {66.578192505447330, 3.682252343338599e03};
+    T = fmin(T, 300.0);
+    T = fmax(T, 4.0);
+    const int i = (T <= 70.0) ? 0 : 1;
+    return A[i] * pow(T, 5.0) + B[i] * pow(T, 4.0) + C[i] * pow(T, 3.0) + D[i] * sq(T) + E[i] * T + F[i];
+}
+/* isobaric_specific_heat_re123, rare_earth_123.py:138-190 */
+static double cp_re123(double T)
+{
+    T = fmin(T, 300.0);
+    T = fmax(T, 4.0);
+    return -7.567485538209158e-10 * pow(T, 5.0) + 6.351452642016898e-07 * pow(T, 4.0) + -1.947975786547597e-04 * pow(T, 3.0)
+           + 0.023616673974415 * sq(T) + 0.239331954284042 * T + -1.096191721280114;
+}
+
 static double mat_density(int mat)   /* density_cu / _nb3sn / _ss / _ge: constants */
 {
     switch (mat) {
     case OSC2_MAT_CU_NIST: return 8900.0;
     case OSC2_MAT_NB3SN: return 8950.0;
     case OSC2_MAT_SS: return 7800.0;
+    case OSC2_MAT_AL: return 2700.0;
+    case OSC2_MAT_RE123: return 6380.0;
     default: return 2000.0;
     }
 }
@@ -197,6 +250,28 @@ static double friction_124(double re)
     if (re > 1e4) f = 2.21 * pow(re, -0.4) / 4.0;
     return fmax(0.0, f);
 }
+/* IFRICTION 122: colebrook_formula channel.py:721-756 started from haaland_equation channel.py:700-717.
+ * The loop runs on the WHOLE array until err.max() <= 1e-5 (or 100 iterations), so every element
+ * performs the same, array-wide, number of iterations.  f[] in/out; returns that number. */
+static int colebrook_array(const double *re, double *f, long n, double rough, double dh)
+{
+    for (long i = 0; i < n; ++i)
+        f[i] = pow(-1.8 * log10(pow(rough / dh / 3.7, 1.11) + (6.9 / re[i])), -2.0) / 4.0;
+    int it = 0;
+    double errmax = 10.0;
+    while (errmax > 1e-5 && it < 100) {
+        errmax = 0.0;
+        for (long i = 0; i < n; ++i) {
+            const double fn = pow(-2.0 * log10((rough / dh / 3.7) + (2.51 / re[i] / sqrt(f[i]))), -2.0) / 4.0;
+            const double err = fabs(f[i] - fn);
+            if (err > errmax || err != err) errmax = err;
+            f[i] = fn;
+        }
+        ++it;
+    }
+    return it;
+}
+
 /* dittus_boelter_nusselt_lower_limit (flag 1), channel.py:1156-1192 */
 static double nusselt_1(double re, double pr)
 {
@@ -211,8 +286,19 @@ static double nusselt_212(double re) { return 0.42 * pow(re, 0.3); }
 
 int osc2o_fit(int which, long n, const double *x, const double *y, const double *z, double p1, double p2, double *out)
 {
-    double tmax = 0.0;
-    if (which == 6) { tmax = x[0]; for (long i = 1; i < n; ++i) if (x[i] > tmax) tmax = x[i]; }
+    double tmax = 0.0, tmin = 0.0;
+    if (which == 6 || which == 13 || which == 14) {
+        tmax = tmin = x[0];
+        for (long i = 1; i < n; ++i) { if (x[i] > tmax) tmax = x[i]; if (x[i] < tmin) tmin = x[i]; }
+    }
+    if (which == 17) {   /* Colebrook on the whole array: x = Reynolds (made positive like _quantities_initialization), p1 = roughness, p2 = Dh */
+        double *re = malloc(sizeof(double) * (size_t)n);
+        for (long i = 0; i < n; ++i) re[i] = fabs(x[i]);
+        colebrook_array(re, out, n, p1, p2);
+        for (long i = 0; i < n; ++i) out[i] = fmax(0.0, out[i]);
+        free(re);
+        return 0;
+    }
     for (long i = 0; i < n; ++i) {
         switch (which) {
         case 0: out[i] = k_cu(x[i], y[i], p1); break;
@@ -228,6 +314,10 @@ int osc2o_fit(int which, long n, const double *x, const double *y, const double 
         case 10: out[i] = nusselt_1(x[i], y[i]); break;
         case 11: out[i] = nusselt_212(x[i]); break;
         case 12: out[i] = rhoecu(x[i], y[i], p1); break;
+        case 13: out[i] = k_al(x[i], tmin, tmax); break;
+        case 14: out[i] = cp_al(x[i], tmin, tmax); break;
+        case 15: out[i] = k_re123(x[i]); break;
+        case 16: out[i] = cp_re123(x[i]); break;
         default: return -1;
         }
     }
@@ -292,6 +382,7 @@ static void one_conductor(const osc2_topology *tp, const osc2_model *md, osc2o_o
     double *ts = malloc(sizeof(double) * 2 * (size_t)(S > 0 ? S : 1) * E);
     double *ks = ts + (size_t)S * E;
 
+    double *rey = malloc(sizeof(double) * 2 * (size_t)E);
     for (int j = 0; j < M; ++j) {
         const osc2o_fluid_table *tab = &io->fluid[md->ch_fluid[j]];
         for (int e = 0; e < E; ++e) {
@@ -307,8 +398,9 @@ static void one_conductor(const osc2_topology *tp, const osc2_model *md, osc2o_o
             /* channel.py:1256-1273 */
             const double nu = (md->ch_htc_corr[j] == 212) ? nusselt_212(re) : nusselt_1(re, f[OSC2_FP_PRANDTL]);
             const double hsteady = nu * f[OSC2_FP_K] / tp->ch_dh[j];
-            /* channel.py:1119-1138 */
+            /* channel.py:1119-1138 (IFRICTION 122 is array-wide: filled in after this loop) */
             const double ftot = ((md->ch_ifriction[j] == 124) ? friction_124(re) : 1.0) * md->ch_friction_mult[j];
+            rey[e] = re;
             fg[((size_t)0 * M + j) * E + e] = v;
             fg[((size_t)1 * M + j) * E + e] = p;
             fg[((size_t)2 * M + j) * E + e] = T;
@@ -323,6 +415,10 @@ static void one_conductor(const osc2_topology *tp, const osc2_model *md, osc2o_o
             kf[(size_t)j * E + e] = f[OSC2_FP_K];
             rf[(size_t)j * E + e] = f[OSC2_FP_RHO];
             cpf[(size_t)j * E + e] = f[OSC2_FP_CP];
+        }
+        if (md->ch_ifriction[j] == 122) {      /* total = max(laminar = 0, turbulent) * multiplier */
+            colebrook_array(rey, rey + E, E, md->ch_roughness[j], tp->ch_dh[j]);
+            for (int e = 0; e < E; ++e) fg[((size_t)8 * M + j) * E + e] = fmax(0.0, rey[E + e]) * md->ch_friction_mult[j];
         }
         /* nodal values the boundary conditions look at (fluid_component.py:255-565) */
         fn[0 * M + j] = x[j];
@@ -340,8 +436,11 @@ static void one_conductor(const osc2_topology *tp, const osc2_model *md, osc2o_o
         const int nmat = md->sol_nmat[l];
         /* conductor.py:4732-4744 */
         for (int e = 0; e < E; ++e) ts[(size_t)l * E + e] = fabs(x[(size_t)e * d + is] + x[(size_t)(e + 1) * d + is]) / 2.0;
-        double tmax = ts[(size_t)l * E];
-        for (int e = 1; e < E; ++e) if (ts[(size_t)l * E + e] > tmax) tmax = ts[(size_t)l * E + e];
+        double tmax = ts[(size_t)l * E], tmin = ts[(size_t)l * E];
+        for (int e = 1; e < E; ++e) {
+            if (ts[(size_t)l * E + e] > tmax) tmax = ts[(size_t)l * E + e];
+            if (ts[(size_t)l * E + e] < tmin) tmin = ts[(size_t)l * E + e];
+        }
         for (int e = 0; e < E; ++e) {
             const double T = ts[(size_t)l * E + e];
             /* solid_component.py:383-408 */
@@ -360,12 +459,15 @@ static void one_conductor(const osc2_topology *tp, const osc2_model *md, osc2o_o
                 case OSC2_MAT_CU_NIST: cp_i[i] = cp_cu(T); k_i[i] = k_cu(T, bg, md->sol_rrr[l]); break;
                 case OSC2_MAT_NB3SN: cp_i[i] = cp_nb3sn(T, tcs, tc, md->sol_tc0m[l]); k_i[i] = k_nb3sn(T); break;
                 case OSC2_MAT_SS: cp_i[i] = cp_ss(T, tmax); k_i[i] = k_ss(T); break;
+                case OSC2_MAT_AL: cp_i[i] = cp_al(T, tmin, tmax); k_i[i] = k_al(T, tmin, tmax); break;
+                case OSC2_MAT_RE123: cp_i[i] = cp_re123(T); k_i[i] = k_re123(T); break;
                 default: cp_i[i] = cp_ge(T); k_i[i] = k_ge(T); break;
                 }
             }
             double rho, cp, kk;
-            if (md->sol_kind[l] == OSC2_SOLID_JACKET && nmat == 1) {
-                /* jacket_component.py:376-377, 414-415, 437-438 */
+            if ((md->sol_kind[l] == OSC2_SOLID_JACKET && nmat == 1) || md->sol_kind[l] == OSC2_SOLID_STRAND_STAB) {
+                /* jacket_component.py:376-377, 414-415, 437-438; strand_stabilizer_component.py:156-198:
+                 * single-material components return the fit itself */
                 rho = rho_i[0]; cp = cp_i[0]; kk = k_i[0];
             } else {
                 /* strand_mixed_component.py:415-514 / jacket_component.py:358-440:
@@ -462,6 +564,7 @@ static void one_conductor(const osc2_topology *tp, const osc2_model *md, osc2o_o
         }
     free(tf);
     free(ts);
+    free(rey);
 }
 
 static void *worker(void *arg)

@@ -29,9 +29,9 @@ sys.path.insert(0, HERE)
 
 import ref_harness as H  # noqa: E402
 from opensc2_b200.model import (FP_BETA, FP_CP, FP_CV, FP_H, FP_K, FP_KAPPA, FP_MU, FP_PRANDTL, FP_RHO, FP_SOUND,  # noqa: E402
-                                case1_model, consistent_initial_state, heat_window, synthetic_helium_table,
+                                case1_model, case2_mini_model, consistent_initial_state, heat_window, synthetic_helium_table,
                                 synthetic_sweep, table_lookup)
-from opensc2_b200.problem import case1_topology  # noqa: E402
+from opensc2_b200.problem import case1_topology, case2_mini_topology  # noqa: E402
 
 ALIAS_TO_PROP = {"isobaric_expansion_coefficient": FP_BETA, "isothermal_compressibility": FP_KAPPA,
                  "Prandtl": FP_PRANDTL, "Dmass": FP_RHO, "viscosity": FP_MU, "Hmass": FP_H, "Cpmass": FP_CP,
@@ -46,6 +46,7 @@ def reference_operating_conditions(topo, model, tab, sweep, sysvar, n_nodes, tim
     from coolant import Coolant
     from jacket_component import JacketComponent
     from strand_mixed_component import StrandMixedComponent
+    from strand_stabilizer_component import StrandStabilizerComponent
 
     def props_si(alias, _t, temperature, _p, pressure, _fluid):
         return table_lookup(tab, ALIAS_TO_PROP[alias], pressure, temperature)
@@ -83,7 +84,8 @@ def reference_operating_conditions(topo, model, tab, sweep, sysvar, n_nodes, tim
         ch = object.__new__(Channel)
         ch.inputs = {"HYDIAMETER": topo.ch_dh[j], "IFRICTION": model.ch_ifriction[j],
                      "FRICTION_MULTIPLIER": model.ch_friction_mult[j], "Flag_htc_steady_corr": model.ch_htc_corr[j],
-                     "Roughness": 0.0, "Side": 1e-3, "Base": 1e-3, "Height": 1e-3}
+                     "Roughness": model.ch_roughness[j] if model.ch_roughness else 0.0, "Side": 1e-3, "Base": 1e-3,
+                     "Height": 1e-3}
         kv = [("laminar", None), ("turbulent", None), ("total", 0.0)]
         ch.dict_friction_factor = {None: dict(kv), True: dict(kv), False: dict(kv)}
         ch.dict_htc_steady, ch.dict_nusselt = {True: None, False: None}, {True: None, False: None}
@@ -92,6 +94,10 @@ def reference_operating_conditions(topo, model, tab, sweep, sysvar, n_nodes, tim
             ch.turbulent_friction_factor_correlation = ch.user_defined_turbulent_friction_factor
             ch.laminar_friction_factor_correlation = ch.user_defined_laminar_friction_factor
             ch.total_friction_factor_correlation = ch.user_defined_friction_factor
+        elif model.ch_ifriction[j] == 122:
+            ch.turbulent_friction_factor_correlation = ch.colebrook_formula
+            ch.laminar_friction_factor_correlation = ch.colebrook_formula
+            ch.total_friction_factor_correlation = ch._eval_total_friction_factor_max
         else:
             ch.turbulent_friction_factor_correlation = ch.rectangular_duct_enea_hts_cicc_trubulent_flow_hole
             ch.laminar_friction_factor_correlation = ch.rectangular_duct_enea_hts_cicc_trubulent_flow_hole
@@ -103,7 +109,7 @@ def reference_operating_conditions(topo, model, tab, sweep, sysvar, n_nodes, tim
 
     solids = []
     names = {0: "STR_MIX", 1: "STR_STAB", 2: "Z_JACKET"}
-    mat_name = {0: "Cu", 1: "Nb3Sn", 2: "ss", 3: "ge"}
+    mat_name = {0: "Cu", 1: "Nb3Sn", 2: "ss", 3: "ge", 4: "Al"}
     for l, sm in enumerate(model.solids):
         if sm.kind == 0:
             s = object.__new__(StrandMixedComponent)
@@ -112,6 +118,10 @@ def reference_operating_conditions(topo, model, tab, sweep, sysvar, n_nodes, tim
                         "Bc20m": sm.bc20m, "c0": 1.21508e11, "CROSSECTION": topo.sol_area[l], "COSTETA": topo.sol_costeta[l]}
             s._StrandMixedComponent__reorganize_input()
             s._StrandMixedComponent__strand_density_flag = False
+        elif sm.kind == 1:
+            s = object.__new__(StrandStabilizerComponent)
+            s.inputs = {"stabilizer_material": mat_name[sm.materials[0]].lower(), "RRR": sm.rrr,
+                        "CROSSECTION": topo.sol_area[l], "COSTETA": topo.sol_costeta[l]}
         else:
             s = object.__new__(JacketComponent)
             s.inputs = {"jacket_material": mat_name[sm.materials[0]],
@@ -232,24 +242,28 @@ def reference_operating_conditions(topo, model, tab, sweep, sysvar, n_nodes, tim
 
 def main():
     assert H.reference_available()
-    topo = case1_topology(1)
     tab = synthetic_helium_table()
     n, batch = 41, 3
-    for tag, corr, time in (("const_t12", False, 12.0), ("corr_t12", True, 12.0), ("corr_t5", True, 5.0)):
-        model = case1_model(corr)
+    for tag, corr, time in (("const_t12", False, 12.0), ("corr_t12", True, 12.0), ("corr_t5", True, 5.0),
+                            ("mini2_t12", None, 12.0)):
+        topo = case1_topology(1) if corr is not None else case2_mini_topology()
+        model = case1_model(corr) if corr is not None else case2_mini_model()
         arr = consistent_initial_state(topo, model, tab, n, batch, seed=3)
         # a warmer, non-uniform state so that every branch of the fits is exercised
         rng = np.random.default_rng(7)
         sv = arr.sysvar.reshape(batch, n, topo.ndf)
-        sv[:, :, 4:] += rng.uniform(0.0, 1.0, (batch, 1, 4)) * np.exp(-((np.linspace(0, 1, n) - 0.2) / 0.1) ** 2)[None, :, None] * 6.0
-        sv[2, :, 7] += 20.0                                   # conductor 2: warm jacket (third SS cp branch)
+        sv[:, :, 2 * topo.n_ch:] += rng.uniform(0.0, 1.0, (batch, 1, topo.ndf - 2 * topo.n_ch)) * np.exp(-((np.linspace(0, 1, n) - 0.2) / 0.1) ** 2)[None, :, None] * 6.0
+        sv[2, :, topo.ndf - 1] += 20.0                        # conductor 2: warm jacket (third SS cp branch)
         sweep = synthetic_sweep(topo, model, n, batch, seed=3)
-        payload = {"sysvar": arr.sysvar, "time": np.array(time), "n_nodes": np.array(n), "correlations": np.array(corr),
+        # (an aluminium solid below 2 K cannot be exercised here: the reference's eval_properties raises in
+        # electrical_resistivity_al, aluminium.py:286, before the zero branch of k/cp could matter)
+        payload = {"sysvar": arr.sysvar, "time": np.array(time), "n_nodes": np.array(n),
+                   "correlations": np.array(-1 if corr is None else int(corr)),
                    "b_field": sweep.b_field, "eps": sweep.eps, "q0": sweep.q0, "q_window": sweep.q_window, "tcs": sweep.tcs}
         outs = [reference_operating_conditions(topo, model, tab, sweep, arr.sysvar, n, time, b=b) for b in range(batch)]
         for key in outs[0]:
             payload["out_" + key] = np.stack([o[key] for o in outs])
-        path = os.path.join(HERE, f"opcond_case1_{tag}.npz")
+        path = os.path.join(HERE, f"opcond_{'case1' if corr is not None else 'case2'}_{tag}.npz")
         np.savez_compressed(path, **payload)
         print(tag, os.path.getsize(path) // 1024, "KiB")
 

@@ -91,6 +91,32 @@ def main():
     ch.eval_steady_state_htc(prop, nodal=True)      # the call of conductor.py:4842-4844: nn stays 0.3
     out["htc_212"] = ch.dict_htc_steady[True].copy()
     out["hydiameter"] = np.array(ch.inputs["HYDIAMETER"])
+    # IFRICTION 122: Colebrook started from Haaland, array-wide convergence (channel.py:700-756); the
+    # laminar slot calls the same function (channel.py:109-112), total = max(0, turbulent) * multiplier
+    for name in ("haaland_equation", "colebrook_formula"):
+        setattr(ch, name, types.MethodType(getattr(Channel, name), ch))
+    ch.inputs["Roughness"] = 2.0e-6
+    ch.laminar_friction_factor_correlation = ch.colebrook_formula
+    ch.turbulent_friction_factor_correlation = ch.colebrook_formula
+    ch.total_friction_factor_correlation = ch._eval_total_friction_factor_max
+    ch.dict_friction_factor = {True: {"laminar": None, "turbulent": None, "total": 0.0}}
+    ch.eval_friction_factor(re.copy(), nodal=True)
+    out["f122_total"] = ch.dict_friction_factor[True]["total"]
+    out["roughness"] = np.array(ch.inputs["Roughness"])
+    # aluminium (whole-array range check) and RE123
+    from properties_of_materials.aluminium import isobaric_specific_heat_al, thermal_conductivity_al
+    from properties_of_materials.rare_earth_123 import isobaric_specific_heat_re123, thermal_conductivity_re123
+    t_al = np.concatenate([rng.uniform(2.0, 12.0, 150), rng.uniform(12.0, 60.0, 150), rng.uniform(60.0, 1000.0, 100),
+                           [2.0, 4.0, 6.0, 11.0578562, 53.2685055, 300.0, 1000.0]])
+    out["t_al"] = t_al
+    out["k_al"], out["cp_al"] = thermal_conductivity_al(t_al), isobaric_specific_heat_al(t_al)
+    t_al_bad = t_al.copy()
+    t_al_bad[5] = 1.5                      # one element below 2 K: the reference returns zeros for the WHOLE array
+    out["t_al_bad"] = t_al_bad
+    out["k_al_bad"], out["cp_al_bad"] = thermal_conductivity_al(t_al_bad), isobaric_specific_heat_al(t_al_bad)
+    t_re = np.concatenate([rng.uniform(2.0, 70.0, 200), rng.uniform(70.0, 350.0, 200)])
+    out["t_re"] = t_re
+    out["k_re123"], out["cp_re123"] = thermal_conductivity_re123(t_re), isobaric_specific_heat_re123(t_re)
     path = os.path.join(HERE, "props_fits.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path) // 1024, "KiB")

@@ -135,7 +135,7 @@ def test_model_validation_rejects_unimplemented_flags():
     from opensc2_b200.batch import BatchedStep
 
     topo = case1_topology(1)
-    bad = dataclasses.replace(case1_model(), ch_ifriction=(-99, 122))
+    bad = dataclasses.replace(case1_model(), ch_ifriction=(-99, 110))   # Blasius-only law: not on the device yet
     with BatchedStep(topo, 2, 9) as bs:
         with pytest.raises(ValueError):
             bs.set_model(bad, [synthetic_helium_table()])
@@ -169,3 +169,49 @@ def test_fused_advance_is_bit_identical_to_separate_kernels(correlations, batch,
     for key, v in results["0"].items():
         assert_bits(results["1"][key], v, key)
     assert np.all(results["1"]["status"] == 0)
+
+
+def test_case2_flavoured_model_colebrook_aluminium_generic_kernels():
+    """d = 9 (generic shared-memory kernels): IFRICTION 122 with its array-wide iteration count,
+    124, Nusselt 1 / 212, aluminium + copper stabilisers, SS jacket, Kapitza-limited HTCs.
+    K_P vs oracle, then three chained steps with per-step tolerance."""
+    from opensc2_b200.batch import BatchedStep
+    from opensc2_b200.model import case2_mini_model
+    from opensc2_b200.problem import case2_mini_topology
+    from oracle import oracle as O
+
+    n, batch, dt = 33, 6, 0.05
+    topo, model, tab = case2_mini_topology(), case2_mini_model(), synthetic_helium_table()
+    arr = consistent_initial_state(topo, model, tab, n, batch, seed=4, dt=dt, length=3.0)
+    sweep = synthetic_sweep(topo, model, n, batch, seed=4, length=3.0, with_tcs=False)
+    host = arr.copy()
+    d, M = topo.ndf, topo.n_ch
+    with BatchedStep(topo, batch, n) as bs:
+        bs.set_model(model, [tab])
+        bs.upload_sweep(sweep)
+        bs.upload_state(arr.sysvar, arr.syslod)
+        bs.upload_geometry(arr)
+        bs.eval_operating_conditions(12.0)
+        bs.synchronize()
+        out = bs.download_step_inputs()
+        ref = O.operating_conditions(topo, model, [tab], sweep, arr.sysvar, n, 12.0)
+        for key in ("fl_gauss", "sol_gauss", "htc_fs", "htc_ss", "htc_es", "fl_node", "sol_q"):
+            assert rel(out[key], ref[key]) <= RTOL_FIT, f"{key}: {rel(out[key], ref[key]):.3e}"
+        assert np.ptp(ref["fl_gauss"][:, 8, 0]) > 0          # Colebrook friction really varies
+        worst_v = worst_pt = 0.0
+        for k in range(1, 4):
+            t = 11.9 + k * dt
+            bs.advance(t, dt, k)
+            bs.synchronize()
+            sv, sl, st = bs.download_state()
+            assert np.all(st == 0)
+            ref_in = O.operating_conditions(topo, model, [tab], sweep, host.sysvar, n, t)
+            for key, v in ref_in.items():
+                setattr(host, key, v)
+            host.num_step, host.dt = k, dt
+            r = O.step(topo, host)
+            a, b = sv.reshape(batch, n, d), r["sysvar"].reshape(batch, n, d)
+            worst_v = max(worst_v, rel_field(a[..., :M], b[..., :M]))
+            worst_pt = max(worst_pt, rel_field(a[..., M:], b[..., M:]))
+            host.sysvar, host.syslod = sv, sl
+    assert worst_v <= RTOL_CHAIN_V and worst_pt <= RTOL_CHAIN, (worst_v, worst_pt)

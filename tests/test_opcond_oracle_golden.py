@@ -12,18 +12,19 @@ import numpy as np
 import pytest
 
 from helpers import GOLDEN_DIR, assert_bits
-from opensc2_b200.model import Sweep, case1_model, synthetic_helium_table
-from opensc2_b200.problem import case1_topology
+from opensc2_b200.model import Sweep, case1_model, case2_mini_model, synthetic_helium_table
+from opensc2_b200.problem import case1_topology, case2_mini_topology
 from oracle import oracle as O
 
 RTOL = 2e-12
 
 
-@pytest.mark.parametrize("tag", ["const_t12", "corr_t12", "corr_t5"])
+@pytest.mark.parametrize("tag", ["const_t12", "corr_t12", "corr_t5", "mini2_t12"])
 def test_operating_conditions_oracle_matches_reference(tag):
-    z = np.load(os.path.join(GOLDEN_DIR, f"opcond_case1_{tag}.npz"))
-    topo = case1_topology(1)
-    model = case1_model(bool(z["correlations"]))
+    mini = tag.startswith("mini2")
+    z = np.load(os.path.join(GOLDEN_DIR, f"opcond_{'case2' if mini else 'case1'}_{tag}.npz"))
+    topo = case2_mini_topology() if mini else case1_topology(1)
+    model = case2_mini_model() if mini else case1_model(bool(z["correlations"]))
     tab = synthetic_helium_table()
     sweep = Sweep(b_field=z["b_field"], eps=z["eps"], q0=z["q0"], q_window=z["q_window"], tcs=z["tcs"])
     out = O.operating_conditions(topo, model, [tab], sweep, z["sysvar"], int(z["n_nodes"]), float(z["time"]))
@@ -36,6 +37,8 @@ def test_operating_conditions_oracle_matches_reference(tag):
     assert_bits(out["htc_es"], z["out_htc_es"], "htc_es")
     for key in ("fl_gauss", "sol_gauss", "htc_ff", "htc_fs", "htc_ss"):
         a, b = out[key], z["out_" + key]
+        if a.size == 0:
+            continue
         err = np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300))
         assert err <= RTOL, f"{key}: {err:.3e}"
     if tag == "const_t12":
@@ -43,4 +46,4 @@ def test_operating_conditions_oracle_matches_reference(tag):
             assert_bits(out[key], z["out_" + key], key)
     # the fixtures exercise what they claim to
     assert (z["out_sol_q"].max() > 0) == (float(z["time"]) == 12.0)
-    assert np.ptp(z["out_sol_gauss"][:, 1, 1]) > 0
+    assert np.ptp(z["out_sol_gauss"][:, 1, -1]) > 0

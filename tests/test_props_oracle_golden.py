@@ -64,3 +64,17 @@ def test_channel_correlations(g):
     dh = float(g["hydiameter"])
     close(O.fit("nusselt_1", g["re"], g["pr"]) * g["kf"] / dh, g["htc_1"], "htc corr 1")
     close(O.fit("nusselt_212", g["re"]) * g["kf"] / dh, g["htc_212"], "htc corr 212")
+
+
+def test_aluminium_whole_array_range_check_and_re123(g):
+    close(O.fit("k_al", g["t_al"]), g["k_al"], "k_al")
+    close(O.fit("cp_al", g["t_al"]), g["cp_al"], "cp_al")
+    assert np.all(g["k_al_bad"] == 0.0) and np.all(g["cp_al_bad"] == 0.0)        # what the reference does
+    assert np.all(O.fit("k_al", g["t_al_bad"]) == 0.0) and np.all(O.fit("cp_al", g["t_al_bad"]) == 0.0)
+    close(O.fit("k_re123", g["t_re"]), g["k_re123"], "k_re123")
+    close(O.fit("cp_re123", g["t_re"]), g["cp_re123"], "cp_re123")
+
+
+def test_colebrook_array_wide_iteration(g):
+    out = O.fit("friction_122", g["re"], p1=float(g["roughness"]), p2=float(g["hydiameter"])) * 0.02
+    close(out, g["f122_total"], "friction 122")
