@@ -555,12 +555,22 @@ __global__ void osc2_forward_fast_kernel(const osc2_topology *__restrict__ tp, S
 }
 
 // ---------------------------------------------------------------------------
-// K_B2
+// K_B2: back substitution (gbacsb, tsf:772-802), node N-1 down to 0.  Every lane keeps the
+// solved unknowns of the current and of the next node in registers; a freshly solved x travels
+// to the other lanes of its conductor by warp shuffle, so the serial chain of a node
+// (the subtractions of one row must follow the reference's column order) carries no
+// shared-memory round trip.  All lanes run the same arithmetic on their own factor row; only
+// lane rr's quotient of turn rr is kept.
 // ---------------------------------------------------------------------------
+#ifdef OSC2_EMU
+inline double osc2_bcast(double v, int src_lane) { return emu_shfl(v, src_lane); }
+#else
+__device__ __forceinline__ double osc2_bcast(double v, int src_lane) { return __shfl_sync(0xffffffffu, v, src_lane); }
+#endif
+
 template <int D, int LPC>
 __global__ void osc2_backward_fast_kernel(StepDev p)
 {
-    OSC2_DYN_SMEM(sm_dyn);
     const int N = p.N;
     const size_t B = (size_t)p.B;
     const int cpb = blockDim.x / LPC;
@@ -568,18 +578,22 @@ __global__ void osc2_backward_fast_kernel(StepDev p)
     const long long b_ll = (long long)blockIdx.x * cpb + grp;
     const bool act = (b_ll < (long long)p.B) && (r < D);
     const size_t b = act ? (size_t)b_ll : 0;
-    double *xcur = sm_dyn + (size_t)grp * (2 * D + 2);    // [D]
-    double *xnxt = xcur + D;                              // [D]
+    const int lane0 = (threadIdx.x & 31) - r;            // first lane of this conductor's group
 
     constexpr int W = 2 * D + 2;      // D' | U | rhs | 1/pivot
     int range_flag = 0;
-    double f[W], fn[W];
+    double f[W], fn[W], xc[D], xn[D];
 #pragma unroll
     for (int c = 0; c < W; ++c) { f[c] = 0.0; fn[c] = 0.0; }
+#pragma unroll
+    for (int c = 0; c < D; ++c) { xc[c] = 0.0; xn[c] = 0.0; }
     if (act) {
         const double *sp = p.spill + (((size_t)(N - 1) * D + r) * W) * B + b;
 #pragma unroll
         for (int c = 0; c < W; ++c) fn[c] = sp[(size_t)c * B];
+    } else {
+        fn[r < D ? r : 0] = 1.0;      // idle lanes divide by 1
+        fn[2 * D + 1] = 1.0;
     }
     for (int n = N - 1; n >= 0; --n) {
 #pragma unroll
@@ -593,25 +607,25 @@ __global__ void osc2_backward_fast_kernel(StepDev p)
         double pu[D];
         const bool hasU = n < N - 1;
 #pragma unroll
-        for (int c = 0; c < D; ++c) pu[c] = hasU ? f[D + c] * xnxt[c] : 0.0;
+        for (int c = 0; c < D; ++c) pu[c] = hasU ? f[D + c] * xn[c] : 0.0;
+        double mine = 0.0;
 #pragma unroll
         for (int rr = D - 1; rr >= 0; --rr) {
-            if (act && r == rr) {
-                double q = f[2 * D];
+            double q = f[2 * D];
 #pragma unroll
-                for (int c = rr + 1; c < D; ++c) q = q - f[c] * xcur[c];
-                if (hasU) {
+            for (int c = rr + 1; c < D; ++c) q = q - f[c] * xc[c];
+            if (hasU) {
 #pragma unroll
-                    for (int c = 0; c < D; ++c) q = q - pu[c];
-                }
-                const double x = osc2_div_flag(q, osc2_rcp_make(f[rr], f[2 * D + 1]), range_flag);
-                xcur[rr] = x;
-                p.sysvar_new[((size_t)n * D + r) * B + b] = x;
+                for (int c = 0; c < D; ++c) q = q - pu[c];
             }
-            __syncwarp();
+            int flag = 0;
+            const double x = osc2_div_flag(q, osc2_rcp_make(f[rr], f[2 * D + 1]), flag);
+            if (r == rr) { mine = x; range_flag |= flag; }
+            xc[rr] = osc2_bcast(x, lane0 + rr);
         }
-        if (act) xnxt[r] = xcur[r];
-        __syncwarp();
+        if (act) p.sysvar_new[((size_t)n * D + r) * B + b] = mine;
+#pragma unroll
+        for (int c = 0; c < D; ++c) xn[c] = xc[c];
     }
     if (act && range_flag && p.status[b] == 0) p.status[b] = OSC2_STATUS_RANGE;
 }

@@ -32,6 +32,16 @@ inline thread_local std::barrier<> *emu_block_barrier = nullptr;
 inline thread_local std::barrier<> *emu_warp_barrier = nullptr;
 inline thread_local std::vector<std::unique_ptr<std::barrier<>>> *emu_named = nullptr;
 inline std::barrier<> *emu_named_barrier(int id) { return (*emu_named)[id].get(); }
+inline thread_local double *emu_shfl_scratch = nullptr;   // [32] per warp
+// __shfl_sync over the full warp: publish, read the source lane, and keep the slot until all have read
+inline double emu_shfl(double v, int src_lane)
+{
+    emu_shfl_scratch[threadIdx.x % 32] = v;
+    emu_warp_barrier->arrive_and_wait();
+    const double out = emu_shfl_scratch[src_lane];
+    emu_warp_barrier->arrive_and_wait();
+    return out;
+}
 
 #define OSC2_DYN_SMEM(name) double *name = emu_dyn_smem
 
@@ -58,6 +68,7 @@ struct EmuLauncher {
                 const unsigned lanes = (w + 1) * 32 <= block ? 32 : block - w * 32;
                 wb.emplace_back(new std::barrier<>((std::ptrdiff_t)lanes));
             }
+            std::vector<double> shfl((size_t)nwarps * 32, 0.0);
             std::vector<std::unique_ptr<std::barrier<>>> named;     // bar.sync / bar.arrive ids 0..15, all CTA-wide
             for (int i = 0; i < 16; ++i) named.emplace_back(new std::barrier<>((std::ptrdiff_t)block));
             // poison shared memory so that reads of unwritten slots show up
@@ -71,6 +82,7 @@ struct EmuLauncher {
                     emu_block_barrier = &bb;
                     emu_warp_barrier = wb[t / 32].get();
                     emu_named = &named;
+                    emu_shfl_scratch = shfl.data() + (size_t)(t / 32) * 32;
                     kernel(args...);
                     // a thread that returns early must not block the others
                     bb.arrive_and_drop();
