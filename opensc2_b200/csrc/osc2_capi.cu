@@ -61,7 +61,7 @@ struct osc2_context {
     bool fast = false;               // register-resident kernels (step_kernels_fast.cuh)
     bool fused_opcond = false;       // K_P + K_G in one kernel (opcond_gauss_fused.cuh), experimental
     int fused_warps = 2;             // warps per CTA of the fused kernel
-    bool fwd_split = false;          // K_F as two specialised warps (step_kernels_split.cuh), experimental
+    int fwd_mode = 0;                // K_F variant, see StepDev::fwd_split
     int max_smem = 0, sm_count = 0;
     std::vector<EventPair> pending, pool;
     double kernel_ms[OSC2_K_COUNT] = {0};
@@ -301,7 +301,8 @@ int osc2_create(const osc2_topology *topo, int batch, int n_nodes, int device, o
     { const char *fo = getenv("OSC2_FUSED_OPCOND"); h->fused_opcond = (fo && fo[0] == '1'); }
     { const char *fw = getenv("OSC2_FUSED_WARPS"); if (fw && atoi(fw) >= 1 && atoi(fw) <= 4) h->fused_warps = atoi(fw); }
     // experimental: slower than the single-warp sweep today, off unless OSC2_FWD_SPLIT=1
-    { const char *sp = getenv("OSC2_FWD_SPLIT"); h->fwd_split = (sp && sp[0] == '1'); }
+    { const char *sp = getenv("OSC2_FWD_SPLIT"); h->fwd_mode = (sp && sp[0] == '1') ? 1 : 0; }
+    { const char *sp = getenv("OSC2_FWD_MODE"); if (sp && sp[0] >= '0' && sp[0] <= '2') h->fwd_mode = sp[0] - '0'; }
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     h->max_smem = (int)prop.sharedMemPerBlockOptin;
@@ -316,7 +317,7 @@ int osc2_create(const osc2_topology *topo, int batch, int n_nodes, int device, o
     const size_t B = batch, E = h->E, N = h->N, M = h->M, S = h->S, d = h->d;
     StepDev &p = h->p;
     memset(&p, 0, sizeof p);
-    p.fwd_split = h->fwd_split ? 1 : 0;
+    p.fwd_split = h->fwd_mode;
     p.B = batch; p.N = h->N; p.E = h->E; p.M = h->M; p.S = h->S; p.d = h->d; p.NS = h->NS;
     p.nff = topo->nff; p.nfs = topo->nfs; p.nss = topo->nss; p.nes = topo->nes;
     struct { const double **dst; size_t k; } ins[] = {

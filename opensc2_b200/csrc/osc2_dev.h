@@ -51,7 +51,8 @@ struct StepDev {
     const int *norm_prog;     // [n_prog]       >= 0: push leaf, -1: add the two on top
     double *norm_part;        // [n_leaves][3][d][B]
     int n_leaves, n_prog;
-    int fwd_split;            // 1: K_F as assembler + eliminator warps (step_kernels_split.cuh)
+    int fwd_split;            // K_F variant: 0 one warp per 32/LPC conductors, 1 assembler + eliminator warps
+                              // (step_kernels_split.cuh), 2 sixteen lanes per conductor (step_kernels_wide.cuh)
     // K_G: SMAT is staged per thread in shared memory; only the entries the topology can touch get a
     // slot (osc2_build_smap), every other (row, col) maps to one shared all-zero slot
     const unsigned char *smap; // [d*d] -> slot

@@ -11,6 +11,7 @@
 #include "step_kernels.cuh"
 #include "step_kernels_fast.cuh"
 #include "step_kernels_split.cuh"
+#include "step_kernels_wide.cuh"
 
 #include <vector>
 
@@ -125,7 +126,18 @@ void osc2_run_fast_sweeps(Launcher &L, const osc2_topology *tp_dev, const StepDe
     const size_t smem_f = (size_t)FastFwdSmem<D>::PER_COND * cpb * sizeof(double);
     const size_t smem_b = (size_t)(2 * D + 2) * cpb * sizeof(double);
     const bool be = (theta == 1.0), cap = (p.cap_sysmat != nullptr);
-    if (p.fwd_split) {
+    if constexpr (D % 8 == 0) {
+        if (p.fwd_split == 2 && be) {      // 16 lanes per conductor (step_kernels_wide.cuh)
+            constexpr int cpw = 32 / (2 * D);
+            const unsigned gridw = (unsigned)((p.B + cpw - 1) / cpw);
+            const size_t smem_w = (size_t)WideFwdSmem<D>::PER_COND * cpw * sizeof(double);
+            if (!cap) L.launch(OSC2_K_FORWARD, osc2_forward_wide_kernel<D, false>, gridw, 32u, smem_w, tp_dev, p);
+            else L.launch(OSC2_K_FORWARD, osc2_forward_wide_kernel<D, true>, gridw, 32u, smem_w, tp_dev, p);
+            L.launch(OSC2_K_BACKWARD, osc2_backward_fast_kernel<D, LPC>, grid, 32u, smem_b, p);
+            return;
+        }
+    }
+    if (p.fwd_split == 1) {
         const bool closed = be && (D % 8 == 0);
         const size_t smem_s = ((size_t)SplitFwdSmem<D>::per_cond(closed) * cpb + 2 * 32 * 2) * sizeof(double);
         if (be && !cap) L.launch(OSC2_K_FORWARD, osc2_forward_split_kernel<D, LPC, true, false>, grid, 64u, smem_s, tp_dev, p);

@@ -27,7 +27,7 @@ def _batched(arr):
 @pytest.mark.parametrize("name", ["case1_pdrop_n21", "case1_pinl_vout_first_step_n17",
                                   "case1_vinl_pout_cn_refined_n12", "case1_min_mesh_n4",
                                   "case3_backward_n15", "case3_rectangular_env_n9"])
-@pytest.mark.parametrize("fast,split", [(False, False), (True, False), (True, True)])
+@pytest.mark.parametrize("fast,split", [(False, 0), (True, 0), (True, 1), (True, 2)])
 def test_emulated_kernels_match_reference_fixture(name, fast, split):
     topo, arr, ref = load_golden(name)
     out = emu.emu_step(topo, _batched(arr), capture=True, fast=fast, split=split)
