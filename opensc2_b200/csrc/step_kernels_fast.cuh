@@ -506,9 +506,15 @@ __global__ void osc2_forward_fast_kernel(const osc2_topology *__restrict__ tp, S
                 else osc2_rcp_check(my_rcp, range_flag);
             }
             __syncwarp();
-            if (act && r > k) {
+            {
+                // rows above the pivot (and idle lanes) take the multiplier 0: x - p * 0 leaves x unchanged
+                // bit for bit, and ONE select on the multiplier replaces a select per updated entry
                 const double *pk = pub_cur + k * PW;
-                const double q = osc2_div_flag(rowD[k], osc2_rcp_make(pk[k], pk[2 * D + 1]), range_flag);
+                int flag_k = 0;
+                double q = osc2_div_flag(rowD[k], osc2_rcp_make(pk[k], pk[2 * D + 1]), flag_k);
+                const bool on = act && r > k;
+                if (on) range_flag |= flag_k;
+                q = on ? q : 0.0;
 #pragma unroll
                 for (int c = k + 1; c < D; ++c) rowD[c] = rowD[c] - pk[c] * q;
 #pragma unroll

@@ -162,6 +162,29 @@ def case2_mini_model() -> Model:
                  ss=((-1, 2.0e5, 1.0, 0.0, 0.0, 0.0), (1, 0.0, 1.0, 5.0e-4, 1.0e-3, 2.0e-4)), es_htc=(0.0,))
 
 
+def case2_model(topo) -> Model:
+    """CASE_2 ENEA HTS CICC on `problem.case2_topology`: 12 slot channels
+    (IFRICTION 124, Nusselt 212) + the central channel (122, Nusselt 1); 6 tape stacks restated as
+    single-material RE123 solids (the legacy STR_SC class is absent from HEAD, Appendix B), 18 aluminium
+    stabilisers, one SS jacket; channel-solid HTCs by correlation (choice 2) except channel-jacket
+    (-2, 0 W/m^2K); solid-solid contacts constant (-1)."""
+    M, nsc, nst = 13, 6, 18
+    S = nsc + nst + 1
+    jk = S - 1
+    solids = tuple([SolidModel(SOLID_STRAND_STAB, (MAT_RE123,), (1.0,), 1.0, heated=(l == 0)) for l in range(nsc)]
+                   + [SolidModel(SOLID_STRAND_STAB, (MAT_AL,), (1.0,), 1.0) for _ in range(nst)]
+                   + [SolidModel(SOLID_JACKET, (MAT_SS,), (1.3972e-4,), 1.3972e-4)])
+    fs = tuple((-2, 0.0, 1.0) if l == jk else (2, 0.0, 1.0) for (_j, l) in topo.fs)
+    def ss_const(a, b):
+        if b == jk:
+            return 0.0 if a < nsc else 1140.0
+        return 32750.0 if a < nsc else 2.0e5
+    ss = tuple((-1, ss_const(a, b), 1.0, 0.0, 0.0, 0.0) for (a, b) in topo.ss)
+    return Model(ch_fluid=(0,) * M, ch_ifriction=(124,) * 12 + (122,), ch_friction_mult=(0.02,) * M,
+                 ch_htc_corr=(212,) * 12 + (1,), ch_roughness=(0.0,) * 12 + (2.0e-6,), solids=solids,
+                 fs=fs, ff=(), ss=ss, es_htc=(0.0,))
+
+
 def synthetic_helium_table(n_p: int = 65, n_t: int = 129) -> FluidTable:
     """Smooth stand-in for supercritical helium near 4.5 K / 6 bar (CoolProp is absent here;
     magnitudes follow SURVEY.md Appendix A).  NOT physical data: benchmarks and parity tests

@@ -215,3 +215,78 @@ def test_case2_flavoured_model_colebrook_aluminium_generic_kernels():
             worst_pt = max(worst_pt, rel_field(a[..., M:], b[..., M:]))
             host.sysvar, host.syslod = sv, sl
     assert worst_v <= RTOL_CHAIN_V and worst_pt <= RTOL_CHAIN, (worst_v, worst_pt)
+
+
+def test_case2_topology_full_step_on_generic_kernels():
+    """CASE_2-sized system (d = 64: 13 channels, 6 RE123 + 18 Al solids, SS jacket, 97 interfaces; one
+    conductor per 64-lane CTA): device-side operating conditions + step vs the oracle."""
+    from opensc2_b200.batch import BatchedStep
+    from opensc2_b200.model import case2_model
+    from opensc2_b200.problem import case2_topology
+    from oracle import oracle as O
+
+    n, batch, dt = 9, 3, 0.05
+    topo = case2_topology()
+    model, tab = case2_model(topo), synthetic_helium_table()
+    arr = consistent_initial_state(topo, model, tab, n, batch, seed=8, dt=dt, length=3.0)
+    sweep = synthetic_sweep(topo, model, n, batch, seed=8, length=3.0, with_tcs=False)
+    host = arr.copy()
+    d, M = topo.ndf, topo.n_ch
+    with BatchedStep(topo, batch, n) as bs:
+        bs.set_model(model, [tab])
+        bs.upload_sweep(sweep)
+        bs.upload_state(arr.sysvar, arr.syslod)
+        bs.upload_geometry(arr)
+        bs.set_capture(True)
+        for k in range(1, 3):
+            t = 11.95 + k * dt
+            bs.advance(t, dt, k)
+            bs.synchronize()
+            ins = bs.download_step_inputs()
+            sv, sl, st = bs.download_state()
+            assert np.all(st == 0)
+            ref_in = O.operating_conditions(topo, model, [tab], sweep, host.sysvar, n, t)
+            for key in ins:
+                assert rel(ins[key], ref_in[key]) <= RTOL_FIT, f"{key}: {rel(ins[key], ref_in[key]):.3e}"
+            for key, v in ref_in.items():
+                setattr(host, key, v)
+            host.num_step, host.dt = k, dt
+            r = O.step(topo, host)
+            assert np.all(r["status"] == 0)
+            a, b = sv.reshape(batch, n, d), r["sysvar"].reshape(batch, n, d)
+            assert rel_field(a[..., :M], b[..., :M]) <= RTOL_CHAIN_V
+            assert rel_field(a[..., M:], b[..., M:]) <= RTOL_CHAIN
+            host.sysvar, host.syslod = sv, sl
+
+
+def test_full_size_mesh_batch_order_invariance():
+    """BASELINE mesh size (10 001 nodes) through a size-independent property: a conductor's result does
+    not depend on its slot in the batch or on its neighbours -- K_P + step on a batch and on its
+    reversal agree bit for bit, slot by slot (also covers a ragged last tile: 37 conductors)."""
+    from opensc2_b200.batch import BatchedStep
+
+    n, batch, dt = 10001, 37, 0.1
+    topo, model, tab, _a, sweep = _setup(True, 17, batch, seed=31)
+    arr = consistent_initial_state(topo, model, tab, n, batch, seed=31, dt=dt)
+    sweep = synthetic_sweep(topo, model, n, batch, seed=31)
+    outs = []
+    for order in (np.arange(batch), np.arange(batch)[::-1]):
+        import dataclasses
+        sub = type(arr)(**{f.name: (getattr(arr, f.name)[order] if isinstance(getattr(arr, f.name), np.ndarray) else getattr(arr, f.name))
+                           for f in dataclasses.fields(arr)})
+        sw = type(sweep)(**{f.name: (getattr(sweep, f.name)[order] if getattr(sweep, f.name) is not None else None)
+                            for f in dataclasses.fields(sweep)})
+        with BatchedStep(topo, batch, n) as bs:
+            bs.set_model(model, [tab])
+            bs.upload_sweep(sw)
+            bs.upload_state(sub.sysvar, sub.syslod)
+            bs.upload_geometry(sub)
+            for k in range(1, 3):
+                bs.advance(9.9 + k * dt, dt, k)
+            bs.synchronize()
+            sv, _sl, st = bs.download_state(want_syslod=False)
+            diag = bs.download_diagnostics(want_k123=False)
+        assert np.all(st == 0) and np.all(np.isfinite(sv))
+        outs.append((sv[np.argsort(order)], diag["norm_change"][np.argsort(order)]))
+    assert_bits(outs[0][0], outs[1][0], "state")
+    assert_bits(outs[0][1], outs[1][1], "norm_change")
