@@ -287,6 +287,7 @@ int osc2_create(const osc2_topology *topo, int batch, int n_nodes, int device, o
     if (device < 0 || device >= ndev) return fail(OSC2_ERR_INVALID, "device %d of %d", device, ndev);
     CK(cudaSetDevice(device));
     osc2_context *h = new osc2_context();
+    struct Guard { osc2_context *h; ~Guard() { if (h) osc2_destroy(h); } } guard{h};   // frees everything on any early return
     h->device = device;
     h->topo = *topo;
     h->B = batch; h->N = n_nodes; h->E = n_nodes - 1;
@@ -332,7 +333,7 @@ int osc2_create(const osc2_topology *topo, int batch, int n_nodes, int device, o
     for (auto &in : ins) {
         double *q = nullptr;
         rc = dev_alloc(h, &q, in.k * B);
-        if (rc) { osc2_destroy(h); return rc; }
+        if (rc) return rc;
         *in.dst = q;
         if (in.k > kmax) kmax = in.k;
     }
@@ -378,12 +379,13 @@ int osc2_create(const osc2_topology *topo, int batch, int n_nodes, int device, o
     }
     h->staging_doubles = kmax * B;
     if (!rc) rc = dev_alloc(h, &h->staging, h->staging_doubles);
-    if (rc) { osc2_destroy(h); return rc; }
+    if (rc) return rc;
     p.sysvar = h->sysvar_a;
     p.sysvar_new = h->sysvar_b;
     cudaMemsetAsync(p.status, 0, sizeof(int) * B, h->stream);
     cudaMemsetAsync(p.syslod, 0, h->total * 2 * B * sizeof(double), h->stream);
     CK(cudaStreamSynchronize(h->stream));
+    guard.h = nullptr;
     *out = h;
     return OSC2_OK;
 }
@@ -536,10 +538,13 @@ int osc2_set_fluid_table(osc2_handle h, int fluid, int n_p, int n_t, double p_mi
     if (fluid < 0 || fluid >= OSC2_MAX_FLUIDS) return fail(OSC2_ERR_INVALID, "fluid index %d", fluid);
     if (n_p < 2 || n_t < 2 || !(p_step > 0.0) || !(t_step > 0.0)) return fail(OSC2_ERR_INVALID, "table needs >= 2 x 2 points and positive steps");
     CK(cudaSetDevice(h->device));
-    double *dev = nullptr;
     const size_t n = (size_t)OSC2_N_FLUID_PROPS * n_p * n_t;
-    int rc = dev_alloc(h, &dev, n);
-    if (rc) return rc;
+    FluidTableDev &old = h->q.fluid[fluid];
+    double *dev = (h->have_table[fluid] && old.n_p == n_p && old.n_t == n_t) ? const_cast<double *>(old.props) : nullptr;
+    if (!dev) {
+        int rc = dev_alloc(h, &dev, n);
+        if (rc) return rc;
+    }
     CK(cudaMemcpy(dev, props, n * sizeof(double), cudaMemcpyHostToDevice));
     FluidTableDev &t = h->q.fluid[fluid];
     t.n_p = n_p; t.n_t = n_t; t.p_min = p_min; t.p_step = p_step; t.t_min = t_min; t.t_step = t_step; t.props = dev;

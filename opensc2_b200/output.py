@@ -1,0 +1,115 @@
+"""`.tsv` writers on the far side of the path: drop-in for the reference's `save_properties`
+(/root/reference/source_code/utility_functions/output.py:8-92) fed from batched device state.
+
+One file per component, one row per node, `%.18e`, the column layout of HEAD:
+  channels  zcoord, pressure, temperature, total_density, velocity, the ten coolant properties in the
+            order of the alias table (simulation.py:89-100), Reynolds, Gruneisen, mass_flow_rate,
+            friction_factor
+  strands   zcoord, temperature, B_field [, T_cur_sharing for components holding a superconductor]
+  jackets   zcoord, temperature
+Host-side post-processing (numpy): nothing here is on the time-step path.  Nodal coolant properties use
+the same bilinear table lookup as the device (`model.table_lookup`)."""
+from __future__ import annotations
+
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+from .model import (FP_BETA, FP_CP, FP_CV, FP_H, FP_K, FP_KAPPA, FP_MU, FP_PRANDTL, FP_RHO, FP_SOUND, SOLID_JACKET,
+                    SOLID_STRAND_MIXED, FluidTable, Model, table_lookup)
+from .problem import Topology
+
+CHAN_COLUMNS = (
+    ("zcoord", "(m)"), ("pressure", "(Pa)"), ("temperature", "(K)"), ("total_density", "(kg/m^3)"),
+    ("velocity", "(m/s)"), ("isobaric_expansion_coefficient", "(1/K)"), ("isothermal_compressibility", "(1/Pa)"),
+    ("Prandtl", "(~)"), ("total_dynamic_viscosity", "(Pa*s)"), ("total_enthalpy", "(J/kg)"),
+    ("total_isobaric_specific_heat", "(J/kg/K)"), ("total_isochoric_specific_heat", "(J/kg/K)"),
+    ("total_speed_of_sound", "(m/s)"), ("total_thermal_conductivity", "(W/m/K)"), ("Reynolds", "(~)"),
+    ("Gruneisen", "(~)"), ("mass_flow_rate", "(kg/s)"), ("friction_factor", "(~)"),
+)
+_ALIAS_ORDER = (FP_BETA, FP_KAPPA, FP_PRANDTL, FP_MU, FP_H, FP_CP, FP_CV, FP_SOUND, FP_K)
+
+
+def nodal_friction_factor(model: Model, topo: Topology, j: int, reynolds: np.ndarray) -> np.ndarray:
+    """`Channel.eval_friction_factor(reynolds, nodal=True)` (channel.py:1119-1138) for the flags on the device."""
+    re = np.fabs(reynolds)
+    flag = model.ch_ifriction[j]
+    if flag == -99:
+        total = np.ones(re.shape)
+    elif flag == 124:
+        f = np.array((0.316 * re ** -0.25) / 4.0)
+        f[re > 1e4] = 2.21 * re[re > 1e4] ** (-0.4) / 4.0
+        total = np.maximum(np.zeros(re.shape), f)
+    elif flag == 122:
+        rough, dh = (model.ch_roughness[j] if model.ch_roughness else 0.0), topo.ch_dh[j]
+        f = ((-1.8 * np.log10((rough / dh / 3.7) ** 1.11 + (6.9 / re))) ** -2) / 4.0
+        err, it = 10.0 * np.ones(re.shape), 0
+        while err.max() > 1e-5 and it < 100:
+            fn = ((-2.0 * np.log10((rough / dh / 3.7) + (2.51 / re / np.sqrt(f)))) ** -2) / 4.0
+            err, f, it = abs(f - fn), fn, it + 1
+        total = np.maximum(np.zeros(re.shape), f)
+    else:
+        raise ValueError(f"IFRICTION {flag} is not implemented")
+    return total * model.ch_friction_mult[j]
+
+
+def channel_table(topo: Topology, model: Model, tab: FluidTable, j: int, zcoord, v, p, t) -> np.ndarray:
+    """(N, 18) array of one channel's file."""
+    rho = table_lookup(tab, FP_RHO, p, t)
+    cols = [zcoord, p, t, rho, v] + [table_lookup(tab, q, p, t) for q in _ALIAS_ORDER]
+    mu, beta, kappa, cv = cols[8], cols[5], cols[6], cols[11]
+    reynolds = np.abs(topo.ch_dh[j] * v * rho / mu)                   # coolant.py:165-180
+    grun = beta / kappa / cv / rho
+    mdot = topo.ch_area[j] * v * rho                                   # coolant.py:247-263
+    cols += [reynolds, grun, mdot, nodal_friction_factor(model, topo, j, reynolds)]
+    return np.stack(cols, axis=1)
+
+
+def save_properties(f_path: str, topo: Topology, model: Model, tables: Sequence[FluidTable], zcoord: np.ndarray,
+                    sysvar: np.ndarray, b_field: np.ndarray, t_cur_sharing: Optional[np.ndarray] = None,
+                    chan_ids: Optional[Sequence[str]] = None, solid_ids: Optional[Sequence[str]] = None) -> None:
+    """Write `<identifier>.tsv` for every component of ONE conductor.
+
+    sysvar: (N*d,) state; b_field: (S, 2) BISS, BOSS; t_cur_sharing: (S, N) nodal current sharing
+    temperature of the superconducting strands (rows of other solids are ignored)."""
+    M, S, d = topo.n_ch, topo.n_sol, topo.ndf
+    N = zcoord.shape[0]
+    x = np.asarray(sysvar, dtype=np.float64).reshape(N, d)
+    chan_ids = chan_ids or [f"CHAN_{j + 1}" for j in range(M)]
+    if solid_ids is None:
+        names = {SOLID_STRAND_MIXED: "STR_MIX", SOLID_JACKET: "Z_JACKET"}
+        count, solid_ids = {}, []
+        for s in model.solids:
+            nm = names.get(s.kind, "STR_STAB")
+            count[nm] = count.get(nm, 0) + 1
+            solid_ids.append(f"{nm}_{count[nm]}")
+    os.makedirs(f_path, exist_ok=True)
+    header_chan = "\t".join(f"{n} {u}" for n, u in CHAN_COLUMNS)
+    for j in range(M):
+        a = channel_table(topo, model, tables[model.ch_fluid[j]], j, zcoord, x[:, j].copy(), x[:, M + j].copy(),
+                          x[:, 2 * M + j].copy())
+        with open(os.path.join(f_path, f"{chan_ids[j]}.tsv"), "w") as w:
+            np.savetxt(w, a, delimiter="\t", header=header_chan, comments="")
+    for l, s in enumerate(model.solids):
+        temp = x[:, 3 * M + l]
+        if s.kind == SOLID_JACKET:
+            a, header = np.stack([zcoord, temp], axis=1), "zcoord (m)\ttemperature (K)"
+        else:
+            bf = np.linspace(b_field[l, 0], b_field[l, 1], N)             # solid_component.py:383-388
+            if s.kind == SOLID_STRAND_MIXED:
+                tcs = np.zeros(N) if t_cur_sharing is None else t_cur_sharing[l]
+                a = np.stack([zcoord, temp, bf, tcs], axis=1)
+                header = "zcoord (m)\ttemperature (K)\tB_field (T)\tT_cur_sharing (K)"
+            else:
+                a, header = np.stack([zcoord, temp, bf], axis=1), "zcoord (m)\ttemperature (K)\tB_field (T)"
+        with open(os.path.join(f_path, f"{solid_ids[l]}.tsv"), "w") as w:
+            np.savetxt(w, a, delimiter="\t", header=header, comments="")
+
+
+def save_properties_batch(root: str, topo: Topology, model: Model, tables, zcoord, sysvar, sweep,
+                          conductors: Optional[Sequence[int]] = None, t_cur_sharing=None) -> None:
+    """`save_properties` for slots of a batch: `<root>/conductor_<b>/...`; sysvar: (B, N*d)."""
+    for b in (range(sysvar.shape[0]) if conductors is None else conductors):
+        save_properties(os.path.join(root, f"conductor_{b}"), topo, model, tables, zcoord, sysvar[b], sweep.b_field[b],
+                        None if t_cur_sharing is None else t_cur_sharing[b])
