@@ -86,6 +86,8 @@ typedef struct {
     const double *htc_es;     /* [B][nes][3][E]    conv (or side), bottom, top */
     const double *qsource;    /* [B][N][S]         step() argument */
     double t_env;             /* environment.inputs["Temperature"] */
+    const double *peri_ss_nodal; /* [B][nss][N]    dict_interf_peri["sol_sol"]["nodal"]: only read for radiative
+                                                   interfaces (|HTC_choice| == 3), may be NULL otherwise */
 } osc2_step_inputs;
 
 /* ---- Operating conditions at the Gauss points (what the reference evaluates every
@@ -127,11 +129,17 @@ typedef struct {
     double fs_htc[OSC2_MAX_INTERFACES], fs_mlt[OSC2_MAX_INTERFACES];
     int ff_choice[OSC2_MAX_INTERFACES];         /* 2 or -2 */
     double ff_htc[OSC2_MAX_INTERFACES], ff_mlt[OSC2_MAX_INTERFACES], ff_thick[OSC2_MAX_INTERFACES];
-    int ss_choice[OSC2_MAX_INTERFACES];         /* 1 or -1 */
+    int ss_choice[OSC2_MAX_INTERFACES];         /* 1, -1 (conduction) or 3, -3 (radiation between jackets) */
     double ss_htc[OSC2_MAX_INTERFACES], ss_mlt[OSC2_MAX_INTERFACES];
     double ss_thick_rc[OSC2_MAX_INTERFACES], ss_thick_cr[OSC2_MAX_INTERFACES], ss_rcontact[OSC2_MAX_INTERFACES];
     double es_htc[OSC2_MAX_INTERFACES];         /* constant convective HTC (choices -2, -4), Phi_conv and multiplier applied */
     double ch_roughness[OSC2_MAX_CHANNELS];     /* Channel.inputs["Roughness"] (IFRICTION 122) */
+    /* radiative exchange between two jackets, HTC_choice 3 (conductor.py:5161-5219, 5428-5443): the
+     * temperature-independent denominator (1-e_i)/e_i + 1/F + (1-e_j)/e_j * (P_out,i / P_in,j) with i the
+     * inner jacket (inf when an emissivity or the view factor is 0), and the multiplier the reference
+     * applies in its second branch only (1 otherwise) */
+    double ss_rad_den[OSC2_MAX_INTERFACES];
+    double ss_rad_mlt[OSC2_MAX_INTERFACES];
 } osc2_model;
 
 /* Swept per-conductor scalars, batch leading. */

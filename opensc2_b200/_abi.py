@@ -50,7 +50,8 @@ class Osc2Topology(C.Structure):
 class Osc2StepInputs(C.Structure):
     _fields_ = [(n, c_dp) for n in (
         "dz", "fl_gauss", "fl_node", "fl_bc", "sol_gauss", "sol_q", "peri_ff", "htc_ff",
-        "peri_fs", "htc_fs", "peri_ss", "htc_ss", "peri_es", "htc_es", "qsource")] + [("t_env", C.c_double)]
+        "peri_fs", "htc_fs", "peri_ss", "htc_ss", "peri_es", "htc_es", "qsource")] + [("t_env", C.c_double),
+                                                                                        ("peri_ss_nodal", c_dp)]
 
 
 OSC2_MAX_MATERIALS = 5
@@ -76,6 +77,7 @@ class Osc2Model(C.Structure):
         ("ss_thick_rc", C.c_double * _IF), ("ss_thick_cr", C.c_double * _IF), ("ss_rcontact", C.c_double * _IF),
         ("es_htc", C.c_double * _IF),
         ("ch_roughness", C.c_double * _CH),
+        ("ss_rad_den", C.c_double * _IF), ("ss_rad_mlt", C.c_double * _IF),
     ]
 
 
@@ -83,7 +85,7 @@ class Osc2Sweep(C.Structure):
     _fields_ = [(n, c_dp) for n in ("b_field", "eps", "q0", "q_window", "tcs")]
 
 
-STEP_INPUT_FIELDS = tuple(n for n, _ in Osc2StepInputs._fields_[:-1])
+STEP_INPUT_FIELDS = tuple(n for n, _ in Osc2StepInputs._fields_[:-2])
 
 
 def topology_struct(topo) -> Osc2Topology:

@@ -91,8 +91,11 @@ class BatchedStep:
         """Only what K_P does not compute: dz, contact perimeters, qsource, boundary values."""
         s = Osc2StepInputs()
         keep = []
-        for name in ("dz", "fl_bc", "peri_ff", "peri_fs", "peri_ss", "peri_es", "qsource"):
-            a = as_f64(getattr(arr, name))
+        for name in ("dz", "fl_bc", "peri_ff", "peri_fs", "peri_ss", "peri_es", "qsource", "peri_ss_nodal"):
+            v = getattr(arr, name)
+            if v is None:
+                continue
+            a = as_f64(v)
             keep.append(a)
             setattr(s, name, dptr(a) if a.size else None)
         s.t_env = self._t_env = float(arr.t_env)

@@ -194,7 +194,9 @@ __global__ void __launch_bounds__(128, 6) osc2_opcond_gauss_kernel(const osc2_to
         } else if (item < p.nfs + p.nff + p.nss) {
             const int k = item - p.nfs - p.nff;
             double h;
-            if (md->ss_choice[k] == 1) {
+            if (md->ss_choice[k] == 3 || md->ss_choice[k] == -3) {
+                h = 0.0;
+            } else if (md->ss_choice[k] == 1) {
                 const double rr = md->ss_thick_rc[k] / IN(sl.sg(2, tp->ss[k][0]));
                 const double rc = md->ss_thick_cr[k] / IN(sl.sg(2, tp->ss[k][1]));
                 h = md->ss_mlt[k] * (1.0 / (rr + md->ss_rcontact[k] + rc));
@@ -207,6 +209,24 @@ __global__ void __launch_bounds__(128, 6) osc2_opcond_gauss_kernel(const osc2_to
             IN(sl.hes(k, 0)) = md->es_htc[k];
             IN(sl.hes(k, 1)) = 0.0;
             IN(sl.hes(k, 2)) = 0.0;
+        }
+    }
+    __syncthreads();
+    // radiative exchange between jackets: one warp walks the interfaces in order (two interfaces may feed
+    // the same solid's source), see osc2_opcond_kernel
+    if (w == 0) {
+        for (int k = 0; k < p.nss; ++k) {
+            const int ch = md->ss_choice[k];
+            if (ch != 3 && ch != -3) continue;
+            const int a = tp->ss[k][0], c = tp->ss[k][1];
+            for (int side = 0; side < 2; ++side) {
+                const double *xn = side ? x1 : x0;
+                const double Ta = xn[(size_t)(3 * M + a) * B], Tc = xn[(size_t)(3 * M + c) * B];
+                const double hr = osc2p::radiative_htc(md, k, Ta, Tc);
+                const double ph = p.peri_ss_nodal[((size_t)k * N + (e + side)) * B + b] * hr;
+                IN(sl.sq(side, a, 0)) += ph * (Tc - Ta);
+                IN(sl.sq(side, c, 0)) += ph * (Ta - Tc);
+            }
         }
     }
     __syncthreads();

@@ -328,6 +328,7 @@ int osc2_create(const osc2_topology *topo, int batch, int n_nodes, int device, o
         {&p.peri_fs, (size_t)p.nfs * E}, {&p.htc_fs, (size_t)p.nfs * E},
         {&p.peri_ss, (size_t)p.nss * E}, {&p.htc_ss, (size_t)p.nss * E},
         {&p.peri_es, (size_t)p.nes * E}, {&p.htc_es, (size_t)p.nes * 3 * E}, {&p.qsource, N * S},
+        {&p.peri_ss_nodal, (size_t)p.nss * N},
     };
     size_t kmax = h->total * 2;   // syslod
     for (auto &in : ins) {
@@ -434,6 +435,10 @@ int osc2_upload_step_inputs(osc2_handle h, const osc2_step_inputs *in)
         {in->peri_es, p.peri_es, (size_t)p.nes * E, "peri_es"}, {in->htc_es, p.htc_es, (size_t)p.nes * 3 * E, "htc_es"},
         {in->qsource, p.qsource, N * S, "qsource"},
     };
+    if (in->peri_ss_nodal && p.nss > 0) {
+        int rc = upload_transposed(h, in->peri_ss_nodal, (double *)p.peri_ss_nodal, (size_t)p.nss * N);
+        if (rc) return rc;
+    }
     for (auto &x : a) {
         if (x.k == 0) continue;
         if (!x.src && h->have_model) continue;   // computed on the device by osc2_eval_operating_conditions
@@ -476,8 +481,8 @@ int osc2_set_model(osc2_handle h, const osc2_model *model)
         if (model->ff_choice[k] != 2 && model->ff_choice[k] != -2)
             return fail(OSC2_ERR_INVALID, "channel-channel interface %d: HTC_choice %d is not implemented on the device (2, -2)", k, model->ff_choice[k]);
     for (int k = 0; k < h->p.nss; ++k)
-        if (model->ss_choice[k] != 1 && model->ss_choice[k] != -1)
-            return fail(OSC2_ERR_INVALID, "solid-solid interface %d: HTC_choice %d is not implemented on the device (1, -1)", k, model->ss_choice[k]);
+        if (model->ss_choice[k] != 1 && model->ss_choice[k] != -1 && model->ss_choice[k] != 3 && model->ss_choice[k] != -3)
+            return fail(OSC2_ERR_INVALID, "solid-solid interface %d: HTC_choice %d is not implemented on the device (1, -1, 3, -3)", k, model->ss_choice[k]);
     if (!h->model_dev) CK(cudaMalloc((void **)&h->model_dev, sizeof(osc2_model)));
     CK(cudaMemcpy(h->model_dev, model, sizeof(osc2_model), cudaMemcpyHostToDevice));
     if (!h->have_model) {

@@ -33,6 +33,7 @@ struct StepDev {
     const double *peri_es;            // [nes][E]
     const double *htc_es;             // [nes][3][E]
     const double *qsource;            // [N][S]
+    const double *peri_ss_nodal;      // [nss][N]  nodal contact perimeters (radiative interfaces)
     // state
     const double *sysvar;     // [N][d]   old solution
     double *sysvar_new;       // [N][d]   new solution

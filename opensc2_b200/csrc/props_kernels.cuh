@@ -292,6 +292,15 @@ __device__ inline double friction_total(const osc2_model *md, const osc2_topolog
     }
     return f * md->ch_friction_mult[j];
 }
+// HTC["sol_sol"]["rad"] of interface k at one node: choice 3 = _inner_radiative_htc (conductor.py:5428-5443,
+// symmetric in the two temperatures; the denominator is prepared on the host), -3 = constant
+__device__ inline double radiative_htc(const osc2_model *md, int k, double Ta, double Tc)
+{
+    if (md->ss_choice[k] == -3) return md->ss_htc[k] * md->ss_mlt[k];
+    const double den = md->ss_rad_den[k];
+    if (!(den < 1.0e300)) return 0.0;          // an emissivity or the view factor is 0: the reference leaves zeros
+    return 5.670374419e-08 * (sq(Ta) + sq(Tc)) * (Ta + Tc) / den * md->ss_rad_mlt[k];
+}
 // cp and k of one constituent material at a Gauss point
 __device__ inline void material_cp_k(int mat, double T, double bg, double tcs, double tc, double tmin, double tmax,
                                      double rrr, double tc0m, double p7, double rho273, double &cp, double &k)
@@ -513,6 +522,23 @@ __global__ void __launch_bounds__(128, 6) osc2_opcond_kernel(const osc2_topology
         }
     }
 
+    // radiative exchange between jackets (HTC_choice +-3): explicit, evaluated at the two NODES of the element
+    // from the nodal temperatures and added to the heat sources of both solids, interface by interface
+    // (jacket_component.py:174-232, conductor.py:5161-5228, 4558-4579)
+    for (int k = 0; k < p.nss; ++k) {
+        const int ch = md->ss_choice[k];
+        if (ch != 3 && ch != -3) continue;
+        const int a = tp->ss[k][0], c = tp->ss[k][1];
+        for (int side = 0; side < 2; ++side) {
+            const double *xn = side ? x1 : x0;
+            const double Ta = xn[(size_t)(3 * M + a) * B], Tc = xn[(size_t)(3 * M + c) * B];
+            const double h = osc2p::radiative_htc(md, k, Ta, Tc);
+            const double ph = p.peri_ss_nodal[((size_t)k * N + (e + side)) * B + b] * h;
+            sqv[(((((size_t)side * S + a) * E + e) * 2) + 0) * B + b] += ph * (Tc - Ta);
+            sqv[(((((size_t)side * S + c) * E + e) * 2) + 0) * B + b] += ph * (Ta - Tc);
+        }
+    }
+
     // interface heat transfer coefficients
     double *hfs = const_cast<double *>(p.htc_fs);
     for (int k = 0; k < p.nfs; ++k) {
@@ -554,7 +580,9 @@ __global__ void __launch_bounds__(128, 6) osc2_opcond_kernel(const osc2_topology
     double *hss = const_cast<double *>(p.htc_ss);
     for (int k = 0; k < p.nss; ++k) {
         double h;
-        if (md->ss_choice[k] == 1) {
+        if (md->ss_choice[k] == 3 || md->ss_choice[k] == -3) {
+            h = 0.0;                   // HTC["sol_sol"]["cond"] keeps its zero initialisation (conductor.py:5109-5113)
+        } else if (md->ss_choice[k] == 1) {
             const double ka = sg[(((size_t)2 * S + tp->ss[k][0]) * E + e) * B + b];
             const double kb = sg[(((size_t)2 * S + tp->ss[k][1]) * E + e) * B + b];
             const double rr = md->ss_thick_rc[k] / ka;

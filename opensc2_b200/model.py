@@ -49,6 +49,7 @@ class Model:
     ss: Tuple[Tuple[int, float, float, float, float, float], ...] = ()   # (+ thick_rc, thick_cr, R_contact)
     es_htc: Tuple[float, ...] = ()          # constant convective HTC incl. Phi_conv and multiplier
     ch_roughness: Tuple[float, ...] = ()    # Channel.inputs["Roughness"], used by IFRICTION 122
+    ss_rad: Tuple[Tuple[float, float], ...] = ()   # per solid-solid interface: (denominator, multiplier) of choice 3
 
     def struct(self, topo) -> Osc2Model:
         assert len(self.ch_fluid) == topo.n_ch and len(self.solids) == topo.n_sol
@@ -74,6 +75,9 @@ class Model:
             m.ss_thick_rc[k], m.ss_thick_cr[k], m.ss_rcontact[k] = t1, t2, rc
         for k, h in enumerate(self.es_htc):
             m.es_htc[k] = h
+        for k in range(len(self.ss)):
+            den, mlt = self.ss_rad[k] if self.ss_rad else (float("inf"), 1.0)
+            m.ss_rad_den[k], m.ss_rad_mlt[k] = den, mlt
         return m
 
 
@@ -111,6 +115,22 @@ class Sweep:
             keep.append(a)
             setattr(s, name, a.ctypes.data_as(c_dp))
         return s, keep
+
+
+def radiative_pair(emis_r: float, emis_c: float, outer_r: float, inner_r: float, outer_c: float, inner_c: float,
+                   view_factor: float, multiplier: float) -> Tuple[float, float]:
+    """(denominator, multiplier) of the radiative HTC between jackets r < c exactly as the reference resolves
+    it (conductor.py:5161-5219 + _inner_radiative_htc :5428-5443): the inner jacket is the one whose outer
+    perimeter is below the other's inner perimeter; the HTC multiplier is applied in the second branch only."""
+    inf = float("inf")
+    if not (emis_r > 0.0 and emis_c > 0.0 and view_factor > 0.0):
+        return inf, 1.0
+    vf_rec = float(np.reciprocal(view_factor))
+    if outer_r < inner_c:
+        return (1.0 - emis_r) / emis_r + vf_rec + (1.0 - emis_c) / emis_c * (outer_r / inner_c), 1.0
+    if outer_c < inner_r:
+        return (1.0 - emis_c) / emis_c + vf_rec + (1.0 - emis_r) / emis_r * (outer_c / inner_r), multiplier
+    return inf, 1.0
 
 
 def heat_window(zcoord: np.ndarray, xq_beg: float, xq_end: float) -> Tuple[int, int]:
@@ -183,6 +203,28 @@ def case2_model(topo) -> Model:
     return Model(ch_fluid=(0,) * M, ch_ifriction=(124,) * 12 + (122,), ch_friction_mult=(0.02,) * M,
                  ch_htc_corr=(212,) * 12 + (1,), ch_roughness=(0.0,) * 12 + (2.0e-6,), solids=solids,
                  fs=fs, ff=(), ss=ss, es_htc=(0.0,))
+
+
+CASE3_MINI_JACKETS = dict(emissivity=(0.8, 0.8), outer_perimeter=(0.060, 0.110), inner_perimeter=(0.050, 0.090),
+                          view_factor=1.0)
+
+
+def case3_mini_model() -> Model:
+    """Model of `problem.case3_mini_topology`: Kapitza-limited channel-solid HTCs, radiation between jackets 1
+    and 2 (HTC_choice 3, emissivity 0.8, view factor 1), a constant contact (-1, 500 W/m^2K) between jackets
+    2 and 3, constant convection to the environment (-4, 5 W/m^2K)."""
+    solids = (
+        SolidModel(SOLID_STRAND_STAB, (MAT_CU_NIST,), (1.0,), 1.0, rrr=100.0),
+        SolidModel(SOLID_JACKET, (MAT_SS,), (2.0e-4,), 2.0e-4),
+        SolidModel(SOLID_JACKET, (MAT_SS,), (1.5e-4,), 1.5e-4),
+        SolidModel(SOLID_JACKET, (MAT_GE,), (3.0e-4,), 3.0e-4),
+    )
+    j = CASE3_MINI_JACKETS
+    rad = radiative_pair(j["emissivity"][0], j["emissivity"][1], j["outer_perimeter"][0], j["inner_perimeter"][0],
+                         j["outer_perimeter"][1], j["inner_perimeter"][1], j["view_factor"], 1.0)
+    return Model(ch_fluid=(0,), ch_ifriction=(-99,), ch_friction_mult=(0.02,), ch_htc_corr=(1,), solids=solids,
+                 fs=((2, 0.0, 1.0), (2, 0.0, 1.0)), ss=((3, 0.0, 1.0, 0.0, 0.0, 0.0), (-1, 500.0, 1.0, 0.0, 0.0, 0.0)),
+                 ss_rad=(rad, (float("inf"), 1.0)), es_htc=(5.0,))
 
 
 def synthetic_helium_table(n_p: int = 65, n_t: int = 129) -> FluidTable:

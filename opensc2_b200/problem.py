@@ -119,6 +119,7 @@ class StepArrays:
     t_env: float = 300.0      # environment.inputs["Temperature"]
     dt: float = 0.1           # conductor.time_step
     num_step: int = 2         # conductor.cond_num_step
+    peri_ss_nodal: np.ndarray = None   # (nss, N) nodal contact perimeters, radiative interfaces only (optional)
 
     def copy(self) -> "StepArrays":
         kw = {}
@@ -172,6 +173,19 @@ def case2_mini_topology(**kw) -> Topology:
         ch_forward=(True, True), ch_intial=(3, 3),
         sol_area=(2.10568e-5, 1.13187e-5, 1.3972e-4), sol_costeta=(1.0, 1.0, 1.0),
         ff=(), fs=((0, 0), (0, 1), (1, 1), (1, 2)), ss=((0, 1), (1, 2)), es=(2,), es_choice2=(False,),
+    )
+    return replace(t, **kw)
+
+
+def case3_mini_topology(**kw) -> Topology:
+    """A small CASE_3-flavoured conductor (d = 7, generic kernels): one He channel cooling a copper
+    stabiliser and the innermost jacket, a radiative gap between jackets 1 and 2, a contact between
+    jackets 2 and 3, convection to the environment on the outermost one."""
+    t = Topology(
+        n_ch=1, n_sol=4,
+        ch_area=(2.356e-4,), ch_dh=(0.015,), ch_forward=(True,), ch_intial=(3,),
+        sol_area=(1.0e-4, 2.0e-4, 1.5e-4, 3.0e-4), sol_costeta=(1.0,) * 4,
+        ff=(), fs=((0, 0), (0, 1)), ss=((1, 2), (2, 3)), es=(3,), es_choice2=(False,),
     )
     return replace(t, **kw)
 

@@ -192,11 +192,11 @@ class _FluidTab(C.Structure):
 class _OpcondIO(C.Structure):
     _fields_ = [("batch", C.c_int), ("n_nodes", C.c_int), ("time", C.c_double), ("sysvar", c_dp),
                 ("fluid", _FluidTab * 4)] + [(n, c_dp) for n in (
-        "b_field", "eps", "q0", "q_window", "tcs",
+        "b_field", "eps", "q0", "q_window", "tcs", "peri_ss_nodal",
         "fl_gauss", "fl_node", "sol_gauss", "sol_q", "htc_ff", "htc_fs", "htc_ss", "htc_es")]
 
 
-def operating_conditions(topo, model, tables, sweep, sysvar, n_nodes, time, n_threads=1):
+def operating_conditions(topo, model, tables, sweep, sysvar, n_nodes, time, n_threads=1, peri_ss_nodal=None):
     """CPU restatement of what K_P computes.  `sysvar`: (B, N*d); returns the dict of
     step-input arrays (batch leading) that `osc2_download_step_inputs` returns."""
     from opensc2_b200._abi import topology_struct      # struct definitions only (the C header's mirror)
@@ -225,6 +225,11 @@ def operating_conditions(topo, model, tables, sweep, sysvar, n_nodes, time, n_th
         a = np.ascontiguousarray(a, dtype=np.float64)
         keep.append(a)
         setattr(io, name, a.ctypes.data_as(c_dp))
+    io.peri_ss_nodal = None
+    if peri_ss_nodal is not None:
+        pn = np.ascontiguousarray(peri_ss_nodal, dtype=np.float64)
+        keep.append(pn)
+        io.peri_ss_nodal = pn.ctypes.data_as(c_dp)
     out = {"fl_gauss": np.zeros((B, 9, M, E)), "fl_node": np.zeros((B, 4, M)), "sol_gauss": np.zeros((B, 3, S, E)),
            "sol_q": np.zeros((B, 2, S, E, 2)), "htc_ff": np.zeros((B, 2, len(topo.ff), E)),
            "htc_fs": np.zeros((B, len(topo.fs), E)), "htc_ss": np.zeros((B, len(topo.ss), E)),

@@ -502,6 +502,28 @@ static void one_conductor(const osc2_topology *tp, const osc2_model *md, osc2o_o
             }
         }
     }
+    /* radiative exchange between jackets (HTC_choice +-3): nodal HTC (conductor.py:5161-5228 with
+     * _inner_radiative_htc :5428-5443), nodal heat P * h * (T_other - T_self) (jacket_component.py:174-232),
+     * added to Q1 / Q2 of both jackets pair by pair (conductor.py:4558-4579); present column only (the
+     * previous column holds the zero of t = 0) */
+    for (int k = 0; k < tp->nss; ++k) {
+        const int ch = md->ss_choice[k];
+        if (ch != 3 && ch != -3) continue;
+        const int a = tp->ss[k][0], c = tp->ss[k][1];
+        const double *pn = io->peri_ss_nodal + ((size_t)bb * tp->nss + k) * N;
+        for (int e = 0; e < E; ++e)
+            for (int side = 0; side < 2; ++side) {
+                const int node = e + side;
+                const double Ta = x[(size_t)node * d + 3 * M + a], Tc = x[(size_t)node * d + 3 * M + c];
+                double h;
+                if (ch == -3) h = md->ss_htc[k] * md->ss_mlt[k];
+                else if (!(md->ss_rad_den[k] < 1.0e300)) h = 0.0;
+                else h = 5.670374419e-08 * (sq(Ta) + sq(Tc)) * (Ta + Tc) / md->ss_rad_den[k] * md->ss_rad_mlt[k];
+                const double ph = pn[node] * h;
+                sqv[((((size_t)side * S + a) * E + e) * 2) + 0] += ph * (Tc - Ta);
+                sqv[((((size_t)side * S + c) * E + e) * 2) + 0] += ph * (Ta - Tc);
+            }
+    }
     /* interface heat transfer coefficients, conductor.py:4867-5160 */
     for (int k = 0; k < tp->nfs; ++k) {
         const int j = tp->fs[k][0], l = tp->fs[k][1];
@@ -546,7 +568,9 @@ static void one_conductor(const osc2_topology *tp, const osc2_model *md, osc2o_o
         const int la = tp->ss[k][0], lb = tp->ss[k][1];
         for (int e = 0; e < E; ++e) {
             double h;
-            if (md->ss_choice[k] == 1) {
+            if (md->ss_choice[k] == 3 || md->ss_choice[k] == -3) {
+                h = 0.0;      /* "cond" keeps its zero initialisation for radiative pairs */
+            } else if (md->ss_choice[k] == 1) {
                 const double rr = md->ss_thick_rc[k] / ks[(size_t)la * E + e];
                 const double rc = md->ss_thick_cr[k] / ks[(size_t)lb * E + e];
                 h = md->ss_mlt[k] * (1.0 / (rr + md->ss_rcontact[k] + rc));

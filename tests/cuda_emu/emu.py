@@ -16,7 +16,7 @@ class StepDev(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("B", "N", "E", "M", "S", "d", "NS", "nff", "nfs", "nss", "nes")] + [
         ("dt", C.c_double), ("t_env", C.c_double), ("num_step", C.c_int)] + [
         (n, c_dp) for n in ("dz", "fl_gauss", "fl_node", "fl_bc", "sol_gauss", "sol_q", "peri_ff", "htc_ff",
-                            "peri_fs", "htc_fs", "peri_ss", "htc_ss", "peri_es", "htc_es", "qsource",
+                            "peri_fs", "htc_fs", "peri_ss", "htc_ss", "peri_es", "htc_es", "qsource", "peri_ss_nodal",
                             "sysvar", "sysvar_new", "syslod", "gm", "k123", "spill",
                             "norm_solution", "norm_change", "eqteig")] + [
         ("status", c_ip), ("cap_sysmat", c_dp), ("cap_known", c_dp),

@@ -26,7 +26,8 @@ def main():
         ref = H.run_reference_step(topo, arr)
         payload = {}
         for f in dataclasses.fields(arr):
-            payload["in_" + f.name] = np.asarray(getattr(arr, f.name))
+            if getattr(arr, f.name) is not None:
+                payload["in_" + f.name] = np.asarray(getattr(arr, f.name))
         for k, v in ref.items():
             if k in ("sysmat", "known") and name not in WITH_SYSTEM:
                 continue

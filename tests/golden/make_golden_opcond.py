@@ -29,16 +29,16 @@ sys.path.insert(0, HERE)
 
 import ref_harness as H  # noqa: E402
 from opensc2_b200.model import (FP_BETA, FP_CP, FP_CV, FP_H, FP_K, FP_KAPPA, FP_MU, FP_PRANDTL, FP_RHO, FP_SOUND,  # noqa: E402
-                                case1_model, case2_mini_model, consistent_initial_state, heat_window, synthetic_helium_table,
+                                CASE3_MINI_JACKETS, case1_model, case2_mini_model, case3_mini_model, consistent_initial_state, heat_window, synthetic_helium_table,
                                 synthetic_sweep, table_lookup)
-from opensc2_b200.problem import case1_topology, case2_mini_topology  # noqa: E402
+from opensc2_b200.problem import case1_topology, case2_mini_topology, case3_mini_topology  # noqa: E402
 
 ALIAS_TO_PROP = {"isobaric_expansion_coefficient": FP_BETA, "isothermal_compressibility": FP_KAPPA,
                  "Prandtl": FP_PRANDTL, "Dmass": FP_RHO, "viscosity": FP_MU, "Hmass": FP_H, "Cpmass": FP_CP,
                  "Cvmass": FP_CV, "speed_of_sound": FP_SOUND, "conductivity": FP_K}
 
 
-def reference_operating_conditions(topo, model, tab, sweep, sysvar, n_nodes, time, b=0, length=10.0):
+def reference_operating_conditions(topo, model, tab, sweep, sysvar, n_nodes, time, b=0, length=10.0, peri_ss_nodal=None):
     H._import_reference()
     import coolant as coolant_mod
     from channel import Channel
@@ -52,6 +52,11 @@ def reference_operating_conditions(topo, model, tab, sweep, sysvar, n_nodes, tim
         return table_lookup(tab, ALIAS_TO_PROP[alias], pressure, temperature)
 
     coolant_mod.PropsSI = props_si
+    # the reference pins scipy == 1.8.0 (requirements.txt), whose CODATA-2018 table gives
+    # Stefan_Boltzmann = 5.670374419e-08; the scipy of this image derives 5.6703744191844314e-08 from the
+    # exact SI constants.  The device and the oracle use the pinned value, so the generator does too.
+    from scipy import constants as _sc
+    _sc.Stefan_Boltzmann = 5.670374419e-08
     # the reference's alias table (simulation.py:89-100)
     aliases = dict(isobaric_expansion_coefficient="isobaric_expansion_coefficient",
                    isothermal_compressibility="isothermal_compressibility", Prandtl="Prandtl",
@@ -129,7 +134,8 @@ def reference_operating_conditions(topo, model, tab, sweep, sysvar, n_nodes, tim
                         "jacket_cross_section": sm.weights[0],
                         "insulation_cross_section": sm.weights[1] if len(sm.materials) > 1 else 0.0,
                         "NUM_MATERIAL_TYPES": len(sm.materials), "CROSSECTION": topo.sol_area[l],
-                        "COSTETA": topo.sol_costeta[l], "Jacket_kind": "whole_enclosure", "Emissivity": 0.0}
+                        "COSTETA": topo.sol_costeta[l], "Jacket_kind": "whole_enclosure", "Emissivity": 0.0,
+                        "Outer_perimeter": 1.0, "Inner_perimeter": 0.5}
             s._JacketComponent__reorganize_input()
             s._JacketComponent__jacket_density_flag = False
         s.name = names[sm.kind]
@@ -193,6 +199,26 @@ def reference_operating_conditions(topo, model, tab, sweep, sysvar, n_nodes, tim
                              "HTC_multiplier": mlt, "interf_thickness": thick, "thermal_contact_resistance": rcont,
                              "view_factors": view}
     cond.dict_topology = topo_names
+    jackets_all = [s for s in solids if s.name == "Z_JACKET"]
+    has_rad = any(abs(c[0]) == 3 for c in model.ss)
+    if has_rad:
+        jk = CASE3_MINI_JACKETS
+        for i, s in enumerate(jackets_all[:2]):
+            s.inputs.update(Emissivity=jk["emissivity"][i], Outer_perimeter=jk["outer_perimeter"][i],
+                            Inner_perimeter=jk["inner_perimeter"][i])
+        cond.dict_df_coupling["contact_perimeter"] = frame(0.0)
+        for k, (la, lb) in enumerate(topo.ss):
+            if abs(model.ss[k][0]) == 3:
+                view.at[solids[la].identifier, solids[lb].identifier] = jk["view_factor"]
+        cond.dict_interf_peri = {"sol_sol": {"nodal": {
+            f"{solids[la].identifier}_{solids[lb].identifier}": peri_ss_nodal[b, k].copy() for k, (la, lb) in enumerate(topo.ss)}}}
+        for s in jackets_all:                      # conductor.py:2759-2770
+            s.radiative_heat_env = np.zeros((N, 2))
+        for i, jr in enumerate(jackets_all):
+            for jc in jackets_all[i + 1:]:
+                key = f"{jr.identifier}_{jc.identifier}"
+                jr.radiative_heat_inn[key] = np.zeros((N, 2))
+                jc.radiative_heat_inn[key] = np.zeros((N, 2))
 
     # ---- the reference's own sequence (simulation.py:375-405 with no current defined) ----------
     for s in solids:                                     # nodal B field first (operating_conditions_em)
@@ -208,6 +234,17 @@ def reference_operating_conditions(topo, model, tab, sweep, sysvar, n_nodes, tim
     for s in solids:
         if s.operations["IQFUN"] != 0:
             s.get_heat(cond)
+    if has_rad:
+        # nodal pass of the transport coefficients (HTC["sol_sol"]["rad"] lives at the nodes), then the
+        # reference's own radiative exchange (conductor.py:4455-4475)
+        for s in solids:
+            s.eval_sol_comp_properties(cond.inventory)
+        cond.dict_node_pt = Conductor.eval_transp_coeff(cond, sim, cond.dict_node_pt, flag_nodal=True)
+        for i, jr in enumerate(jackets_all):
+            for jc in jackets_all[i + 1:]:
+                if abs(choice.at[jr.identifier, jc.identifier]) == 3:
+                    jr._radiative_heat_exc_inner(cond, jc)
+                    jc._radiative_heat_exc_inner(cond, jr)
     Conductor._Conductor__build_heat_source_gauss_pt(cond)
 
     E = N - 1
@@ -245,25 +282,37 @@ def main():
     tab = synthetic_helium_table()
     n, batch = 41, 3
     for tag, corr, time in (("const_t12", False, 12.0), ("corr_t12", True, 12.0), ("corr_t5", True, 5.0),
-                            ("mini2_t12", None, 12.0)):
-        topo = case1_topology(1) if corr is not None else case2_mini_topology()
-        model = case1_model(corr) if corr is not None else case2_mini_model()
+                            ("mini2_t12", None, 12.0), ("mini3_t12", "rad", 12.0)):
+        if corr == "rad":
+            topo, model = case3_mini_topology(), case3_mini_model()
+        else:
+            topo = case1_topology(1) if corr is not None else case2_mini_topology()
+            model = case1_model(corr) if corr is not None else case2_mini_model()
         arr = consistent_initial_state(topo, model, tab, n, batch, seed=3)
         # a warmer, non-uniform state so that every branch of the fits is exercised
         rng = np.random.default_rng(7)
         sv = arr.sysvar.reshape(batch, n, topo.ndf)
         sv[:, :, 2 * topo.n_ch:] += rng.uniform(0.0, 1.0, (batch, 1, topo.ndf - 2 * topo.n_ch)) * np.exp(-((np.linspace(0, 1, n) - 0.2) / 0.1) ** 2)[None, :, None] * 6.0
         sv[2, :, topo.ndf - 1] += 20.0                        # conductor 2: warm jacket (third SS cp branch)
-        sweep = synthetic_sweep(topo, model, n, batch, seed=3)
+        sweep = synthetic_sweep(topo, model, n, batch, seed=3, with_tcs=any(sm.kind == 0 for sm in model.solids))
+        pn = None
+        if corr == "rad":
+            sv[:, :, topo.ndf - 3:] += np.array([10.0, 40.0, 60.0])[None, None, :]      # a temperature ladder across the jackets
+            pn = rng.uniform(0.05, 0.06, (batch, len(topo.ss), 1)) * np.ones(n)
         # (an aluminium solid below 2 K cannot be exercised here: the reference's eval_properties raises in
         # electrical_resistivity_al, aluminium.py:286, before the zero branch of k/cp could matter)
         payload = {"sysvar": arr.sysvar, "time": np.array(time), "n_nodes": np.array(n),
-                   "correlations": np.array(-1 if corr is None else int(corr)),
-                   "b_field": sweep.b_field, "eps": sweep.eps, "q0": sweep.q0, "q_window": sweep.q_window, "tcs": sweep.tcs}
-        outs = [reference_operating_conditions(topo, model, tab, sweep, arr.sysvar, n, time, b=b) for b in range(batch)]
+                   "correlations": np.array(-1 if corr in (None, "rad") else int(corr)),
+                   "b_field": sweep.b_field, "eps": sweep.eps, "q0": sweep.q0, "q_window": sweep.q_window}
+        if sweep.tcs is not None:
+            payload["tcs"] = sweep.tcs
+        if pn is not None:
+            payload["peri_ss_nodal"] = pn
+        outs = [reference_operating_conditions(topo, model, tab, sweep, arr.sysvar, n, time, b=b, peri_ss_nodal=pn)
+                for b in range(batch)]
         for key in outs[0]:
             payload["out_" + key] = np.stack([o[key] for o in outs])
-        path = os.path.join(HERE, f"opcond_{'case1' if corr is not None else 'case2'}_{tag}.npz")
+        path = os.path.join(HERE, f"opcond_{'case3' if corr == 'rad' else 'case1' if corr is not None else 'case2'}_{tag}.npz")
         np.savez_compressed(path, **payload)
         print(tag, os.path.getsize(path) // 1024, "KiB")
 

@@ -141,7 +141,7 @@ def test_model_validation_rejects_unimplemented_flags():
             bs.set_model(bad, [synthetic_helium_table()])
 
 
-@pytest.mark.parametrize("correlations", [False, True])
+@pytest.mark.parametrize("correlations", [False, True, "radiative"])
 @pytest.mark.parametrize("batch", [9, 70])
 def test_fused_advance_is_bit_identical_to_separate_kernels(correlations, batch, monkeypatch):
     """osc2_advance: the fused K_PG kernel (properties -> row records in shared memory) against the
@@ -149,9 +149,15 @@ def test_fused_advance_is_bit_identical_to_separate_kernels(correlations, batch,
     materialised coefficient arrays must agree bit for bit (ragged last tile of 32 included)."""
     from opensc2_b200.batch import BatchedStep
 
+    import dataclasses
+
     n, dt = 37, 0.1
-    topo, model, tab, _arr, sweep = _setup(correlations, n, batch, seed=21)
+    topo, model, tab, _arr, sweep = _setup(correlations is True, n, batch, seed=21)
     arr = consistent_initial_state(topo, model, tab, n, batch, seed=21, dt=dt)
+    if correlations == "radiative":      # a constant radiative exchange (-3) on the strand-jacket interface
+        model = dataclasses.replace(model, ss=((-3, 7.0, 1.5, 0.0, 0.0, 0.0),))
+        arr.peri_ss_nodal = np.full((batch, 1, n), 0.03)
+        arr.sysvar.reshape(batch, n, topo.ndf)[:, :, -1] += 3.0
     results = {}
     for fused in ("0", "1"):
         monkeypatch.setenv("OSC2_FUSED_OPCOND", fused)
@@ -290,3 +296,52 @@ def test_full_size_mesh_batch_order_invariance():
         outs.append((sv[np.argsort(order)], diag["norm_change"][np.argsort(order)]))
     assert_bits(outs[0][0], outs[1][0], "state")
     assert_bits(outs[0][1], outs[1][1], "norm_change")
+
+
+@pytest.mark.parametrize("fused", ["0", "1"])
+def test_case3_flavoured_model_radiative_exchange(fused, monkeypatch):
+    """d = 7: radiation between two jackets (HTC_choice 3, nodal HTC, explicit source on both solids), a
+    constant contact, convection to the environment; K_P vs oracle (sources bit-exact) and two chained
+    steps.  The fused K_PG kernel does not apply to d = 7 (generic path), so both settings must agree."""
+    from opensc2_b200.batch import BatchedStep
+    from opensc2_b200.model import case3_mini_model
+    from opensc2_b200.problem import case3_mini_topology
+    from oracle import oracle as O
+
+    monkeypatch.setenv("OSC2_FUSED_OPCOND", fused)
+    n, batch, dt = 21, 5, 0.1
+    topo, model, tab = case3_mini_topology(), case3_mini_model(), synthetic_helium_table()
+    arr = consistent_initial_state(topo, model, tab, n, batch, seed=6, dt=dt)
+    sv0 = arr.sysvar.reshape(batch, n, topo.ndf)
+    sv0[:, :, topo.ndf - 3:] += np.array([10.0, 40.0, 60.0])[None, None, :]
+    rng = np.random.default_rng(2)
+    arr.peri_ss_nodal = rng.uniform(0.05, 0.06, (batch, len(topo.ss), 1)) * np.ones(n)
+    sweep = synthetic_sweep(topo, model, n, batch, seed=6, with_tcs=False)
+    host = arr.copy()
+    d, M = topo.ndf, topo.n_ch
+    with BatchedStep(topo, batch, n) as bs:
+        bs.set_model(model, [tab])
+        bs.upload_sweep(sweep)
+        bs.upload_state(arr.sysvar, arr.syslod)
+        bs.upload_geometry(arr)
+        bs.set_capture(True)
+        for k in range(1, 3):
+            t = 11.9 + k * dt
+            bs.advance(t, dt, k)
+            bs.synchronize()
+            ins = bs.download_step_inputs()
+            sv, sl, st = bs.download_state()
+            assert np.all(st == 0)
+            ref_in = O.operating_conditions(topo, model, [tab], sweep, host.sysvar, n, t, peri_ss_nodal=arr.peri_ss_nodal)
+            assert_bits(ins["sol_q"], ref_in["sol_q"], "Q1/Q2 with radiative exchange")
+            assert np.abs(ref_in["sol_q"][:, :, 1:3]).max() > 0
+            for key in ins:
+                assert rel(ins[key], ref_in[key]) <= RTOL_FIT, f"{key}: {rel(ins[key], ref_in[key]):.3e}"
+            for key, v in ref_in.items():
+                setattr(host, key, v)
+            host.num_step, host.dt = k, dt
+            r = O.step(topo, host)
+            a, b = sv.reshape(batch, n, d), r["sysvar"].reshape(batch, n, d)
+            assert rel_field(a[..., :M], b[..., :M]) <= RTOL_CHAIN_V
+            assert rel_field(a[..., M:], b[..., M:]) <= RTOL_CHAIN
+            host.sysvar, host.syslod = sv, sl
