@@ -143,7 +143,7 @@ def case1_topology(intial: int = 1, **kw) -> Topology:
         n_ch=2, n_sol=2,
         ch_area=(5.0265e-5, 3.6965e-4), ch_dh=(8e-3, 3.2676e-4),
         ch_forward=(True, True), ch_intial=(intial, intial),
-        sol_area=(7.5395e-4, 3.0699e-4 + 2.7966e-4), sol_costeta=(0.9699, 1.0),
+        sol_area=(0.000753951765, 3.0699e-4 + 2.7966e-4), sol_costeta=(0.9699, 1.0),
         ff=((0, 1),), fs=((1, 0), (1, 1)), ss=((0, 1),), es=(1,), es_choice2=(False,),
     )
     return replace(t, **kw)
