@@ -307,8 +307,9 @@ def run_ours(args, rank, world, local_rank):
         achieved = alg[dom] * dom_units / (per_step[dom] * 1e-3) / 1e9
         step_ms_kernels = sum(per_step[k] for k in per_step if k in alg)
         fracs = {k: alg[k] * BATCH * NODES / (per_step[k] * 1e-3) / 1e9 / peak for k in per_step if k in alg}
-        # measured DRAM traffic per node of the forward sweep (profiles/): read + write, ncu --set full
-        traffic_per_unit = {"forward": 2384.0, "gauss": 1379.0, "backward": 1215.0}.get(dom)
+        # measured DRAM traffic per node (read + write) of one launch at THIS size, ncu --set full
+        # (profiles/r1_fullsize_ncu_summary.txt; backward: the N = 201 capture, its full-size counter came back empty)
+        traffic_per_unit = {"forward": 2899.7, "gauss": 1456.9, "props": 447.3, "backward": 1223.0}.get(dom)
         cpu_threads = os.cpu_count() or 1
         n_cpu = max(8 * cpu_threads, 16)
         cpu_val, cpu_dt = cpu_sample(topo, model, tab, arr, sweep, n_cpu, cpu_threads)
@@ -330,7 +331,7 @@ def run_ours(args, rank, world, local_rank):
                 "frac": achieved / peak, "peak_source": peak_src,
                 "alg_bytes_per_unit": alg[dom], "units_per_launch": dom_units, "launch_ms": per_step[dom],
                 "traffic": (traffic_per_unit * dom_units) if traffic_per_unit else None,
-                "traffic_source": "ncu dram__bytes_read+write per node at N=201 (profiles/), scaled to this launch" if traffic_per_unit else None,
+                "traffic_source": "ncu --set full dram__bytes_read+write of this kernel at this size (profiles/r1_fullsize_ncu_summary.txt)" if traffic_per_unit else None,
                 "per_kernel_frac": fracs,
                 "step": {"alg_bytes_per_node_timestep": b_alg(d), "model": "SURVEY.md 8(d) two-kernel model (assembly + solve)",
                          "achieved": b_alg(d) * BATCH * NODES / (step_ms_kernels * 1e-3) / 1e9,
