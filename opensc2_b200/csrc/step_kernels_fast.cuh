@@ -198,8 +198,14 @@ __global__ void osc2_gauss2_kernel(const osc2_topology *__restrict__ tp, StepDev
         GOUT(sl.lod(is, LOD_UP_PREV)) = (2. * sp0 + sp1) * dz_6;
         GOUT(sl.lod(is, LOD_LO_PREV)) = (sp0 + 2. * sp1) * dz_6;
     }
+    // S * dz / 3 (smc:1126-1163): 3 is a shared divisor, so its reciprocal is refined once (bit-identical
+    // quotients, osc2_div.cuh); entries the topology cannot touch are +0 and need no arithmetic at all
+    const Osc2Rcp r3 = osc2_rcp_prepare(3.0);
     for (int r = 0; r < d; ++r)
-        for (int c = 0; c < d; ++c) GOUT(sl.sd(r, c)) = SM_(r, c) * dz / 3.;
+        for (int c = 0; c < d; ++c) {
+            const int slot = smap[r * d + c];
+            GOUT(sl.sd(r, c)) = slot ? osc2_div(Sb[(size_t)slot * Ss] * dz, r3) : 0.0;
+        }
 #undef SM_
 #undef FG
 #undef GOUT
