@@ -233,6 +233,17 @@ __global__ void osc2_div_selftest_kernel(unsigned long long seed, long long per_
         const double q = osc2_div(a, r);
         const double ref = a / b;
         if (__double_as_longlong(q) != __double_as_longlong(ref) && !(q != q && ref != ref)) ++bad;
+        // the forward sweep's forms: with the divisor in [2^-100, 2^101) a quotient that is not
+        // poisoned must be a / b (a zero may come back with the other sign, see osc2_div.cuh);
+        // a numerator at or above 2^900 is left to the non-finite propagation described there
+        const bool div_ok = osc2_abs_hi(b) - OSC2_HI_DIV_LO < OSC2_HI_DIV_SPAN;
+        const double qp = osc2_div_p(a, r);
+        if (div_ok && qp == qp && osc2_abs_hi(a) < OSC2_HI_2P900 &&
+            __double_as_longlong(qp) != __double_as_longlong(ref) && !(a == 0.0 && qp == 0.0)) ++bad;
+        if (div_ok && osc2_num_key(a) >= OSC2_KEY_MIN && osc2_abs_hi(a) < OSC2_HI_2P900) {
+            const double qf = osc2_div_fast(a, r);
+            if (__double_as_longlong(qf) != __double_as_longlong(ref) && !(a == 0.0 && qf == 0.0)) ++bad;
+        }
     }
     if (bad) atomicAdd(mismatch, bad);
 }

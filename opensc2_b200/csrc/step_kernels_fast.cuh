@@ -211,50 +211,95 @@ __global__ void osc2_gauss2_kernel(const osc2_topology *__restrict__ tp, StepDev
 #undef GOUT
 }
 
+// max(m, |v|) as one compare and one select (a NaN never wins, as in `if (|v| > m) m = |v|`)
+__device__ __forceinline__ double osc2_absmax(double m, double v)
+{
+    const double a = fabs(v);
+    return (a > m) ? a : m;
+}
+
 // shared-memory doubles per conductor of the fast forward sweep
-template <int D>
+template <int D, bool CLOSED>       // CLOSED: closed-form Known, no old-solution ring and no product strips
 struct FastFwdSmem {
     static constexpr int PW = 2 * D + 2;                 // published row: D' | U | rhs | 1/pivot
     static constexpr int PUB = 2 * D * PW;               // two nodes (double buffer)
     static constexpr int XS = 3 * D;                     // old solution ring
     static constexpr int STRIP = 5 * D + 1;              // per-lane product strip with zero pads
-    static constexpr int RAW = PUB + XS + D * STRIP;
+    // per-lane landing slot of the asynchronous prefetch (element record, next old solution value,
+    // SYSLOD row); stride == 2 (mod 4) doubles keeps the 16-byte reads of eight lanes conflict-free
+    static constexpr int PF_FIELDS = D + 12;
+    static constexpr int PF = PF_FIELDS + ((6 - (PF_FIELDS % 4)) % 4);
+    static constexpr int PRE = D * PF;
+    static constexpr int RAW = PRE + PUB + (CLOSED ? 0 : XS + D * STRIP);
     static constexpr int PER_COND = RAW + ((18 - (RAW % 16)) % 16);   // == 2 (mod 16): bank spread
 };
+
+// 8-byte global -> shared copy that occupies no register while in flight (LDGSTS)
+__device__ __forceinline__ void osc2_async_copy8(double *dst_shared, const double *src_global)
+{
+#ifdef OSC2_EMU
+    *dst_shared = *src_global;
+#else
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_shared);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src_global) : "memory");
+#endif
+}
+
+__device__ __forceinline__ void osc2_async_wait_all()
+{
+#ifndef OSC2_EMU
+    asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+}
 
 // ---------------------------------------------------------------------------
 // K_F2.  BE: theta == 1 (Backward Euler; the Known coefficients off the block
 // diagonals vanish and, for D % 8 == 0, numpy's pairwise sum of the three
 // surviving products is (pL + pD) + pU for every row).  CAPTURE: also write
 // the pre-solve system in the reference band layout.
+//
+// Lane = matrix row.  A row of the three blocks differs from "S*dz/3 halves" in
+// two columns only -- its own (mass, advection, diffusion) and, for fluid rows,
+// the partner column of the AMAT entry -- so those two entries are formed as
+// scalars and every other column costs one multiply or add and two selects.
+// The element records alternate between two register sets (nodes are processed
+// in pairs), the next element is fetched straight into the set that died.
 // ---------------------------------------------------------------------------
-template <int D, int LPC, bool BE, bool CAPTURE>
+template <int D, int LPC, bool BE, bool CAPTURE, bool FULL = false>
 __global__ void osc2_forward_fast_kernel(const osc2_topology *__restrict__ tp, StepDev p)
 {
+    static_assert(!FULL || LPC == D, "FULL: every lane owns a row");
     OSC2_DYN_SMEM(sm_dyn);
-    using SM = FastFwdSmem<D>;
-    constexpr int PW = SM::PW, STRIP = SM::STRIP, RW = D + 9;
     constexpr bool CLOSED_KNOWN = BE && (D % 8 == 0);
+    using SM = FastFwdSmem<D, CLOSED_KNOWN>;
+    constexpr int PW = SM::PW, STRIP = SM::STRIP, RW = D + 9;
     const int M = p.M, N = p.N;
     const size_t B = (size_t)p.B;
+    // field k of a batch-innermost record: ONE multiply-add on the 32-bit batch size, so that the
+    // compiler has no 64-bit k * B to hoist out of the node loop (dozens of registers otherwise)
+    const unsigned Bu = (unsigned)p.B;
+    auto fld = [Bu](auto *ptr, const int k) {
+        return (decltype(ptr))((const char *)ptr + (unsigned long long)Bu * (unsigned)(8 * k));
+    };
     const int cpb = blockDim.x / LPC;
     const int grp = threadIdx.x / LPC, r = threadIdx.x % LPC;
     const long long b_ll = (long long)blockIdx.x * cpb + grp;
-    const bool act = (b_ll < (long long)p.B) && (r < D);
+    const bool act = FULL || ((b_ll < (long long)p.B) && (r < D));
     const size_t b = act ? (size_t)b_ll : 0;
-    const int rr_ = (r < D) ? r : 0;
+    const int rr_ = (FULL || r < D) ? r : 0;
     const long long Total = (long long)D * N;
     constexpr int Half = 2 * D;
     const double theta = tp->theta, omt = 1.0 - tp->theta;
     const Osc2Rcp rdt = osc2_rcp_prepare(p.dt);
     const bool first = (p.num_step == 1);
     const bool shift = (p.num_step > 1);
-    int dt_flag = 0;
-    osc2_rcp_check(rdt, dt_flag);
+    // divisor range: dt here, the pivots at the end of every node (max of hi(|b|) - hi(2^-100))
+    unsigned div_span = osc2_abs_hi(p.dt) - OSC2_HI_DIV_LO;
 
     double *base = sm_dyn + (size_t)grp * SM::PER_COND;
-    double *pub = base;                                  // [2][D][PW]
-    double *xs = base + SM::PUB;                         // [3][D]
+    double *pre = base + (size_t)rr_ * SM::PF;           // this lane's prefetch slot
+    double *pub = base + SM::PRE;                        // [2][D][PW]
+    double *xs = pub + SM::PUB;                          // [3][D]   (general Known only)
     double *strip = xs + SM::XS + (size_t)rr_ * STRIP;   // [5D+1], products live at [D, 4D)
 
     // column of the off-diagonal AMAT entry of this row (smc:62-101)
@@ -296,79 +341,108 @@ __global__ void osc2_forward_fast_kernel(const osc2_topology *__restrict__ tp, S
 #undef FND
     }
     long long bad_row = -1;
-    int range_flag = 0;     // set when a value leaves the exact range of osc2_div_flag
 
-    // this lane's row record of one element
+    // This lane's row record of one element, plus the two entries of its S row that meet the
+    // special columns (fetched a second time with a lane-dependent offset).  The record of the
+    // next element, the next old-solution value and the next SYSLOD row travel global -> shared
+    // asynchronously while the current node is eliminated: a register-held prefetch would be
+    // spilled at 255 registers, and a spilled load target stalls the warp for the DRAM latency.
     struct Elem {
         double sd[D];
-        double kb, md, mo, ahd, aho, lodu, lodl, lodup, lodlp;
+        double sdr, sdo, kb, md, mo, ahd, aho, lodu, lodl;
     };
+    enum { PF_SDR = D, PF_SDO, PF_KB, PF_MD, PF_MO, PF_AHD, PF_AHO, PF_LODU, PF_LODL, PF_X, PF_SL0, PF_SL1 };
+    static_assert(PF_SL1 + 1 == SM::PF_FIELDS, "prefetch slot layout");
     const size_t gstep = (size_t)p.NS * B;                       // one element further
     const double *gptr = p.gm + (size_t)rr_ * RW * B + b;        // row record of element 0
-    auto load_elem = [&](const double *g, Elem &el) {
-#pragma unroll
-        for (int c = 0; c < D; ++c) el.sd[c] = g[(size_t)c * B];
-        el.kb = g[(size_t)(D + 0) * B];
-        el.md = g[(size_t)(D + 1) * B];
-        el.mo = g[(size_t)(D + 2) * B];
-        el.ahd = g[(size_t)(D + 3) * B];
-        el.aho = g[(size_t)(D + 4) * B];
-        el.lodu = g[(size_t)(D + 5) * B];
-        el.lodl = g[(size_t)(D + 6) * B];
-        if (first) { el.lodup = g[(size_t)(D + 7) * B]; el.lodlp = g[(size_t)(D + 8) * B]; }
-        else { el.lodup = 0.0; el.lodlp = 0.0; }
-    };
-    auto zero_elem = [&](Elem &el) {
-#pragma unroll
-        for (int c = 0; c < D; ++c) el.sd[c] = 0.0;
-        el.md = el.mo = el.kb = el.ahd = el.aho = el.lodu = el.lodl = el.lodup = el.lodlp = 0.0;
-    };
-
-    Elem eL, eR, eN;
-    zero_elem(eL); zero_elem(eR); zero_elem(eN);
-    double x_next = 0.0, sl0_next = 0.0, sl1_next = 0.0;
+    const size_t off_r = (size_t)rr_ * B, off_o = (size_t)(aoffcol >= 0 ? aoffcol : 0) * B;
     const size_t xstep = (size_t)D * B;
     const double *xptr = p.sysvar + (size_t)rr_ * B + b;                 // x[node][r]
     double *lodptr = p.syslod + (size_t)rr_ * 2 * B + b;                 // SYSLOD[node][r][0]
     double *spptr = p.spill + (size_t)rr_ * (2 * D + 2) * B + b;         // spill[node][r][0]
+    // start the copies node m needs: element m, x[m+1], SYSLOD[m] (g, xq, lq point at them)
+    auto prefetch = [&](const int m, const double *g, const double *xq, const double *lq) {
+        if (m < N - 1) {
+#pragma unroll
+            for (int c = 0; c < D; ++c) osc2_async_copy8(pre + c, fld(g, c));
+            osc2_async_copy8(pre + PF_SDR, g + off_r);
+            osc2_async_copy8(pre + PF_SDO, g + off_o);
+#pragma unroll
+            for (int q = 0; q < 7; ++q) osc2_async_copy8(pre + PF_KB + q, fld(g, D + q));
+            osc2_async_copy8(pre + PF_X, xq);
+        }
+        if (m < N) {
+            osc2_async_copy8(pre + PF_SL0, lq);
+            osc2_async_copy8(pre + PF_SL1, fld(lq, 1));
+        }
+    };
+    auto zero_elem = [&](Elem &el) {
+#pragma unroll
+        for (int c = 0; c < D; ++c) el.sd[c] = 0.0;
+        el.sdr = el.sdo = 0.0;
+        el.md = el.mo = el.kb = el.ahd = el.aho = el.lodu = el.lodl = 0.0;
+    };
+
+    Elem eA, eB;
+    zero_elem(eA); zero_elem(eB);
+    double xm = 0.0, x0 = 0.0, xp = 0.0;                                 // own old solution at nodes n-1, n, n+1
+    double mas_carry = 0.0;                                              // MASMAT/dt of the element to the left
+    double x_pre = 0.0, sl0_pre = 0.0, sl1_pre = 0.0;
+    auto load_elem = [&](const double *g, Elem &el) {
+#pragma unroll
+        for (int c = 0; c < D; ++c) el.sd[c] = *fld(g, c);
+        el.sdr = g[off_r];
+        el.sdo = g[off_o];
+        el.kb = *fld(g, D + 0); el.md = *fld(g, D + 1); el.mo = *fld(g, D + 2); el.ahd = *fld(g, D + 3);
+        el.aho = *fld(g, D + 4); el.lodu = *fld(g, D + 5); el.lodl = *fld(g, D + 6);
+    };
     if (act) {
-        load_elem(gptr, eR);
-        xs[0 * D + r] = xptr[0];
-        xs[1 * D + r] = xptr[xstep];
-        sl0_next = lodptr[0];
-        sl1_next = lodptr[B];
+        load_elem(gptr, eB);
+        x0 = xptr[0];
+        x_pre = xptr[xstep];
+        sl0_pre = lodptr[0];
+        sl1_pre = *fld(lodptr, 1);
+        if (!CLOSED_KNOWN) xs[0 * D + r] = x0;
     }
-    if (r < D) for (int q = 0; q < STRIP; ++q) strip[q] = 0.0;   // zero pads, once
+    if (!CLOSED_KNOWN) { if (r < D) for (int q = 0; q < STRIP; ++q) strip[q] = 0.0; }   // zero pads, once
     double *xa = xs, *xb = xs + D, *xc = xs + 2 * D;             // nodes n-1, n, n+1 (rotating)
-    {   // at n = 0: node -1 does not exist; ring holds nodes 0, 1 in slots 0, 1
+    {   // at n = 0: node -1 does not exist; ring holds node 0 in slot 0, node 1 arrives in slot 1
         double *t = xa; xa = xc; xc = xb; xb = t;                 // xb = slot0 (node 0), xc = slot1 (node 1)
     }
 
-    // One node of the sweep.  The first and the last node are compiled separately
-    // (no left / right element, boundary rows possible), so the interior loop has
-    // neither of those branches.
-    auto node = [&](auto HL, auto HR, const int n) {
+    // One node of the sweep: A is the element to its left, B the one to its right.  The first
+    // and the last node are compiled separately (no left / right element, boundary rows
+    // possible), so the interior nodes have neither of those branches.
+    auto node = [&](auto HL, auto HR, const int n, Elem &A, Elem &Bv) {
         constexpr bool hasL = decltype(HL)::value, hasR = decltype(HR)::value;
         double *pub_cur = pub + (size_t)(n & 1) * D * PW;
         const double *pub_prev = pub + (size_t)((n + 1) & 1) * D * PW;
         const long long i_row = (long long)n * D + r;
-        double sl0 = sl0_next, sl1 = sl1_next;
-        // ---- prefetch for node n+1: element n+1, x[n+2], SYSLOD row ---------
+        double sl0 = 0.0, sl1 = 0.0;
+        // ---- prefetched by the previous node: element n (in Bv), x[n+1], SYSLOD row n ----------
         if (act) {
-            if (n + 1 < N - 1) load_elem(gptr + gstep, eN);
-            if (n + 2 < N) x_next = xptr[2 * xstep];
-            if (n + 1 < N) { sl0_next = lodptr[2 * xstep]; sl1_next = lodptr[2 * xstep + B]; }
+            if (hasR) { xp = x_pre; if (!CLOSED_KNOWN) xc[r] = xp; }
+            sl0 = sl0_pre; sl1 = sl1_pre;
+            if (n + 2 < N) x_pre = xptr[2 * xstep];
+            if (n + 1 < N) { sl0_pre = lodptr[2 * xstep]; sl1_pre = *fld(lodptr + 2 * xstep, 1); }
         }
-        __syncwarp();   // old-solution ring of this node visible; pub reuse ordered
+        if (!CLOSED_KNOWN) __syncwarp();   // old-solution ring of this node visible
 
         double rowL[D], rowD[D], rowU[D], rhs = 0.0;
         if (act) {
             // SYSLOD (smc:1165-1318); fluid rows carry zero loads
             if (shift) { sl1 = sl0; sl0 = 0.0; }
-            if (hasL) { sl0 += eL.lodl; if (first) sl1 += eL.lodlp; }
-            if (hasR) { sl0 += eR.lodu; if (first) sl1 += eR.lodup; }
+            // (the previous-step halves exist at the first step only: read in place, not prefetched)
+            if (hasL) { sl0 += A.lodl; if (first) sl1 += *fld(gptr - gstep, D + 8); }
+            if (hasR) { sl0 += Bv.lodu; if (first) sl1 += *fld(gptr, D + 7); }
             lodptr[0] = sl0;
-            lodptr[B] = sl1;
+            *fld(lodptr, 1) = sl1;
+
+            // MASMAT/dt is non-zero on the diagonal entry of each block only; the U-block
+            // value of this node is the L-block value of the next one
+            const double masL = hasL ? mas_carry : 0.0;
+            const double masU = hasR ? osc2_div_p(Bv.mo, rdt) : 0.0;
+            mas_carry = masU;
 
             const bool is_bc = (!hasL && bc_first) || (!hasR && bc_last);
             if (is_bc) {
@@ -376,62 +450,84 @@ __global__ void osc2_forward_fast_kernel(const osc2_topology *__restrict__ tp, S
                 for (int c = 0; c < D; ++c) { rowL[c] = 0.0; rowD[c] = (c == r) ? 1.0 : 0.0; rowU[c] = 0.0; }
                 rhs = (!hasL) ? val_first : val_last;
             } else {
-                double mx = 0.0;
-                // MASMAT/dt is non-zero on the diagonal entry of each block only
-                const double masL = hasL ? osc2_div_flag(eL.mo, rdt, range_flag) : 0.0;
-                const double masD = osc2_div_flag((hasL ? eL.md : 0.0) + (hasR ? eR.md : 0.0), rdt, range_flag);
-                const double masU = hasR ? osc2_div_flag(eR.mo, rdt, range_flag) : 0.0;
+                const double masD = osc2_div_p((hasL ? A.md : 0.0) + (hasR ? Bv.md : 0.0), rdt);
+                // FDS = FLX + DIF + SOR (smc:1015-1163) of the two special columns, same operation
+                // order as the reference; adding the zeros of the other columns changes no bit
+                //   L block: lower-left of element n-1;  U block: upper-right of element n
+                //   D block: lower-right of element n-1 + upper-left of element n
+                double fLd = 0.0, fLo = 0.0, fUd = 0.0, fUo = 0.0, fDd, fDo;
+                if (hasL) { fLd = (-A.ahd + -A.kb) + A.sdr / 2.; fLo = -A.aho + A.sdo / 2.; }
+                if (hasR) { fUd = (Bv.ahd + -Bv.kb) + Bv.sdr / 2.; fUo = Bv.aho + Bv.sdo / 2.; }
+                if (hasL && hasR) {
+                    fDd = ((A.ahd + -Bv.ahd) + (A.kb + Bv.kb)) + (A.sdr + Bv.sdr);
+                    fDo = (A.aho + -Bv.aho) + (A.sdo + Bv.sdo);
+                } else if (hasL) {
+                    fDd = (A.ahd + A.kb) + A.sdr;
+                    fDo = A.aho + A.sdo;
+                } else {
+                    fDd = (-Bv.ahd + Bv.kb) + Bv.sdr;
+                    fDo = -Bv.aho + Bv.sdo;
+                }
+                double mxL = 0.0, mxD = 0.0, mxU = 0.0;
+                if (CLOSED_KNOWN) {
+                    const double sLd = masL + fLd, sDd = masD + fDd, sUd = masU + fUd;
 #pragma unroll
-                for (int c = 0; c < D; ++c) {
-                    const bool dg = (c == r);
-                    const double avL = dg ? eL.ahd : (c == aoffcol ? eL.aho : 0.0);
-                    const double avR = dg ? eR.ahd : (c == aoffcol ? eR.aho : 0.0);
-                    // L block: lower-left of element n-1
-                    {
-                        double sys = 0.0;
-                        if (hasL) {
-                            const double fds = (-avL + (dg ? -eL.kb : 0.0)) + eL.sd[c] / 2.;
-                            const double m = dg ? masL : 0.0;
-                            sys = BE ? m + fds : m + theta * fds;
-                            if (!CLOSED_KNOWN) strip[D + c] = (m - omt * fds) * xa[c];
-                        } else if (!CLOSED_KNOWN) strip[D + c] = 0.0;
-                        rowL[c] = sys;
-                        { const double a_ = fabs(sys); if (a_ > mx) mx = a_; }
+                    for (int c = 0; c < D; ++c) {
+                        const bool dg = (c == r), of = (c == aoffcol);
+                        const double gD = (hasL && hasR) ? A.sd[c] + Bv.sd[c] : (hasL ? A.sd[c] : Bv.sd[c]);
+                        rowL[c] = hasL ? (dg ? sLd : (of ? fLo : A.sd[c] / 2.)) : 0.0;
+                        rowD[c] = dg ? sDd : (of ? fDo : gD);
+                        rowU[c] = hasR ? (dg ? sUd : (of ? fUo : Bv.sd[c] / 2.)) : 0.0;
+                        if (hasL) mxL = osc2_absmax(mxL, rowL[c]);
+                        mxD = osc2_absmax(mxD, rowD[c]);
+                        if (hasR) mxU = osc2_absmax(mxU, rowU[c]);
                     }
-                    // D block: lower-right of element n-1 + upper-left of element n
-                    {
-                        double flx = 0.0, dif = 0.0, sor = 0.0;
-                        if (hasL) { if (dg) dif += eL.kb; flx += avL; sor += eL.sd[c]; }
-                        if (hasR) { if (dg) dif += eR.kb; flx += -avR; sor += eR.sd[c]; }
-                        const double fds = (flx + dif) + sor;
-                        const double m = dg ? masD : 0.0;
-                        const double sys = BE ? m + fds : m + theta * fds;
-                        if (!CLOSED_KNOWN) strip[2 * D + c] = (m - omt * fds) * xb[c];
-                        rowD[c] = sys;
-                        { const double a_ = fabs(sys); if (a_ > mx) mx = a_; }
-                    }
-                    // U block: upper-right of element n
-                    {
-                        double sys = 0.0;
-                        if (hasR) {
-                            const double fds = (avR + (dg ? -eR.kb : 0.0)) + eR.sd[c] / 2.;
-                            const double m = dg ? masU : 0.0;
-                            sys = BE ? m + fds : m + theta * fds;
-                            if (!CLOSED_KNOWN) strip[3 * D + c] = (m - omt * fds) * xc[c];
-                        } else if (!CLOSED_KNOWN) strip[3 * D + c] = 0.0;
-                        rowU[c] = sys;
-                        { const double a_ = fabs(sys); if (a_ > mx) mx = a_; }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < D; ++c) {
+                        const bool dg = (c == r), of = (c == aoffcol);
+                        const double gD = (hasL && hasR) ? A.sd[c] + Bv.sd[c] : (hasL ? A.sd[c] : Bv.sd[c]);
+                        {
+                            double sys = 0.0;
+                            if (hasL) {
+                                const double fds = dg ? fLd : (of ? fLo : A.sd[c] / 2.);
+                                const double m = dg ? masL : 0.0;
+                                sys = BE ? m + fds : m + theta * fds;
+                                strip[D + c] = (m - omt * fds) * xa[c];
+                            } else strip[D + c] = 0.0;
+                            rowL[c] = sys;
+                        }
+                        {
+                            const double fds = dg ? fDd : (of ? fDo : gD);
+                            const double m = dg ? masD : 0.0;
+                            rowD[c] = BE ? m + fds : m + theta * fds;
+                            strip[2 * D + c] = (m - omt * fds) * xb[c];
+                        }
+                        {
+                            double sys = 0.0;
+                            if (hasR) {
+                                const double fds = dg ? fUd : (of ? fUo : Bv.sd[c] / 2.);
+                                const double m = dg ? masU : 0.0;
+                                sys = BE ? m + fds : m + theta * fds;
+                                strip[3 * D + c] = (m - omt * fds) * xc[c];
+                            } else strip[3 * D + c] = 0.0;
+                            rowU[c] = sys;
+                        }
+                        if (hasL) mxL = osc2_absmax(mxL, rowL[c]);
+                        mxD = osc2_absmax(mxD, rowD[c]);
+                        if (hasR) mxU = osc2_absmax(mxU, rowU[c]);
                     }
                 }
+                const double mx = osc2_absmax(osc2_absmax(mxL, mxD), mxU);
                 // Known (smc:1366-1443)
                 double known;
                 if (CLOSED_KNOWN) {
                     // only MASMAT/dt * x_old survives; the three products sit 8k band
                     // positions apart, i.e. in one numpy accumulator (or its tail)
                     known = 0.0;
-                    if (hasL) known = masL * xa[rr_];
-                    known = hasL ? known + masD * xb[rr_] : masD * xb[rr_];
-                    if (hasR) known = known + masU * xc[rr_];
+                    if (hasL) known = masL * xm;
+                    known = hasL ? known + masD * x0 : masD * x0;
+                    if (hasR) known = known + masU * xp;
                 } else {
                     long long lo, hi;
                     if (i_row <= Half - 1) { lo = 0; hi = Half + i_row; }
@@ -456,15 +552,25 @@ __global__ void osc2_forward_fast_kernel(const osc2_topology *__restrict__ tp, S
                 }
                 known += BE ? sl0 : (theta * sl0 + omt * sl1);
                 // row scaling (tsf:538-551)
-                const Osc2Rcp rmx = osc2_rcp_prepare(mx);
-                osc2_rcp_check(rmx, range_flag);
+                // one range check for the whole row (runs beside the Newton steps of 1/mx): a numerator
+                // or the divisor outside the exact range poisons the reciprocal, hence every quotient
+                Osc2Rcp rmx = osc2_rcp_prepare(mx);
+                unsigned kmin = osc2_num_key(known);
 #pragma unroll
                 for (int c = 0; c < D; ++c) {
-                    rowL[c] = osc2_div_flag(rowL[c], rmx, range_flag);
-                    rowD[c] = osc2_div_flag(rowD[c], rmx, range_flag);
-                    rowU[c] = osc2_div_flag(rowU[c], rmx, range_flag);
+                    if (hasL) kmin = osc2_umin(kmin, osc2_num_key(rowL[c]));
+                    kmin = osc2_umin(kmin, osc2_num_key(rowD[c]));
+                    if (hasR) kmin = osc2_umin(kmin, osc2_num_key(rowU[c]));
                 }
-                rhs = osc2_div_flag(known, rmx, range_flag);
+                osc2_rcp_poison_if(rmx, (kmin < OSC2_KEY_MIN) || (osc2_abs_hi(known) >= OSC2_HI_2P900) ||
+                                            (osc2_abs_hi(mx) - OSC2_HI_DIV_LO >= OSC2_HI_DIV_SPAN));
+#pragma unroll
+                for (int c = 0; c < D; ++c) {
+                    if (hasL) rowL[c] = osc2_div_fast(rowL[c], rmx);
+                    rowD[c] = osc2_div_fast(rowD[c], rmx);
+                    if (hasR) rowU[c] = osc2_div_fast(rowU[c], rmx);
+                }
+                rhs = osc2_div_fast(known, rmx);
             }
             if (CAPTURE) {
 #pragma unroll
@@ -483,7 +589,7 @@ __global__ void osc2_forward_fast_kernel(const osc2_topology *__restrict__ tp, S
 #pragma unroll
                 for (int k = 0; k < D; ++k) {
                     const double *pk = pub_prev + k * PW;
-                    const double q = osc2_div_flag(rowL[k], osc2_rcp_make(pk[k], pk[2 * D + 1]), range_flag);
+                    const double q = osc2_div_p(rowL[k], osc2_rcp_make(pk[k], pk[2 * D + 1]));
 #pragma unroll
                     for (int c = k + 1; c < D; ++c) rowL[c] = rowL[c] - pk[c] * q;
 #pragma unroll
@@ -491,6 +597,8 @@ __global__ void osc2_forward_fast_kernel(const osc2_topology *__restrict__ tp, S
                     rhs = rhs - pk[2 * D] * q;
                 }
             }
+            // element n-1 and the L block are dead: fetch element n+1 into the left element's registers
+            if (hasR && n + 1 < N - 1) load_elem(gptr + gstep, A);
         } else {
 #pragma unroll
             for (int c = 0; c < D; ++c) { rowL[c] = 0.0; rowD[c] = 0.0; rowU[c] = 0.0; }
@@ -508,18 +616,14 @@ __global__ void osc2_forward_fast_kernel(const osc2_topology *__restrict__ tp, S
                 pk[2 * D] = rhs;
                 my_rcp = osc2_rcp_prepare(rowD[k]);
                 pk[2 * D + 1] = my_rcp.y;
-                if (fabs(rowD[k]) <= OSC2_TINY_PIVOT) { if (bad_row < 0) bad_row = i_row; }
-                else osc2_rcp_check(my_rcp, range_flag);
             }
             __syncwarp();
             {
                 // rows above the pivot (and idle lanes) take the multiplier 0: x - p * 0 leaves x unchanged
                 // bit for bit, and ONE select on the multiplier replaces a select per updated entry
                 const double *pk = pub_cur + k * PW;
-                int flag_k = 0;
-                double q = osc2_div_flag(rowD[k], osc2_rcp_make(pk[k], pk[2 * D + 1]), flag_k);
                 const bool on = act && r > k;
-                if (on) range_flag |= flag_k;
+                double q = osc2_div_p(rowD[k], osc2_rcp_make(pk[k], pk[2 * D + 1]));
                 q = on ? q : 0.0;
 #pragma unroll
                 for (int c = k + 1; c < D; ++c) rowD[c] = rowD[c] - pk[c] * q;
@@ -529,16 +633,18 @@ __global__ void osc2_forward_fast_kernel(const osc2_topology *__restrict__ tp, S
             }
         }
         if (act) {
+            // this lane's pivot: singular (tsf:676-682) or outside the exact range of the division
+            const bool tiny = fabs(my_rcp.b) <= OSC2_TINY_PIVOT;
+            if (tiny && bad_row < 0) bad_row = i_row;
+            div_span = osc2_umax(div_span, tiny ? 0u : osc2_abs_hi(my_rcp.b) - OSC2_HI_DIV_LO);
 #pragma unroll
-            for (int c = 0; c < D; ++c) spptr[(size_t)c * B] = rowD[c];
+            for (int c = 0; c < D; ++c) *fld(spptr, c) = rowD[c];
 #pragma unroll
-            for (int c = 0; c < D; ++c) spptr[(size_t)(D + c) * B] = rowU[c];
-            spptr[(size_t)(2 * D) * B] = rhs;
-            spptr[(size_t)(2 * D + 1) * B] = my_rcp.y;
-            // rotate the element records and the old-solution ring
-            eL = eR;
-            eR = eN;
-            if (n + 2 < N) xa[r] = x_next;     // slot of node n-1 is free now: holds node n+2
+            for (int c = 0; c < D; ++c) *fld(spptr, D + c) = rowU[c];
+            *fld(spptr, 2 * D) = rhs;
+            *fld(spptr, 2 * D + 1) = my_rcp.y;
+            xm = x0; x0 = xp;       // rotate the old solution
+            if (hasR) { const Elem t = A; A = Bv; Bv = t; }   // left <- right, right <- the prefetched element
         }
         { double *t = xa; xa = xb; xb = xc; xc = t; }
         gptr += gstep;
@@ -546,12 +652,15 @@ __global__ void osc2_forward_fast_kernel(const osc2_topology *__restrict__ tp, S
         lodptr += 2 * xstep;
         spptr += (size_t)D * (2 * D + 2) * B;
     };
-    node(std::false_type(), std::true_type(), 0);
-    for (int n = 1; n < N - 1; ++n) node(std::true_type(), std::true_type(), n);
-    node(std::true_type(), std::false_type(), N - 1);
+    // (one body for all interior nodes: a two-node body that alternates the register sets saves the
+    //  copy of the element record but doubles the loop to 50 KB of code, and instruction-cache
+    //  misses then cost more than the copy)
+    node(std::false_type(), std::true_type(), 0, eA, eB);
+    for (int n = 1; n < N - 1; ++n) node(std::true_type(), std::true_type(), n, eA, eB);
+    node(std::true_type(), std::false_type(), N - 1, eA, eB);
     __syncwarp();
     double *scratch = base;
-    if (r < D) { scratch[r] = (double)bad_row; scratch[D + r] = (double)(range_flag | dt_flag); }
+    if (r < D) { scratch[r] = (double)bad_row; scratch[D + r] = (div_span >= OSC2_HI_DIV_SPAN) ? 1.0 : 0.0; }
     __syncwarp();
     if (act && r == 0) {
         long long worst = -1;

@@ -123,9 +123,10 @@ void osc2_run_fast_sweeps(Launcher &L, const osc2_topology *tp_dev, const StepDe
     // over all SMs (4096 conductors x 8 lanes = 1024 warps on 148 SMs)
     constexpr int cpb = 32 / LPC;
     const unsigned grid = (unsigned)((p.B + cpb - 1) / cpb);
-    const size_t smem_f = (size_t)FastFwdSmem<D>::PER_COND * cpb * sizeof(double);
-    const size_t smem_b = (size_t)(2 * D + 2) * cpb * sizeof(double);
     const bool be = (theta == 1.0), cap = (p.cap_sysmat != nullptr);
+    const size_t smem_f = (size_t)((be && D % 8 == 0) ? FastFwdSmem<D, true>::PER_COND : FastFwdSmem<D, false>::PER_COND) *
+                          cpb * sizeof(double);
+    const size_t smem_b = (size_t)(2 * D + 2) * cpb * sizeof(double);
     if constexpr (D % 8 == 0) {
         if (p.fwd_split == 2 && be) {      // 16 lanes per conductor (step_kernels_wide.cuh)
             constexpr int cpw = 32 / (2 * D);
@@ -147,7 +148,13 @@ void osc2_run_fast_sweeps(Launcher &L, const osc2_topology *tp_dev, const StepDe
         L.launch(OSC2_K_BACKWARD, osc2_backward_fast_kernel<D, LPC>, grid, 32u, smem_b, p);
         return;
     }
-    if (be && !cap) L.launch(OSC2_K_FORWARD, osc2_forward_fast_kernel<D, LPC, true, false>, grid, 32u, smem_f, tp_dev, p);
+    bool full = false;       // every lane of every warp owns a row: the kernel drops its lane predicates
+    if constexpr (LPC == D) full = be && !cap && (p.B % cpb == 0);
+    if (full) {
+        if constexpr (LPC == D)
+            L.launch(OSC2_K_FORWARD, osc2_forward_fast_kernel<D, LPC, true, false, true>, grid, 32u, smem_f, tp_dev, p);
+    }
+    else if (be && !cap) L.launch(OSC2_K_FORWARD, osc2_forward_fast_kernel<D, LPC, true, false>, grid, 32u, smem_f, tp_dev, p);
     else if (be) L.launch(OSC2_K_FORWARD, osc2_forward_fast_kernel<D, LPC, true, true>, grid, 32u, smem_f, tp_dev, p);
     else if (!cap) L.launch(OSC2_K_FORWARD, osc2_forward_fast_kernel<D, LPC, false, false>, grid, 32u, smem_f, tp_dev, p);
     else L.launch(OSC2_K_FORWARD, osc2_forward_fast_kernel<D, LPC, false, true>, grid, 32u, smem_f, tp_dev, p);

@@ -132,6 +132,35 @@ def test_singular_system_raises_like_reference():
     assert st[0] == 0 and st[1] == -9
 
 
+def test_value_outside_the_exact_division_range_is_reported_not_returned():
+    """A non-zero matrix entry below 2^-900 cannot go through the shared-divisor division
+    bit-exactly; the sweep must say so for that conductor (OSC2_STATUS_RANGE) and leave the
+    rest of the batch bit-exact."""
+    from opensc2_b200._abi import OSC2_STATUS_RANGE
+    from opensc2_b200.batch import BatchedStep
+    from oracle import oracle as O
+
+    topo = case1_topology(1)
+    n, batch = 33, 8
+    arr = synthetic_step_arrays(topo, n, batch=batch, seed=5, exact_squares=False)
+    from opensc2_b200 import _lib
+
+    arr.htc_fs[3, 0, 10] = 1.0e-290          # times a perimeter and dz/3: far below 2^-900 = 1.2e-271
+    with BatchedStep(topo, batch, n) as bs:
+        bs.upload_state(arr.sysvar, arr.syslod)
+        bs.upload_step_inputs(arr)
+        bs.step(arr.dt, arr.num_step)
+        with pytest.raises(_lib.Osc2Error) as err:
+            bs.synchronize()
+        assert err.value.code == -6
+        sv, sl, st = bs.download_state()
+    ok = np.arange(batch) != 3
+    assert st[3] == OSC2_STATUS_RANGE and np.all(st[ok] == 0)
+    ref = O.step(topo, arr)
+    assert_bits(sv[ok], ref["sysvar"][ok], "range:sysvar")
+    assert_bits(sl[ok], ref["syslod"][ok], "range:syslod")
+
+
 def test_shared_divisor_division_is_ieee():
     """csrc/osc2_div.cuh returns exactly a / b (incl. signed zeros, tiny/huge operands)."""
     import ctypes as C
