@@ -308,8 +308,8 @@ def run_ours(args, rank, world, local_rank):
         step_ms_kernels = sum(per_step[k] for k in per_step if k in alg)
         fracs = {k: alg[k] * BATCH * NODES / (per_step[k] * 1e-3) / 1e9 / peak for k in per_step if k in alg}
         # measured DRAM traffic per node (read + write) of one launch at THIS size, ncu --set full
-        # (profiles/r1_fullsize_ncu_summary.txt; backward: the N = 201 capture, its full-size counter came back empty)
-        traffic_per_unit = {"forward": 2899.7, "gauss": 1456.9, "props": 447.3, "backward": 1223.0}.get(dom)
+        # (profiles/r1_fullsize_ncu_summary.txt)
+        traffic_per_unit = {"forward": 3386.0, "gauss": 1464.0, "props": 447.0, "backward": 1216.0}.get(dom)
         cpu_threads = os.cpu_count() or 1
         n_cpu = max(8 * cpu_threads, 16)
         cpu_val, cpu_dt = cpu_sample(topo, model, tab, arr, sweep, n_cpu, cpu_threads)
