@@ -603,8 +603,12 @@ __global__ void osc2_forward_fast_kernel(const osc2_topology *__restrict__ tp, S
 #pragma unroll
             for (int c = 0; c < D; ++c) { rowL[c] = 0.0; rowD[c] = 0.0; rowU[c] = 0.0; }
         }
-        // pivots inside node n
+        // pivots inside node n.  The reciprocal of pivot k+1 is started by EVERY lane on its own
+        // rowD[k+1] as soon as pivot step k has updated that entry (only lane k+1's is meaningful):
+        // outside the divergent publish block its seed + five dependent DFMA interleave with the other
+        // sixteen updates of step k instead of holding the whole warp at the head of step k+1
         Osc2Rcp my_rcp = osc2_rcp_make(1.0, 1.0);
+        Osc2Rcp nxt = osc2_rcp_prepare(rowD[0]);
 #pragma unroll
         for (int k = 0; k < D; ++k) {
             if (act && r == k) {
@@ -614,8 +618,8 @@ __global__ void osc2_forward_fast_kernel(const osc2_topology *__restrict__ tp, S
 #pragma unroll
                 for (int c = 0; c < D; ++c) pk[D + c] = rowU[c];
                 pk[2 * D] = rhs;
-                my_rcp = osc2_rcp_prepare(rowD[k]);
-                pk[2 * D + 1] = my_rcp.y;
+                my_rcp = nxt;
+                pk[2 * D + 1] = nxt.y;
             }
             __syncwarp();
             {
@@ -625,8 +629,12 @@ __global__ void osc2_forward_fast_kernel(const osc2_topology *__restrict__ tp, S
                 const bool on = act && r > k;
                 double q = osc2_div_p(rowD[k], osc2_rcp_make(pk[k], pk[2 * D + 1]));
                 q = on ? q : 0.0;
+                if (k + 1 < D) {
+                    rowD[k + 1] = rowD[k + 1] - pk[k + 1] * q;
+                    nxt = osc2_rcp_prepare(rowD[k + 1]);
+                }
 #pragma unroll
-                for (int c = k + 1; c < D; ++c) rowD[c] = rowD[c] - pk[c] * q;
+                for (int c = k + 2; c < D; ++c) rowD[c] = rowD[c] - pk[c] * q;
 #pragma unroll
                 for (int c = 0; c < D; ++c) rowU[c] = rowU[c] - pk[D + c] * q;
                 rhs = rhs - pk[2 * D] * q;

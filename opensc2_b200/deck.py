@@ -197,10 +197,18 @@ def load_deck(folder: str, conductor: int = 1, legacy_no_field: bool = True,
                     m_ss_rad.append((float("inf"), 1.0))
         if abs(at(flag, "Environment", a)) == 1:
             ch = int(at(choice, "Environment", a))
-            if ch not in (-2, -4):
-                raise ValueError(f"Environment-{a}: HTC_choice {ch} is not implemented on the device (-2, -4)")
+            if ch not in (-2, -3, 3, -4):
+                raise ValueError(f"Environment-{a}: HTC_choice {ch} (free convection from air properties) is not "
+                                 "implemented on the device (-2, 3, -3, -4 are)")
             es.append(l); p_es.append(at(perim, "Environment", a))
-            h = at(htc, "Environment", a) * (phi_conv if ch == -2 else 1.0) * at(mlt, "Environment", a, 1.0)   # conductor.py:5302-5386
+            if abs(ch) == 3:
+                # radiation only: the reference stores the coefficient under "rad" (conductor.py:5320-5350), and the
+                # step reads "conv" alone (smc:851-853, 969-971), which stays zero -- no exchange reaches the system
+                h = 0.0
+                notes.append(f"Environment-{a}: HTC_choice {ch}: radiative coefficient is output-only in the reference; "
+                             "the step sees a zero convective coefficient")
+            else:
+                h = at(htc, "Environment", a) * (phi_conv if ch == -2 else 1.0) * at(mlt, "Environment", a, 1.0)   # conductor.py:5302-5386
             m_es.append(h)
 
     method = str(_get(cin, "METHOD", default="BE"))
