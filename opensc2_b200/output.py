@@ -113,3 +113,90 @@ def save_properties_batch(root: str, topo: Topology, model: Model, tables, zcoor
     for b in (range(sysvar.shape[0]) if conductors is None else conductors):
         save_properties(os.path.join(root, f"conductor_{b}"), topo, model, tables, zcoord, sysvar[b], sweep.b_field[b],
                         None if t_cur_sharing is None else t_cur_sharing[b])
+
+
+_SD_CHAN_HEADER = ("zcoord (m)\tvelocity (m/s)\tpressure (Pa)\ttemperature (K)\ttotal_density (kg/m^3)\t"
+                   "friction_factor (~)")
+_SD_GAUSS_HEADER = "zcoord_gauss (m)\tcurrent_along (A)\tdelta_voltage_along (V)\tP_along (W/m)"
+_SD_TABLES = (("heat_rad_inner", "Heat_rad_inner"), ("heat_exch_env", "Heat_exch_env"), ("htc_ch_ch_open", "HTC_ch_ch_o"),
+              ("htc_ch_ch_close", "HTC_ch_ch_c"), ("htc_ch_sol", "HTC_ch_sol"), ("htc_sol_sol_cond", "HTC_sol_sol_cond"),
+              ("htc_sol_sol_rad", "HTC_sol_sol_rad"))
+
+
+def save_simulation_space(f_path: str, topo: Topology, model: Model, tables: Sequence[FluidTable], zcoord: np.ndarray,
+                          sysvar: np.ndarray, cond_num_step: int, time: float, first_store: bool, *,
+                          zcoord_gauss: Optional[np.ndarray] = None, j_critical: Optional[np.ndarray] = None,
+                          t_cur_sharing: Optional[np.ndarray] = None, tcs_evaluation: bool = False,
+                          electric: Optional[np.ndarray] = None, nodal_tables: Optional[dict] = None,
+                          chan_ids: Optional[Sequence[str]] = None, solid_ids: Optional[Sequence[str]] = None) -> None:
+    """Spatial distributions of ONE conductor at one stored time: drop-in for the reference's
+    `save_simulation_space` (utility_functions/output.py:98-347) — same file names, headers, formats.
+
+      <channel>_(<step>)_sd.tsv        zcoord, velocity, pressure, temperature, total_density, friction_factor
+      <strand>_(<step>)_sd.tsv         zcoord, temperature [, current sharing temperature], critical current density
+                                       (stabilisers: zcoord, temperature)
+      <jacket>_(<step>)_sd.tsv         zcoord, temperature
+      <solid>_(<step>)_gauss_sd.tsv    zcoord_gauss, current, voltage drop, Joule power per length (electric module
+                                       arrays; zeros when `electric` is None, as with the electric module off)
+      <table>_(<step>)_sd.tsv          optional nodal tables (`nodal_tables`: heat_rad_inner, heat_exch_env,
+                                       htc_ch_ch_open, htc_ch_ch_close, htc_ch_sol, htc_sol_sol_cond, htc_sol_sol_rad;
+                                       each {column name: (N,) array}), written with pandas like the reference
+      Time_sd_actual.tsv               created at the first store, appended afterwards
+
+    sysvar: (N*d,); j_critical, t_cur_sharing: (S, N) (rows of non-superconducting solids ignored);
+    electric: (S, E, 3) current_along, delta_voltage_along, linear_power_el_resistance[:, 0]."""
+    import pandas as pd
+
+    M, d = topo.n_ch, topo.ndf
+    N = zcoord.shape[0]
+    x = np.asarray(sysvar, dtype=np.float64).reshape(N, d)
+    zg = (zcoord[:-1] + zcoord[1:]) / 2.0 if zcoord_gauss is None else zcoord_gauss
+    chan_ids = chan_ids or [f"CHAN_{j + 1}" for j in range(M)]
+    if solid_ids is None:
+        names = {SOLID_STRAND_MIXED: "STR_MIX", SOLID_JACKET: "Z_JACKET"}
+        count, solid_ids = {}, []
+        for s in model.solids:
+            nm = names.get(s.kind, "STR_STAB")
+            count[nm] = count.get(nm, 0) + 1
+            solid_ids.append(f"{nm}_{count[nm]}")
+    os.makedirs(f_path, exist_ok=True)
+
+    def write(name, a, header):
+        with open(os.path.join(f_path, name), "w") as w:
+            np.savetxt(w, a, delimiter="\t", header=header, comments="")
+
+    for j in range(M):
+        full = channel_table(topo, model, tables[model.ch_fluid[j]], j, zcoord, x[:, j].copy(), x[:, M + j].copy(),
+                             x[:, 2 * M + j].copy())
+        # channel_table columns: zcoord, pressure, temperature, total_density, velocity, ..., friction_factor
+        write(f"{chan_ids[j]}_({cond_num_step})_sd.tsv", full[:, [0, 4, 1, 2, 3, -1]], _SD_CHAN_HEADER)
+    for l, s in enumerate(model.solids):
+        temp = x[:, 3 * M + l]
+        if s.kind == SOLID_JACKET:
+            a, header = np.stack([zcoord, temp], axis=1), "zcoord (m)\ttemperature (K)"
+        elif s.kind == SOLID_STRAND_MIXED:
+            jc = np.zeros(N) if j_critical is None else j_critical[l]
+            if tcs_evaluation:
+                tcs = np.zeros(N) if t_cur_sharing is None else t_cur_sharing[l]
+                a = np.stack([zcoord, temp, tcs, jc], axis=1)
+                header = ("zcoord (m)\ttemperature (K)\tcurrent_sharing_temperature (K)\t"
+                          "critical_current_density (A/m^2)")
+            else:
+                a = np.stack([zcoord, temp, jc], axis=1)
+                header = "zcoord (m)\ttemperature (K)\tcritical_current_density (A/m^2)"
+        else:
+            a, header = np.stack([zcoord, temp], axis=1), "zcoord (m)\ttemperature (K)"
+        write(f"{solid_ids[l]}_({cond_num_step})_sd.tsv", a, header)
+    for l in range(topo.n_sol):
+        el = np.zeros((N - 1, 3)) if electric is None else electric[l]
+        write(f"{solid_ids[l]}_({cond_num_step})_gauss_sd.tsv", np.concatenate([zg[:, None], el], axis=1), _SD_GAUSS_HEADER)
+    for key, stem in _SD_TABLES:
+        tab = (nodal_tables or {}).get(key)
+        if tab:
+            pd.DataFrame.from_dict(tab, dtype=float).to_csv(os.path.join(f_path, f"{stem}_({cond_num_step})_sd.tsv"),
+                                                            sep="\t", index=False, header=True)
+    with open(os.path.join(f_path, "Time_sd_actual.tsv"), "w" if first_store else "a") as w:
+        if first_store:
+            np.savetxt(w, np.array([time]), header="time (s)", comments="", delimiter="\t")
+        else:
+            np.savetxt(w, np.array([time]), comments="", delimiter="\t")

@@ -80,6 +80,49 @@ def main():
     np.savez(os.path.join(out_dir, "inputs.npz"), sysvar=x.reshape(-1), zcoord=zcoord, b_field=sweep.b_field[0], tcs=tcs)
     print(sorted(os.listdir(out_dir)))
 
+    # ---- save_simulation_space (utility_functions/output.py:98-347): two stores of the same conductor, the
+    # second with TCS_EVALUATION on, so that both strand layouts and the append branch of Time_sd_actual.tsv exist
+    from utility_functions.output import save_simulation_space
+
+    E = n - 1
+    jc = np.linspace(2.0e9, 2.5e9, n)
+    zg = (zcoord[:-1] + zcoord[1:]) / 2.0
+    el = rng.uniform(0.0, 1.0, (2, E, 3))
+    gauss = lambda q: {"current_along": el[q, :, 0], "delta_voltage_along": el[q, :, 1],
+                       "linear_power_el_resistance": np.stack([el[q, :, 2], np.zeros(E)], axis=1)}
+    strand.KIND, strand.operations = "StrandMixedComponent", {"TCS_EVALUATION": False}
+    strand.dict_node_pt["J_critical"] = jc
+    strand.dict_Gauss_pt, jacket.dict_Gauss_pt = gauss(0), gauss(1)
+    htc_nodal = {"ch_ch": {"Open": {"CHAN_1_CHAN_2": rng.uniform(100.0, 200.0, n)}, "Close": {"CHAN_1_CHAN_2": rng.uniform(10.0, 20.0, n)}},
+                 "ch_sol": {"CHAN_1_STR_MIX_1": rng.uniform(500.0, 900.0, n), "CHAN_2_Z_JACKET_1": rng.uniform(500.0, 900.0, n)},
+                 "sol_sol": {"cond": {"STR_MIX_1_Z_JACKET_1": np.full(n, 500.0)}, "rad": {}}}
+    cond.grid_features["zcoord_gauss"] = zg
+    cond.grid_input = {"NELEMS": E}
+    cond.inventory["SolidComponent"] = coll([strand, jacket], "SOLID")
+    cond.Space_save = np.array([0.0, 0.25])
+    cond.num_step_save = np.zeros(2, dtype=int)
+    cond.i_save = 0
+    cond.cond_num_step = 0
+    cond.cond_time = [0.0]
+    cond.heat_rad_jk, cond.heat_exchange_jk_env = {}, {}
+    cond.dict_node_pt = {"HTC": htc_nodal}
+    out2 = os.path.join(HERE, "save_simulation_space")
+    os.makedirs(out2, exist_ok=True)
+    for f in os.listdir(out2):
+        os.remove(os.path.join(out2, f))
+    save_simulation_space(cond, out2, 4)
+    cond.cond_num_step, strand.operations["TCS_EVALUATION"] = 25, True
+    cond.cond_time.append(0.25)
+    cond.heat_rad_jk = {"Z_JACKET_1_Z_JACKET_2": rng.uniform(0.0, 3.0, n)}
+    cond.heat_exchange_jk_env = {"Environment_Z_JACKET_1": rng.uniform(0.0, 3.0, n)}
+    save_simulation_space(cond, out2, 4)
+    np.savez(os.path.join(out2, "inputs.npz"), sysvar=x.reshape(-1), zcoord=zcoord, zcoord_gauss=zg, tcs=tcs, jc=jc, el=el,
+             htc_open=htc_nodal["ch_ch"]["Open"]["CHAN_1_CHAN_2"], htc_close=htc_nodal["ch_ch"]["Close"]["CHAN_1_CHAN_2"],
+             htc_fs0=htc_nodal["ch_sol"]["CHAN_1_STR_MIX_1"], htc_fs1=htc_nodal["ch_sol"]["CHAN_2_Z_JACKET_1"],
+             htc_ss=htc_nodal["sol_sol"]["cond"]["STR_MIX_1_Z_JACKET_1"],
+             heat_rad=cond.heat_rad_jk["Z_JACKET_1_Z_JACKET_2"], heat_env=cond.heat_exchange_jk_env["Environment_Z_JACKET_1"])
+    print(sorted(os.listdir(out2)), cond.num_step_save, cond.i_save)
+
 
 if __name__ == "__main__":
     main()
