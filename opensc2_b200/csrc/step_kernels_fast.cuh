@@ -711,26 +711,35 @@ __global__ void osc2_backward_fast_kernel(StepDev p)
 
     constexpr int W = 2 * D + 2;      // D' | U | rhs | 1/pivot
     int range_flag = 0;
-    double f[W], fn[W], xc[D], xn[D];
+    // factor rows of the current node and of the two nodes below it: a node takes ~2500 cycles, about
+    // one DRAM round trip under load, so a one-node prefetch still left 0.6 of them exposed (ncu)
+    double f[W], fn[W], fnn[W], xc[D], xn[D];
 #pragma unroll
-    for (int c = 0; c < W; ++c) { f[c] = 0.0; fn[c] = 0.0; }
+    for (int c = 0; c < W; ++c) { f[c] = 0.0; fn[c] = 0.0; fnn[c] = 0.0; }
 #pragma unroll
     for (int c = 0; c < D; ++c) { xc[c] = 0.0; xn[c] = 0.0; }
     if (act) {
         const double *sp = p.spill + (((size_t)(N - 1) * D + r) * W) * B + b;
 #pragma unroll
         for (int c = 0; c < W; ++c) fn[c] = sp[(size_t)c * B];
+        if (N > 1) {
+            const double *sq = p.spill + (((size_t)(N - 2) * D + r) * W) * B + b;
+#pragma unroll
+            for (int c = 0; c < W; ++c) fnn[c] = sq[(size_t)c * B];
+        }
     } else {
         fn[r < D ? r : 0] = 1.0;      // idle lanes divide by 1
         fn[2 * D + 1] = 1.0;
+#pragma unroll
+        for (int c = 0; c < W; ++c) fnn[c] = fn[c];
     }
     for (int n = N - 1; n >= 0; --n) {
 #pragma unroll
-        for (int c = 0; c < W; ++c) f[c] = fn[c];
-        if (act && n > 0) {
-            const double *sp = p.spill + (((size_t)(n - 1) * D + r) * W) * B + b;
+        for (int c = 0; c < W; ++c) { f[c] = fn[c]; fn[c] = fnn[c]; }
+        if (act && n > 1) {
+            const double *sp = p.spill + (((size_t)(n - 2) * D + r) * W) * B + b;
 #pragma unroll
-            for (int c = 0; c < W; ++c) fn[c] = sp[(size_t)c * B];
+            for (int c = 0; c < W; ++c) fnn[c] = sp[(size_t)c * B];
         }
         // products with the already known node n+1 are off the dependency chain
         double pu[D];
