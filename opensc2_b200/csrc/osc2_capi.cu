@@ -314,7 +314,7 @@ int osc2_create(const osc2_topology *topo, int batch, int n_nodes, int device, o
     { const char *fw = getenv("OSC2_FUSED_WARPS"); if (fw && atoi(fw) >= 1 && atoi(fw) <= 4) h->fused_warps = atoi(fw); }
     // experimental: slower than the single-warp sweep today, off unless OSC2_FWD_SPLIT=1
     { const char *sp = getenv("OSC2_FWD_SPLIT"); h->fwd_mode = (sp && sp[0] == '1') ? 1 : 0; }
-    { const char *sp = getenv("OSC2_FWD_MODE"); if (sp && sp[0] >= '0' && sp[0] <= '2') h->fwd_mode = sp[0] - '0'; }
+    { const char *sp = getenv("OSC2_FWD_MODE"); if (sp && sp[0] >= '0' && sp[0] <= '3') h->fwd_mode = sp[0] - '0'; }
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     h->max_smem = (int)prop.sharedMemPerBlockOptin;

@@ -12,6 +12,7 @@
 #include "step_kernels_fast.cuh"
 #include "step_kernels_split.cuh"
 #include "step_kernels_wide.cuh"
+#include "step_kernels_pipe.cuh"
 
 #include <vector>
 
@@ -128,6 +129,16 @@ void osc2_run_fast_sweeps(Launcher &L, const osc2_topology *tp_dev, const StepDe
                           cpb * sizeof(double);
     const size_t smem_b = (size_t)(2 * D + 2) * cpb * sizeof(double);
     if constexpr (D % 8 == 0) {
+        if (p.fwd_split == 3 && be && !cap) {      // two phases per round (step_kernels_pipe.cuh)
+            const size_t smem_p = (size_t)PipeFwdSmem<D>::PER_COND * cpb * sizeof(double);
+            bool fullp = false;
+            if constexpr (LPC == D) fullp = (p.B % cpb == 0);
+            if (fullp) {
+                if constexpr (LPC == D) L.launch(OSC2_K_FORWARD, osc2_forward_pipe_kernel<D, LPC, true>, grid, 32u, smem_p, tp_dev, p);
+            } else L.launch(OSC2_K_FORWARD, osc2_forward_pipe_kernel<D, LPC, false>, grid, 32u, smem_p, tp_dev, p);
+            L.launch(OSC2_K_BACKWARD, osc2_backward_fast_kernel<D, LPC>, grid, 32u, smem_b, p);
+            return;
+        }
         if (p.fwd_split == 2 && be) {      // 16 lanes per conductor (step_kernels_wide.cuh)
             constexpr int cpw = 32 / (2 * D);
             const unsigned gridw = (unsigned)((p.B + cpw - 1) / cpw);

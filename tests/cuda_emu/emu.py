@@ -31,7 +31,8 @@ def lib():
     if _LIB is None:
         so = os.path.join(HERE, "libosc2_emu.so")
         srcs = [os.path.join(HERE, f) for f in ("emu_step.cpp", "cuda_emu.h")]
-        srcs += [os.path.join(ROOT, "opensc2_b200", "csrc", f) for f in ("step_kernels.cuh", "step_kernels_fast.cuh", "step_kernels_split.cuh", "step_launch.h", "osc2_dev.h")]
+        csrc = os.path.join(ROOT, "opensc2_b200", "csrc")
+        srcs += [os.path.join(csrc, f) for f in sorted(os.listdir(csrc)) if f.endswith((".cuh", ".h"))]
         srcs += [os.path.join(ROOT, "include", "opensc2_b200.h")]
         if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
             subprocess.run(["g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-ffp-contract=off", "-pthread",

@@ -38,6 +38,28 @@ def test_emulated_kernels_match_reference_fixture(name, fast, split):
         assert_bits(out[key][0], ref[key], f"{name}:{key}")
 
 
+@pytest.mark.parametrize("name", ["case1_pdrop_n21", "case1_pinl_vout_first_step_n17", "case1_min_mesh_n4"])
+def test_emulated_pipelined_sweep_matches_reference_fixture(name):
+    """OSC2_FWD_MODE=3 (step_kernels_pipe.cuh: rounds of node n and of node n+1 merged), no capture."""
+    topo, arr, ref = load_golden(name)
+    out = emu.emu_step(topo, _batched(arr), fast=True, split=3)
+    assert out["status"][0] == 0
+    for key in KEYS:
+        assert_bits(out[key][0], ref[key], f"{name}:{key}")
+
+
+@pytest.mark.parametrize("intial,n,batch", [(1, 9, 8), (2, 7, 6), (3, 23, 5)])
+def test_emulated_pipelined_sweep_batches(intial, n, batch):
+    """Full and ragged warps, every boundary-condition mode, against the oracle."""
+    topo = case1_topology(intial)
+    arr = synthetic_step_arrays(topo, n, batch=batch, seed=40 + n)
+    out = emu.emu_step(topo, arr, fast=True, split=3)
+    ref = O.step(topo, arr)
+    assert np.all(out["status"] == 0)
+    for key in KEYS:
+        assert_bits(out[key], ref[key], key)
+
+
 def test_emulated_batch_ragged_tail():
     """B not a multiple of the conductors-per-warp; every slot matches the oracle."""
     topo = case1_topology(2)
