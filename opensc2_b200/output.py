@@ -200,3 +200,137 @@ def save_simulation_space(f_path: str, topo: Topology, model: Model, tables: Seq
             np.savetxt(w, np.array([time]), header="time (s)", comments="", delimiter="\t")
         else:
             np.savetxt(w, np.array([time]), comments="", delimiter="\t")
+
+
+_IO_KEYS = ("velocity", "pressure", "temperature", "total_density", "mass_flow_rate")
+_IO_UNITS = {"velocity": "(m/s)", "pressure": "(Pa)", "temperature": "(K)", "total_density": "(kg/m^3)",
+             "mass_flow_rate": "(kg/s)"}
+_GAUSS_KEYS = ("current_along", "delta_voltage_along", "linear_power_el_resistance", "delta_voltage_along_sum")
+
+
+class TimeEvolutionWriter:
+    """Time evolutions of ONE conductor at the user's axial coordinates: drop-in for the reference's
+    `save_simulation_time` (utility_functions/output.py:647-977) with its buffering — header-only files at the
+    first call, rows appended every `chunk_size` calls (`Conductor.CHUNCK_SIZE`, conductor.py:97) and when
+    TEND is reached, `Time.tsv` at TEND.
+
+      <channel>_{velocity,pressure,temperature,total_density,friction_factor}_te.tsv   value at each coordinate
+      <channel>_inlet_outlet_te.tsv      v, p, T, rho, mass flow rate at the inlet and at the outlet node
+      <solid>_<key>_te.tsv               temperature (+ B_field, T_cur_sharing, J_critical for strands: mixed
+                                         strands all four, stabilisers the first two) and the Gauss-point arrays of
+                                         the electric module (current_along, delta_voltage_along,
+                                         linear_power_el_resistance[:, 0], delta_voltage_along_sum; jackets: first three)
+    The coordinate -> node rule is the reference's: the last node with z <= round(coordinate, n_digit_z); the
+    first Gauss coordinate always maps to element 0 (output.py:661-678)."""
+
+    def __init__(self, f_path: str, topo: Topology, model: Model, tables: Sequence[FluidTable], time_save: np.ndarray,
+                 tend: float, *, n_digit_z: int = 3, chunk_size: int = 100, ch_forward: Optional[Sequence[bool]] = None,
+                 chan_ids: Optional[Sequence[str]] = None, solid_ids: Optional[Sequence[str]] = None):
+        self.f_path, self.topo, self.model, self.tables = f_path, topo, model, tables
+        self.time_save, self.tend, self.n_digit_z, self.chunk = np.asarray(time_save, dtype=float), tend, n_digit_z, chunk_size
+        self.ch_forward = list(ch_forward) if ch_forward is not None else [bool(f) for f in topo.ch_forward]
+        self.chan_ids = list(chan_ids) if chan_ids else [f"CHAN_{j + 1}" for j in range(topo.n_ch)]
+        if solid_ids is None:
+            names = {SOLID_STRAND_MIXED: "STR_MIX", SOLID_JACKET: "Z_JACKET"}
+            count, solid_ids = {}, []
+            for s in model.solids:
+                nm = names.get(s.kind, "STR_STAB")
+                count[nm] = count.get(nm, 0) + 1
+                solid_ids.append(f"{nm}_{count[nm]}")
+        self.solid_ids = list(solid_ids)
+        self.cond_time: list = []
+        self.buf: dict = {}          # file name -> {column: list}
+        self.started = False
+
+    def _solid_keys(self, l):
+        kind = self.model.solids[l].kind
+        if kind == SOLID_JACKET:
+            return ("temperature",), _GAUSS_KEYS[:3]
+        if kind == SOLID_STRAND_MIXED:
+            return ("temperature", "B_field", "T_cur_sharing", "J_critical"), _GAUSS_KEYS
+        return ("temperature", "B_field"), _GAUSS_KEYS
+
+    def _path(self, name):
+        return os.path.join(self.f_path, name)
+
+    def _flush(self, name, at_tend):
+        import pandas as pd
+
+        val = self.buf[name]
+        if len(val["time (s)"]) == self.chunk or at_tend:
+            pd.DataFrame(val, columns=list(val.keys()), dtype=float).to_csv(self._path(name), sep="\t", mode="a",
+                                                                            chunksize=self.chunk, index=False, header=False)
+            if len(val["time (s)"]) == self.chunk:
+                self.buf[name] = {k: [] for k in val}
+
+    def store(self, time: float, zcoord: np.ndarray, sysvar: np.ndarray, *, zcoord_gauss: Optional[np.ndarray] = None,
+              solid_nodal: Optional[dict] = None, solid_gauss: Optional[dict] = None) -> None:
+        """One call per time step.  sysvar: (N*d,); solid_nodal: {key: (S, N)} for B_field, T_cur_sharing,
+        J_critical; solid_gauss: {key: (S, E)} for the electric-module arrays (missing ones are zeros)."""
+        import pandas as pd
+
+        topo, model = self.topo, self.model
+        M, S, d = topo.n_ch, topo.n_sol, topo.ndf
+        N = zcoord.shape[0]
+        x = np.asarray(sysvar, dtype=np.float64).reshape(N, d)
+        zg = (zcoord[:-1] + zcoord[1:]) / 2.0 if zcoord_gauss is None else zcoord_gauss
+        ts = self.time_save
+        ind = {f"zcoord = {ts[i]} (m)": int(np.max(np.nonzero(zcoord <= round(ts[i], self.n_digit_z)))) for i in range(ts.size)}
+        ind_g = {f"zcoord_g = {ts[0]} (m)": 0}
+        ind_g.update({f"zcoord_g = {ts[i]} (m)": int(np.max(np.nonzero(zg <= round(ts[i], self.n_digit_z)))) for i in range(1, ts.size)})
+        io_cols = ["time (s)"] + [f"{k}_{side} {_IO_UNITS[k]}" for side in ("inl", "out") for k in _IO_KEYS]
+        if not self.started:
+            os.makedirs(self.f_path, exist_ok=True)
+
+            def create(name, columns):
+                pd.DataFrame(columns=columns).to_csv(self._path(name), sep="\t", index=False, header=True)
+                self.buf[name] = {c: [] for c in columns}
+
+            for j in range(M):
+                for key in ("velocity", "pressure", "temperature", "total_density", "friction_factor"):
+                    create(f"{self.chan_ids[j]}_{key}_te.tsv", ["time (s)"] + list(ind))
+                create(f"{self.chan_ids[j]}_inlet_outlet_te.tsv", io_cols)
+            for l in range(S):
+                nodal, gauss = self._solid_keys(l)
+                for key in nodal:
+                    create(f"{self.solid_ids[l]}_{key}_te.tsv", ["time (s)"] + list(ind))
+                for key in gauss:
+                    create(f"{self.solid_ids[l]}_{key}_te.tsv", ["time (s)"] + list(ind_g))
+            self.started = True
+        self.cond_time.append(time)
+        at_tend = abs(time - self.tend) / self.tend <= 1e-6
+
+        def push(name, prop, index):
+            val = self.buf[name]
+            val["time (s)"].append(time)
+            for key, i in index.items():
+                val[key].append(prop[i])
+            self._flush(name, at_tend)
+
+        for j in range(M):
+            full = channel_table(topo, model, self.tables[model.ch_fluid[j]], j, zcoord, x[:, j].copy(), x[:, M + j].copy(),
+                                 x[:, 2 * M + j].copy())
+            cols = {"velocity": full[:, 4], "pressure": full[:, 1], "temperature": full[:, 2], "total_density": full[:, 3],
+                    "mass_flow_rate": full[:, 16], "friction_factor": full[:, 17]}
+            for key in ("velocity", "pressure", "temperature", "total_density", "friction_factor"):
+                push(f"{self.chan_ids[j]}_{key}_te.tsv", cols[key], ind)
+            i_in, i_out = (0, -1) if self.ch_forward[j] else (-1, 0)
+            name = f"{self.chan_ids[j]}_inlet_outlet_te.tsv"
+            val = self.buf[name]
+            val["time (s)"].append(time)
+            for side, i in (("inl", i_in), ("out", i_out)):
+                for k in _IO_KEYS:
+                    val[f"{k}_{side} {_IO_UNITS[k]}"].append(cols[k][i])
+            self._flush(name, at_tend)
+        for l in range(S):
+            nodal, gauss = self._solid_keys(l)
+            for key in nodal:
+                prop = x[:, 3 * M + l] if key == "temperature" else (
+                    np.zeros(N) if not solid_nodal or key not in solid_nodal else solid_nodal[key][l])
+                push(f"{self.solid_ids[l]}_{key}_te.tsv", prop, ind)
+            for key in gauss:
+                prop = np.zeros(N - 1) if not solid_gauss or key not in solid_gauss else solid_gauss[key][l]
+                push(f"{self.solid_ids[l]}_{key}_te.tsv", prop, ind_g)
+        if at_tend:
+            pd.Series(self.cond_time, name="time (s)", dtype=float).to_csv(self._path("Time.tsv"), sep="\t", header=True,
+                                                                           index=False)

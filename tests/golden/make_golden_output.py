@@ -123,6 +123,62 @@ def main():
              heat_rad=cond.heat_rad_jk["Z_JACKET_1_Z_JACKET_2"], heat_env=cond.heat_exchange_jk_env["Environment_Z_JACKET_1"])
     print(sorted(os.listdir(out2)), cond.num_step_save, cond.i_save)
 
+    # ---- save_simulation_time (utility_functions/output.py:647-977): 5 calls with a chunk size of 3, TEND reached at
+    # the last one -> header creation, a chunk flush, the final flush and Time.tsv
+    from utility_functions.output import save_simulation_time
+
+    out3 = os.path.join(HERE, "save_simulation_time")
+    os.makedirs(out3, exist_ok=True)
+    for f in os.listdir(out3):
+        os.remove(os.path.join(out3, f))
+    n_calls, tend = 5, 0.4
+    states = np.stack([x * (1.0 + 1e-3 * k) for k in range(n_calls)])                  # (calls, N, d)
+    extra = rng.uniform(1.0, 2.0, (n_calls, 2, 3, n))                                   # B_field, T_cur_sharing, J_critical per solid
+    elg = rng.uniform(0.0, 1.0, (n_calls, 2, E, 4))                                     # the four Gauss-point arrays per solid
+    cond.identifier = "CONDUCTOR_1"
+    cond.Time_save = np.array([0.0, 3.4, 10.0])
+    cond.n_digit_z = 3
+    cond.CHUNCK_SIZE = 3
+    cond.cond_time = []
+    sim = types.SimpleNamespace(num_step=0, transient_input={"TEND": tend},
+                                dict_path={"Output_Time_evolution_CONDUCTOR_1_dir": out3})
+    for fc in fluids:
+        fc.coolant.time_evol = dict(velocity=dict(), pressure=dict(), temperature=dict(), total_density=dict())
+        fc.coolant.time_evol_io = {k: list() for k in (
+            "time (s)", "velocity_inl (m/s)", "pressure_inl (Pa)", "temperature_inl (K)", "total_density_inl (kg/m^3)",
+            "mass_flow_rate_inl (kg/s)", "velocity_out (m/s)", "pressure_out (Pa)", "temperature_out (K)",
+            "total_density_out (kg/m^3)", "mass_flow_rate_out (kg/s)")}
+        fc.channel.time_evol = dict(friction_factor=dict())
+        fc.channel.flow_dir = ("forward", 1.0)
+    fluids[1].channel.flow_dir = ("backward", -1.0)
+    strand.time_evol = dict(temperature=dict(), B_field=dict(), T_cur_sharing=dict(), J_critical=dict())
+    strand.time_evol_gauss = dict(current_along=dict(), delta_voltage_along=dict(), linear_power_el_resistance=dict(),
+                                  delta_voltage_along_sum=dict())
+    jacket.time_evol = dict(temperature=dict())
+    jacket.time_evol_gauss = dict(current_along=dict(), delta_voltage_along=dict(), linear_power_el_resistance=dict())
+    for k in range(n_calls):
+        xk = states[k]
+        for j, fc in enumerate(fluids):
+            co = fc.coolant
+            co.dict_node_pt = {"pressure": xk[:, M + j].copy(), "temperature": xk[:, 2 * M + j].copy()}
+            co.dict_node_pt["total_density"] = coolant_mod.PropsSI("Dmass", "T", co.dict_node_pt["temperature"], "P", co.dict_node_pt["pressure"], "He")
+            co.dict_node_pt["velocity"] = xk[:, j].copy()
+            co.dict_node_pt = co._eval_properties(co.dict_node_pt, aliases)
+            co.dict_node_pt = co._compute_density_and_mass_flow_rates(co.dict_node_pt)
+            fc.channel.eval_friction_factor(co.dict_node_pt["Reynolds"], nodal=True)
+        for q, sc in enumerate((strand, jacket)):
+            sc.dict_node_pt = {"temperature": xk[:, 3 * M + q].copy(), "B_field": extra[k, q, 0], "T_cur_sharing": extra[k, q, 1],
+                               "J_critical": extra[k, q, 2]}
+            sc.dict_Gauss_pt = {"current_along": elg[k, q, :, 0], "delta_voltage_along": elg[k, q, :, 1],
+                                "linear_power_el_resistance": np.stack([elg[k, q, :, 2], np.zeros(E)], axis=1),
+                                "delta_voltage_along_sum": elg[k, q, :, 3]}
+        cond.cond_time.append(tend * k / (n_calls - 1))
+        sim.num_step = k
+        save_simulation_time(sim, cond)
+    np.savez(os.path.join(out3, "inputs.npz"), states=states.reshape(n_calls, -1), zcoord=zcoord, zcoord_gauss=zg, extra=extra,
+             elg=elg, time_save=cond.Time_save, times=np.array(cond.cond_time), tend=tend)
+    print(sorted(os.listdir(out3)))
+
 
 if __name__ == "__main__":
     main()
