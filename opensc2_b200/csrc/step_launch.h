@@ -14,6 +14,7 @@
 #include "step_kernels_wide.cuh"
 #include "step_kernels_pipe.cuh"
 
+#include <cstdlib>
 #include <vector>
 
 // numpy pairwise summation (loops_utils.h.src, PW_BLOCKSIZE = 128) of n values:
@@ -159,17 +160,21 @@ void osc2_run_fast_sweeps(Launcher &L, const osc2_topology *tp_dev, const StepDe
         L.launch(OSC2_K_BACKWARD, osc2_backward_fast_kernel<D, LPC>, grid, 32u, smem_b, p);
         return;
     }
+    // warps per CTA of the two sweeps (experiment knob OSC2_SWEEP_WARPS, default 1): with 2, the two
+    // 32-byte halves of a 64-byte DRAM burst are requested from the same SM
+    static const int W = [] { const char *e = getenv("OSC2_SWEEP_WARPS"); return (e && e[0] == '2') ? 2 : 1; }();
+    const unsigned blk = 32u * W, gridW = (unsigned)((p.B + cpb * W - 1) / (cpb * W));
     bool full = false;       // every lane of every warp owns a row: the kernel drops its lane predicates
-    if constexpr (LPC == D) full = be && !cap && (p.B % cpb == 0);
+    if constexpr (LPC == D) full = be && !cap && (p.B % (cpb * W) == 0);
     if (full) {
         if constexpr (LPC == D)
-            L.launch(OSC2_K_FORWARD, osc2_forward_fast_kernel<D, LPC, true, false, true>, grid, 32u, smem_f, tp_dev, p);
+            L.launch(OSC2_K_FORWARD, osc2_forward_fast_kernel<D, LPC, true, false, true>, gridW, blk, smem_f * W, tp_dev, p);
     }
-    else if (be && !cap) L.launch(OSC2_K_FORWARD, osc2_forward_fast_kernel<D, LPC, true, false>, grid, 32u, smem_f, tp_dev, p);
-    else if (be) L.launch(OSC2_K_FORWARD, osc2_forward_fast_kernel<D, LPC, true, true>, grid, 32u, smem_f, tp_dev, p);
-    else if (!cap) L.launch(OSC2_K_FORWARD, osc2_forward_fast_kernel<D, LPC, false, false>, grid, 32u, smem_f, tp_dev, p);
-    else L.launch(OSC2_K_FORWARD, osc2_forward_fast_kernel<D, LPC, false, true>, grid, 32u, smem_f, tp_dev, p);
-    L.launch(OSC2_K_BACKWARD, osc2_backward_fast_kernel<D, LPC>, grid, 32u, smem_b, p);
+    else if (be && !cap) L.launch(OSC2_K_FORWARD, osc2_forward_fast_kernel<D, LPC, true, false>, gridW, blk, smem_f * W, tp_dev, p);
+    else if (be) L.launch(OSC2_K_FORWARD, osc2_forward_fast_kernel<D, LPC, true, true>, gridW, blk, smem_f * W, tp_dev, p);
+    else if (!cap) L.launch(OSC2_K_FORWARD, osc2_forward_fast_kernel<D, LPC, false, false>, gridW, blk, smem_f * W, tp_dev, p);
+    else L.launch(OSC2_K_FORWARD, osc2_forward_fast_kernel<D, LPC, false, true>, gridW, blk, smem_f * W, tp_dev, p);
+    L.launch(OSC2_K_BACKWARD, osc2_backward_fast_kernel<D, LPC>, gridW, blk, smem_b * W, p);
 }
 
 // `records_ready`: the element row records were already produced by the fused K_PG kernel
