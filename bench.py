@@ -333,6 +333,8 @@ def run_ours(args, rank, world, local_rank):
                 "traffic": (traffic_per_unit * dom_units) if traffic_per_unit else None,
                 "traffic_source": "ncu --set full dram__bytes_read+write of this kernel at this size (profiles/r1_fullsize_ncu_summary.txt)" if traffic_per_unit else None,
                 "per_kernel_frac": fracs,
+                "note": "the forward sweep is a serial latency chain per conductor (all 4096 conductors are in flight at once: "
+                        "time = nodes x cycles per node), not byte bound; DESIGN.md section 5",
                 "step": {"alg_bytes_per_node_timestep": b_alg(d), "model": "SURVEY.md 8(d) two-kernel model (assembly + solve)",
                          "achieved": b_alg(d) * BATCH * NODES / (step_ms_kernels * 1e-3) / 1e9,
                          "frac": b_alg(d) * BATCH * NODES / (step_ms_kernels * 1e-3) / 1e9 / peak,
