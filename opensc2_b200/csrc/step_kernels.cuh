@@ -257,6 +257,23 @@ __device__ inline double osc2_pairwise_window(const double *strip, int len, long
 // elimination with forward substitution folded in.  Marches node by node;
 // spills D' (upper part), U and the reduced right-hand side for K_B.
 // ---------------------------------------------------------------------------
+// y[i] = y[i] - x[i] * q for i < n, eight entries per trip: the row being updated and the pivot row are
+// different rows of the shared-memory block, but the compiler cannot know that and would order every
+// load behind the previous store -- one exposed shared-memory round trip per entry.  Same arithmetic
+// per entry, so the result is unchanged bit for bit.
+__device__ __forceinline__ void osc2_row_update(double *__restrict__ y, const double *__restrict__ x, const double q, const int n)
+{
+    int i = 0;
+    for (; i + 8 <= n; i += 8) {
+        double a[8], b[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { a[u] = y[i + u]; b[u] = x[i + u]; }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) y[i + u] = a[u] - b[u] * q;
+    }
+    for (; i < n; ++i) y[i] = y[i] - x[i] * q;
+}
+
 template <int LPC>
 __global__ void osc2_forward_kernel(const osc2_topology *__restrict__ tp, StepDev p)
 {
@@ -501,8 +518,8 @@ __global__ void osc2_forward_kernel(const osc2_topology *__restrict__ tp, StepDe
                 for (int k = 0; k < d; ++k) {
                     const double *pk = prev + (size_t)k * RS;
                     const double q = row[k] / pk[d + k];
-                    for (int c = k + 1; c < d; ++c) row[c] = row[c] - pk[d + c] * q;
-                    for (int c = 0; c < d; ++c) row[d + c] = row[d + c] - pk[2 * d + c] * q;
+                    osc2_row_update(row + k + 1, pk + d + k + 1, q, d - k - 1);
+                    osc2_row_update(row + d, pk + 2 * d, q, d);
                     rhs = rhs - pk[3 * d] * q;
                 }
             }
@@ -519,8 +536,8 @@ __global__ void osc2_forward_kernel(const osc2_topology *__restrict__ tp, StepDe
             if (act && r > k) {
                 const double *pk = cur + (size_t)k * RS;
                 const double q = row[d + k] / pk[d + k];
-                for (int c = k + 1; c < d; ++c) row[d + c] = row[d + c] - pk[d + c] * q;
-                for (int c = 0; c < d; ++c) row[2 * d + c] = row[2 * d + c] - pk[2 * d + c] * q;
+                osc2_row_update(row + d + k + 1, pk + d + k + 1, q, d - k - 1);
+                osc2_row_update(row + 2 * d, pk + 2 * d, q, d);
                 rhs = rhs - pk[3 * d] * q;
             }
         }
