@@ -1,0 +1,543 @@
+// K_F64 / K_B64: the two sweeps of step() for systems with NODOFS = 64 (CASE_2: 13 channels,
+// 25 solids), register tiled.
+//
+// Reference being reproduced, operation for operation (same operand order, no FMA contraction):
+//   SYSMAT / Known   step_matrix_construction.py:1320-1474
+//   boundary rows    fluid_component.py:117-565
+//   row scaling      transient_solution_functions.py:538-551
+//   gredub           transient_solution_functions.py:602-698
+//   gbacsb           transient_solution_functions.py:701-808
+//
+// The generic sweep (step_kernels.cuh) keeps the block row [L D U | rhs] of a node in shared
+// memory, one thread per matrix row: 64 threads per conductor and two shared-memory loads + one
+// store per multiply-subtract.  Here one CTA of 256 threads owns a conductor: matrix row r lives in
+// the REGISTERS of four neighbouring lanes (3 x 16 entries each, columns dealt in pairs so that a
+// pivot row is read with 128-bit loads), the elimination multiplier travels by warp shuffle, and only
+// the pivot rows go through shared memory (one row of 130 doubles per pivot, read as a broadcast).
+// A d = 64 node costs 2.3 d^3 = 6.1e5 multiply-subtract pairs, i.e. the path is bound by the FP64
+// pipe and by the serial chain of 128 pivots per node, not by bytes (SURVEY.md 8d flags CASE_2).
+//
+// Row assembly uses the sparsity of the Gauss-point matrices: an entry (r, c) that is neither the
+// diagonal, nor the AMAT partner column, nor a position the topology's interface statements can
+// write (the same enumeration as osc2_build_smap) has SYSMAT value +0 and Known coefficient +0 in
+// the reference, so only its product 0 * x_old enters the (order-preserving) pairwise sum.
+//
+// Factor rows are spilled per conductor as [node][row][130] = D' (64) | U (64) | rhs | 1/pivot
+// refinement, contiguous, so that the forward sweep writes and the backward sweep reads full lines.
+#pragma once
+
+#include "step_kernels.cuh"
+#include "step_kernels_fast.cuh"   // osc2_bcast
+#include "osc2_div.cuh"
+
+#define OSC2_D64_SW 200   /* strip row stride (doubles): even, 64-byte shift between neighbouring rows */
+#define OSC2_D64_PW 130   /* pivot / factor row: D'(64) U(64) rhs rcp */
+
+struct alignas(16) Osc2Pair { double x, y; };
+
+__host__ __device__ inline size_t osc2_d64_fwd_smem_doubles() { return (size_t)64 * OSC2_D64_SW + 64 * OSC2_D64_PW + 3 * 64; }
+
+__device__ __forceinline__ Osc2Pair osc2_ld2(const double *q) { return *reinterpret_cast<const Osc2Pair *>(q); }
+__device__ __forceinline__ void osc2_st2(double *q, double a, double b)
+{
+    Osc2Pair v; v.x = a; v.y = b;
+    *reinterpret_cast<Osc2Pair *>(q) = v;
+}
+
+// numpy's pairwise sum of n <= 255 values splits into at most three leaves of <= 128 values:
+// sum = leaf0 [+ leaf1 | + (leaf1 + leaf2)]   (loops_utils.h.src, PW_BLOCKSIZE 128)
+__device__ inline int osc2_leaf_split(int n, int *start, int *len)
+{
+    if (n <= 128) { start[0] = 0; len[0] = n; return 1; }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    start[0] = 0; len[0] = n2;
+    const int m = n - n2;
+    if (m <= 128) { start[1] = n2; len[1] = m; return 2; }
+    int m2 = m / 2;
+    m2 -= m2 % 8;
+    start[1] = n2; len[1] = m2;
+    start[2] = n2 + m2; len[2] = m - m2;
+    return 3;
+}
+
+__device__ __forceinline__ int osc2_ctz(unsigned m)
+{
+#ifdef OSC2_EMU
+    return __builtin_ctz(m);
+#else
+    return __ffs((int)m) - 1;
+#endif
+}
+
+// ---------------------------------------------------------------------------
+// K_F64
+// ---------------------------------------------------------------------------
+template <bool CAP>
+__global__ void __launch_bounds__(256, 1) osc2_forward64_kernel(const osc2_topology *__restrict__ tp, StepDev p)
+{
+    OSC2_DYN_SMEM(sm_dyn);
+    constexpr int d = 64, SW = OSC2_D64_SW, PW = OSC2_D64_PW;
+    const int M = p.M, N = p.N;
+    const size_t B = (size_t)p.B;
+    const size_t b = (size_t)blockIdx.x;
+    const int tid = (int)threadIdx.x;
+    const int r = tid >> 2, h = tid & 3, lane = tid & 31, lane0 = lane & ~3, warp = tid >> 5;
+    const GmSlots sl{d, M, p.S};
+    const long long Total = (long long)d * N;
+    constexpr int Half = 2 * d, Main = 2 * d - 1;
+    const double dt = p.dt, theta = tp->theta;
+    const bool first = (p.num_step == 1);
+
+    double *strip = sm_dyn;                 // [64][SW]  products / unscaled row entries of the node
+    double *piv = strip + 64 * SW;          // [64][PW]  final rows of node n-1, then of node n
+    double *xs = piv + 64 * PW;             // [3][64]   old solution at nodes n-1, n, n+1
+    double *srow = strip + r * SW;
+    double *fac_out = p.spill + b * ((size_t)N * 64 * PW);
+
+    // ---- row kind, AMAT pattern, boundary rows (as the generic sweep) ------
+    int kind = 3, j = 0, aoffcol = -1, aoffq = 0;
+    if (r < M) { kind = 0; j = r; aoffcol = M + j; aoffq = 1; }
+    else if (r < 2 * M) { kind = 1; j = r - M; aoffcol = j; aoffq = 2; }
+    else if (r < 3 * M) { kind = 2; j = r - 2 * M; aoffcol = j; aoffq = 3; }
+    else { kind = 3; j = r - 3 * M; }
+    bool bc_first = false, bc_last = false;
+    double val_first = 0.0, val_last = 0.0;
+    if (kind < 3) {
+        const bool fwd = tp->ch_forward[j] != 0;
+        const int intial = tp->ch_intial[j];
+#define FBC(q) p.fl_bc[((size_t)(q) * M + j) * B + b]
+#define FND(q) p.fl_node[((size_t)(q) * M + j) * B + b]
+        if (kind == 1) {
+            if (intial == 1 || intial == 2) { if (fwd) { bc_first = true; val_first = FBC(0); } else { bc_last = true; val_last = FBC(0); } }
+            if (intial == 1 || intial == 3) { if (fwd) { bc_last = true; val_last = FBC(1); } else { bc_first = true; val_first = FBC(1); } }
+        } else if (kind == 0) {
+            const double area = tp->ch_area[j];
+            if (intial == 2) {
+                if (fwd) { bc_last = true; val_last = FBC(5) / FND(3) / area; }
+                else { bc_first = true; val_first = FBC(5) / FND(2) / area; }
+            } else if (intial == 3) {
+                if (fwd) { bc_first = true; val_first = FBC(4) / FND(2) / area; }
+                else { bc_last = true; val_last = FBC(4) / FND(3) / area; }
+            }
+        } else {
+            const double v_first = FND(0), v_last = FND(1);
+            if (fwd) {
+                if (v_first > 0) { bc_first = true; val_first = FBC(2); }
+                if (v_last < 0) { bc_last = true; val_last = FBC(3); }
+            } else {
+                if (v_last < 0) { bc_last = true; val_last = FBC(2); }
+                if (v_first > 0) { bc_first = true; val_first = FBC(3); }
+            }
+        }
+#undef FBC
+#undef FND
+    }
+
+    // ---- columns of row r the Gauss-point matrices can touch ----------------
+    unsigned long long rowbits = 1ull << r;
+    if (aoffcol >= 0) rowbits |= 1ull << aoffcol;
+    {
+        auto add = [&](int rr, int cc) { if (rr == r) rowbits |= 1ull << cc; };
+        for (int q = 0; q < M; ++q) { add(q, q); add(M + q, q); add(2 * M + q, q); }
+        for (int k = 0; k < p.nff; ++k)
+            for (int side = 0; side < 2; ++side) {
+                const int c1 = tp->ff[k][side], c2 = tp->ff[k][1 - side];
+                const int v1 = c1, p1 = M + c1, t1 = 2 * M + c1, p2 = M + c2, t2 = 2 * M + c2;
+                add(v1, p1); add(v1, p2); add(p1, p1); add(p1, p2); add(p1, t1); add(p1, t2);
+                add(t1, p1); add(t1, p2); add(t1, t1); add(t1, t2);
+            }
+        for (int k = 0; k < p.nfs; ++k) {
+            const int jj = tp->fs[k][0], ip = M + jj, it = 2 * M + jj, is = 3 * M + tp->fs[k][1];
+            add(ip, it); add(ip, is); add(it, it); add(it, is); add(is, is); add(is, it);
+        }
+        for (int k = 0; k < p.nss; ++k) {
+            const int a = 3 * M + tp->ss[k][0], c = 3 * M + tp->ss[k][1];
+            add(a, a); add(a, c); add(c, c); add(c, a);
+        }
+        for (int k = 0; k < p.nes; ++k) add(3 * M + tp->es[k], 3 * M + tp->es[k]);
+    }
+    // bit i of `mask`: local column i (pair i/2, element i%2) = column 8 (i/2) + 2 h + i%2 is touched
+    unsigned mask = 0, diagbit = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int c = ((i >> 1) << 3) + 2 * h + (i & 1);
+        if ((rowbits >> c) & 1ull) mask |= 1u << i;
+        if (c == r) diagbit = 1u << i;
+    }
+
+    long long bad_row = -1;
+    if (tid < 64) {
+        xs[0 * d + tid] = p.sysvar[((size_t)0 * d + tid) * B + b];
+        xs[1 * d + tid] = p.sysvar[((size_t)1 * d + tid) * B + b];
+    }
+
+    double Lr[16], Dr[16], Ur[16];
+
+    for (int n = 0; n < N; ++n) {
+        if (tid < 64 && n + 1 < N && n >= 1)
+            xs[((n + 1) % 3) * d + tid] = p.sysvar[((size_t)(n + 1) * d + tid) * B + b];
+        __syncthreads();
+
+        const bool hasL = n > 0, hasR = n < N - 1;
+        const long long i_row = (long long)n * d + r;
+        const double *gL = p.gm + ((size_t)(hasL ? n - 1 : 0) * p.NS) * B + b;
+        const double *gR = p.gm + ((size_t)(hasR ? n : 0) * p.NS) * B + b;
+#define GL(slot) gL[(size_t)(slot) * B]
+#define GR(slot) gR[(size_t)(slot) * B]
+        double dzL = 1.0, dzR = 1.0, mL = 0.0, mR = 0.0, kbL = 0.0, kbR = 0.0;
+        double adL = 0.0, aoL = 0.0, adR = 0.0, aoR = 0.0;
+        if (hasL) {
+            dzL = p.dz[(size_t)(n - 1) * B + b];
+            mL = (kind < 3) ? 1.0 : GL(sl.msol(j));
+            kbL = GL(sl.k(r)) / dzL;
+            if (kind < 3) { adL = GL(sl.a(j, 0)); aoL = GL(sl.a(j, aoffq)); }
+        }
+        if (hasR) {
+            dzR = p.dz[(size_t)n * B + b];
+            mR = (kind < 3) ? 1.0 : GR(sl.msol(j));
+            kbR = GR(sl.k(r)) / dzR;
+            if (kind < 3) { adR = GR(sl.a(j, 0)); aoR = GR(sl.a(j, aoffq)); }
+        }
+        const double alpha = 0.0;   // ALFA (tsf:265): consistent mass
+        const double cdL = dzL * (1. / 3. + alpha), coL = dzL * (1. / 6. - alpha);
+        const double cdR = dzR * (1. / 3. + alpha), coR = dzR * (1. / 6. - alpha);
+
+        // SYSLOD (smc:1165-1318): lane h = 0 of the row owns it
+        double slterm = 0.0;
+        if (h == 0) {
+            double sl0 = p.syslod[((size_t)i_row * 2 + 0) * B + b];
+            double sl1 = p.syslod[((size_t)i_row * 2 + 1) * B + b];
+            if (p.num_step > 1) { sl1 = sl0; sl0 = 0.0; }
+            if (kind == 3) {
+                if (hasL) {
+                    const double dz_6 = dzL / 6.;
+                    sl0 += (GL(sl.sv(j, 0)) + 2. * GL(sl.sv(j, 1))) * dz_6;
+                    if (first) sl1 += (GL(sl.svp(j, 0)) + 2. * GL(sl.svp(j, 1))) * dz_6;
+                }
+                if (hasR) {
+                    const double dz_6 = dzR / 6.;
+                    sl0 += (2. * GR(sl.sv(j, 0)) + GR(sl.sv(j, 1))) * dz_6;
+                    if (first) sl1 += (2. * GR(sl.svp(j, 0)) + GR(sl.svp(j, 1))) * dz_6;
+                }
+            }
+            p.syslod[((size_t)i_row * 2 + 0) * B + b] = sl0;
+            p.syslod[((size_t)i_row * 2 + 1) * B + b] = sl1;
+            slterm = theta * sl0 + (1.0 - theta) * sl1;
+        }
+
+        // one band entry: SYSMAT value and the Known coefficient (smc:1343-1346, 1432-1441)
+        auto entry = [&](int part, int c, double &sys, double &ck) {
+            const bool dg = (c == r);
+            double mas, flx, dif, sor;
+            if (part == 0) {
+                const double aval = dg ? adL : (c == aoffcol ? aoL : 0.0);
+                mas = dg ? coL * mL : 0.0;
+                flx = -(aval / 2.);
+                dif = dg ? -kbL : 0.0;
+                sor = (GL(sl.s(r, c)) * dzL / 3.) / 2.;
+            } else if (part == 2) {
+                const double aval = dg ? adR : (c == aoffcol ? aoR : 0.0);
+                mas = dg ? coR * mR : 0.0;
+                flx = aval / 2.;
+                dif = dg ? -kbR : 0.0;
+                sor = (GR(sl.s(r, c)) * dzR / 3.) / 2.;
+            } else {
+                mas = 0.0; flx = 0.0; dif = 0.0; sor = 0.0;
+                if (hasL) {
+                    const double aval = dg ? adL : (c == aoffcol ? aoL : 0.0);
+                    if (dg) { mas += cdL * mL; dif += kbL; }
+                    flx += aval / 2.;
+                    sor += GL(sl.s(r, c)) * dzL / 3.;
+                }
+                if (hasR) {
+                    const double aval = dg ? adR : (c == aoffcol ? aoR : 0.0);
+                    if (dg) { mas += cdR * mR; dif += kbR; }
+                    flx += -(aval / 2.);
+                    sor += GR(sl.s(r, c)) * dzR / 3.;
+                }
+            }
+            const double fds = (flx + dif) + sor;
+            sys = mas / dt + theta * fds;
+            ck = mas / dt - (1.0 - theta) * fds;
+        };
+
+        const bool is_bc = (n == 0 && bc_first) || (n == N - 1 && bc_last);
+        double rhs, zero = 0.0;
+        unsigned pm0 = 0, pm1 = 0, pm2 = 0;    // which of my 16 columns of L / D / U come from the strip
+        // Shuffles and warp barriers stay outside the boundary-row branch: the eight rows of a warp
+        // may take different sides of it.
+        // ---- Known (smc:1366-1443): products into the strip, numpy pairwise sum ----
+        if (!is_bc) {
+#pragma unroll
+            for (int part = 0; part < 3; ++part) {
+                const bool present = (part == 0) ? hasL : (part == 2 ? hasR : true);
+                const double *xo = xs + ((n - 1 + part + 3) % 3) * d;
+#pragma unroll
+                for (int pp = 0; pp < 8; ++pp) {
+                    const int c = 8 * pp + 2 * h;
+                    // untouched entry: Known coefficient +0 (see the header)
+                    osc2_st2(srow + part * d + c, present ? 0.0 * xo[c] : 0.0, present ? 0.0 * xo[c + 1] : 0.0);
+                }
+            }
+            for (unsigned m = mask; m; m &= m - 1) {
+                const int i = osc2_ctz(m);
+                const int c = ((i >> 1) << 3) + 2 * h + (i & 1);
+                for (int part = 0; part < 3; ++part) {
+                    const bool present = (part == 0) ? hasL : (part == 2 ? hasR : true);
+                    if (!present) continue;
+                    const double *xo = xs + ((n - 1 + part + 3) % 3) * d;
+                    double sys, ck;
+                    entry(part, c, sys, ck);
+                    srow[part * d + c] = ck * xo[c];
+                }
+            }
+        }
+        __syncwarp();
+        double part_sum = 0.0;
+        int nleaf = 1;
+        if (!is_bc) {
+            long long lo, hi;
+            if (i_row <= Half - 1) { lo = 0; hi = Half + i_row; }
+            else if (i_row >= Total - (Half - 1)) { lo = i_row - (Half - 1); hi = Total; }
+            else { lo = i_row - (Half - 1); hi = i_row + Half; }
+            const int Lfull = (int)(hi - lo);
+            const long long off = (long long)(n - 1) * d - lo;
+            int lstart[3], llen[3];
+            nleaf = osc2_leaf_split(Lfull, lstart, llen);
+            if (h < nleaf) part_sum = osc2_pairwise_window(srow, 3 * d, off, lstart[h], llen[h]);
+        }
+        const double s0 = osc2_bcast(part_sum, lane0), s1 = osc2_bcast(part_sum, lane0 + 1), s2 = osc2_bcast(part_sum, lane0 + 2);
+        double known = (nleaf == 1) ? s0 : (nleaf == 2 ? s0 + s1 : s0 + (s1 + s2));
+        known += osc2_bcast(slterm, lane0);
+        __syncwarp();
+
+        // ---- SYSMAT entries, row scaling (tsf:538-551) ----
+        double mx = 0.0;
+        if (!is_bc) {
+            for (unsigned m = mask; m; m &= m - 1) {
+                const int i = osc2_ctz(m);
+                const int c = ((i >> 1) << 3) + 2 * h + (i & 1);
+                for (int part = 0; part < 3; ++part) {
+                    const bool present = (part == 0) ? hasL : (part == 2 ? hasR : true);
+                    if (!present) continue;
+                    double sys, ck;
+                    entry(part, c, sys, ck);
+                    srow[part * d + c] = sys;
+                    const double a = fabs(sys);
+                    if (a > mx) mx = a;
+                }
+            }
+        }
+        { const double o = osc2_bcast(mx, lane ^ 1); if (o > mx) mx = o; }
+        { const double o = osc2_bcast(mx, lane ^ 2); if (o > mx) mx = o; }
+        if (!is_bc) {
+            for (unsigned m = mask; m; m &= m - 1) {
+                const int i = osc2_ctz(m);
+                const int c = ((i >> 1) << 3) + 2 * h + (i & 1);
+                for (int part = 0; part < 3; ++part) {
+                    const bool present = (part == 0) ? hasL : (part == 2 ? hasR : true);
+                    if (!present) continue;
+                    srow[part * d + c] = srow[part * d + c] / mx;
+                }
+            }
+            zero = 0.0 / mx;       // every other entry of the row: 0 / max|row|
+            rhs = known / mx;
+            pm0 = hasL ? mask : 0u; pm1 = mask; pm2 = hasR ? mask : 0u;
+        } else {
+            // boundary row (fc:117-565): identity row, Known = imposed value
+            if (diagbit) srow[d + r] = 1.0;
+            pm1 = diagbit;
+            rhs = (n == 0) ? val_first : val_last;
+        }
+#undef GL
+#undef GR
+#pragma unroll
+        for (int pp = 0; pp < 8; ++pp) {
+            const int c = 8 * pp + 2 * h;
+            const Osc2Pair l2 = osc2_ld2(srow + c), d2 = osc2_ld2(srow + d + c), u2 = osc2_ld2(srow + 2 * d + c);
+            Lr[2 * pp] = ((pm0 >> (2 * pp)) & 1u) ? l2.x : zero;
+            Lr[2 * pp + 1] = ((pm0 >> (2 * pp + 1)) & 1u) ? l2.y : zero;
+            Dr[2 * pp] = ((pm1 >> (2 * pp)) & 1u) ? d2.x : zero;
+            Dr[2 * pp + 1] = ((pm1 >> (2 * pp + 1)) & 1u) ? d2.y : zero;
+            Ur[2 * pp] = ((pm2 >> (2 * pp)) & 1u) ? u2.x : zero;
+            Ur[2 * pp + 1] = ((pm2 >> (2 * pp + 1)) & 1u) ? u2.y : zero;
+        }
+        if (CAP) {
+            if (p.cap_sysmat) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int c = ((i >> 1) << 3) + 2 * h + (i & 1);
+                    const double vals[3] = {Lr[i], Dr[i], Ur[i]};
+#pragma unroll
+                    for (int part = 0; part < 3; ++part) {
+                        const long long col = (long long)(n - 1 + part) * d + c;
+                        if (col < 0 || col >= Total) continue;
+                        const long long kb = Main + (col - i_row);
+                        p.cap_sysmat[((size_t)kb * Total + i_row) * B + b] = vals[part];
+                    }
+                }
+                if (h == 0) p.cap_known[(size_t)i_row * B + b] = rhs;
+            }
+        }
+
+        // ---- gredub + forward part of gbacsb against the final rows of node n-1 ----
+        if (hasL) {
+#pragma unroll
+            for (int k8 = 0; k8 < 8; ++k8) {
+#pragma unroll 1
+                for (int kk = 0; kk < 8; ++kk) {
+                    const int k = 8 * k8 + kk;
+                    const double *pk = piv + k * PW;
+                    const double num = (kk & 1) ? Lr[2 * k8 + 1] : Lr[2 * k8];
+                    const double v = osc2_bcast(num, lane0 | (kk >> 1));
+                    const double q = osc2_div(v, osc2_rcp_make(pk[k], pk[2 * d + 1]));
+                    {
+                        const Osc2Pair x = osc2_ld2(pk + 8 * k8 + 2 * h);
+                        if (2 * h > kk) Lr[2 * k8] = Lr[2 * k8] - x.x * q;
+                        if (2 * h + 1 > kk) Lr[2 * k8 + 1] = Lr[2 * k8 + 1] - x.y * q;
+                    }
+#pragma unroll
+                    for (int pp = k8 + 1; pp < 8; ++pp) {
+                        const Osc2Pair x = osc2_ld2(pk + 8 * pp + 2 * h);
+                        Lr[2 * pp] = Lr[2 * pp] - x.x * q;
+                        Lr[2 * pp + 1] = Lr[2 * pp + 1] - x.y * q;
+                    }
+#pragma unroll
+                    for (int pp = 0; pp < 8; ++pp) {
+                        const Osc2Pair x = osc2_ld2(pk + d + 8 * pp + 2 * h);
+                        Dr[2 * pp] = Dr[2 * pp] - x.x * q;
+                        Dr[2 * pp + 1] = Dr[2 * pp + 1] - x.y * q;
+                    }
+                    rhs = rhs - pk[2 * d] * q;
+                }
+            }
+        }
+        __syncthreads();      // every row is done with the rows of node n-1: `piv` may be rewritten
+
+        // ---- pivots inside node n: row k is final once it has seen rows < k ----
+#pragma unroll
+        for (int k8 = 0; k8 < 8; ++k8) {
+#pragma unroll 1
+            for (int kk = 0; kk < 8; ++kk) {
+                const int k = 8 * k8 + kk;
+                double *pk = piv + k * PW;
+                if (r == k) {
+#pragma unroll
+                    for (int pp = 0; pp < 8; ++pp) {
+                        osc2_st2(pk + 8 * pp + 2 * h, Dr[2 * pp], Dr[2 * pp + 1]);
+                        osc2_st2(pk + d + 8 * pp + 2 * h, Ur[2 * pp], Ur[2 * pp + 1]);
+                    }
+                    if (h == (kk >> 1)) {
+                        const double pv = (kk & 1) ? Dr[2 * k8 + 1] : Dr[2 * k8];
+                        pk[2 * d + 1] = osc2_rcp_prepare(pv).y;
+                        if (fabs(pv) <= OSC2_TINY_PIVOT && bad_row < 0) bad_row = (long long)n * d + k;
+                    }
+                    if (h == 0) pk[2 * d] = rhs;
+                }
+                __syncthreads();
+                if (8 * warp + 7 > k) {
+                    const double num = (kk & 1) ? Dr[2 * k8 + 1] : Dr[2 * k8];
+                    const double v = osc2_bcast(num, lane0 | (kk >> 1));
+                    if (r > k) {
+                        const double q = osc2_div(v, osc2_rcp_make(pk[k], pk[2 * d + 1]));
+                        {
+                            const Osc2Pair x = osc2_ld2(pk + 8 * k8 + 2 * h);
+                            if (2 * h > kk) Dr[2 * k8] = Dr[2 * k8] - x.x * q;
+                            if (2 * h + 1 > kk) Dr[2 * k8 + 1] = Dr[2 * k8 + 1] - x.y * q;
+                        }
+#pragma unroll
+                        for (int pp = k8 + 1; pp < 8; ++pp) {
+                            const Osc2Pair x = osc2_ld2(pk + 8 * pp + 2 * h);
+                            Dr[2 * pp] = Dr[2 * pp] - x.x * q;
+                            Dr[2 * pp + 1] = Dr[2 * pp + 1] - x.y * q;
+                        }
+#pragma unroll
+                        for (int pp = 0; pp < 8; ++pp) {
+                            const Osc2Pair x = osc2_ld2(pk + d + 8 * pp + 2 * h);
+                            Ur[2 * pp] = Ur[2 * pp] - x.x * q;
+                            Ur[2 * pp + 1] = Ur[2 * pp + 1] - x.y * q;
+                        }
+                        rhs = rhs - pk[2 * d] * q;
+                    }
+                }
+            }
+        }
+        // the last publish (row 63) was followed by a barrier: spill the 64 final rows as they lie
+        {
+            double *out = fac_out + (size_t)n * (64 * PW);
+            for (int q = tid; q < 64 * PW / 2; q += 256) {
+                const Osc2Pair x = osc2_ld2(piv + 2 * q);
+                osc2_st2(out + 2 * q, x.x, x.y);
+            }
+        }
+    }
+    // first singular row of the conductor (gredub/gbacsb raise on abs(pivot) <= 1e-20)
+    __syncthreads();
+    strip[tid] = (double)bad_row;
+    __syncthreads();
+    if (tid == 0) {
+        long long worst = -1;
+        for (int q = 0; q < 256; ++q) {
+            const long long v = (long long)strip[q];
+            if (v >= 0 && (worst < 0 || v < worst)) worst = v;
+        }
+        p.status[b] = (worst < 0) ? 0 : -(int)(worst + 1);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K_B64: back substitution (gbacsb, tsf:772-802).  The subtractions of one row must follow the
+// reference's column order (in-node columns r+1.., then the 64 columns of node n+1) and start with
+// the unknown solved last, so a node is one serial chain of sum_r (127 - r) = 6112 dependent
+// subtractions whatever the thread mapping.  One warp per conductor: the lanes form the products
+// of a row in parallel (two in-node columns, two next-node columns each), hand them over through
+// shared memory and every lane walks the chain, so the solved unknown needs no broadcast.  Seven
+// conductors per SM are resident at a 1024-conductor batch; the factor rows stream from HBM one row
+// ahead of the chain.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) osc2_backward64_kernel(StepDev p)
+{
+    constexpr int d = 64, PW = OSC2_D64_PW;
+    OSC2_DYN_SMEM(sm_dyn);
+    double *prod = sm_dyn;     // [2][128]
+    const int N = p.N, lane = (int)threadIdx.x;
+    const size_t B = (size_t)p.B, b = (size_t)blockIdx.x;
+    const double *fac = p.spill + b * ((size_t)N * 64 * PW);
+    double xn0 = 0.0, xn1 = 0.0;
+    for (int n = N - 1; n >= 0; --n) {
+        const double *nd = fac + (size_t)n * (64 * PW);
+        const bool hasR = n < N - 1;
+        double x0 = 0.0, x1 = 0.0;
+        // row 63 in flight
+        const double *row = nd + 63 * PW;
+        double dlo = row[lane], dhi = row[lane + 32], ulo = row[d + lane], uhi = row[d + 32 + lane];
+        double rhs = row[2 * d], ry = row[2 * d + 1], pv = row[63];
+        for (int r = d - 1; r >= 0; --r) {
+            double *pr = prod + (r & 1) * 128;
+            pr[lane] = dlo * x0;
+            pr[lane + 32] = dhi * x1;
+            pr[d + lane] = ulo * xn0;
+            pr[d + 32 + lane] = uhi * xn1;
+            double q = rhs;
+            const Osc2Rcp rc = osc2_rcp_make(pv, ry);
+            if (r > 0) {      // next row's factors
+                row = nd + (r - 1) * PW;
+                dlo = row[lane]; dhi = row[lane + 32]; ulo = row[d + lane]; uhi = row[d + 32 + lane];
+                rhs = row[2 * d]; ry = row[2 * d + 1]; pv = row[r - 1];
+            }
+            __syncwarp();
+#pragma unroll 8
+            for (int c = r + 1; c < d; ++c) q = q - pr[c];
+            if (hasR) {
+#pragma unroll 8
+                for (int c = 0; c < d; ++c) q = q - pr[d + c];
+            }
+            const double x = osc2_div(q, rc);
+            if (lane == (r & 31)) { if (r < 32) x0 = x; else x1 = x; }
+        }
+        p.sysvar_new[((size_t)n * d + lane) * B + b] = x0;
+        p.sysvar_new[((size_t)n * d + 32 + lane) * B + b] = x1;
+        xn0 = x0; xn1 = x1;
+    }
+}

@@ -13,6 +13,7 @@
 #include "step_kernels_split.cuh"
 #include "step_kernels_wide.cuh"
 #include "step_kernels_pipe.cuh"
+#include "step_kernels_d64.cuh"
 
 #include <cstdlib>
 #include <vector>
@@ -209,6 +210,19 @@ void osc2_run_step(Launcher &L, const osc2_topology *tp_dev, const StepDev &p, b
         else L.launch(OSC2_K_GAUSS, osc2_gauss_kernel<false>, grid, pl.gauss_block, (size_t)0, tp_dev, p);
     }
     // K_F, K_B
+    // NODOFS = 64 (CASE_2): register-tiled sweeps, one 256-thread CTA (forward) / one warp (backward)
+    // per conductor (step_kernels_d64.cuh); OSC2_D64=0 keeps the generic shared-memory sweeps
+    static const bool d64_on = [] { const char *e = getenv("OSC2_D64"); return !(e && e[0] == '0'); }();
+    if (p.d == 64 && d64_on && osc2_d64_fwd_smem_doubles() * sizeof(double) <= L.max_smem()) {
+        const size_t smem64 = osc2_d64_fwd_smem_doubles() * sizeof(double);
+        if (p.cap_sysmat) L.launch(OSC2_K_FORWARD, osc2_forward64_kernel<true>, (unsigned)p.B, 256u, smem64, tp_dev, p);
+        else L.launch(OSC2_K_FORWARD, osc2_forward64_kernel<false>, (unsigned)p.B, 256u, smem64, tp_dev, p);
+        L.launch(OSC2_K_BACKWARD, osc2_backward64_kernel, (unsigned)p.B, 32u, (size_t)(2 * 128 * sizeof(double)), p);
+        const long long nl = (long long)p.d * p.B * p.n_leaves, nw = (long long)p.d * p.B;
+        L.launch(OSC2_K_NORMS, osc2_norm_leaves_kernel, (unsigned)((nl + 127) / 128), 128u, (size_t)0, p);
+        L.launch(OSC2_K_NORMS, osc2_norm_combine_kernel, (unsigned)((nw + 127) / 128), 128u, (size_t)0, p);
+        return;
+    }
     const unsigned gridf = (unsigned)((p.B + pl.cpb_fwd - 1) / pl.cpb_fwd);
     const unsigned blockf = (unsigned)(pl.lpc * pl.cpb_fwd);
     const unsigned gridb = (unsigned)((p.B + pl.cpb_bwd - 1) / pl.cpb_bwd);

@@ -190,3 +190,31 @@ def test_shared_divisor_division_is_ieee():
     bad = C.c_ulonglong(123)
     _lib.check(L.osc2_selftest_division(0, 400_000_000, 20261019, C.byref(bad)))
     assert bad.value == 0
+
+
+@pytest.mark.parametrize("n,batch,num_step,d64", [(151, 5, 2, "1"), (9, 3, 1, "1"), (9, 3, 1, "0")])
+def test_case2_sized_sweeps_match_oracle_with_system(n, batch, num_step, d64, monkeypatch):
+    """NODOFS = 64 at the shipped CASE_2 mesh size: the register-tiled sweeps (step_kernels_d64.cuh,
+    default) and the generic shared-memory sweeps (OSC2_D64=0) both reproduce the oracle's SYSMAT,
+    Known and outputs bit for bit."""
+    import subprocess, sys, os, textwrap
+    # the switch is read once per process: run the comparison in a child
+    code = textwrap.dedent(f"""
+        import sys, numpy as np
+        sys.path[:0] = [{os.path.dirname(os.path.abspath(__file__))!r}, {os.path.dirname(os.path.dirname(os.path.abspath(__file__)))!r}]
+        from opensc2_b200.batch import BatchedStep
+        from opensc2_b200.problem import case2_topology, synthetic_step_arrays
+        from oracle import oracle as O
+        topo = case2_topology()
+        arr = synthetic_step_arrays(topo, {n}, batch={batch}, seed=77, num_step={num_step}, exact_squares=False)
+        with BatchedStep(topo, {batch}, {n}) as bs:
+            out = bs.run(arr, capture=True)
+        ref = O.step(topo, arr, want_system=True)
+        assert np.all(out["status"] == 0)
+        for key in ("sysmat", "known", "sysvar", "syslod", "k123", "norm_solution", "norm_change", "eqteig"):
+            assert np.array_equal(out[key], ref[key]), key
+        print("bits-equal")
+    """)
+    env = dict(os.environ, OSC2_D64=d64)
+    res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0 and "bits-equal" in res.stdout, res.stdout + res.stderr

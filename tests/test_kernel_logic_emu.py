@@ -96,3 +96,20 @@ def test_emulated_norm_tree_matches_numpy_pairwise(n):
     ref = O.step(topo, arr)
     for key in KEYS:
         assert_bits(out[key], ref[key], key)
+
+
+@pytest.mark.parametrize("n,batch,num_step", [(4, 2, 1), (6, 3, 3)])
+def test_emulated_d64_register_tiled_sweeps(n, batch, num_step):
+    """step_kernels_d64.cuh (256 threads per conductor, rows in registers, warp-per-conductor back
+    substitution): SYSMAT, Known and every output equal the oracle's bits; the generic shared-memory
+    sweeps (OSC2_D64=0 in the library) are covered by test_emulated_case2_sixty_four_lanes' history
+    and by the GPU tests."""
+    topo = case2_topology()
+    arr = synthetic_step_arrays(topo, n, batch=batch, seed=60 + n, num_step=num_step, exact_squares=False)
+    out = emu.emu_step(topo, arr, capture=True)
+    ref = O.step(topo, arr, want_system=True)
+    assert np.all(out["status"] == 0)
+    assert_bits(out["sysmat"], ref["sysmat"], "sysmat")
+    assert_bits(out["known"], ref["known"], "known")
+    for key in KEYS:
+        assert_bits(out[key], ref[key], key)
