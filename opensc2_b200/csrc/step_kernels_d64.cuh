@@ -35,7 +35,28 @@
 
 struct alignas(16) Osc2Pair { double x, y; };
 
-__host__ __device__ inline size_t osc2_d64_fwd_smem_doubles() { return (size_t)64 * OSC2_D64_SW + 64 * OSC2_D64_PW + 3 * 64; }
+// shared memory of K_F64 (doubles): strip | pivot rows | old solution at three nodes | touched SMAT
+// entries of two elements, eight per thread | row scalars of two elements, ten per row | SYSLOD of two nodes
+#define OSC2_D64_TS 8     /* prefetched touched entries per thread; further ones are read from global memory */
+#define OSC2_D64_RS 10    /* dz, K, Msol, A diag, A partner, SV0, SV1, SVP0, SVP1, pad */
+__host__ __device__ inline size_t osc2_d64_fwd_smem_doubles()
+{
+    return (size_t)64 * OSC2_D64_SW + 64 * OSC2_D64_PW + 3 * 64 + 2 * 256 * OSC2_D64_TS + 2 * 64 * OSC2_D64_RS + 2 * 64 * 2;
+}
+
+// 8-byte asynchronous copy global -> shared (LDGSTS): the element record of node n+1 travels while
+// node n is eliminated, no registers in flight
+#ifdef OSC2_EMU
+inline void osc2_cp8(double *dst, const double *src) { *dst = *src; }
+inline void osc2_cp_wait_all() {}
+#else
+__device__ __forceinline__ void osc2_cp8(double *dst, const double *src)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(src) : "memory");
+}
+__device__ __forceinline__ void osc2_cp_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+#endif
 
 __device__ __forceinline__ Osc2Pair osc2_ld2(const double *q) { return *reinterpret_cast<const Osc2Pair *>(q); }
 __device__ __forceinline__ void osc2_st2(double *q, double a, double b)
@@ -70,6 +91,36 @@ __device__ __forceinline__ int osc2_ctz(unsigned m)
 #endif
 }
 
+#ifdef OSC2_EMU
+inline bool osc2_any(bool pred) { return emu_any(pred); }
+#else
+__device__ __forceinline__ bool osc2_any(bool pred) { return __any_sync(0xffffffffu, pred) != 0; }
+#endif
+
+// numpy pairwise sum (n <= 128: one block, loops_utils.h.src) of window positions j0 .. j0+n-1; the
+// window position j is strip[cbase + (j - j0)] when that index lies in [0, 192) and +0 otherwise
+// (band positions outside the three blocks).
+__device__ __forceinline__ double osc2_leaf_sum(const double *strip, int cbase, int n)
+{
+    auto at = [&](int i) { const unsigned c = (unsigned)(cbase + i); return c < 192u ? strip[c] : 0.0; };
+    if (n < 8) {
+        double res = 0.0;
+        for (int i = 0; i < n; ++i) res += at(i);
+        return res;
+    }
+    double rr[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) rr[k] = at(k);
+    int i;
+    for (i = 8; i < n - (n % 8); i += 8) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) rr[k] += at(i + k);
+    }
+    double res = ((rr[0] + rr[1]) + (rr[2] + rr[3])) + ((rr[4] + rr[5]) + (rr[6] + rr[7]));
+    for (; i < n; ++i) res += at(i);
+    return res;
+}
+
 // ---------------------------------------------------------------------------
 // K_F64
 // ---------------------------------------------------------------------------
@@ -92,6 +143,9 @@ __global__ void __launch_bounds__(256, 1) osc2_forward64_kernel(const osc2_topol
     double *strip = sm_dyn;                 // [64][SW]  products / unscaled row entries of the node
     double *piv = strip + 64 * SW;          // [64][PW]  final rows of node n-1, then of node n
     double *xs = piv + 64 * PW;             // [3][64]   old solution at nodes n-1, n, n+1
+    double *sS = xs + 3 * 64;               // [2][256][TS]  touched SMAT entries of elements e, e+1 (by parity)
+    double *sR = sS + 2 * 256 * OSC2_D64_TS;   // [2][64][RS] row scalars of those elements
+    double *sSL = sR + 2 * 64 * OSC2_D64_RS;   // [2][64][2]  SYSLOD of the node (by parity)
     double *srow = strip + r * SW;
     double *fac_out = p.spill + b * ((size_t)N * 64 * PW);
 
@@ -166,6 +220,7 @@ __global__ void __launch_bounds__(256, 1) osc2_forward64_kernel(const osc2_topol
         if (c == r) diagbit = 1u << i;
     }
 
+    const Osc2Rcp third = osc2_rcp_prepare(3.0);     // x / 3. with the shared-divisor division (exact, osc2_div.cuh)
     long long bad_row = -1;
     if (tid < 64) {
         xs[0 * d + tid] = p.sysvar[((size_t)0 * d + tid) * B + b];
@@ -174,30 +229,68 @@ __global__ void __launch_bounds__(256, 1) osc2_forward64_kernel(const osc2_topol
 
     double Lr[16], Dr[16], Ur[16];
 
+    // element e (between nodes e and e+1) and SYSLOD of node e
+    auto prefetch = [&](int e) {
+        if (e < N - 1) {
+            const double *g = p.gm + ((size_t)e * p.NS) * B + b;
+            double *ds = sS + ((e & 1) * 256 + tid) * OSC2_D64_TS;
+            int t = 0;
+            for (unsigned m = mask; m && t < OSC2_D64_TS; m &= m - 1, ++t) {
+                const int i = osc2_ctz(m);
+                const int c = ((i >> 1) << 3) + 2 * h + (i & 1);
+                osc2_cp8(ds + t, g + (size_t)sl.s(r, c) * B);
+            }
+            if (h == 0) {
+                double *dr = sR + ((e & 1) * 64 + r) * OSC2_D64_RS;
+                osc2_cp8(dr + 0, p.dz + (size_t)e * B + b);
+                osc2_cp8(dr + 1, g + (size_t)sl.k(r) * B);
+                if (kind == 3) {
+                    osc2_cp8(dr + 2, g + (size_t)sl.msol(j) * B);
+                    osc2_cp8(dr + 5, g + (size_t)sl.sv(j, 0) * B);
+                    osc2_cp8(dr + 6, g + (size_t)sl.sv(j, 1) * B);
+                    if (first) {
+                        osc2_cp8(dr + 7, g + (size_t)sl.svp(j, 0) * B);
+                        osc2_cp8(dr + 8, g + (size_t)sl.svp(j, 1) * B);
+                    }
+                } else {
+                    osc2_cp8(dr + 3, g + (size_t)sl.a(j, 0) * B);
+                    osc2_cp8(dr + 4, g + (size_t)sl.a(j, aoffq) * B);
+                }
+            }
+        }
+        if (e < N && h == 0) {
+            const size_t i_row = (size_t)e * d + r;
+            osc2_cp8(sSL + ((e & 1) * 64 + r) * 2 + 0, p.syslod + (i_row * 2 + 0) * B + b);
+            osc2_cp8(sSL + ((e & 1) * 64 + r) * 2 + 1, p.syslod + (i_row * 2 + 1) * B + b);
+        }
+    };
+    prefetch(0);
+
     for (int n = 0; n < N; ++n) {
-        if (tid < 64 && n + 1 < N && n >= 1)
-            xs[((n + 1) % 3) * d + tid] = p.sysvar[((size_t)(n + 1) * d + tid) * B + b];
+        osc2_cp_wait_all();
         __syncthreads();
 
         const bool hasL = n > 0, hasR = n < N - 1;
         const long long i_row = (long long)n * d + r;
-        const double *gL = p.gm + ((size_t)(hasL ? n - 1 : 0) * p.NS) * B + b;
+        const double *gL = p.gm + ((size_t)(hasL ? n - 1 : 0) * p.NS) * B + b;   // entries beyond the prefetched eight
         const double *gR = p.gm + ((size_t)(hasR ? n : 0) * p.NS) * B + b;
 #define GL(slot) gL[(size_t)(slot) * B]
 #define GR(slot) gR[(size_t)(slot) * B]
+        const double *tL = sS + (((n + 1) & 1) * 256 + tid) * OSC2_D64_TS, *tR = sS + ((n & 1) * 256 + tid) * OSC2_D64_TS;
+        const double *rL = sR + (((n + 1) & 1) * 64 + r) * OSC2_D64_RS, *rR = sR + ((n & 1) * 64 + r) * OSC2_D64_RS;
         double dzL = 1.0, dzR = 1.0, mL = 0.0, mR = 0.0, kbL = 0.0, kbR = 0.0;
         double adL = 0.0, aoL = 0.0, adR = 0.0, aoR = 0.0;
         if (hasL) {
-            dzL = p.dz[(size_t)(n - 1) * B + b];
-            mL = (kind < 3) ? 1.0 : GL(sl.msol(j));
-            kbL = GL(sl.k(r)) / dzL;
-            if (kind < 3) { adL = GL(sl.a(j, 0)); aoL = GL(sl.a(j, aoffq)); }
+            dzL = rL[0];
+            mL = (kind < 3) ? 1.0 : rL[2];
+            kbL = rL[1] / dzL;
+            if (kind < 3) { adL = rL[3]; aoL = rL[4]; }
         }
         if (hasR) {
-            dzR = p.dz[(size_t)n * B + b];
-            mR = (kind < 3) ? 1.0 : GR(sl.msol(j));
-            kbR = GR(sl.k(r)) / dzR;
-            if (kind < 3) { adR = GR(sl.a(j, 0)); aoR = GR(sl.a(j, aoffq)); }
+            dzR = rR[0];
+            mR = (kind < 3) ? 1.0 : rR[2];
+            kbR = rR[1] / dzR;
+            if (kind < 3) { adR = rR[3]; aoR = rR[4]; }
         }
         const double alpha = 0.0;   // ALFA (tsf:265): consistent mass
         const double cdL = dzL * (1. / 3. + alpha), coL = dzL * (1. / 6. - alpha);
@@ -206,19 +299,19 @@ __global__ void __launch_bounds__(256, 1) osc2_forward64_kernel(const osc2_topol
         // SYSLOD (smc:1165-1318): lane h = 0 of the row owns it
         double slterm = 0.0;
         if (h == 0) {
-            double sl0 = p.syslod[((size_t)i_row * 2 + 0) * B + b];
-            double sl1 = p.syslod[((size_t)i_row * 2 + 1) * B + b];
+            double sl0 = sSL[((n & 1) * 64 + r) * 2 + 0];
+            double sl1 = sSL[((n & 1) * 64 + r) * 2 + 1];
             if (p.num_step > 1) { sl1 = sl0; sl0 = 0.0; }
             if (kind == 3) {
                 if (hasL) {
                     const double dz_6 = dzL / 6.;
-                    sl0 += (GL(sl.sv(j, 0)) + 2. * GL(sl.sv(j, 1))) * dz_6;
-                    if (first) sl1 += (GL(sl.svp(j, 0)) + 2. * GL(sl.svp(j, 1))) * dz_6;
+                    sl0 += (rL[5] + 2. * rL[6]) * dz_6;
+                    if (first) sl1 += (rL[7] + 2. * rL[8]) * dz_6;
                 }
                 if (hasR) {
                     const double dz_6 = dzR / 6.;
-                    sl0 += (2. * GR(sl.sv(j, 0)) + GR(sl.sv(j, 1))) * dz_6;
-                    if (first) sl1 += (2. * GR(sl.svp(j, 0)) + GR(sl.svp(j, 1))) * dz_6;
+                    sl0 += (2. * rR[5] + rR[6]) * dz_6;
+                    if (first) sl1 += (2. * rR[7] + rR[8]) * dz_6;
                 }
             }
             p.syslod[((size_t)i_row * 2 + 0) * B + b] = sl0;
@@ -227,7 +320,9 @@ __global__ void __launch_bounds__(256, 1) osc2_forward64_kernel(const osc2_topol
         }
 
         // one band entry: SYSMAT value and the Known coefficient (smc:1343-1346, 1432-1441)
-        auto entry = [&](int part, int c, double &sys, double &ck) {
+        auto entry = [&](int part, int c, int t, double &sys, double &ck) {
+            const double sLv = hasL ? (t < OSC2_D64_TS ? tL[t] : GL(sl.s(r, c))) : 0.0;
+            const double sRv = hasR ? (t < OSC2_D64_TS ? tR[t] : GR(sl.s(r, c))) : 0.0;
             const bool dg = (c == r);
             double mas, flx, dif, sor;
             if (part == 0) {
@@ -235,31 +330,34 @@ __global__ void __launch_bounds__(256, 1) osc2_forward64_kernel(const osc2_topol
                 mas = dg ? coL * mL : 0.0;
                 flx = -(aval / 2.);
                 dif = dg ? -kbL : 0.0;
-                sor = (GL(sl.s(r, c)) * dzL / 3.) / 2.;
+                sor = osc2_div(sLv * dzL, third) / 2.;
             } else if (part == 2) {
                 const double aval = dg ? adR : (c == aoffcol ? aoR : 0.0);
                 mas = dg ? coR * mR : 0.0;
                 flx = aval / 2.;
                 dif = dg ? -kbR : 0.0;
-                sor = (GR(sl.s(r, c)) * dzR / 3.) / 2.;
+                sor = osc2_div(sRv * dzR, third) / 2.;
             } else {
                 mas = 0.0; flx = 0.0; dif = 0.0; sor = 0.0;
                 if (hasL) {
                     const double aval = dg ? adL : (c == aoffcol ? aoL : 0.0);
                     if (dg) { mas += cdL * mL; dif += kbL; }
                     flx += aval / 2.;
-                    sor += GL(sl.s(r, c)) * dzL / 3.;
+                    sor += osc2_div(sLv * dzL, third);
                 }
                 if (hasR) {
                     const double aval = dg ? adR : (c == aoffcol ? aoR : 0.0);
                     if (dg) { mas += cdR * mR; dif += kbR; }
                     flx += -(aval / 2.);
-                    sor += GR(sl.s(r, c)) * dzR / 3.;
+                    sor += osc2_div(sRv * dzR, third);
                 }
             }
             const double fds = (flx + dif) + sor;
-            sys = mas / dt + theta * fds;
-            ck = mas / dt - (1.0 - theta) * fds;
+            // off the diagonal the mass term is +0: 0 / dt is +0 for a positive time step (nvcc's own
+            // division sends a zero numerator to its slow subroutine)
+            const double mdt = (dg || !(dt > 0.0)) ? mas / dt : 0.0;
+            sys = mdt + theta * fds;
+            ck = mdt - (1.0 - theta) * fds;
         };
 
         const bool is_bc = (n == 0 && bc_first) || (n == N - 1 && bc_last);
@@ -280,7 +378,8 @@ __global__ void __launch_bounds__(256, 1) osc2_forward64_kernel(const osc2_topol
                     osc2_st2(srow + part * d + c, present ? 0.0 * xo[c] : 0.0, present ? 0.0 * xo[c + 1] : 0.0);
                 }
             }
-            for (unsigned m = mask; m; m &= m - 1) {
+            int t = 0;
+            for (unsigned m = mask; m; m &= m - 1, ++t) {
                 const int i = osc2_ctz(m);
                 const int c = ((i >> 1) << 3) + 2 * h + (i & 1);
                 for (int part = 0; part < 3; ++part) {
@@ -288,7 +387,7 @@ __global__ void __launch_bounds__(256, 1) osc2_forward64_kernel(const osc2_topol
                     if (!present) continue;
                     const double *xo = xs + ((n - 1 + part + 3) % 3) * d;
                     double sys, ck;
-                    entry(part, c, sys, ck);
+                    entry(part, c, t, sys, ck);
                     srow[part * d + c] = ck * xo[c];
                 }
             }
@@ -305,7 +404,7 @@ __global__ void __launch_bounds__(256, 1) osc2_forward64_kernel(const osc2_topol
             const long long off = (long long)(n - 1) * d - lo;
             int lstart[3], llen[3];
             nleaf = osc2_leaf_split(Lfull, lstart, llen);
-            if (h < nleaf) part_sum = osc2_pairwise_window(srow, 3 * d, off, lstart[h], llen[h]);
+            if (h < nleaf) part_sum = osc2_leaf_sum(srow, lstart[h] - (int)off, llen[h]);
         }
         const double s0 = osc2_bcast(part_sum, lane0), s1 = osc2_bcast(part_sum, lane0 + 1), s2 = osc2_bcast(part_sum, lane0 + 2);
         double known = (nleaf == 1) ? s0 : (nleaf == 2 ? s0 + s1 : s0 + (s1 + s2));
@@ -315,14 +414,15 @@ __global__ void __launch_bounds__(256, 1) osc2_forward64_kernel(const osc2_topol
         // ---- SYSMAT entries, row scaling (tsf:538-551) ----
         double mx = 0.0;
         if (!is_bc) {
-            for (unsigned m = mask; m; m &= m - 1) {
+            int t = 0;
+            for (unsigned m = mask; m; m &= m - 1, ++t) {
                 const int i = osc2_ctz(m);
                 const int c = ((i >> 1) << 3) + 2 * h + (i & 1);
                 for (int part = 0; part < 3; ++part) {
                     const bool present = (part == 0) ? hasL : (part == 2 ? hasR : true);
                     if (!present) continue;
                     double sys, ck;
-                    entry(part, c, sys, ck);
+                    entry(part, c, t, sys, ck);
                     srow[part * d + c] = sys;
                     const double a = fabs(sys);
                     if (a > mx) mx = a;
@@ -332,17 +432,18 @@ __global__ void __launch_bounds__(256, 1) osc2_forward64_kernel(const osc2_topol
         { const double o = osc2_bcast(mx, lane ^ 1); if (o > mx) mx = o; }
         { const double o = osc2_bcast(mx, lane ^ 2); if (o > mx) mx = o; }
         if (!is_bc) {
+            const Osc2Rcp rmx = osc2_rcp_prepare(mx);
             for (unsigned m = mask; m; m &= m - 1) {
                 const int i = osc2_ctz(m);
                 const int c = ((i >> 1) << 3) + 2 * h + (i & 1);
                 for (int part = 0; part < 3; ++part) {
                     const bool present = (part == 0) ? hasL : (part == 2 ? hasR : true);
                     if (!present) continue;
-                    srow[part * d + c] = srow[part * d + c] / mx;
+                    srow[part * d + c] = osc2_div(srow[part * d + c], rmx);
                 }
             }
-            zero = 0.0 / mx;       // every other entry of the row: 0 / max|row|
-            rhs = known / mx;
+            zero = (mx > 0.0) ? 0.0 : 0.0 / mx;       // every other entry of the row: 0 / max|row|
+            rhs = osc2_div(known, rmx);
             pm0 = hasL ? mask : 0u; pm1 = mask; pm2 = hasR ? mask : 0u;
         } else {
             // boundary row (fc:117-565): identity row, Known = imposed value
@@ -363,6 +464,8 @@ __global__ void __launch_bounds__(256, 1) osc2_forward64_kernel(const osc2_topol
             Ur[2 * pp] = ((pm2 >> (2 * pp)) & 1u) ? u2.x : zero;
             Ur[2 * pp + 1] = ((pm2 >> (2 * pp + 1)) & 1u) ? u2.y : zero;
         }
+        __syncwarp();          // the four lanes of a row are done with the row scalars of element n-1
+        prefetch(n + 1);
         if (CAP) {
             if (p.cap_sysmat) {
 #pragma unroll
@@ -391,6 +494,9 @@ __global__ void __launch_bounds__(256, 1) osc2_forward64_kernel(const osc2_topol
                     const double *pk = piv + k * PW;
                     const double num = (kk & 1) ? Lr[2 * k8 + 1] : Lr[2 * k8];
                     const double v = osc2_bcast(num, lane0 | (kk >> 1));
+                    // a multiplier of zero leaves the row as it is (up to the sign of an exact zero): skipped
+                    // when that holds for all eight rows of the warp -- the blocks of CASE_2 are sparse
+                    if (!osc2_any(v != 0.0)) continue;
                     const double q = osc2_div(v, osc2_rcp_make(pk[k], pk[2 * d + 1]));
                     {
                         const Osc2Pair x = osc2_ld2(pk + 8 * k8 + 2 * h);
@@ -414,6 +520,8 @@ __global__ void __launch_bounds__(256, 1) osc2_forward64_kernel(const osc2_topol
             }
         }
         __syncthreads();      // every row is done with the rows of node n-1: `piv` may be rewritten
+        // ... and with the old solution of node n-1: its slot takes the one of node n+2
+        if (tid < 64 && n + 2 < N) osc2_cp8(xs + ((n + 2) % 3) * d + tid, p.sysvar + ((size_t)(n + 2) * d + tid) * B + b);
 
         // ---- pivots inside node n: row k is final once it has seen rows < k ----
 #pragma unroll
@@ -439,7 +547,7 @@ __global__ void __launch_bounds__(256, 1) osc2_forward64_kernel(const osc2_topol
                 if (8 * warp + 7 > k) {
                     const double num = (kk & 1) ? Dr[2 * k8 + 1] : Dr[2 * k8];
                     const double v = osc2_bcast(num, lane0 | (kk >> 1));
-                    if (r > k) {
+                    if (osc2_any(r > k && v != 0.0) && r > k) {
                         const double q = osc2_div(v, osc2_rcp_make(pk[k], pk[2 * d + 1]));
                         {
                             const Osc2Pair x = osc2_ld2(pk + 8 * k8 + 2 * h);

@@ -43,6 +43,17 @@ inline double emu_shfl(double v, int src_lane)
     return out;
 }
 
+// __any_sync over the full warp
+inline bool emu_any(bool pred)
+{
+    emu_shfl_scratch[threadIdx.x % 32] = pred ? 1.0 : 0.0;
+    emu_warp_barrier->arrive_and_wait();
+    bool out = false;
+    for (int i = 0; i < 32; ++i) out = out || (emu_shfl_scratch[i] != 0.0);
+    emu_warp_barrier->arrive_and_wait();
+    return out;
+}
+
 #define OSC2_DYN_SMEM(name) double *name = emu_dyn_smem
 
 inline void __syncthreads() { emu_block_barrier->arrive_and_wait(); }

@@ -7,7 +7,7 @@ from opensc2_b200.batch import BatchedStep
 from opensc2_b200.model import case2_model, consistent_initial_state, synthetic_helium_table, synthetic_sweep
 from opensc2_b200.problem import case2_topology
 
-batch, n, dt, steps = int(sys.argv[1]) if len(sys.argv) > 1 else 1024, 151, 0.05, 3
+batch, n, dt, steps = int(sys.argv[1]) if len(sys.argv) > 1 else 1024, int(sys.argv[2]) if len(sys.argv) > 2 else 151, 0.05, 3
 topo = case2_topology(); model = case2_model(topo); tab = synthetic_helium_table()
 small = consistent_initial_state(topo, model, tab, n, 16, seed=1, dt=dt, length=3.0)
 sw = synthetic_sweep(topo, model, n, 16, seed=1, length=3.0, with_tcs=False)
