@@ -46,3 +46,24 @@ def singular_case():
     arr.sol_gauss[1, 0] = 0.0
     arr.sol_gauss[1, 2] = 100.0
     return topo, arr
+
+
+def case2_with_isolated_massless_solid(n, batch, bad):
+    """CASE_2 conductors; in conductor `bad` solid 5 has no mass term and no thermal contact, so its
+    (uniform-mesh, Neumann) diffusion rows [1 -1], [-1/2 1 -1/2], ..., [-1 1] eliminate to an exact
+    zero pivot in the last node -- the reference raises `Matrix is singular` there (tsf:763-786)."""
+    from opensc2_b200.problem import case2_topology, synthetic_step_arrays
+
+    topo = case2_topology()
+    arr = synthetic_step_arrays(topo, n, batch=batch, seed=9, num_step=2, exact_squares=False, heated=False)
+    l = 5
+    arr.dz[bad, :] = 0.02
+    arr.sol_gauss[bad, 0, l] = 0.0            # density -> mass term 0
+    arr.sol_gauss[bad, 2, l] = 128.0          # conductivity
+    for k, (_j, s) in enumerate(topo.fs):
+        if s == l:
+            arr.htc_fs[bad, k] = 0.0
+    for k, (a, c) in enumerate(topo.ss):
+        if l in (a, c):
+            arr.htc_ss[bad, k] = 0.0
+    return topo, arr, (n - 1) * topo.ndf + 3 * topo.n_ch + l

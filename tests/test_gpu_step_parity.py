@@ -218,3 +218,26 @@ def test_case2_sized_sweeps_match_oracle_with_system(n, batch, num_step, d64, mo
     env = dict(os.environ, OSC2_D64=d64)
     res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
     assert res.returncode == 0 and "bits-equal" in res.stdout, res.stdout + res.stderr
+
+
+def test_case2_singular_conductor_is_reported_by_the_d64_sweep():
+    """NODOFS = 64: an exact zero pivot in one conductor gives status -(row+1) (`Matrix is singular at
+    line row`, tsf:763-786) while its neighbours in the batch stay bit-exact."""
+    from helpers import case2_with_isolated_massless_solid
+    from opensc2_b200 import _lib
+    from opensc2_b200.batch import BatchedStep
+    from oracle import oracle as O
+
+    topo, arr, row = case2_with_isolated_massless_solid(7, 3, bad=1)
+    ref = O.step(topo, arr)
+    assert list(ref["status"]) == [0, -(row + 1), 0]
+    with BatchedStep(topo, 3, 7) as bs:
+        bs.upload_state(arr.sysvar, arr.syslod)
+        bs.upload_step_inputs(arr)
+        bs.step(arr.dt, arr.num_step)
+        with pytest.raises(_lib.SingularMatrixError):
+            bs.synchronize()
+        sv, _sl, st = bs.download_state(want_syslod=False)
+    assert list(st) == [0, -(row + 1), 0]
+    assert_bits(sv[0], ref["sysvar"][0], "conductor 0")
+    assert_bits(sv[2], ref["sysvar"][2], "conductor 2")

@@ -113,3 +113,14 @@ def test_emulated_d64_register_tiled_sweeps(n, batch, num_step):
     assert_bits(out["known"], ref["known"], "known")
     for key in KEYS:
         assert_bits(out[key], ref[key], key)
+
+
+def test_emulated_d64_singular_status():
+    from helpers import case2_with_isolated_massless_solid
+
+    topo, arr, row = case2_with_isolated_massless_solid(5, 2, bad=1)
+    ref = O.step(topo, arr)
+    assert list(np.atleast_1d(ref["status"])) == [0, -(row + 1)]
+    out = emu.emu_step(topo, arr)
+    assert list(out["status"]) == [0, -(row + 1)]
+    assert_bits(out["sysvar"][0], ref["sysvar"][0], "healthy conductor next to the singular one")
