@@ -41,7 +41,7 @@ struct alignas(16) Osc2Pair { double x, y; };
 #define OSC2_D64_RS 10    /* dz, K, Msol, A diag, A partner, SV0, SV1, SVP0, SVP1, pad */
 __host__ __device__ inline size_t osc2_d64_fwd_smem_doubles()
 {
-    return (size_t)64 * OSC2_D64_SW + 64 * OSC2_D64_PW + 3 * 64 + 2 * 256 * OSC2_D64_TS + 2 * 64 * OSC2_D64_RS + 2 * 64 * 2;
+    return (size_t)64 * OSC2_D64_SW + 64 * OSC2_D64_PW + 3 * 64 + 2 * 256 * OSC2_D64_TS + 2 * 64 * OSC2_D64_RS + 2 * 64 * 2 + 64;
 }
 
 // 8-byte asynchronous copy global -> shared (LDGSTS): the element record of node n+1 travels while
@@ -91,6 +91,20 @@ __device__ __forceinline__ int osc2_ctz(unsigned m)
 #endif
 }
 
+// publish / wait on a shared-memory flag (in-node pivot rounds without a CTA barrier)
+#ifdef OSC2_EMU
+#include <thread>
+inline void osc2_fence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline double osc2_vload(const double *q) { double v; __atomic_load((const long long *)q, (long long *)&v, __ATOMIC_ACQUIRE); return v; }
+inline void osc2_vstore(double *q, double v) { __atomic_store((long long *)q, (long long *)&v, __ATOMIC_RELEASE); }
+inline void osc2_pause() { std::this_thread::yield(); }
+#else
+__device__ __forceinline__ void osc2_fence_block() { __threadfence_block(); }
+__device__ __forceinline__ double osc2_vload(const double *q) { return *(const volatile double *)q; }
+__device__ __forceinline__ void osc2_vstore(double *q, double v) { *(volatile double *)q = v; }
+__device__ __forceinline__ void osc2_pause() {}
+#endif
+
 #ifdef OSC2_EMU
 inline bool osc2_any(bool pred) { return emu_any(pred); }
 #else
@@ -124,7 +138,7 @@ __device__ __forceinline__ double osc2_leaf_sum(const double *strip, int cbase, 
 // ---------------------------------------------------------------------------
 // K_F64
 // ---------------------------------------------------------------------------
-template <bool CAP>
+template <bool CAP, bool FLAGS>
 __global__ void __launch_bounds__(256, 1) osc2_forward64_kernel(const osc2_topology *__restrict__ tp, StepDev p)
 {
     OSC2_DYN_SMEM(sm_dyn);
@@ -146,6 +160,7 @@ __global__ void __launch_bounds__(256, 1) osc2_forward64_kernel(const osc2_topol
     double *sS = xs + 3 * 64;               // [2][256][TS]  touched SMAT entries of elements e, e+1 (by parity)
     double *sR = sS + 2 * 256 * OSC2_D64_TS;   // [2][64][RS] row scalars of those elements
     double *sSL = sR + 2 * 64 * OSC2_D64_RS;   // [2][64][2]  SYSLOD of the node (by parity)
+    double *rdy = sSL + 2 * 64 * 2;            // [64] FLAGS: node count up to which pivot row k has been published
     double *srow = strip + r * SW;
     double *fac_out = p.spill + b * ((size_t)N * 64 * PW);
 
@@ -222,7 +237,9 @@ __global__ void __launch_bounds__(256, 1) osc2_forward64_kernel(const osc2_topol
 
     const Osc2Rcp third = osc2_rcp_prepare(3.0);     // x / 3. with the shared-divisor division (exact, osc2_div.cuh)
     long long bad_row = -1;
+    bool hung = false;
     if (tid < 64) {
+        rdy[tid] = 0.0;
         xs[0 * d + tid] = p.sysvar[((size_t)0 * d + tid) * B + b];
         xs[1 * d + tid] = p.sysvar[((size_t)1 * d + tid) * B + b];
     }
@@ -543,7 +560,26 @@ __global__ void __launch_bounds__(256, 1) osc2_forward64_kernel(const osc2_topol
                     }
                     if (h == 0) pk[2 * d] = rhs;
                 }
-                __syncthreads();
+                if (FLAGS) {
+                    // no CTA barrier per round: the owner warp raises the row's flag, the warps below it
+                    // wait for that flag only, so a warp that is late does not hold up the pivot chain
+                    const double epoch = (double)(n + 1);
+                    if (warp == k8) {
+                        __syncwarp();
+                        if (lane == 0) { osc2_fence_block(); osc2_vstore(rdy + k, epoch); }
+                    } else if (warp > k8) {
+                        if (!hung) {
+                            int it = 0;
+                            while (osc2_vload(rdy + k) < epoch) {
+                                if (++it > (1 << 22)) { hung = true; break; }
+                                osc2_pause();
+                            }
+                        }
+                        osc2_fence_block();
+                    }
+                } else {
+                    __syncthreads();
+                }
                 if (8 * warp + 7 > k) {
                     const double num = (kk & 1) ? Dr[2 * k8 + 1] : Dr[2 * k8];
                     const double v = osc2_bcast(num, lane0 | (kk >> 1));
@@ -571,7 +607,8 @@ __global__ void __launch_bounds__(256, 1) osc2_forward64_kernel(const osc2_topol
                 }
             }
         }
-        // the last publish (row 63) was followed by a barrier: spill the 64 final rows as they lie
+        // all 64 final rows are in `piv` (the last publish was followed by a barrier): spill them as they lie
+        if (FLAGS) __syncthreads();
         {
             double *out = fac_out + (size_t)n * (64 * PW);
             for (int q = tid; q < 64 * PW / 2; q += 256) {
@@ -582,6 +619,7 @@ __global__ void __launch_bounds__(256, 1) osc2_forward64_kernel(const osc2_topol
     }
     // first singular row of the conductor (gredub/gbacsb raise on abs(pivot) <= 1e-20)
     __syncthreads();
+    if (hung) bad_row = 0;          // a flag never came (cannot happen; guards against a hang): conductor reported failed
     strip[tid] = (double)bad_row;
     __syncthreads();
     if (tid == 0) {

@@ -215,8 +215,13 @@ void osc2_run_step(Launcher &L, const osc2_topology *tp_dev, const StepDev &p, b
     static const bool d64_on = [] { const char *e = getenv("OSC2_D64"); return !(e && e[0] == '0'); }();
     if (p.d == 64 && d64_on && osc2_d64_fwd_smem_doubles() * sizeof(double) <= L.max_smem()) {
         const size_t smem64 = osc2_d64_fwd_smem_doubles() * sizeof(double);
-        if (p.cap_sysmat) L.launch(OSC2_K_FORWARD, osc2_forward64_kernel<true>, (unsigned)p.B, 256u, smem64, tp_dev, p);
-        else L.launch(OSC2_K_FORWARD, osc2_forward64_kernel<false>, (unsigned)p.B, 256u, smem64, tp_dev, p);
+        // OSC2_D64_SYNC=flags (experiment): per-row shared-memory flags instead of one __syncthreads per
+        // in-node pivot round -- 76.3 vs 77.1 ms: the owner warp's own chain is the limit, not the waiting
+        static const bool flags = [] { const char *e = getenv("OSC2_D64_SYNC"); return e && e[0] == 'f'; }();
+        if (p.cap_sysmat && flags) L.launch(OSC2_K_FORWARD, osc2_forward64_kernel<true, true>, (unsigned)p.B, 256u, smem64, tp_dev, p);
+        else if (p.cap_sysmat) L.launch(OSC2_K_FORWARD, osc2_forward64_kernel<true, false>, (unsigned)p.B, 256u, smem64, tp_dev, p);
+        else if (flags) L.launch(OSC2_K_FORWARD, osc2_forward64_kernel<false, true>, (unsigned)p.B, 256u, smem64, tp_dev, p);
+        else L.launch(OSC2_K_FORWARD, osc2_forward64_kernel<false, false>, (unsigned)p.B, 256u, smem64, tp_dev, p);
         L.launch(OSC2_K_BACKWARD, osc2_backward64_kernel, (unsigned)p.B, 32u, (size_t)(2 * 128 * sizeof(double)), p);
         const long long nl = (long long)p.d * p.B * p.n_leaves, nw = (long long)p.d * p.B;
         L.launch(OSC2_K_NORMS, osc2_norm_leaves_kernel, (unsigned)((nl + 127) / 128), 128u, (size_t)0, p);

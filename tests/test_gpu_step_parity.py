@@ -192,10 +192,10 @@ def test_shared_divisor_division_is_ieee():
     assert bad.value == 0
 
 
-@pytest.mark.parametrize("n,batch,num_step,d64", [(151, 5, 2, "1"), (9, 3, 1, "1"), (9, 3, 1, "0")])
+@pytest.mark.parametrize("n,batch,num_step,d64", [(151, 5, 2, "1"), (9, 3, 1, "1"), (9, 3, 1, "0"), (31, 4, 2, "flags")])
 def test_case2_sized_sweeps_match_oracle_with_system(n, batch, num_step, d64, monkeypatch):
     """NODOFS = 64 at the shipped CASE_2 mesh size: the register-tiled sweeps (step_kernels_d64.cuh,
-    default) and the generic shared-memory sweeps (OSC2_D64=0) both reproduce the oracle's SYSMAT,
+    default; also with the opt-in per-row flags, OSC2_D64_SYNC=flags) and the generic shared-memory sweeps (OSC2_D64=0) reproduce the oracle's SYSMAT,
     Known and outputs bit for bit."""
     import subprocess, sys, os, textwrap
     # the switch is read once per process: run the comparison in a child
@@ -215,7 +215,7 @@ def test_case2_sized_sweeps_match_oracle_with_system(n, batch, num_step, d64, mo
             assert np.array_equal(out[key], ref[key]), key
         print("bits-equal")
     """)
-    env = dict(os.environ, OSC2_D64=d64)
+    env = dict(os.environ, OSC2_D64=d64) if d64 != "flags" else dict(os.environ, OSC2_D64="1", OSC2_D64_SYNC="flags")
     res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
     assert res.returncode == 0 and "bits-equal" in res.stdout, res.stdout + res.stderr
 

@@ -124,3 +124,28 @@ def test_emulated_d64_singular_status():
     out = emu.emu_step(topo, arr)
     assert list(out["status"]) == [0, -(row + 1)]
     assert_bits(out["sysvar"][0], ref["sysvar"][0], "healthy conductor next to the singular one")
+
+
+def test_emulated_d64_flag_synchronised_rounds():
+    """Opt-in OSC2_D64_SYNC=flags (per-row shared-memory flags instead of a CTA barrier per in-node pivot
+    round): same bits.  The switch is read once per process, hence the child."""
+    import os, subprocess, sys, textwrap
+    here = os.path.dirname(os.path.abspath(__file__))
+    code = textwrap.dedent(f"""
+        import sys, numpy as np
+        sys.path[:0] = [{here!r}, {os.path.dirname(here)!r}]
+        from cuda_emu import emu
+        from opensc2_b200.problem import case2_topology, synthetic_step_arrays
+        from oracle import oracle as O
+        topo = case2_topology()
+        arr = synthetic_step_arrays(topo, 5, batch=2, seed=31, num_step=2, exact_squares=False)
+        out = emu.emu_step(topo, arr, capture=True)
+        ref = O.step(topo, arr, want_system=True)
+        for key in ("sysmat", "known", "sysvar", "syslod", "norm_solution", "norm_change", "eqteig"):
+            assert np.array_equal(out[key], ref[key]), key
+        assert np.all(out["status"] == 0)
+        print("bits-equal")
+    """)
+    res = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, OSC2_D64_SYNC="flags"),
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and "bits-equal" in res.stdout, res.stdout + res.stderr
