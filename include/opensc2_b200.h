@@ -94,7 +94,7 @@ typedef struct {
  * time step BEFORE step(): Conductor.operating_conditions_em / _th, conductor.py:4591-4744,
  * eval_transp_coeff conductor.py:4822-5406, build_heat_source conductor.py:4423-4581).
  * osc2_model is uniform across the batch; osc2_sweep holds the swept per-conductor scalars. */
-#define OSC2_MAX_MATERIALS 5
+#define OSC2_MAX_MATERIALS 8
 #define OSC2_MAX_FLUIDS 4
 #define OSC2_N_FLUID_PROPS 10
 /* property order of a fluid table = the reference's alias table (simulation.py:89-100) */
@@ -104,9 +104,15 @@ enum { OSC2_FP_BETA = 0,   /* isobaric_expansion_coefficient */
        OSC2_FP_SOUND, OSC2_FP_K };
 /* materials (the fits of properties_of_materials/) */
 enum { OSC2_MAT_CU_NIST = 0, OSC2_MAT_NB3SN = 1, OSC2_MAT_SS = 2, OSC2_MAT_GE = 3, OSC2_MAT_AL = 4,
-       OSC2_MAT_RE123 = 5, OSC2_MAT_COUNT };
-/* solid kinds: StrandMixedComponent, StrandStabilizerComponent, JacketComponent */
-enum { OSC2_SOLID_STRAND_MIXED = 0, OSC2_SOLID_STRAND_STAB = 1, OSC2_SOLID_JACKET = 2 };
+       OSC2_MAT_RE123 = 5,
+       OSC2_MAT_AG = 6,        /* silver.py */
+       OSC2_MAT_HC276 = 7,     /* hastelloy_c276.py */
+       OSC2_MAT_SN60PB40 = 8,  /* solder_sn60_pb40.py */
+       OSC2_MAT_COUNT };
+/* solid kinds: StrandMixedComponent, StrandStabilizerComponent, JacketComponent, StackComponent (HTS tapes:
+ * layers homogenised by thickness, stack_component.py:398-476; weights = material_thickness,
+ * weight_sum = tape_thickness) */
+enum { OSC2_SOLID_STRAND_MIXED = 0, OSC2_SOLID_STRAND_STAB = 1, OSC2_SOLID_JACKET = 2, OSC2_SOLID_STACK = 3 };
 
 typedef struct {
     /* channels (channel.py:43-169) */

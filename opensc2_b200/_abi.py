@@ -54,7 +54,7 @@ class Osc2StepInputs(C.Structure):
                                                                                         ("peri_ss_nodal", c_dp)]
 
 
-OSC2_MAX_MATERIALS = 5
+OSC2_MAX_MATERIALS = 8
 OSC2_MAX_FLUIDS = 4
 OSC2_N_FLUID_PROPS = 10
 _CH, _SO, _IF = OSC2_MAX_CHANNELS, OSC2_MAX_SOLIDS, OSC2_MAX_INTERFACES

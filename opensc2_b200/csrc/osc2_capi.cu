@@ -479,7 +479,7 @@ int osc2_set_model(osc2_handle h, const osc2_model *model)
     for (int l = 0; l < h->S; ++l) {
         if (model->sol_nmat[l] < 1 || model->sol_nmat[l] > OSC2_MAX_MATERIALS)
             return fail(OSC2_ERR_INVALID, "solid %d: %d materials", l, model->sol_nmat[l]);
-        if (model->sol_kind[l] < OSC2_SOLID_STRAND_MIXED || model->sol_kind[l] > OSC2_SOLID_JACKET)
+        if (model->sol_kind[l] < OSC2_SOLID_STRAND_MIXED || model->sol_kind[l] > OSC2_SOLID_STACK)
             return fail(OSC2_ERR_INVALID, "solid %d: unknown kind %d", l, model->sol_kind[l]);
         for (int i = 0; i < model->sol_nmat[l]; ++i)
             if (model->sol_mat[l][i] < 0 || model->sol_mat[l][i] >= OSC2_MAT_COUNT)
@@ -522,7 +522,7 @@ int osc2_set_model(osc2_handle h, const osc2_model *model)
     }
     h->q.model = h->model_dev;
     {   // greedy balance of the component items over the warps of the fused kernel by pow() count
-        static const int mat_cost[OSC2_MAT_COUNT] = {14, 9, 8, 8};   // Cu, Nb3Sn, SS, glass-epoxy
+        static const int mat_cost[OSC2_MAT_COUNT] = {14, 9, 8, 8, 8, 4, 4, 4, 4};   // Cu, Nb3Sn, SS, glass-epoxy, Al, RE123, Ag, HC276, Sn60Pb40
         const int n_items = h->M + h->S + 1;
         std::vector<std::pair<int, int>> items;     // (cost, item)
         for (int j = 0; j < h->M; ++j) items.push_back({2 + (model->ch_ifriction[j] == 124 ? 2 : 0), j});

@@ -248,10 +248,75 @@ __device__ inline double cp_re123(double T)
     return -7.567485538209158e-10 * T5 + 6.351452642016898e-07 * T4 + -1.947975786547597e-04 * T3 + 0.023616673974415 * T2
            + 0.239331954284042 * T + -1.096191721280114;
 }
+// silver.py:5-110, hastelloy_c276.py:5-105, solder_sn60_pb40.py:5-96 (StackComponent layers).  np.piecewise:
+// where two conditions hold the later one wins, where none holds the value is 0.
+__device__ __noinline__ double k_ag(double T)
+{
+    T = fmin(T, 1234.0);
+    T = fmax(T, 1.0);
+    const double T2 = sq(T), T3 = T2 * T, T4 = T2 * T2;
+    if (T < 13.0) return 3.5389 * T4 - 8.2624e1 * T3 + 2.7138e2 * T2 + 3.6897e3 * T;
+    if (T < 35.0) return -1.3578 * T3 + 1.2791e2 * T2 - 4.1285e3 * T + 4.7377e4;
+    if (T < 100.0) return 1.8407e-4 * T4 - 5.9684e-2 * T3 + 7.241 * T2 - 3.9169e2 * T + 8.4877e3;
+    if (T < 273.0) return 1.4878e-7 * T4 - 1.2548e-4 * T3 + 3.9209e-2 * T2 - 5.4107 * T + 7.0959e2;
+    if (T < 1234.0) return 9.3528e-9 * T3 - 2.6629e-5 * T2 - 5.4314e-2 * T + 4.4529e2;
+    return 0.0;
+}
+__device__ __noinline__ double cp_ag(double T)
+{
+    T = fmin(T, 300.0);
+    T = fmax(T, 1.0);
+    const double T2 = sq(T), T3 = T2 * T, T4 = T2 * T2;
+    double v;
+    if (T >= 285.0) v = (2.343447902350777e2 - 2.343414867962295e2) / (285 - 284.9) * (T - 295) + 2.343447902350777e2;
+    else if (T > 50.0)
+        v = -0.000000104620955 * T4 + 0.000091884831207 * T3 - 0.030295300516950 * T2 + 4.598581892940776 * T - 52.331891977926269;
+    else v = 0.047220784283425 * T2 - 0.018765676876719 * T - 1.946839691056091;
+    return fmax(v, 1.0);
+}
+__device__ __noinline__ double k_hc276(double T)
+{
+    T = fmin(T, 350.0);
+    T = fmax(T, 1.0);
+    const double T2 = sq(T), T3 = T2 * T;
+    if (T >= 300.0) return (12.240619439579623 - 12.219768038241552) / (300 - 299) * (T - 300) + 12.240619439579623;
+    if (T > 60.0) return 0.000000124577333 * T3 - 0.000079993515434 * T2 + 0.035243632195403 * T + 5.503358179018721;
+    return 0.000028975912976 * T3 - 0.004655231435231 * T2 + 0.293992451992451 * T + 0.166939393939405;
+}
+__device__ __noinline__ double cp_hc276(double T)
+{
+    T = fmin(T, 350.0);
+    T = fmax(T, 1.0);
+    const double T2 = sq(T), T3 = T2 * T;
+    if (T >= 300.0) return (4.049021473239762e2 - 4.043151575124803e002) / (300 - 299) * (T - 300) + 4.049021473239762e2;
+    if (T > 60.0) return 0.0000302086983 * T3 - 0.0226456716880 * T2 + 6.0225562313795 * T - 179.3891242698739;
+    return 0.000092969696970 * T3 + 0.046381858141858 * T2 - 0.738681152181147 * T + 4.091909090909040;
+}
+__device__ __noinline__ double k_sn60pb40(double T)
+{
+    T = fmin(T, 350.0);
+    T = fmax(T, 4.0);
+    if (T >= 300.0) return 0.0902 * (T - 300.0) + 51.1010;
+    const double T2 = sq(T), T3 = T2 * T, T4 = T2 * T2, T5 = T4 * T;
+    return 2.667e-010 * T5 - 2.483e-7 * T4 + 8.769e-005 * T3 - 0.01453 * T2 + 1.147 * T + 10.22;
+}
+__device__ __noinline__ double cp_sn60pb40(double T)
+{
+    T = fmin(T, 350.0);
+    T = fmax(T, 1.0);
+    double v;
+    if (T >= 300.0) v = 0.2316 * (T - 300.0) + 181.0480;
+    else {
+        const double T2 = sq(T), T3 = T2 * T, T4 = T2 * T2, T5 = T4 * T;
+        v = 6.856e-010 * T5 - 6.764e-7 * T4 + 0.0002604 * T3 - 0.0492 * T2 + 4.728 * T - 27.32;
+    }
+    return fmax(v, 1.0);
+}
 __device__ inline double mat_density(int mat)
 {
     return mat == OSC2_MAT_CU_NIST ? 8900.0 : mat == OSC2_MAT_NB3SN ? 8950.0 : mat == OSC2_MAT_SS ? 7800.0
-           : mat == OSC2_MAT_AL ? 2700.0 : mat == OSC2_MAT_RE123 ? 6380.0 : 2000.0;
+           : mat == OSC2_MAT_AL ? 2700.0 : mat == OSC2_MAT_RE123 ? 6380.0 : mat == OSC2_MAT_AG ? 10630.0
+           : mat == OSC2_MAT_HC276 ? 8890.0 : mat == OSC2_MAT_SN60PB40 ? (7310.0 * 0.6 + 11340.0 * 0.4) : 2000.0;
 }
 __device__ inline double friction_124(double re);
 // IFRICTION 122: haaland_equation channel.py:700-717 as the start, colebrook_formula channel.py:721-756
@@ -312,6 +377,9 @@ __device__ inline void material_cp_k(int mat, double T, double bg, double tcs, d
     else if (mat == OSC2_MAT_SS) { cp = cp_ss(T, tmax); k = k_ss(T); }
     else if (mat == OSC2_MAT_AL) { cp = cp_al(T, tmin, tmax); k = k_al(T, tmin, tmax); }
     else if (mat == OSC2_MAT_RE123) { cp = cp_re123(T); k = k_re123(T); }
+    else if (mat == OSC2_MAT_AG) { cp = cp_ag(T); k = k_ag(T); }
+    else if (mat == OSC2_MAT_HC276) { cp = cp_hc276(T); k = k_hc276(T); }
+    else if (mat == OSC2_MAT_SN60PB40) { cp = cp_sn60pb40(T); k = k_sn60pb40(T); }
     else { cp = cp_ge(T); k = k_ge(T); }
 }
 // channel.py:392-401, 782-795, 1104-1115

@@ -228,6 +228,69 @@ static double cp_re123(double T)
            + 0.023616673974415 * sq(T) + 0.239331954284042 * T + -1.096191721280114;
 }
 
+/* silver.py:5-60 (np.piecewise: where two conditions hold the later one wins; none: 0) */
+static double k_ag(double T)
+{
+    T = fmin(T, 1234.0);
+    T = fmax(T, 1.0);
+    if (T >= 1.0 && T < 13.0) return 3.5389 * pow(T, 4.0) - 8.2624e1 * pow(T, 3.0) + 2.7138e2 * sq(T) + 3.6897e3 * T;
+    if (T >= 13.0 && T < 35.0) return -1.3578 * pow(T, 3.0) + 1.2791e2 * sq(T) - 4.1285e3 * T + 4.7377e4;
+    if (T >= 35.0 && T < 100.0)
+        return 1.8407e-4 * pow(T, 4.0) - 5.9684e-2 * pow(T, 3.0) + 7.241 * sq(T) - 3.9169e2 * T + 8.4877e3;
+    if (T >= 100.0 && T < 273.0)
+        return 1.4878e-7 * pow(T, 4.0) - 1.2548e-4 * pow(T, 3.0) + 3.9209e-2 * sq(T) - 5.4107 * T + 7.0959e2;
+    if (T >= 273.0 && T < 1234.0) return 9.3528e-9 * pow(T, 3.0) - 2.6629e-5 * sq(T) - 5.4314e-2 * T + 4.4529e2;
+    return 0.0;
+}
+/* silver.py:63-110 */
+static double cp_ag(double T)
+{
+    T = fmin(T, 300.0);
+    T = fmax(T, 1.0);
+    double v;
+    if (T >= 285.0) v = (2.343447902350777e2 - 2.343414867962295e2) / (285 - 284.9) * (T - 295) + 2.343447902350777e2;
+    else if (T > 50.0)
+        v = -0.000000104620955 * pow(T, 4.0) + 0.000091884831207 * pow(T, 3.0) - 0.030295300516950 * sq(T)
+            + 4.598581892940776 * T - 52.331891977926269;
+    else v = 0.047220784283425 * sq(T) - 0.018765676876719 * T - 1.946839691056091;
+    return fmax(v, 1.0);
+}
+/* hastelloy_c276.py:5-53 */
+static double k_hc276(double T)
+{
+    T = fmin(T, 350.0);
+    T = fmax(T, 1.0);
+    if (T >= 300.0) return (12.240619439579623 - 12.219768038241552) / (300 - 299) * (T - 300) + 12.240619439579623;
+    if (T > 60.0) return 0.000000124577333 * pow(T, 3.0) - 0.000079993515434 * sq(T) + 0.035243632195403 * T + 5.503358179018721;
+    return 0.000028975912976 * pow(T, 3.0) - 0.004655231435231 * sq(T) + 0.293992451992451 * T + 0.166939393939405;
+}
+/* hastelloy_c276.py:57-105 */
+static double cp_hc276(double T)
+{
+    T = fmin(T, 350.0);
+    T = fmax(T, 1.0);
+    if (T >= 300.0) return (4.049021473239762e2 - 4.043151575124803e002) / (300 - 299) * (T - 300) + 4.049021473239762e2;
+    if (T > 60.0) return 0.0000302086983 * pow(T, 3.0) - 0.0226456716880 * sq(T) + 6.0225562313795 * T - 179.3891242698739;
+    return 0.000092969696970 * pow(T, 3.0) + 0.046381858141858 * sq(T) - 0.738681152181147 * T + 4.091909090909040;
+}
+/* solder_sn60_pb40.py:5-48 */
+static double k_sn60pb40(double T)
+{
+    T = fmin(T, 350.0);
+    T = fmax(T, 4.0);
+    if (T >= 300.0) return 0.0902 * (T - 300.0) + 51.1010;
+    return 2.667e-010 * pow(T, 5.0) - 2.483e-7 * pow(T, 4.0) + 8.769e-005 * pow(T, 3.0) - 0.01453 * sq(T) + 1.147 * T + 10.22;
+}
+/* solder_sn60_pb40.py:52-96 */
+static double cp_sn60pb40(double T)
+{
+    T = fmin(T, 350.0);
+    T = fmax(T, 1.0);
+    double v;
+    if (T >= 300.0) v = 0.2316 * (T - 300.0) + 181.0480;
+    else v = 6.856e-010 * pow(T, 5.0) - 6.764e-7 * pow(T, 4.0) + 0.0002604 * pow(T, 3.0) - 0.0492 * sq(T) + 4.728 * T - 27.32;
+    return fmax(v, 1.0);
+}
 static double mat_density(int mat)   /* density_cu / _nb3sn / _ss / _ge: constants */
 {
     switch (mat) {
@@ -236,6 +299,9 @@ static double mat_density(int mat)   /* density_cu / _nb3sn / _ss / _ge: constan
     case OSC2_MAT_SS: return 7800.0;
     case OSC2_MAT_AL: return 2700.0;
     case OSC2_MAT_RE123: return 6380.0;
+    case OSC2_MAT_AG: return 10630.0;                       /* silver.py density_ag */
+    case OSC2_MAT_HC276: return 8890.0;                    /* hastelloy_c276.py density_hc276 */
+    case OSC2_MAT_SN60PB40: return 7310.0 * 0.6 + 11340.0 * 0.4;   /* solder_sn60_pb40.py density_sn60pb40 */
     default: return 2000.0;
     }
 }
@@ -318,6 +384,12 @@ int osc2o_fit(int which, long n, const double *x, const double *y, const double 
         case 14: out[i] = cp_al(x[i], tmin, tmax); break;
         case 15: out[i] = k_re123(x[i]); break;
         case 16: out[i] = cp_re123(x[i]); break;
+        case 18: out[i] = k_ag(x[i]); break;
+        case 19: out[i] = cp_ag(x[i]); break;
+        case 20: out[i] = k_hc276(x[i]); break;
+        case 21: out[i] = cp_hc276(x[i]); break;
+        case 22: out[i] = k_sn60pb40(x[i]); break;
+        case 23: out[i] = cp_sn60pb40(x[i]); break;
         default: return -1;
         }
     }
@@ -461,6 +533,9 @@ static void one_conductor(const osc2_topology *tp, const osc2_model *md, osc2o_o
                 case OSC2_MAT_SS: cp_i[i] = cp_ss(T, tmax); k_i[i] = k_ss(T); break;
                 case OSC2_MAT_AL: cp_i[i] = cp_al(T, tmin, tmax); k_i[i] = k_al(T, tmin, tmax); break;
                 case OSC2_MAT_RE123: cp_i[i] = cp_re123(T); k_i[i] = k_re123(T); break;
+                case OSC2_MAT_AG: cp_i[i] = cp_ag(T); k_i[i] = k_ag(T); break;
+                case OSC2_MAT_HC276: cp_i[i] = cp_hc276(T); k_i[i] = k_hc276(T); break;
+                case OSC2_MAT_SN60PB40: cp_i[i] = cp_sn60pb40(T); k_i[i] = k_sn60pb40(T); break;
                 default: cp_i[i] = cp_ge(T); k_i[i] = k_ge(T); break;
                 }
             }
@@ -470,7 +545,8 @@ static void one_conductor(const osc2_topology *tp, const osc2_model *md, osc2o_o
                  * single-material components return the fit itself */
                 rho = rho_i[0]; cp = cp_i[0]; kk = k_i[0];
             } else {
-                /* strand_mixed_component.py:415-514 / jacket_component.py:358-440:
+                /* strand_mixed_component.py:415-514 / jacket_component.py:358-440 / stack_component.py:398-476
+                 * (weights = layer thicknesses, sum = tape thickness):
                  * numerator = rho_i * w_i; sums over the material axis are sequential */
                 double num[OSC2_MAX_MATERIALS], nsum = 0.0, cps = 0.0, ksum = 0.0;
                 for (int i = 0; i < nmat; ++i) num[i] = rho_i[i] * md->sol_weight[l][i];

@@ -1,0 +1,59 @@
+"""Generate tests/golden/props_stack.npz by running the UNMODIFIED reference: the silver, Hastelloy C276 and
+Sn60Pb40 fits (properties_of_materials/) and the StackComponent homogenisers (stack_component.py:398-476) on
+a bare StackComponent object (its constructor needs openpyxl).
+
+Build-container only (needs /root/reference):  python tests/golden/make_golden_stack.py
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+sys.path.insert(0, HERE)
+
+import ref_harness as H  # noqa: E402
+
+# tape of the reference's StackComponent: (material key, layer thickness in m), in tape order
+TAPE = (("ag", 2.0e-6), ("cu", 40.0e-6), ("hc276", 50.0e-6), ("re123", 1.0e-6), ("sn60pb40", 10.0e-6))
+RRR = 100.0
+
+
+def main():
+    assert H.reference_available()
+    H._import_reference()
+    import stack_component as SC
+
+    rng = np.random.default_rng(20261020)
+    n = 600
+    t = np.concatenate([rng.uniform(0.5, 70.0, n // 3), rng.uniform(40.0, 360.0, n // 3), rng.uniform(250.0, 1300.0, n // 3 - 12),
+                        [1.0, 13.0, 35.0, 50.0, 60.0, 100.0, 273.0, 285.0, 300.0, 350.0, 1234.0, 4.0]])
+    out = {"t": t}
+    for key in ("ag", "hc276", "sn60pb40"):
+        out[f"k_{key}"] = SC.THERMAL_CONDUCTIVITY_FUNC[key](t)
+        out[f"cp_{key}"] = SC.ISOBARIC_SPECIFIC_HEAT_FUNC[key](t)
+        out[f"rho_{key}"] = SC.DENSITY_FUNC[key](t)
+    # homogenised stack through the reference's own methods
+    st = object.__new__(SC.StackComponent)
+    keys = [k for k, _ in TAPE]
+    st.inputs = {"Material_number": len(TAPE), "RRR": RRR}
+    st.material_thickness = np.array([s for _, s in TAPE])
+    st.tape_thickness = st.material_thickness.sum()
+    st.density_function = np.array([SC.DENSITY_FUNC[k] for k in keys])
+    st.isobaric_specific_heat_function = np.array([SC.ISOBARIC_SPECIFIC_HEAT_FUNC[k] for k in keys])
+    st.thermal_conductivity_function = np.array([SC.THERMAL_CONDUCTIVITY_FUNC[k] for k in keys])
+    ts = np.concatenate([rng.uniform(4.0, 100.0, 200), rng.uniform(20.0, 320.0, 100)])
+    bs = rng.uniform(0.0, 12.0, ts.size)
+    prop = {"temperature": ts, "B_field": bs}
+    out["stack_t"], out["stack_b"] = ts, bs
+    out["stack_rho"] = st.stack_density(prop)
+    out["stack_cp"] = st.stack_isobaric_specific_heat(prop)
+    out["stack_k"] = st.stack_thermal_conductivity(prop)
+    out["stack_thickness"] = st.material_thickness
+    np.savez_compressed(os.path.join(HERE, "props_stack.npz"), **out)
+    print("wrote props_stack.npz", {k: v.shape for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    main()

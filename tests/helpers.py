@@ -67,3 +67,33 @@ def case2_with_isolated_massless_solid(n, batch, bad):
         if l in (a, c):
             arr.htc_ss[bad, k] = 0.0
     return topo, arr, (n - 1) * topo.ndf + 3 * topo.n_ch + l
+
+
+STACK_TAPE = (("ag", 2.0e-6), ("cu", 40.0e-6), ("hc276", 50.0e-6), ("re123", 1.0e-6), ("sn60pb40", 10.0e-6))
+
+
+def stack_case(n_nodes=5):
+    """CASE_1 topology whose first solid is a StackComponent (HTS tape: Ag / Cu / Hastelloy / REBCO / solder,
+    tests/golden/make_golden_stack.py): one conductor per golden (T, B) pair, solid temperature and field
+    uniform along the conductor so that every Gauss point sees exactly that pair."""
+    import dataclasses
+
+    from opensc2_b200 import model as Mdl
+    from opensc2_b200.problem import case1_topology, synthetic_step_arrays
+
+    g = np.load(os.path.join(GOLDEN_DIR, "props_stack.npz"))
+    mats = {"ag": Mdl.MAT_AG, "cu": Mdl.MAT_CU_NIST, "hc276": Mdl.MAT_HC276, "re123": Mdl.MAT_RE123, "sn60pb40": Mdl.MAT_SN60PB40}
+    thick = tuple(s for _k, s in STACK_TAPE)
+    stack = Mdl.SolidModel(Mdl.SOLID_STACK, tuple(mats[k] for k, _s in STACK_TAPE), thick, float(np.array(thick).sum()), rrr=100.0)
+    base = Mdl.case1_model(False)
+    model = dataclasses.replace(base, solids=(stack,) + base.solids[1:])
+    topo = case1_topology(1)
+    batch = g["stack_t"].size
+    arr = synthetic_step_arrays(topo, n_nodes, batch=batch, seed=4)
+    sv = arr.sysvar.reshape(batch, n_nodes, topo.ndf)
+    sv[:, :, 3 * topo.n_ch + 0] = g["stack_t"][:, None]
+    sweep = Mdl.synthetic_sweep(topo, model, n_nodes, batch, seed=4, with_tcs=False)
+    bf = np.array(sweep.b_field, copy=True)
+    bf[:, 0, :] = g["stack_b"][:, None]
+    sweep = dataclasses.replace(sweep, b_field=bf)
+    return topo, model, Mdl.synthetic_helium_table(), arr, sweep, g

@@ -345,3 +345,28 @@ def test_case3_flavoured_model_radiative_exchange(fused, monkeypatch):
             assert rel_field(a[..., :M], b[..., :M]) <= RTOL_CHAIN_V
             assert rel_field(a[..., M:], b[..., M:]) <= RTOL_CHAIN
             host.sysvar, host.syslod = sv, sl
+
+
+def test_stack_component_solid_on_the_device():
+    """SOLID_STACK (StackComponent: Ag / Cu / Hastelloy C276 / REBCO / Sn60Pb40 layers homogenised by
+    thickness, stack_component.py:398-476): K_P against the oracle and against the values the reference's
+    own StackComponent methods gave for the same temperatures and fields (tests/golden/props_stack.npz)."""
+    from helpers import stack_case
+    from opensc2_b200.batch import BatchedStep
+    from oracle import oracle as O
+
+    topo, model, tab, arr, sweep, g = stack_case()
+    n, batch = arr.n_nodes, arr.sysvar.shape[0]
+    with BatchedStep(topo, batch, n) as bs:
+        bs.set_model(model, [tab])
+        bs.upload_sweep(sweep)
+        bs.upload_state(arr.sysvar, arr.syslod)
+        bs.upload_geometry(arr)
+        bs.eval_operating_conditions(5.0)
+        bs.synchronize()
+        out = bs.download_step_inputs()
+    ref = O.operating_conditions(topo, model, [tab], sweep, arr.sysvar, n, 5.0)
+    assert rel(out["sol_gauss"], ref["sol_gauss"]) <= RTOL_FIT
+    for q, key in enumerate(("stack_rho", "stack_cp", "stack_k")):
+        for e in range(n - 1):
+            assert np.max(np.abs(out["sol_gauss"][:, q, 0, e] - g[key]) / np.abs(g[key])) <= RTOL_FIT, key

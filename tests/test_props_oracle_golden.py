@@ -78,3 +78,31 @@ def test_aluminium_whole_array_range_check_and_re123(g):
 def test_colebrook_array_wide_iteration(g):
     out = O.fit("friction_122", g["re"], p1=float(g["roughness"]), p2=float(g["hydiameter"])) * 0.02
     close(out, g["f122_total"], "friction 122")
+
+
+def test_stack_layer_materials_against_the_reference_fits():
+    """Silver, Hastelloy C276, Sn60Pb40 (StackComponent layers): oracle fits vs the reference functions,
+    including the np.piecewise edge values (T = 13, 35, 60, 285, 300, 1234 K ...)."""
+    import os
+    from helpers import GOLDEN_DIR
+    g = np.load(os.path.join(GOLDEN_DIR, "props_stack.npz"))
+    for key in ("ag", "hc276", "sn60pb40"):
+        for q in ("k", "cp"):
+            got = O.fit(f"{q}_{key}", g["t"])
+            ref = g[f"{q}_{key}"]
+            err = np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-300))
+            assert err <= 2e-12, f"{q}_{key}: {err:.3e}"
+            assert np.array_equal(got == 0.0, ref == 0.0)
+
+
+def test_stack_component_homogenisation_against_the_reference():
+    """StackComponent.stack_density / stack_isobaric_specific_heat / stack_thermal_conductivity run by the
+    reference on a five-layer tape vs the oracle's operating conditions for a SOLID_STACK solid."""
+    from helpers import stack_case
+    topo, model, tab, arr, sweep, g = stack_case()
+    ref = O.operating_conditions(topo, model, [tab], sweep, arr.sysvar, arr.n_nodes, 5.0)
+    sg = ref["sol_gauss"]            # (B, 3, S, E)
+    for q, key in enumerate(("stack_rho", "stack_cp", "stack_k")):
+        for e in range(arr.n_nodes - 1):
+            err = np.max(np.abs(sg[:, q, 0, e] - g[key]) / np.abs(g[key]))
+            assert err <= 2e-12, f"{key}: {err:.3e}"
