@@ -117,7 +117,7 @@ enum { OSC2_SOLID_STRAND_MIXED = 0, OSC2_SOLID_STRAND_STAB = 1, OSC2_SOLID_JACKE
 typedef struct {
     /* channels (channel.py:43-169) */
     int ch_fluid[OSC2_MAX_CHANNELS];            /* which fluid table */
-    int ch_ifriction[OSC2_MAX_CHANNELS];        /* IFRICTION: -99, 122 (Colebrook) or 124 */
+    int ch_ifriction[OSC2_MAX_CHANNELS];        /* IFRICTION: -99, 110 (Blasius), 111 (Bhatti-Shah), 112 (LHC), 121 (Haaland), 122 (Colebrook) or 124 */
     double ch_friction_mult[OSC2_MAX_CHANNELS]; /* FRICTION_MULTIPLIER */
     int ch_htc_corr[OSC2_MAX_CHANNELS];         /* Flag_htc_steady_corr: 1 or 212 */
     /* solids */

@@ -347,10 +347,31 @@ __device__ inline int colebrook_count(double re, double rough, double dh)
     return it;
 }
 // total friction factor of channel j (channel.py:1119-1138)
+// IFRICTION 110 (Blasius), 111 (Bhatti-Shah), 112 (LHC magnets recipe), 121 (Haaland): channel.py:392-438, 700-717;
+// total = max(laminar, turbulent) with the general laminar correlation 16/Re (channel.py:284-299, 1104-1115);
+// for 121 the laminar slot calls the Haaland method again, which writes the turbulent array: laminar stays 0
+__device__ __noinline__ double friction_simple(int ifr, double re, double rough, double dh)
+{
+    re = fabs(re);
+    double turb = 0.0, lam = 0.0;
+    if (ifr == 121) return fmax(0.0, haaland(re, rough, dh));
+    lam = re >= 1.0e-5 ? 16.0 / re : 0.0;
+    if (ifr == 110) turb = (0.316 * pw(re, -0.25)) / 4.0;
+    else if (ifr == 111) turb = 0.00128 + 0.1143 * pw(fmax(re, 4000.0), -0.311);
+    else {
+        if (re <= 2.0e3) turb = 64 / re / 4.0;
+        if (re > 2.0e3 && re < 4.0e3) turb = 2.6471e-3 * pw(re, 0.3279) / 4.0;
+        if (re > 4.0e3 && re < 3.0e4) turb = 0.3194 * pw(re, -0.25) / 4.0;
+        if (re >= 3.0e4) { const double x = 1.8 * log10(re) / 1.0 - 1.64; turb = 1.0 / (x * x) / 4.0; }
+    }
+    return fmax(lam, turb);
+}
 __device__ inline double friction_total(const osc2_model *md, const osc2_topology *tp, int j, double re, int cb_iters)
 {
     double f = 1.0;
-    if (md->ch_ifriction[j] == 124) f = friction_124(re);
+    const int ifr = md->ch_ifriction[j];
+    if (ifr == 124) f = friction_124(re);
+    else if (ifr == 110 || ifr == 111 || ifr == 112 || ifr == 121) f = friction_simple(ifr, re, md->ch_roughness[j], tp->ch_dh[j]);
     else if (md->ch_ifriction[j] == 122) {
         const double rough = md->ch_roughness[j], dh = tp->ch_dh[j];
         f = haaland(fabs(re), rough, dh);

@@ -42,7 +42,7 @@ class SolidModel:
 @dataclass(frozen=True)
 class Model:
     ch_fluid: Tuple[int, ...]
-    ch_ifriction: Tuple[int, ...]           # -99 | 122 | 124
+    ch_ifriction: Tuple[int, ...]           # -99 | 110 | 111 | 112 | 121 | 122 | 124
     ch_friction_mult: Tuple[float, ...]
     ch_htc_corr: Tuple[int, ...]            # 1 | 212
     solids: Tuple[SolidModel, ...]

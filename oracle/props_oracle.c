@@ -316,6 +316,31 @@ static double friction_124(double re)
     if (re > 1e4) f = 2.21 * pow(re, -0.4) / 4.0;
     return fmax(0.0, f);
 }
+/* general_laminar_correlation channel.py:284-299: 16/Re where Re >= 1e-5, else the initial 0 */
+static double friction_laminar(double re) { return re >= 1.0e-5 ? 16.0 / re : 0.0; }
+/* IFRICTION 110, 111, 112, 121 (channel.py:392-401, 403-413, 415-438, 700-717): total = max(laminar, turbulent)
+ * (channel.py:1104-1115).  110-112: laminar slot = general_laminar_correlation.  121: the laminar slot calls
+ * haaland_equation again, which writes the TURBULENT array, so laminar stays 0.  112 assigns by masks that
+ * leave Re = 2e3 < . , Re = 4e3 exactly at the initial 0 of the turbulent array. */
+static double friction_simple(int ifr, double re, double rough, double dh)
+{
+    re = fabs(re);
+    double turb = 0.0, lam = 0.0;
+    switch (ifr) {
+    case 110: turb = (0.316 * pow(re, -0.25)) / 4.0; lam = friction_laminar(re); break;
+    case 111: turb = 0.00128 + 0.1143 * pow(fmax(re, 4000.0), -0.311); lam = friction_laminar(re); break;
+    case 112:
+        if (re <= 2.0e3) turb = 64 / re / 4.0;
+        if (re > 2.0e3 && re < 4.0e3) turb = 2.6471e-3 * pow(re, 0.3279) / 4.0;
+        if (re > 4.0e3 && re < 3.0e4) turb = 0.3194 * pow(re, -0.25) / 4.0;
+        if (re >= 3.0e4) turb = 1.0 / pow(1.8 * log10(re) / log10(10.0) - 1.64, 2.0) / 4.0;
+        lam = friction_laminar(re);
+        break;
+    case 121: turb = pow(-1.8 * log10(pow(rough / dh / 3.7, 1.11) + (6.9 / re)), -2.0) / 4.0; break;
+    default: break;
+    }
+    return fmax(lam, turb);
+}
 /* IFRICTION 122: colebrook_formula channel.py:721-756 started from haaland_equation channel.py:700-717.
  * The loop runs on the WHOLE array until err.max() <= 1e-5 (or 100 iterations), so every element
  * performs the same, array-wide, number of iterations.  f[] in/out; returns that number. */
@@ -390,6 +415,7 @@ int osc2o_fit(int which, long n, const double *x, const double *y, const double 
         case 21: out[i] = cp_hc276(x[i]); break;
         case 22: out[i] = k_sn60pb40(x[i]); break;
         case 23: out[i] = cp_sn60pb40(x[i]); break;
+        case 24: out[i] = friction_simple((int)p1, x[i], y[i], z[i]); break;   /* p1 = IFRICTION, y = roughness, z = Dh */
         default: return -1;
         }
     }
@@ -471,7 +497,10 @@ static void one_conductor(const osc2_topology *tp, const osc2_model *md, osc2o_o
             const double nu = (md->ch_htc_corr[j] == 212) ? nusselt_212(re) : nusselt_1(re, f[OSC2_FP_PRANDTL]);
             const double hsteady = nu * f[OSC2_FP_K] / tp->ch_dh[j];
             /* channel.py:1119-1138 (IFRICTION 122 is array-wide: filled in after this loop) */
-            const double ftot = ((md->ch_ifriction[j] == 124) ? friction_124(re) : 1.0) * md->ch_friction_mult[j];
+            const int ifr = md->ch_ifriction[j];
+            const double ftot = ((ifr == 124) ? friction_124(re)
+                                 : (ifr == 110 || ifr == 111 || ifr == 112 || ifr == 121) ? friction_simple(ifr, re, md->ch_roughness[j], tp->ch_dh[j])
+                                 : 1.0) * md->ch_friction_mult[j];
             rey[e] = re;
             fg[((size_t)0 * M + j) * E + e] = v;
             fg[((size_t)1 * M + j) * E + e] = p;

@@ -1,6 +1,7 @@
 """Generate tests/golden/props_stack.npz by running the UNMODIFIED reference: the silver, Hastelloy C276 and
 Sn60Pb40 fits (properties_of_materials/) and the StackComponent homogenisers (stack_component.py:398-476) on
-a bare StackComponent object (its constructor needs openpyxl).
+a bare StackComponent object (its constructor needs openpyxl); and the friction laws IFRICTION 110, 111, 112,
+121 through Channel.eval_friction_factor on a bare object wired like Channel.__init__ (channel.py:43-169).
 
 Build-container only (needs /root/reference):  python tests/golden/make_golden_stack.py
 """
@@ -51,6 +52,29 @@ def main():
     out["stack_cp"] = st.stack_isobaric_specific_heat(prop)
     out["stack_k"] = st.stack_thermal_conductivity(prop)
     out["stack_thickness"] = st.material_thickness
+    # friction laws through the reference's own three-slot evaluation (laminar, turbulent, total)
+    import types
+    from channel import Channel
+    re = np.concatenate([rng.uniform(1.0, 2.0e3, 100), rng.uniform(2.0e3, 4.0e3, 60), rng.uniform(4.0e3, 3.0e4, 100),
+                         rng.uniform(3.0e4, 1.0e6, 100), [2.0e3, 4.0e3, 3.0e4, 1.0e-6, 0.5]])
+    re = re * np.where(rng.uniform(size=re.size) < 0.2, -1.0, 1.0)          # backward flow: Reynolds made positive inside
+    out["re"] = re
+    out["roughness"], out["hydiameter"] = np.array(2.0e-6), np.array(2.499e-3)
+    wiring = {110: ("general_laminar_correlation", "blasius_formula"),
+              111: ("general_laminar_correlation", "bhatti_shah_correlation_turbulent_flow_hole"),
+              112: ("general_laminar_correlation", "lhc_magnets_recipe_hole"),
+              121: ("haaland_equation", "haaland_equation")}
+    for ifr, (lam, turb) in wiring.items():
+        ch = types.SimpleNamespace()
+        for name in ("_quantities_initialization", "_eval_total_friction_factor_max", "eval_friction_factor", lam, turb):
+            setattr(ch, name, types.MethodType(getattr(Channel, name), ch))
+        ch.inputs = {"FRICTION_MULTIPLIER": 0.02, "HYDIAMETER": 2.499e-3, "Roughness": 2.0e-6, "IFRICTION": ifr}
+        ch.dict_friction_factor = {True: {"laminar": None, "turbulent": None, "total": 0.0}}
+        ch.laminar_friction_factor_correlation = getattr(ch, lam)
+        ch.turbulent_friction_factor_correlation = getattr(ch, turb)
+        ch.total_friction_factor_correlation = ch._eval_total_friction_factor_max
+        ch.eval_friction_factor(re.copy(), nodal=True)
+        out[f"f{ifr}_total"] = np.array(ch.dict_friction_factor[True]["total"])
     np.savez_compressed(os.path.join(HERE, "props_stack.npz"), **out)
     print("wrote props_stack.npz", {k: v.shape for k, v in out.items()})
 

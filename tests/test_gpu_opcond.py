@@ -135,7 +135,7 @@ def test_model_validation_rejects_unimplemented_flags():
     from opensc2_b200.batch import BatchedStep
 
     topo = case1_topology(1)
-    bad = dataclasses.replace(case1_model(), ch_ifriction=(-99, 110))   # Blasius-only law: not on the device yet
+    bad = dataclasses.replace(case1_model(), ch_ifriction=(-99, 123))   # Petukhov: not on the device (and it raises on arrays in the reference)
     with BatchedStep(topo, 2, 9) as bs:
         with pytest.raises(ValueError):
             bs.set_model(bad, [synthetic_helium_table()])
@@ -370,3 +370,28 @@ def test_stack_component_solid_on_the_device():
     for q, key in enumerate(("stack_rho", "stack_cp", "stack_k")):
         for e in range(n - 1):
             assert np.max(np.abs(out["sol_gauss"][:, q, 0, e] - g[key]) / np.abs(g[key])) <= RTOL_FIT, key
+
+
+@pytest.mark.parametrize("laws", [(110, 121), (111, 112)])
+def test_more_friction_laws_on_the_device(laws):
+    """IFRICTION 110 (Blasius), 111 (Bhatti-Shah), 112 (LHC recipe), 121 (Haaland) in K_P vs the oracle (which
+    is pinned to the reference's Channel.eval_friction_factor, tests/test_props_oracle_golden.py)."""
+    import dataclasses
+    from opensc2_b200.batch import BatchedStep
+    from oracle import oracle as O
+
+    n, batch = 33, 21
+    topo, model, tab, arr, sweep = _setup(True, n, batch)
+    model = dataclasses.replace(model, ch_ifriction=laws, ch_roughness=(2.0e-6, 2.0e-6))
+    with BatchedStep(topo, batch, n) as bs:
+        bs.set_model(model, [tab])
+        bs.upload_sweep(sweep)
+        bs.upload_state(arr.sysvar, arr.syslod)
+        bs.upload_geometry(arr)
+        bs.eval_operating_conditions(5.0)
+        bs.synchronize()
+        out = bs.download_step_inputs()
+    ref = O.operating_conditions(topo, model, [tab], sweep, arr.sysvar, n, 5.0)
+    assert np.all(ref["fl_gauss"][:, 8] > 0.0)
+    assert rel(out["fl_gauss"][:, 8], ref["fl_gauss"][:, 8]) <= RTOL_FIT
+    assert rel(out["fl_gauss"], ref["fl_gauss"]) <= RTOL_FIT

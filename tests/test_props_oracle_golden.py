@@ -106,3 +106,18 @@ def test_stack_component_homogenisation_against_the_reference():
         for e in range(arr.n_nodes - 1):
             err = np.max(np.abs(sg[:, q, 0, e] - g[key]) / np.abs(g[key]))
             assert err <= 2e-12, f"{key}: {err:.3e}"
+
+
+@pytest.mark.parametrize("ifr", [110, 111, 112, 121])
+def test_more_friction_laws_against_the_reference_channel(ifr):
+    """IFRICTION 110 / 111 / 112 / 121 through the reference's Channel.eval_friction_factor (laminar, turbulent
+    and total slots, multiplier 0.02) vs the oracle, including negative Reynolds numbers, the mask gaps of the
+    LHC recipe at Re = 2e3 / 4e3 and the laminar cut at Re < 1e-5."""
+    import os
+    from helpers import GOLDEN_DIR
+    g = np.load(os.path.join(GOLDEN_DIR, "props_stack.npz"))
+    re = g["re"]
+    got = O.fit("friction_simple", re, np.full_like(re, float(g["roughness"])), np.full_like(re, float(g["hydiameter"])), p1=ifr) * 0.02
+    ref = g[f"f{ifr}_total"]
+    err = np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-300))
+    assert err <= 2e-12, f"IFRICTION {ifr}: {err:.3e}"
