@@ -110,7 +110,10 @@ __global__ void __launch_bounds__(128, 6) osc2_opcond_gauss_kernel(const osc2_to
             double tc = 0.0, tcs = 0.0;
             if (kind == OSC2_SOLID_STRAND_MIXED) {
                 const double eps = q.eps[(size_t)l * B + b];
-                tc = osc2p::tc_nb3sn(bg, (eps + eps) / 2.0, md->sol_tc0m[l], md->sol_bc20m[l]);
+                bool nbti = false;
+                for (int i = 0; i < md->sol_nmat[l]; ++i) nbti = nbti || (md->sol_mat[l][i] == OSC2_MAT_NBTI);
+                tc = nbti ? osc2p::tc_nbti(bg, md->sol_bc20m[l], md->sol_tc0m[l])
+                          : osc2p::tc_nb3sn(bg, (eps + eps) / 2.0, md->sol_tc0m[l], md->sol_bc20m[l]);
                 tcs = q.tcs ? q.tcs[((size_t)l * E + e) * B + b] : 0.0;
             }
             const double tmax = q.tmax[(size_t)l * B + b], tmin = q.tmin[(size_t)l * B + b];

@@ -248,6 +248,43 @@ __device__ inline double cp_re123(double T)
     return -7.567485538209158e-10 * T5 + 6.351452642016898e-07 * T4 + -1.947975786547597e-04 * T3 + 0.023616673974415 * T2
            + 0.239331954284042 * T + -1.096191721280114;
 }
+// niobium_titanium.py:9-62, 64-209, 274-286 (superconductor of a StrandMixedComponent)
+__device__ __noinline__ double k_nbti(double T)
+{
+    T = fmin(T, 750.0);
+    T = fmax(T, 1.0);
+    double k = 6.5 * T / (1.0 + cube(T / 25.0));
+    if (T >= 50.0) k = k + 21.5 * (1.0 - exp(-(T - 50.0) / 50.0));
+    return k;
+}
+__device__ __noinline__ double tc_nbti(double b, double bc20, double tc0)
+{
+    return (b <= bc20) ? tc0 * pw(1 - b / bc20, 1 / 1.7) : 0.0;
+}
+__device__ __noinline__ double cp_nbti(double T, double B, double TCS, double TC)
+{
+    if (T > 1.0) {
+        T = fmin(T, 1000.0);
+        return 17.971311 * pw(T / (88.768525 + T), 1.0456476) + -3215.18087 * pw(T / (3.66034399 + T), 51.7204943)
+               + 4325.5737 * pw(T / (38.0453266 + T), 4.20661339) + -711.296119 * pw(T / (14.67806 + T), 6.01104574);
+    }
+    // T <= 1 K: field-dependent superconducting-state table, mixed between Tcs and Tc
+    const double ab[7] = {0.341000e-01, 0.282900e-01, 0.219200e-01, 0.158600e-01, 0.993000e-02, 0.491000e-02, 0.152000e-02};
+    const double ee[7] = {0.233300e01, 0.244600e01, 0.259700e01, 0.280600e01, 0.310700e01, 0.356800e01, 0.434800e01};
+    const double fb = fabs(B);
+    const int I = fb >= 7.0 ? 6 : fb >= 6.0 ? 5 : fb >= 5.0 ? 4 : fb >= 4.0 ? 3 : fb >= 3.0 ? 2 : fb >= 2.0 ? 1 : 0;
+    double CP = 0.0;
+    if (T > TC) CP = 0.161 * T + 0.00279 * cube(T);
+    if (T < TCS) CP = ab[I] * pw(fabs(T), ee[I]);
+    if (T <= TC && T >= TCS) {
+        const double CPS = ab[I] * pw(fabs(T), ee[I]);
+        const double CPN = 0.161 * T + 0.00279 * cube(T);
+        double F = 1.0;
+        if (TCS < TC) F = (T - TCS) / (TC - TCS);
+        CP = F * CPN + (1.0 - F) * CPS;
+    }
+    return CP;
+}
 // silver.py:5-110, hastelloy_c276.py:5-105, solder_sn60_pb40.py:5-96 (StackComponent layers).  np.piecewise:
 // where two conditions hold the later one wins, where none holds the value is 0.
 __device__ __noinline__ double k_ag(double T)
@@ -315,7 +352,7 @@ __device__ __noinline__ double cp_sn60pb40(double T)
 __device__ inline double mat_density(int mat)
 {
     return mat == OSC2_MAT_CU_NIST ? 8900.0 : mat == OSC2_MAT_NB3SN ? 8950.0 : mat == OSC2_MAT_SS ? 7800.0
-           : mat == OSC2_MAT_AL ? 2700.0 : mat == OSC2_MAT_RE123 ? 6380.0 : mat == OSC2_MAT_AG ? 10630.0
+           : mat == OSC2_MAT_AL ? 2700.0 : mat == OSC2_MAT_RE123 ? 6380.0 : mat == OSC2_MAT_AG ? 10630.0 : mat == OSC2_MAT_NBTI ? 6160.0
            : mat == OSC2_MAT_HC276 ? 8890.0 : mat == OSC2_MAT_SN60PB40 ? (7310.0 * 0.6 + 11340.0 * 0.4) : 2000.0;
 }
 __device__ inline double friction_124(double re);
@@ -399,6 +436,7 @@ __device__ inline void material_cp_k(int mat, double T, double bg, double tcs, d
     else if (mat == OSC2_MAT_AL) { cp = cp_al(T, tmin, tmax); k = k_al(T, tmin, tmax); }
     else if (mat == OSC2_MAT_RE123) { cp = cp_re123(T); k = k_re123(T); }
     else if (mat == OSC2_MAT_AG) { cp = cp_ag(T); k = k_ag(T); }
+    else if (mat == OSC2_MAT_NBTI) { cp = cp_nbti(T, bg, tcs, tc); k = k_nbti(T); }
     else if (mat == OSC2_MAT_HC276) { cp = cp_hc276(T); k = k_hc276(T); }
     else if (mat == OSC2_MAT_SN60PB40) { cp = cp_sn60pb40(T); k = k_sn60pb40(T); }
     else { cp = cp_ge(T); k = k_ge(T); }
@@ -577,7 +615,10 @@ __global__ void __launch_bounds__(128, 6) osc2_opcond_kernel(const osc2_topology
         double tc = 0.0, tcs = 0.0;
         if (kind == OSC2_SOLID_STRAND_MIXED) {
             const double eps = q.eps[(size_t)l * B + b];
-            tc = osc2p::tc_nb3sn(bg, (eps + eps) / 2.0, md->sol_tc0m[l], md->sol_bc20m[l]);
+            bool nbti = false;      // strand_component.py:191-246: Tc by superconducting_material
+            for (int i = 0; i < nmat; ++i) nbti = nbti || (md->sol_mat[l][i] == OSC2_MAT_NBTI);
+            tc = nbti ? osc2p::tc_nbti(bg, md->sol_bc20m[l], md->sol_tc0m[l])
+                      : osc2p::tc_nb3sn(bg, (eps + eps) / 2.0, md->sol_tc0m[l], md->sol_bc20m[l]);
             tcs = q.tcs ? q.tcs[((size_t)l * E + e) * B + b] : 0.0;
         }
         const double tmax = q.tmax[(size_t)l * B + b], tmin = q.tmin[(size_t)l * B + b];

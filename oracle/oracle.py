@@ -169,15 +169,16 @@ def pairwise_sum(a, stride: int = 1) -> float:
 FITS = {"k_cu": 0, "cp_cu": 1, "k_nb3sn": 2, "cp_nb3sn": 3, "tc_nb3sn": 4, "k_ss": 5, "cp_ss": 6, "k_ge": 7,
         "cp_ge": 8, "friction_124": 9, "nusselt_1": 10, "nusselt_212": 11, "rhoe_cu": 12,
         "k_al": 13, "cp_al": 14, "k_re123": 15, "cp_re123": 16, "friction_122": 17,
-        "k_ag": 18, "cp_ag": 19, "k_hc276": 20, "cp_hc276": 21, "k_sn60pb40": 22, "cp_sn60pb40": 23, "friction_simple": 24}
+        "k_ag": 18, "cp_ag": 19, "k_hc276": 20, "cp_hc276": 21, "k_sn60pb40": 22, "cp_sn60pb40": 23, "friction_simple": 24, "k_nbti": 25, "cp_nbti": 26, "tc_nbti": 27}
 
 
-def fit(name, x, y=None, z=None, p1=0.0, p2=0.0):
-    """Element-wise material / correlation fit of oracle/props_oracle.c (see props_oracle.h)."""
+def fit(name, x, y=None, z=None, p1=0.0, p2=0.0, out_init=None):
+    """Element-wise material / correlation fit of oracle/props_oracle.c (see props_oracle.h).  `out_init`: a
+    fourth per-element argument for the fits that need one (cp_nbti: the critical temperature)."""
     x = np.ascontiguousarray(x, dtype=np.float64)
     y = np.ascontiguousarray(x if y is None else y, dtype=np.float64)
     z = np.ascontiguousarray(x if z is None else z, dtype=np.float64)
-    out = np.empty_like(x)
+    out = np.empty_like(x) if out_init is None else np.array(out_init, dtype=np.float64, copy=True)
     rc = lib().osc2o_fit(FITS[name], x.size, x.ctypes.data_as(c_dp), y.ctypes.data_as(c_dp), z.ctypes.data_as(c_dp),
                          float(p1), float(p2), out.ctypes.data_as(c_dp))
     assert rc == 0

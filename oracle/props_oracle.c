@@ -228,6 +228,48 @@ static double cp_re123(double T)
            + 0.023616673974415 * sq(T) + 0.239331954284042 * T + -1.096191721280114;
 }
 
+/* niobium_titanium.py:9-62 */
+static double k_nbti(double T)
+{
+    const double A = 6.5, Tm = 25.0, Tnb = 50.0, K0 = 21.5;
+    T = fmin(T, 750.0);
+    T = fmax(T, 1.0);
+    double k = A * T / (1.0 + pow(T / Tm, 3.0));
+    if (T >= Tnb) k = k + K0 * (1.0 - exp(-(T - Tnb) / Tnb));
+    return k;
+}
+/* niobium_titanium.py:274-286 */
+static double tc_nbti(double b, double bc20, double tc0)
+{
+    return (b <= bc20) ? tc0 * pow(1 - b / bc20, 1 / 1.7) : 0.0;
+}
+/* niobium_titanium.py:64-209 */
+static double cp_nbti(double T, double B, double TCS, double TC)
+{
+    static const double X[7] = {0.0, 2.0, 3.0, 4.0, 5.0, 6.0, 7.0};
+    static const double AB[7] = {0.341000e-01, 0.282900e-01, 0.219200e-01, 0.158600e-01, 0.993000e-02, 0.491000e-02, 0.152000e-02};
+    static const double E[7] = {0.233300e01, 0.244600e01, 0.259700e01, 0.280600e01, 0.310700e01, 0.356800e01, 0.434800e01};
+    const double AA = 17.971311, BB = -3215.18087, CC = 4325.5737, DD = -711.296119;
+    const double a = 88.768525, b = 3.66034399, c = 38.0453266, d = 14.67806;
+    const double na = 1.0456476, nb = 51.7204943, nc = 4.20661339, nd = 6.01104574;
+    if (T > 1.0) {
+        T = fmin(T, 1000.0);
+        return AA * pow(T / (a + T), na) + BB * pow(T / (b + T), nb) + CC * pow(T / (c + T), nc) + DD * pow(T / (d + T), nd);
+    }
+    int I = 0;
+    for (int jj = 1; jj < 7; ++jj) if (fabs(B) >= X[jj]) I = jj;
+    double CP = 0.0;
+    if (T > TC) CP = 0.161 * T + 0.00279 * pow(T, 3.0);
+    if (T < TCS) CP = AB[I] * pow(fabs(T), E[I]);
+    if (T <= TC && T >= TCS) {
+        const double CPS = AB[I] * pow(fabs(T), E[I]);
+        const double CPN = 0.161 * T + 0.00279 * pow(T, 3.0);
+        double F = 1.0;
+        if (TCS < TC) F = (T - TCS) / (TC - TCS);
+        CP = F * CPN + (1.0 - F) * CPS;
+    }
+    return CP;
+}
 /* silver.py:5-60 (np.piecewise: where two conditions hold the later one wins; none: 0) */
 static double k_ag(double T)
 {
@@ -299,6 +341,7 @@ static double mat_density(int mat)   /* density_cu / _nb3sn / _ss / _ge: constan
     case OSC2_MAT_SS: return 7800.0;
     case OSC2_MAT_AL: return 2700.0;
     case OSC2_MAT_RE123: return 6380.0;
+    case OSC2_MAT_NBTI: return 6160.0;                     /* niobium_titanium.py density_nbti */
     case OSC2_MAT_AG: return 10630.0;                       /* silver.py density_ag */
     case OSC2_MAT_HC276: return 8890.0;                    /* hastelloy_c276.py density_hc276 */
     case OSC2_MAT_SN60PB40: return 7310.0 * 0.6 + 11340.0 * 0.4;   /* solder_sn60_pb40.py density_sn60pb40 */
@@ -415,6 +458,9 @@ int osc2o_fit(int which, long n, const double *x, const double *y, const double 
         case 21: out[i] = cp_hc276(x[i]); break;
         case 22: out[i] = k_sn60pb40(x[i]); break;
         case 23: out[i] = cp_sn60pb40(x[i]); break;
+        case 25: out[i] = k_nbti(x[i]); break;
+        case 26: out[i] = cp_nbti(x[i], y[i], z[i], out[i]); break;   /* x = T, y = B, z = Tcs; out[] holds Tc on entry */
+        case 27: out[i] = tc_nbti(x[i], p1, p2); break;                            /* x = B, p1 = Bc20m, p2 = Tc0m */
         case 24: out[i] = friction_simple((int)p1, x[i], y[i], z[i]); break;   /* p1 = IFRICTION, y = roughness, z = Dh */
         default: return -1;
         }
@@ -549,7 +595,10 @@ static void one_conductor(const osc2_topology *tp, const osc2_model *md, osc2o_o
             double tc = 0.0, tcs = 0.0;
             if (md->sol_kind[l] == OSC2_SOLID_STRAND_MIXED) {
                 /* eps at Gauss = (eps + eps) / 2 (strand_component.py:392-399) */
-                tc = tc_nb3sn(bg, (eps + eps) / 2.0, md->sol_tc0m[l], md->sol_bc20m[l]);
+                int nbti = 0;      /* strand_component.py:191-246: Tc by superconducting_material */
+                for (int i = 0; i < md->sol_nmat[l]; ++i) nbti |= (md->sol_mat[l][i] == OSC2_MAT_NBTI);
+                tc = nbti ? tc_nbti(bg, md->sol_bc20m[l], md->sol_tc0m[l])
+                          : tc_nb3sn(bg, (eps + eps) / 2.0, md->sol_tc0m[l], md->sol_bc20m[l]);
                 tcs = io->tcs ? io->tcs[((size_t)bb * S + l) * E + e] : 0.0;
             }
             double rho_i[OSC2_MAX_MATERIALS], cp_i[OSC2_MAX_MATERIALS], k_i[OSC2_MAX_MATERIALS];
@@ -563,6 +612,7 @@ static void one_conductor(const osc2_topology *tp, const osc2_model *md, osc2o_o
                 case OSC2_MAT_AL: cp_i[i] = cp_al(T, tmin, tmax); k_i[i] = k_al(T, tmin, tmax); break;
                 case OSC2_MAT_RE123: cp_i[i] = cp_re123(T); k_i[i] = k_re123(T); break;
                 case OSC2_MAT_AG: cp_i[i] = cp_ag(T); k_i[i] = k_ag(T); break;
+                case OSC2_MAT_NBTI: cp_i[i] = cp_nbti(T, bg, tcs, tc); k_i[i] = k_nbti(T); break;
                 case OSC2_MAT_HC276: cp_i[i] = cp_hc276(T); k_i[i] = k_hc276(T); break;
                 case OSC2_MAT_SN60PB40: cp_i[i] = cp_sn60pb40(T); k_i[i] = k_sn60pb40(T); break;
                 default: cp_i[i] = cp_ge(T); k_i[i] = k_ge(T); break;

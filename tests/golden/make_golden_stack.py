@@ -75,6 +75,18 @@ def main():
         ch.total_friction_factor_correlation = ch._eval_total_friction_factor_max
         ch.eval_friction_factor(re.copy(), nodal=True)
         out[f"f{ifr}_total"] = np.array(ch.dict_friction_factor[True]["total"])
+    # NbTi (superconductor of a StrandMixedComponent): conductivity, Tc(B), cp(T, B, Tcs, Tc) incl. the T <= 1 K table
+    from properties_of_materials.niobium_titanium import (critical_temperature_nbti, isobaric_specific_heat_nbti,
+                                                          thermal_conductivity_nbti)
+    tn = np.concatenate([rng.uniform(0.2, 1.0, 120), rng.uniform(1.0, 30.0, 200), rng.uniform(30.0, 1100.0, 76), [1.0, 50.0, 750.0, 1000.0]])
+    bn = np.concatenate([rng.uniform(0.0, 8.0, 380), rng.uniform(13.0, 16.0, 16), [2.0, 3.0, 7.0, 14.5]])
+    bc20m, tc0m = 14.5, 9.03
+    tcn = critical_temperature_nbti(bn, bc20m, tc0m)
+    tcsn = np.where(rng.uniform(size=tn.size) < 0.8, tcn * rng.uniform(0.05, 1.0, tn.size), tcn * 1.05)
+    out["nbti_t"], out["nbti_b"], out["nbti_tc"], out["nbti_tcs"] = tn, bn, tcn, tcsn
+    out["nbti_bc20m_tc0m"] = np.array([bc20m, tc0m])
+    out["k_nbti"] = thermal_conductivity_nbti(tn)
+    out["cp_nbti"] = isobaric_specific_heat_nbti(tn.copy(), bn, tcsn, tcn)
     np.savez_compressed(os.path.join(HERE, "props_stack.npz"), **out)
     print("wrote props_stack.npz", {k: v.shape for k, v in out.items()})
 

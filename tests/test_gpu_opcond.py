@@ -395,3 +395,31 @@ def test_more_friction_laws_on_the_device(laws):
     assert np.all(ref["fl_gauss"][:, 8] > 0.0)
     assert rel(out["fl_gauss"][:, 8], ref["fl_gauss"][:, 8]) <= RTOL_FIT
     assert rel(out["fl_gauss"], ref["fl_gauss"]) <= RTOL_FIT
+
+
+def test_niobium_titanium_strand_on_the_device():
+    """StrandMixedComponent with NbTi as superconductor (Tc from critical_temperature_nbti, cp from
+    isobaric_specific_heat_nbti with the current-sharing temperature of the sweep): K_P vs the oracle, which is
+    pinned to the reference fits (tests/test_props_oracle_golden.py)."""
+    import dataclasses
+    from opensc2_b200 import model as Mdl
+    from opensc2_b200.batch import BatchedStep
+    from oracle import oracle as O
+
+    n, batch = 33, 19
+    topo, model, tab, arr, sweep = _setup(True, n, batch)
+    strand = Mdl.SolidModel(Mdl.SOLID_STRAND_MIXED, (Mdl.MAT_CU_NIST, Mdl.MAT_NBTI), (1.6, 1.0), 2.6, rrr=120.0,
+                            tc0m=9.03, bc20m=14.5, heated=True)
+    model = dataclasses.replace(model, solids=(strand,) + model.solids[1:])
+    with BatchedStep(topo, batch, n) as bs:
+        bs.set_model(model, [tab])
+        bs.upload_sweep(sweep)
+        bs.upload_state(arr.sysvar, arr.syslod)
+        bs.upload_geometry(arr)
+        bs.eval_operating_conditions(12.0)
+        bs.synchronize()
+        out = bs.download_step_inputs()
+    ref = O.operating_conditions(topo, model, [tab], sweep, arr.sysvar, n, 12.0)
+    assert rel(out["sol_gauss"], ref["sol_gauss"]) <= RTOL_FIT
+    for key in ("htc_fs", "htc_ss", "sol_q"):
+        assert rel(out[key], ref[key]) <= RTOL_FIT, key

@@ -121,3 +121,21 @@ def test_more_friction_laws_against_the_reference_channel(ifr):
     ref = g[f"f{ifr}_total"]
     err = np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-300))
     assert err <= 2e-12, f"IFRICTION {ifr}: {err:.3e}"
+
+
+def test_niobium_titanium_against_the_reference_fits():
+    """NbTi: thermal conductivity, Tc(B) and cp(T, B, Tcs, Tc) -- the four-term fit above 1 K and the
+    field-indexed superconducting-state table mixed between Tcs and Tc below it."""
+    import os
+    from helpers import GOLDEN_DIR
+    g = np.load(os.path.join(GOLDEN_DIR, "props_stack.npz"))
+    bc20m, tc0m = g["nbti_bc20m_tc0m"]
+    checks = {
+        "k_nbti": (O.fit("k_nbti", g["nbti_t"]), g["k_nbti"]),
+        "tc_nbti": (O.fit("tc_nbti", g["nbti_b"], p1=bc20m, p2=tc0m), g["nbti_tc"]),
+        "cp_nbti": (O.fit("cp_nbti", g["nbti_t"], g["nbti_b"], g["nbti_tcs"], out_init=g["nbti_tc"]), g["cp_nbti"]),
+    }
+    for key, (got, ref) in checks.items():
+        err = np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-300))
+        assert err <= 2e-12, f"{key}: {err:.3e}"
+    assert np.any(g["nbti_tc"] == 0.0) and np.any(g["nbti_t"] <= 1.0)
