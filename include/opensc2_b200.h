@@ -119,7 +119,8 @@ enum { OSC2_SOLID_STRAND_MIXED = 0, OSC2_SOLID_STRAND_STAB = 1, OSC2_SOLID_JACKE
 typedef struct {
     /* channels (channel.py:43-169) */
     int ch_fluid[OSC2_MAX_CHANNELS];            /* which fluid table */
-    int ch_ifriction[OSC2_MAX_CHANNELS];        /* IFRICTION: -99, 110 (Blasius), 111 (Bhatti-Shah), 112 (LHC), 121 (Haaland), 122 (Colebrook) or 124 */
+    int ch_ifriction[OSC2_MAX_CHANNELS];        /* IFRICTION: -99, 110 (Blasius), 111 (Bhatti-Shah), 112 (LHC), 121 (Haaland), 122 (Colebrook), 124,
+                                                   204 / 205 (Katheder bundle), 206 / 209 (Darcy-Forchheimer bundle) */
     double ch_friction_mult[OSC2_MAX_CHANNELS]; /* FRICTION_MULTIPLIER */
     int ch_htc_corr[OSC2_MAX_CHANNELS];         /* Flag_htc_steady_corr: 1 or 212 */
     /* solids */
@@ -148,6 +149,7 @@ typedef struct {
      * applies in its second branch only (1 otherwise) */
     double ss_rad_den[OSC2_MAX_INTERFACES];
     double ss_rad_mlt[OSC2_MAX_INTERFACES];
+    double ch_void_fraction[OSC2_MAX_CHANNELS]; /* Channel.inputs["VOID_FRACTION"] (bundle laws 204, 205, 206, 209) */
 } osc2_model;
 
 /* Swept per-conductor scalars, batch leading. */

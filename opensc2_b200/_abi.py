@@ -78,6 +78,7 @@ class Osc2Model(C.Structure):
         ("es_htc", C.c_double * _IF),
         ("ch_roughness", C.c_double * _CH),
         ("ss_rad_den", C.c_double * _IF), ("ss_rad_mlt", C.c_double * _IF),
+        ("ch_void_fraction", C.c_double * _CH),
     ]
 
 

@@ -473,8 +473,9 @@ int osc2_set_model(osc2_handle h, const osc2_model *model)
         if (model->ch_fluid[j] + 1 > nf) nf = model->ch_fluid[j] + 1;
         {
             const int ifr = model->ch_ifriction[j];
-            if (ifr != -99 && ifr != 124 && ifr != 122 && ifr != 110 && ifr != 111 && ifr != 112 && ifr != 121)
-                return fail(OSC2_ERR_INVALID, "channel %d: IFRICTION %d is not implemented on the device (-99, 110, 111, 112, 121, 122, 124)", j, ifr);
+            if (ifr != -99 && ifr != 124 && ifr != 122 && ifr != 110 && ifr != 111 && ifr != 112 && ifr != 121 && ifr != 204 &&
+                ifr != 205 && ifr != 206 && ifr != 209)
+                return fail(OSC2_ERR_INVALID, "channel %d: IFRICTION %d is not implemented on the device (-99, 110, 111, 112, 121, 122, 124, 204, 205, 206, 209)", j, ifr);
         }
         if (model->ch_htc_corr[j] != 1 && model->ch_htc_corr[j] != 212)
             return fail(OSC2_ERR_INVALID, "channel %d: Flag_htc_steady_corr %d is not implemented on the device (1, 212)", j, model->ch_htc_corr[j]);

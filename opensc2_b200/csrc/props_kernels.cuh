@@ -384,16 +384,25 @@ __device__ inline int colebrook_count(double re, double rough, double dh)
     return it;
 }
 // total friction factor of channel j (channel.py:1119-1138)
-// IFRICTION 110 (Blasius), 111 (Bhatti-Shah), 112 (LHC magnets recipe), 121 (Haaland): channel.py:392-438, 700-717;
+// IFRICTION 110 (Blasius), 111 (Bhatti-Shah), 112 (LHC magnets recipe), 121 (Haaland), 204 / 205 (Katheder), 206 / 209
+// (Darcy-Forchheimer porous medium): channel.py:392-438, 700-717, katheder_correlation_bundle, _eval_jj_and_kk;
 // total = max(laminar, turbulent) with the general laminar correlation 16/Re (channel.py:284-299, 1104-1115);
 // for 121 the laminar slot calls the Haaland method again, which writes the turbulent array: laminar stays 0
-__device__ __noinline__ double friction_simple(int ifr, double re, double rough, double dh)
+__device__ __noinline__ double friction_simple(int ifr, double re, double rough, double dh, double vf)
 {
     re = fabs(re);
     double turb = 0.0, lam = 0.0;
     if (ifr == 121) return fmax(0.0, haaland(re, rough, dh));
     lam = re >= 1.0e-5 ? 16.0 / re : 0.0;
-    if (ifr == 110) turb = (0.316 * pw(re, -0.25)) / 4.0;
+    if (ifr == 204) turb = pw(vf, 0.72) * (19.5 / pw(re, 0.843) + 0.0265) / 4.0;        // Katheder (bundle)
+    else if (ifr == 205) turb = pw(vf, 0.72) * (19.5 / pw(re, 0.88) + 0.051) / 4.0;
+    else if (ifr == 206 || ifr == 209) {                                                // Darcy-Forchheimer (bundle)
+        const double c0 = (ifr == 206) ? 19.6e-9 : 20.9e-9, c1 = (ifr == 206) ? 2.42 : 19.1, c2 = (ifr == 206) ? 5.80 : 4.23;
+        const double jj = c1 / pw(vf, c2);
+        const double kk = c0 * cube(vf) / sq(1 - vf);
+        turb = sq(dh) * vf / 2.0 / kk / re + (dh * sq(vf)) / 2.0 * jj;
+    }
+    else if (ifr == 110) turb = (0.316 * pw(re, -0.25)) / 4.0;
     else if (ifr == 111) turb = 0.00128 + 0.1143 * pw(fmax(re, 4000.0), -0.311);
     else {
         if (re <= 2.0e3) turb = 64 / re / 4.0;
@@ -408,7 +417,8 @@ __device__ inline double friction_total(const osc2_model *md, const osc2_topolog
     double f = 1.0;
     const int ifr = md->ch_ifriction[j];
     if (ifr == 124) f = friction_124(re);
-    else if (ifr == 110 || ifr == 111 || ifr == 112 || ifr == 121) f = friction_simple(ifr, re, md->ch_roughness[j], tp->ch_dh[j]);
+    else if (ifr == 110 || ifr == 111 || ifr == 112 || ifr == 121 || ifr == 204 || ifr == 205 || ifr == 206 || ifr == 209)
+        f = friction_simple(ifr, re, md->ch_roughness[j], tp->ch_dh[j], md->ch_void_fraction[j]);
     else if (md->ch_ifriction[j] == 122) {
         const double rough = md->ch_roughness[j], dh = tp->ch_dh[j];
         f = haaland(fabs(re), rough, dh);

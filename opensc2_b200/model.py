@@ -42,7 +42,7 @@ class SolidModel:
 @dataclass(frozen=True)
 class Model:
     ch_fluid: Tuple[int, ...]
-    ch_ifriction: Tuple[int, ...]           # -99 | 110 | 111 | 112 | 121 | 122 | 124
+    ch_ifriction: Tuple[int, ...]           # -99 | 110 | 111 | 112 | 121 | 122 | 124 | 204 | 205 | 206 | 209
     ch_friction_mult: Tuple[float, ...]
     ch_htc_corr: Tuple[int, ...]            # 1 | 212
     solids: Tuple[SolidModel, ...]
@@ -50,7 +50,8 @@ class Model:
     ff: Tuple[Tuple[int, float, float, float], ...] = ()                 # (+ interf_thickness)
     ss: Tuple[Tuple[int, float, float, float, float, float], ...] = ()   # (+ thick_rc, thick_cr, R_contact)
     es_htc: Tuple[float, ...] = ()          # constant convective HTC incl. Phi_conv and multiplier
-    ch_roughness: Tuple[float, ...] = ()    # Channel.inputs["Roughness"], used by IFRICTION 122
+    ch_roughness: Tuple[float, ...] = ()    # Channel.inputs["Roughness"], used by IFRICTION 121, 122
+    ch_void_fraction: Tuple[float, ...] = ()   # Channel.inputs["VOID_FRACTION"], used by the bundle laws 204-206, 209
     ss_rad: Tuple[Tuple[float, float], ...] = ()   # per solid-solid interface: (denominator, multiplier) of choice 3
 
     def struct(self, topo) -> Osc2Model:
@@ -62,6 +63,7 @@ class Model:
             m.ch_fluid[j], m.ch_ifriction[j] = self.ch_fluid[j], self.ch_ifriction[j]
             m.ch_friction_mult[j], m.ch_htc_corr[j] = self.ch_friction_mult[j], self.ch_htc_corr[j]
             m.ch_roughness[j] = self.ch_roughness[j] if self.ch_roughness else 0.0
+            m.ch_void_fraction[j] = self.ch_void_fraction[j] if self.ch_void_fraction else 0.0
         for l, s in enumerate(self.solids):
             m.sol_kind[l], m.sol_nmat[l] = s.kind, len(s.materials)
             for i, (mat, w) in enumerate(zip(s.materials, s.weights)):

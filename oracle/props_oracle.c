@@ -365,7 +365,7 @@ static double friction_laminar(double re) { return re >= 1.0e-5 ? 16.0 / re : 0.
  * (channel.py:1104-1115).  110-112: laminar slot = general_laminar_correlation.  121: the laminar slot calls
  * haaland_equation again, which writes the TURBULENT array, so laminar stays 0.  112 assigns by masks that
  * leave Re = 2e3 < . , Re = 4e3 exactly at the initial 0 of the turbulent array. */
-static double friction_simple(int ifr, double re, double rough, double dh)
+static double friction_simple(int ifr, double re, double rough, double dh, double vf)
 {
     re = fabs(re);
     double turb = 0.0, lam = 0.0;
@@ -380,6 +380,18 @@ static double friction_simple(int ifr, double re, double rough, double dh)
         lam = friction_laminar(re);
         break;
     case 121: turb = pow(-1.8 * log10(pow(rough / dh / 3.7, 1.11) + (6.9 / re)), -2.0) / 4.0; break;
+    /* katheder_correlation_bundle channel.py (204: 0.843, 0.0265; 205: 0.88, 0.051) */
+    case 204: turb = pow(vf, 0.72) * (19.5 / pow(re, 0.843) + 0.0265) / 4.0; lam = friction_laminar(re); break;
+    case 205: turb = pow(vf, 0.72) * (19.5 / pow(re, 0.88) + 0.051) / 4.0; lam = friction_laminar(re); break;
+    /* darcy_forcheimer_porus_medium_correlation_bundle + _eval_jj_and_kk (206: 19.6e-9, 2.42, 5.80; 209: 20.9e-9, 19.1, 4.23) */
+    case 206: case 209: {
+        const double c0 = (ifr == 206) ? 19.6e-9 : 20.9e-9, c1 = (ifr == 206) ? 2.42 : 19.1, c2 = (ifr == 206) ? 5.80 : 4.23;
+        const double jj = c1 / pow(vf, c2);
+        const double kk = c0 * pow(vf, 3.0) / pow(1 - vf, 2.0);
+        turb = pow(dh, 2.0) * vf / 2.0 / kk / re + (dh * pow(vf, 2.0)) / 2.0 * jj;
+        lam = friction_laminar(re);
+        break;
+    }
     default: break;
     }
     return fmax(lam, turb);
@@ -461,7 +473,7 @@ int osc2o_fit(int which, long n, const double *x, const double *y, const double 
         case 25: out[i] = k_nbti(x[i]); break;
         case 26: out[i] = cp_nbti(x[i], y[i], z[i], out[i]); break;   /* x = T, y = B, z = Tcs; out[] holds Tc on entry */
         case 27: out[i] = tc_nbti(x[i], p1, p2); break;                            /* x = B, p1 = Bc20m, p2 = Tc0m */
-        case 24: out[i] = friction_simple((int)p1, x[i], y[i], z[i]); break;   /* p1 = IFRICTION, y = roughness, z = Dh */
+        case 24: out[i] = friction_simple((int)p1, x[i], y[i], z[i], p2); break;   /* p1 = IFRICTION, y = roughness, z = Dh, p2 = void fraction */
         default: return -1;
         }
     }
@@ -545,7 +557,8 @@ static void one_conductor(const osc2_topology *tp, const osc2_model *md, osc2o_o
             /* channel.py:1119-1138 (IFRICTION 122 is array-wide: filled in after this loop) */
             const int ifr = md->ch_ifriction[j];
             const double ftot = ((ifr == 124) ? friction_124(re)
-                                 : (ifr == 110 || ifr == 111 || ifr == 112 || ifr == 121) ? friction_simple(ifr, re, md->ch_roughness[j], tp->ch_dh[j])
+                                 : (ifr == 110 || ifr == 111 || ifr == 112 || ifr == 121 || ifr == 204 || ifr == 205 || ifr == 206 || ifr == 209)
+                                     ? friction_simple(ifr, re, md->ch_roughness[j], tp->ch_dh[j], md->ch_void_fraction[j])
                                  : 1.0) * md->ch_friction_mult[j];
             rey[e] = re;
             fg[((size_t)0 * M + j) * E + e] = v;

@@ -1,7 +1,7 @@
 """Generate tests/golden/props_stack.npz by running the UNMODIFIED reference: the silver, Hastelloy C276 and
 Sn60Pb40 fits (properties_of_materials/) and the StackComponent homogenisers (stack_component.py:398-476) on
 a bare StackComponent object (its constructor needs openpyxl); and the friction laws IFRICTION 110, 111, 112,
-121 through Channel.eval_friction_factor on a bare object wired like Channel.__init__ (channel.py:43-169).
+121, 204, 205, 206, 209 through Channel.eval_friction_factor on a bare object wired like Channel.__init__ (channel.py:43-169).
 
 Build-container only (needs /root/reference):  python tests/golden/make_golden_stack.py
 """
@@ -63,12 +63,17 @@ def main():
     wiring = {110: ("general_laminar_correlation", "blasius_formula"),
               111: ("general_laminar_correlation", "bhatti_shah_correlation_turbulent_flow_hole"),
               112: ("general_laminar_correlation", "lhc_magnets_recipe_hole"),
-              121: ("haaland_equation", "haaland_equation")}
+              121: ("haaland_equation", "haaland_equation"),
+              204: ("general_laminar_correlation", "katheder_correlation_bundle"),
+              205: ("general_laminar_correlation", "katheder_correlation_bundle"),
+              206: ("general_laminar_correlation", "darcy_forcheimer_porus_medium_correlation_bundle"),
+              209: ("general_laminar_correlation", "darcy_forcheimer_porus_medium_correlation_bundle")}
+    out["void_fraction"] = np.array(0.33)
     for ifr, (lam, turb) in wiring.items():
         ch = types.SimpleNamespace()
-        for name in ("_quantities_initialization", "_eval_total_friction_factor_max", "eval_friction_factor", lam, turb):
+        for name in ("_quantities_initialization", "_eval_total_friction_factor_max", "eval_friction_factor", "_eval_jj_and_kk", lam, turb):
             setattr(ch, name, types.MethodType(getattr(Channel, name), ch))
-        ch.inputs = {"FRICTION_MULTIPLIER": 0.02, "HYDIAMETER": 2.499e-3, "Roughness": 2.0e-6, "IFRICTION": ifr}
+        ch.inputs = {"FRICTION_MULTIPLIER": 0.02, "HYDIAMETER": 2.499e-3, "Roughness": 2.0e-6, "IFRICTION": ifr, "VOID_FRACTION": 0.33}
         ch.dict_friction_factor = {True: {"laminar": None, "turbulent": None, "total": 0.0}}
         ch.laminar_friction_factor_correlation = getattr(ch, lam)
         ch.turbulent_friction_factor_correlation = getattr(ch, turb)

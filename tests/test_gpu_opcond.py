@@ -372,9 +372,10 @@ def test_stack_component_solid_on_the_device():
             assert np.max(np.abs(out["sol_gauss"][:, q, 0, e] - g[key]) / np.abs(g[key])) <= RTOL_FIT, key
 
 
-@pytest.mark.parametrize("laws", [(110, 121), (111, 112)])
+@pytest.mark.parametrize("laws", [(110, 121), (111, 112), (204, 206), (205, 209)])
 def test_more_friction_laws_on_the_device(laws):
-    """IFRICTION 110 (Blasius), 111 (Bhatti-Shah), 112 (LHC recipe), 121 (Haaland) in K_P vs the oracle (which
+    """IFRICTION 110 (Blasius), 111 (Bhatti-Shah), 112 (LHC recipe), 121 (Haaland), 204 / 205 (Katheder bundle),
+    206 / 209 (Darcy-Forchheimer bundle) in K_P vs the oracle (which
     is pinned to the reference's Channel.eval_friction_factor, tests/test_props_oracle_golden.py)."""
     import dataclasses
     from opensc2_b200.batch import BatchedStep
@@ -382,7 +383,7 @@ def test_more_friction_laws_on_the_device(laws):
 
     n, batch = 33, 21
     topo, model, tab, arr, sweep = _setup(True, n, batch)
-    model = dataclasses.replace(model, ch_ifriction=laws, ch_roughness=(2.0e-6, 2.0e-6))
+    model = dataclasses.replace(model, ch_ifriction=laws, ch_roughness=(2.0e-6, 2.0e-6), ch_void_fraction=(0.33, 0.36))
     with BatchedStep(topo, batch, n) as bs:
         bs.set_model(model, [tab])
         bs.upload_sweep(sweep)

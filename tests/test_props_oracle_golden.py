@@ -108,16 +108,18 @@ def test_stack_component_homogenisation_against_the_reference():
             assert err <= 2e-12, f"{key}: {err:.3e}"
 
 
-@pytest.mark.parametrize("ifr", [110, 111, 112, 121])
+@pytest.mark.parametrize("ifr", [110, 111, 112, 121, 204, 205, 206, 209])
 def test_more_friction_laws_against_the_reference_channel(ifr):
-    """IFRICTION 110 / 111 / 112 / 121 through the reference's Channel.eval_friction_factor (laminar, turbulent
+    """IFRICTION 110 / 111 / 112 / 121 and the bundle laws 204 / 205 (Katheder), 206 / 209 (Darcy-Forchheimer)
+    through the reference's Channel.eval_friction_factor (laminar, turbulent
     and total slots, multiplier 0.02) vs the oracle, including negative Reynolds numbers, the mask gaps of the
     LHC recipe at Re = 2e3 / 4e3 and the laminar cut at Re < 1e-5."""
     import os
     from helpers import GOLDEN_DIR
     g = np.load(os.path.join(GOLDEN_DIR, "props_stack.npz"))
     re = g["re"]
-    got = O.fit("friction_simple", re, np.full_like(re, float(g["roughness"])), np.full_like(re, float(g["hydiameter"])), p1=ifr) * 0.02
+    got = O.fit("friction_simple", re, np.full_like(re, float(g["roughness"])), np.full_like(re, float(g["hydiameter"])), p1=ifr,
+                p2=float(g["void_fraction"])) * 0.02
     ref = g[f"f{ifr}_total"]
     err = np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-300))
     assert err <= 2e-12, f"IFRICTION {ifr}: {err:.3e}"
