@@ -349,11 +349,16 @@ __device__ __noinline__ double cp_sn60pb40(double T)
     }
     return fmax(v, 1.0);
 }
+__device__ __noinline__ double mat_density_more(int mat)
+{
+    return mat == OSC2_MAT_AG ? 10630.0 : mat == OSC2_MAT_NBTI ? 6160.0 : mat == OSC2_MAT_HC276 ? 8890.0
+           : (7310.0 * 0.6 + 11340.0 * 0.4);
+}
 __device__ inline double mat_density(int mat)
 {
+    if (mat > OSC2_MAT_RE123) return mat_density_more(mat);
     return mat == OSC2_MAT_CU_NIST ? 8900.0 : mat == OSC2_MAT_NB3SN ? 8950.0 : mat == OSC2_MAT_SS ? 7800.0
-           : mat == OSC2_MAT_AL ? 2700.0 : mat == OSC2_MAT_RE123 ? 6380.0 : mat == OSC2_MAT_AG ? 10630.0 : mat == OSC2_MAT_NBTI ? 6160.0
-           : mat == OSC2_MAT_HC276 ? 8890.0 : mat == OSC2_MAT_SN60PB40 ? (7310.0 * 0.6 + 11340.0 * 0.4) : 2000.0;
+           : mat == OSC2_MAT_AL ? 2700.0 : mat == OSC2_MAT_RE123 ? 6380.0 : 2000.0;
 }
 __device__ inline double friction_124(double re);
 // IFRICTION 122: haaland_equation channel.py:700-717 as the start, colebrook_formula channel.py:721-756
@@ -417,7 +422,7 @@ __device__ inline double friction_total(const osc2_model *md, const osc2_topolog
     double f = 1.0;
     const int ifr = md->ch_ifriction[j];
     if (ifr == 124) f = friction_124(re);
-    else if (ifr == 110 || ifr == 111 || ifr == 112 || ifr == 121 || ifr == 204 || ifr == 205 || ifr == 206 || ifr == 209)
+    else if (ifr != -99 && ifr != 122)      // 110, 111, 112, 121, 204, 205, 206, 209 (validated by osc2_set_model)
         f = friction_simple(ifr, re, md->ch_roughness[j], tp->ch_dh[j], md->ch_void_fraction[j]);
     else if (md->ch_ifriction[j] == 122) {
         const double rough = md->ch_roughness[j], dh = tp->ch_dh[j];
@@ -436,6 +441,18 @@ __device__ inline double radiative_htc(const osc2_model *md, int k, double Ta, d
     if (!(den < 1.0e300)) return 0.0;          // an emissivity or the view factor is 0: the reference leaves zeros
     return 5.670374419e-08 * (sq(Ta) + sq(Tc)) * (Ta + Tc) / den * md->ss_rad_mlt[k];
 }
+// the materials outside the shipped decks (StackComponent layers, NbTi) sit behind two calls that RETURN their
+// value (no reference arguments: those would pin cp and k of the hot path to local memory), so that the
+// straight-line code of K_P, which is instruction-cache bound, does not grow with them
+__device__ __noinline__ double material_cp_more(int mat, double T, double bg, double tcs, double tc)
+{
+    return mat == OSC2_MAT_AG ? cp_ag(T) : mat == OSC2_MAT_HC276 ? cp_hc276(T) : mat == OSC2_MAT_SN60PB40 ? cp_sn60pb40(T)
+           : cp_nbti(T, bg, tcs, tc);
+}
+__device__ __noinline__ double material_k_more(int mat, double T)
+{
+    return mat == OSC2_MAT_AG ? k_ag(T) : mat == OSC2_MAT_HC276 ? k_hc276(T) : mat == OSC2_MAT_SN60PB40 ? k_sn60pb40(T) : k_nbti(T);
+}
 // cp and k of one constituent material at a Gauss point
 __device__ inline void material_cp_k(int mat, double T, double bg, double tcs, double tc, double tmin, double tmax,
                                      double rrr, double tc0m, double p7, double rho273, double &cp, double &k)
@@ -445,11 +462,8 @@ __device__ inline void material_cp_k(int mat, double T, double bg, double tcs, d
     else if (mat == OSC2_MAT_SS) { cp = cp_ss(T, tmax); k = k_ss(T); }
     else if (mat == OSC2_MAT_AL) { cp = cp_al(T, tmin, tmax); k = k_al(T, tmin, tmax); }
     else if (mat == OSC2_MAT_RE123) { cp = cp_re123(T); k = k_re123(T); }
-    else if (mat == OSC2_MAT_AG) { cp = cp_ag(T); k = k_ag(T); }
-    else if (mat == OSC2_MAT_NBTI) { cp = cp_nbti(T, bg, tcs, tc); k = k_nbti(T); }
-    else if (mat == OSC2_MAT_HC276) { cp = cp_hc276(T); k = k_hc276(T); }
-    else if (mat == OSC2_MAT_SN60PB40) { cp = cp_sn60pb40(T); k = k_sn60pb40(T); }
-    else { cp = cp_ge(T); k = k_ge(T); }
+    else if (mat == OSC2_MAT_GE) { cp = cp_ge(T); k = k_ge(T); }
+    else { cp = material_cp_more(mat, T, bg, tcs, tc); k = material_k_more(mat, T); }
 }
 // channel.py:392-401, 782-795, 1104-1115
 __device__ inline double friction_124(double re)
@@ -625,10 +639,11 @@ __global__ void __launch_bounds__(128, 6) osc2_opcond_kernel(const osc2_topology
         double tc = 0.0, tcs = 0.0;
         if (kind == OSC2_SOLID_STRAND_MIXED) {
             const double eps = q.eps[(size_t)l * B + b];
-            bool nbti = false;      // strand_component.py:191-246: Tc by superconducting_material
-            for (int i = 0; i < nmat; ++i) nbti = nbti || (md->sol_mat[l][i] == OSC2_MAT_NBTI);
-            tc = nbti ? osc2p::tc_nbti(bg, md->sol_bc20m[l], md->sol_tc0m[l])
-                      : osc2p::tc_nb3sn(bg, (eps + eps) / 2.0, md->sol_tc0m[l], md->sol_bc20m[l]);
+            // strand_component.py:191-246: Tc by superconducting_material (a StrandMixedComponent has two
+            // materials, stabiliser and superconductor)
+            tc = (md->sol_mat[l][0] == OSC2_MAT_NBTI || md->sol_mat[l][nmat - 1] == OSC2_MAT_NBTI)
+                     ? osc2p::tc_nbti(bg, md->sol_bc20m[l], md->sol_tc0m[l])
+                 : osc2p::tc_nb3sn(bg, (eps + eps) / 2.0, md->sol_tc0m[l], md->sol_bc20m[l]);
             tcs = q.tcs ? q.tcs[((size_t)l * E + e) * B + b] : 0.0;
         }
         const double tmax = q.tmax[(size_t)l * B + b], tmin = q.tmin[(size_t)l * B + b];
