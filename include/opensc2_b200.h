@@ -122,7 +122,7 @@ typedef struct {
     int ch_ifriction[OSC2_MAX_CHANNELS];        /* IFRICTION: -99, 110 (Blasius), 111 (Bhatti-Shah), 112 (LHC), 121 (Haaland), 122 (Colebrook), 124,
                                                    204 / 205 (Katheder bundle), 206 / 209 (Darcy-Forchheimer bundle) */
     double ch_friction_mult[OSC2_MAX_CHANNELS]; /* FRICTION_MULTIPLIER */
-    int ch_htc_corr[OSC2_MAX_CHANNELS];         /* Flag_htc_steady_corr: 1 or 212 */
+    int ch_htc_corr[OSC2_MAX_CHANNELS];         /* Flag_htc_steady_corr: 1, 119, 120, 121, 211 or 212 */
     /* solids */
     int sol_kind[OSC2_MAX_SOLIDS];
     int sol_nmat[OSC2_MAX_SOLIDS];

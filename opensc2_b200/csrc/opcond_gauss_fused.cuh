@@ -78,8 +78,10 @@ __global__ void __launch_bounds__(128, 6) osc2_opcond_gauss_kernel(const osc2_to
             const double cv = osc2p::lookup(tab, c, OSC2_FP_CV), kk = osc2p::lookup(tab, c, OSC2_FP_K);
             const double re = fabs(tp->ch_dh[j] * v * rho / mu);
             const double grun = osc2p::lookup(tab, c, OSC2_FP_BETA) / osc2p::lookup(tab, c, OSC2_FP_KAPPA) / cv / rho;
-            const double nu = (md->ch_htc_corr[j] == 212) ? osc2p::nusselt_212(re)
-                                                          : osc2p::nusselt_1(re, osc2p::lookup(tab, c, OSC2_FP_PRANDTL));
+            const int hcorr = md->ch_htc_corr[j];
+            const double nu = (hcorr == 212) ? osc2p::nusselt_212(re)
+                              : (hcorr == 1) ? osc2p::nusselt_1(re, osc2p::lookup(tab, c, OSC2_FP_PRANDTL))
+                                             : osc2p::nusselt_more(hcorr, re, osc2p::lookup(tab, c, OSC2_FP_PRANDTL), tp->ch_dh[j]);
             const double ftot = osc2p::friction_total(md, tp, j, re, q.cb_iters[(size_t)j * B + b]);
             IN(sl.fg(0, j)) = v; IN(sl.fg(1, j)) = pr; IN(sl.fg(2, j)) = T; IN(sl.fg(3, j)) = rho;
             IN(sl.fg(4, j)) = osc2p::lookup(tab, c, OSC2_FP_SOUND);

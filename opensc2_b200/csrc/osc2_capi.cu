@@ -477,8 +477,11 @@ int osc2_set_model(osc2_handle h, const osc2_model *model)
                 ifr != 205 && ifr != 206 && ifr != 209)
                 return fail(OSC2_ERR_INVALID, "channel %d: IFRICTION %d is not implemented on the device (-99, 110, 111, 112, 121, 122, 124, 204, 205, 206, 209)", j, ifr);
         }
-        if (model->ch_htc_corr[j] != 1 && model->ch_htc_corr[j] != 212)
-            return fail(OSC2_ERR_INVALID, "channel %d: Flag_htc_steady_corr %d is not implemented on the device (1, 212)", j, model->ch_htc_corr[j]);
+        {
+            const int hc = model->ch_htc_corr[j];
+            if (hc != 1 && hc != 212 && hc != 119 && hc != 120 && hc != 121 && hc != 211)
+                return fail(OSC2_ERR_INVALID, "channel %d: Flag_htc_steady_corr %d is not implemented on the device (1, 119, 120, 121, 211, 212)", j, hc);
+        }
     }
     for (int l = 0; l < h->S; ++l) {
         if (model->sol_nmat[l] < 1 || model->sol_nmat[l] > OSC2_MAX_MATERIALS)

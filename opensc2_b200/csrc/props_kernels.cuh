@@ -482,6 +482,30 @@ __device__ inline double nusselt_1(double re, double pr)
 }
 // channel.py:1245-1273: the exponent really used is eval_steady_state_htc's nn = 0.3
 __device__ inline double nusselt_212(double re) { return 0.42 * pw(re, 0.3); }
+// Flag_htc_steady_corr 119 / 120 / 121 (Dittus-Boelter with another lower limit, channel.py:1171-1243) and 211
+// (correlation_211: masks on Reynolds over an array of zeros)
+__device__ __noinline__ double nusselt_more(int corr, double re, double pr, double dh)
+{
+    if (corr == 211) {
+        double nu = 0.0;
+        if (re < 1000.0) nu = 5.0969 * pw(re, 0.10);
+        if (re >= 1000.0 && re < 2000.0) nu = 10.2029 - 3.3242e-5 * re;
+        if (re >= 2000.0) nu = 0.0395 * pw(re, 0.73);
+        return nu;
+    }
+    double lim = 4.01;
+    if (corr == 120) lim = 2.181;
+    if (corr == 119) {
+        const double a = dh / (dh + 2 * 1e-3), a2 = a * a, a3 = a2 * a, a4 = a2 * a2, a5 = a4 * a;
+        const double NuTemp = 7.541 * (1.0 - 2.610 * a + 4.970 * a2 - 5.119 * a3 + 2.702 * a4 - 0.548 * a5);
+        const double Nuflux = 8.235 * (1.0 - 10.6044 * a + 61.1755 * a2 - 155.1803 * a3 + 176.9203 * a4 - 72.9236 * a5);
+        lim = (NuTemp + Nuflux) / 2.0;
+    }
+    double nu = 0.023 * pw(re, 0.8) * pw(pr, 0.3);
+    if (nu < lim) nu = lim;
+    return nu;
+}
+
 
 // bilinear (p, T) table lookup: cell index and weights once per point, then one
 // 4-value stencil per property
@@ -602,8 +626,10 @@ __global__ void __launch_bounds__(128, 6) osc2_opcond_kernel(const osc2_topology
         const double cv = osc2p::lookup(tab, c, OSC2_FP_CV), kk = osc2p::lookup(tab, c, OSC2_FP_K);
         const double re = fabs(tp->ch_dh[j] * v * rho / mu);
         const double grun = osc2p::lookup(tab, c, OSC2_FP_BETA) / osc2p::lookup(tab, c, OSC2_FP_KAPPA) / cv / rho;
-        const double nu = (md->ch_htc_corr[j] == 212) ? osc2p::nusselt_212(re)
-                                                      : osc2p::nusselt_1(re, osc2p::lookup(tab, c, OSC2_FP_PRANDTL));
+        const int hcorr = md->ch_htc_corr[j];
+        const double nu = (hcorr == 212) ? osc2p::nusselt_212(re)
+                          : (hcorr == 1) ? osc2p::nusselt_1(re, osc2p::lookup(tab, c, OSC2_FP_PRANDTL))
+                                         : osc2p::nusselt_more(hcorr, re, osc2p::lookup(tab, c, OSC2_FP_PRANDTL), tp->ch_dh[j]);
         const double ftot = osc2p::friction_total(md, tp, j, re, q.cb_iters[(size_t)j * B + b]);
 #define FGW(qq) fg[((((size_t)(qq) * M + j) * E) + e) * B + b]
         FGW(0) = v; FGW(1) = pr; FGW(2) = T; FGW(3) = rho;

@@ -44,7 +44,7 @@ class Model:
     ch_fluid: Tuple[int, ...]
     ch_ifriction: Tuple[int, ...]           # -99 | 110 | 111 | 112 | 121 | 122 | 124 | 204 | 205 | 206 | 209
     ch_friction_mult: Tuple[float, ...]
-    ch_htc_corr: Tuple[int, ...]            # 1 | 212
+    ch_htc_corr: Tuple[int, ...]            # 1 | 119 | 120 | 121 | 211 | 212
     solids: Tuple[SolidModel, ...]
     fs: Tuple[Tuple[int, float, float], ...] = ()                        # (HTC_choice, contact_HTC, multiplier)
     ff: Tuple[Tuple[int, float, float, float], ...] = ()                 # (+ interf_thickness)

@@ -428,6 +428,31 @@ static double nusselt_1(double re, double pr)
 /* rectangular_duct_enea_hts_cicc_htc (flag 212), channel.py:1245-1253.  Observable quirk:
  * eval_steady_state_htc (channel.py:1256-1273) forwards its own default nn = 0.3 positionally,
  * so the exponent the reference really uses is 0.3, not the correlation's default 0.71. */
+/* Flag_htc_steady_corr 119 / 120 / 121: Dittus-Boelter with another lower limit (channel.py:1171-1243);
+ * 211: correlation_211 (masks on Reynolds over an array of zeros) */
+static double nusselt_more(int corr, double re, double pr, double dh)
+{
+    if (corr == 211) {
+        double nu = 0.0;
+        if (re < 1000.0) nu = 5.0969 * pow(re, 0.10);
+        if (re >= 1000.0 && re < 2000.0) nu = 10.2029 - 3.3242e-5 * re;
+        if (re >= 2000.0) nu = 0.0395 * pow(re, 0.73);
+        return nu;
+    }
+    double lim = 4.01;                     /* 121 */
+    if (corr == 120) lim = 2.181;
+    if (corr == 119) {                     /* _eval_nusselt_lower_limit_119 */
+        const double alpha = dh / (dh + 2 * 1e-3);
+        const double NuTemp = 7.541 * (1.0 - 2.610 * alpha + 4.970 * pow(alpha, 2.0) - 5.119 * pow(alpha, 3.0) + 2.702 * pow(alpha, 4.0)
+                                       - 0.548 * pow(alpha, 5.0));
+        const double Nuflux = 8.235 * (1.0 - 10.6044 * alpha + 61.1755 * pow(alpha, 2.0) - 155.1803 * pow(alpha, 3.0)
+                                       + 176.9203 * pow(alpha, 4.0) - 72.9236 * pow(alpha, 5.0));
+        lim = (NuTemp + Nuflux) / 2.0;
+    }
+    double nu = 0.023 * pow(re, 0.8) * pow(pr, 0.3);
+    if (nu < lim) nu = lim;
+    return nu;
+}
 static double nusselt_212(double re) { return 0.42 * pow(re, 0.3); }
 
 int osc2o_fit(int which, long n, const double *x, const double *y, const double *z, double p1, double p2, double *out)
@@ -459,6 +484,7 @@ int osc2o_fit(int which, long n, const double *x, const double *y, const double 
         case 9: out[i] = friction_124(x[i]); break;
         case 10: out[i] = nusselt_1(x[i], y[i]); break;
         case 11: out[i] = nusselt_212(x[i]); break;
+        case 28: out[i] = nusselt_more((int)p1, x[i], y[i], p2); break;   /* p1 = Flag_htc_steady_corr, x = Re, y = Pr, p2 = Dh */
         case 12: out[i] = rhoecu(x[i], y[i], p1); break;
         case 13: out[i] = k_al(x[i], tmin, tmax); break;
         case 14: out[i] = cp_al(x[i], tmin, tmax); break;
@@ -552,7 +578,8 @@ static void one_conductor(const osc2_topology *tp, const osc2_model *md, osc2o_o
             const double re = fabs(tp->ch_dh[j] * v * f[OSC2_FP_RHO] / f[OSC2_FP_MU]);
             const double grun = f[OSC2_FP_BETA] / f[OSC2_FP_KAPPA] / f[OSC2_FP_CV] / f[OSC2_FP_RHO];
             /* channel.py:1256-1273 */
-            const double nu = (md->ch_htc_corr[j] == 212) ? nusselt_212(re) : nusselt_1(re, f[OSC2_FP_PRANDTL]);
+            const double nu = (md->ch_htc_corr[j] == 212) ? nusselt_212(re) : (md->ch_htc_corr[j] == 1) ? nusselt_1(re, f[OSC2_FP_PRANDTL])
+                              : nusselt_more(md->ch_htc_corr[j], re, f[OSC2_FP_PRANDTL], tp->ch_dh[j]);
             const double hsteady = nu * f[OSC2_FP_K] / tp->ch_dh[j];
             /* channel.py:1119-1138 (IFRICTION 122 is array-wide: filled in after this loop) */
             const int ifr = md->ch_ifriction[j];

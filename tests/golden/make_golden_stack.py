@@ -80,6 +80,22 @@ def main():
         ch.total_friction_factor_correlation = ch._eval_total_friction_factor_max
         ch.eval_friction_factor(re.copy(), nodal=True)
         out[f"f{ifr}_total"] = np.array(ch.dict_friction_factor[True]["total"])
+    # steady-state heat transfer: Flag_htc_steady_corr 119 / 120 / 121 / 211 through Channel.eval_steady_state_htc
+    pr = rng.uniform(0.5, 2.0, re.size)
+    kf = rng.uniform(0.01, 0.03, re.size)
+    rea = np.abs(re)
+    out["pr"], out["kf"] = pr, kf
+    for corr, method in ((119, "dittus_boelter_nusselt_lower_limit"), (120, "dittus_boelter_nusselt_lower_limit"),
+                         (121, "dittus_boelter_nusselt_lower_limit"), (211, "correlation_211")):
+        ch = types.SimpleNamespace()
+        for name in ("dittus_boelter", "dittus_boelter_nusselt_lower_limit", "correlation_211", "_initialize_nusselt_and_htc",
+                     "eval_steady_state_htc", "_eval_nusselt_lower_limit_119"):
+            setattr(ch, name, types.MethodType(getattr(Channel, name), ch))
+        ch.inputs = {"HYDIAMETER": 2.499e-3, "Flag_htc_steady_corr": corr}
+        ch.dict_nusselt, ch.dict_htc_steady = {True: None}, {True: None}
+        ch.nusselt_correlation = getattr(ch, method)
+        ch.eval_steady_state_htc({"Reynolds": rea, "Prandtl": pr, "total_thermal_conductivity": kf}, nodal=True)   # conductor.py:4842-4844
+        out[f"htc_{corr}"] = np.array(ch.dict_htc_steady[True])
     # NbTi (superconductor of a StrandMixedComponent): conductivity, Tc(B), cp(T, B, Tcs, Tc) incl. the T <= 1 K table
     from properties_of_materials.niobium_titanium import (critical_temperature_nbti, isobaric_specific_heat_nbti,
                                                           thermal_conductivity_nbti)

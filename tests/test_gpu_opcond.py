@@ -424,3 +424,30 @@ def test_niobium_titanium_strand_on_the_device():
     assert rel(out["sol_gauss"], ref["sol_gauss"]) <= RTOL_FIT
     for key in ("htc_fs", "htc_ss", "sol_q"):
         assert rel(out[key], ref[key]) <= RTOL_FIT, key
+
+
+@pytest.mark.parametrize("corrs", [(119, 211), (120, 121)])
+def test_more_steady_state_htc_correlations_on_the_device(corrs):
+    """Flag_htc_steady_corr 119 / 120 / 121 / 211 feeding the channel-solid and channel-channel heat-transfer
+    models (HTC_choice 2) in K_P vs the oracle."""
+    import dataclasses
+    from opensc2_b200.batch import BatchedStep
+    from oracle import oracle as O
+
+    n, batch = 33, 21
+    topo, model, tab, arr, sweep = _setup(True, n, batch)
+    model = dataclasses.replace(model, ch_htc_corr=corrs)
+    with BatchedStep(topo, batch, n) as bs:
+        bs.set_model(model, [tab])
+        bs.upload_sweep(sweep)
+        bs.upload_state(arr.sysvar, arr.syslod)
+        bs.upload_geometry(arr)
+        bs.eval_operating_conditions(12.0)
+        bs.synchronize()
+        out = bs.download_step_inputs()
+    ref = O.operating_conditions(topo, model, [tab], sweep, arr.sysvar, n, 12.0)
+    for key in ("htc_fs", "htc_ff", "htc_ss", "fl_gauss", "sol_gauss"):
+        assert rel(out[key], ref[key]) <= RTOL_FIT, f"{key}: {rel(out[key], ref[key]):.3e}"
+    if 211 in corrs:      # (the other three only move the lower limit, which this flow does not reach)
+        base = O.operating_conditions(topo, dataclasses.replace(model, ch_htc_corr=(1, 1)), [tab], sweep, arr.sysvar, n, 12.0)
+        assert np.max(np.abs(base["htc_fs"] - ref["htc_fs"])) > 0.0

@@ -141,3 +141,17 @@ def test_niobium_titanium_against_the_reference_fits():
         err = np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-300))
         assert err <= 2e-12, f"{key}: {err:.3e}"
     assert np.any(g["nbti_tc"] == 0.0) and np.any(g["nbti_t"] <= 1.0)
+
+
+@pytest.mark.parametrize("corr", [119, 120, 121, 211])
+def test_more_steady_state_htc_correlations_against_the_reference_channel(corr):
+    """Flag_htc_steady_corr 119 / 120 / 121 (Dittus-Boelter with the lower limits of channel.py:1171-1243) and 211,
+    through the reference's Channel.eval_steady_state_htc: h = Nu k / Dh."""
+    import os
+    from helpers import GOLDEN_DIR
+    g = np.load(os.path.join(GOLDEN_DIR, "props_stack.npz"))
+    dh = float(g["hydiameter"])
+    got = O.fit("nusselt_more", np.abs(g["re"]), g["pr"], p1=corr, p2=dh) * g["kf"] / dh
+    ref = g[f"htc_{corr}"]
+    err = np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-300))
+    assert err <= 2e-12, f"Flag_htc_steady_corr {corr}: {err:.3e}"
