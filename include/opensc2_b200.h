@@ -110,6 +110,7 @@ enum { OSC2_MAT_CU_NIST = 0, OSC2_MAT_NB3SN = 1, OSC2_MAT_SS = 2, OSC2_MAT_GE = 
        OSC2_MAT_SN60PB40 = 8,  /* solder_sn60_pb40.py */
        OSC2_MAT_NBTI = 9,      /* niobium_titanium.py: superconductor of a StrandMixedComponent (Tc from
                                   critical_temperature_nbti; sol_tc0m, sol_bc20m as for Nb3Sn) */
+       OSC2_MAT_MGB2 = 10,     /* magnesium_diboride.py: conductivity (T, B) at its fixed RRR = 100, cp(T) */
        OSC2_MAT_COUNT };
 /* solid kinds: StrandMixedComponent, StrandStabilizerComponent, JacketComponent, StackComponent (HTS tapes:
  * layers homogenised by thickness, stack_component.py:398-476; weights = material_thickness,

@@ -529,7 +529,7 @@ int osc2_set_model(osc2_handle h, const osc2_model *model)
     }
     h->q.model = h->model_dev;
     {   // greedy balance of the component items over the warps of the fused kernel by pow() count
-        static const int mat_cost[OSC2_MAT_COUNT] = {14, 9, 8, 8, 8, 4, 4, 4, 4, 8};   // Cu, Nb3Sn, SS, glass-epoxy, Al, RE123, Ag, HC276, Sn60Pb40, NbTi
+        static const int mat_cost[OSC2_MAT_COUNT] = {14, 9, 8, 8, 8, 4, 4, 4, 4, 8, 14};   // Cu, Nb3Sn, SS, glass-epoxy, Al, RE123, Ag, HC276, Sn60Pb40, NbTi, MgB2
         const int n_items = h->M + h->S + 1;
         std::vector<std::pair<int, int>> items;     // (cost, item)
         for (int j = 0; j < h->M; ++j) items.push_back({2 + (model->ch_ifriction[j] == 124 ? 2 : 0), j});

@@ -248,6 +248,18 @@ __device__ inline double cp_re123(double T)
     return -7.567485538209158e-10 * T5 + 6.351452642016898e-07 * T4 + -1.947975786547597e-04 * T3 + 0.023616673974415 * T2
            + 0.239331954284042 * T + -1.096191721280114;
 }
+// magnesium_diboride.py:8-77 (the copper NIST form at its default rrr = 100), :79-139
+__device__ __noinline__ double k_mgb2(double t, double b)
+{
+    const double beta = 0.634 / 100.0, betat = beta / 0.0003;
+    return k_cu(t, b, 100.0, 0.838 / pw(betat, 0.1661), rhoecu0(273.0, 100.0));
+}
+__device__ __noinline__ double cp_mgb2(double t)
+{
+    if (!(t >= 4 && t <= 300)) return 0.0;
+    const double L = log10(t), L2 = L * L, L3 = L2 * L, L4 = L2 * L2, L5 = L4 * L, L6 = L3 * L3, L7 = L6 * L;
+    return pw10(-1.91844 + -0.15973 * L + 8.61013 * L2 + -18.996 * L3 + 21.9661 * L4 + -12.7328 * L5 + 3.54322 * L6 + -0.3797 * L7);
+}
 // niobium_titanium.py:9-62, 64-209, 274-286 (superconductor of a StrandMixedComponent)
 __device__ __noinline__ double k_nbti(double T)
 {
@@ -351,7 +363,7 @@ __device__ __noinline__ double cp_sn60pb40(double T)
 }
 __device__ __noinline__ double mat_density_more(int mat)
 {
-    return mat == OSC2_MAT_AG ? 10630.0 : mat == OSC2_MAT_NBTI ? 6160.0 : mat == OSC2_MAT_HC276 ? 8890.0
+    return mat == OSC2_MAT_AG ? 10630.0 : mat == OSC2_MAT_NBTI ? 6160.0 : mat == OSC2_MAT_HC276 ? 8890.0 : mat == OSC2_MAT_MGB2 ? 2570.0
            : (7310.0 * 0.6 + 11340.0 * 0.4);
 }
 __device__ inline double mat_density(int mat)
@@ -447,11 +459,12 @@ __device__ inline double radiative_htc(const osc2_model *md, int k, double Ta, d
 __device__ __noinline__ double material_cp_more(int mat, double T, double bg, double tcs, double tc)
 {
     return mat == OSC2_MAT_AG ? cp_ag(T) : mat == OSC2_MAT_HC276 ? cp_hc276(T) : mat == OSC2_MAT_SN60PB40 ? cp_sn60pb40(T)
-           : cp_nbti(T, bg, tcs, tc);
+           : mat == OSC2_MAT_MGB2 ? cp_mgb2(T) : cp_nbti(T, bg, tcs, tc);
 }
-__device__ __noinline__ double material_k_more(int mat, double T)
+__device__ __noinline__ double material_k_more(int mat, double T, double bg)
 {
-    return mat == OSC2_MAT_AG ? k_ag(T) : mat == OSC2_MAT_HC276 ? k_hc276(T) : mat == OSC2_MAT_SN60PB40 ? k_sn60pb40(T) : k_nbti(T);
+    return mat == OSC2_MAT_AG ? k_ag(T) : mat == OSC2_MAT_HC276 ? k_hc276(T) : mat == OSC2_MAT_SN60PB40 ? k_sn60pb40(T)
+           : mat == OSC2_MAT_MGB2 ? k_mgb2(T, bg) : k_nbti(T);
 }
 // cp and k of one constituent material at a Gauss point
 __device__ inline void material_cp_k(int mat, double T, double bg, double tcs, double tc, double tmin, double tmax,
@@ -463,7 +476,7 @@ __device__ inline void material_cp_k(int mat, double T, double bg, double tcs, d
     else if (mat == OSC2_MAT_AL) { cp = cp_al(T, tmin, tmax); k = k_al(T, tmin, tmax); }
     else if (mat == OSC2_MAT_RE123) { cp = cp_re123(T); k = k_re123(T); }
     else if (mat == OSC2_MAT_GE) { cp = cp_ge(T); k = k_ge(T); }
-    else { cp = material_cp_more(mat, T, bg, tcs, tc); k = material_k_more(mat, T); }
+    else { cp = material_cp_more(mat, T, bg, tcs, tc); k = material_k_more(mat, T, bg); }
 }
 // channel.py:392-401, 782-795, 1104-1115
 __device__ inline double friction_124(double re)

@@ -22,13 +22,13 @@ from typing import Dict, List, Optional, Tuple
 import numpy as np
 
 from . import xlsx
-from .model import (MAT_AL, MAT_CU_NIST, MAT_GE, MAT_NB3SN, MAT_NBTI, MAT_RE123, MAT_SS, SOLID_JACKET, SOLID_STRAND_MIXED,
+from .model import (MAT_AL, MAT_CU_NIST, MAT_GE, MAT_MGB2, MAT_NB3SN, MAT_NBTI, MAT_RE123, MAT_SS, SOLID_JACKET, SOLID_STRAND_MIXED,
                     SOLID_STRAND_STAB, Model, SolidModel, radiative_pair)
 from .problem import Topology
 
 _MATERIALS = {"cu": MAT_CU_NIST, "copper": MAT_CU_NIST, "nb3sn": MAT_NB3SN, "ss": MAT_SS, "steinless_steel": MAT_SS,
               "stainless_steel": MAT_SS, "ge": MAT_GE, "glass_epoxy": MAT_GE, "al": MAT_AL, "aluminium": MAT_AL,
-              "hts": MAT_RE123, "re123": MAT_RE123, "ybco": MAT_RE123, "nbti": MAT_NBTI}
+              "hts": MAT_RE123, "re123": MAT_RE123, "ybco": MAT_RE123, "nbti": MAT_NBTI, "mgb2": MAT_MGB2}
 
 
 @dataclass

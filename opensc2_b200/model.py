@@ -21,7 +21,7 @@ from ._abi import OSC2_N_FLUID_PROPS, Osc2Model, Osc2Sweep, c_dp
 
 # fluid-table property order = the reference's alias table (simulation.py:89-100)
 FP_BETA, FP_KAPPA, FP_PRANDTL, FP_RHO, FP_MU, FP_H, FP_CP, FP_CV, FP_SOUND, FP_K = range(10)
-MAT_CU_NIST, MAT_NB3SN, MAT_SS, MAT_GE, MAT_AL, MAT_RE123, MAT_AG, MAT_HC276, MAT_SN60PB40, MAT_NBTI = range(10)
+MAT_CU_NIST, MAT_NB3SN, MAT_SS, MAT_GE, MAT_AL, MAT_RE123, MAT_AG, MAT_HC276, MAT_SN60PB40, MAT_NBTI, MAT_MGB2 = range(11)
 # SOLID_STACK: StackComponent (HTS tapes): materials = tape layers, weights = layer thicknesses, weight_sum = tape
 # thickness (stack_component.py:262-330, 398-476)
 SOLID_STRAND_MIXED, SOLID_STRAND_STAB, SOLID_JACKET, SOLID_STACK = range(4)

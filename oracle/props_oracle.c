@@ -228,6 +228,17 @@ static double cp_re123(double T)
            + 0.023616673974415 * sq(T) + 0.239331954284042 * T + -1.096191721280114;
 }
 
+/* magnesium_diboride.py:8-77 (the copper NIST form at the default rrr = 100: strand_mixed_component.py calls it
+ * with temperature and field only), :79-139 */
+static double k_mgb2(double t, double b) { return k_cu(t, b, 100.0); }
+static double cp_mgb2(double t)
+{
+    static const double A[8] = {-1.91844, -0.15973, 8.61013, -18.996, 21.9661, -12.7328, 3.54322, -0.3797};
+    if (!(t >= 4 && t <= 300)) return 0.0;
+    const double L = log10(t);
+    return pow(10.0, A[0] + A[1] * L + A[2] * sq(L) + A[3] * pow(L, 3.0) + A[4] * pow(L, 4.0) + A[5] * pow(L, 5.0)
+                         + A[6] * pow(L, 6.0) + A[7] * pow(L, 7.0));
+}
 /* niobium_titanium.py:9-62 */
 static double k_nbti(double T)
 {
@@ -341,6 +352,7 @@ static double mat_density(int mat)   /* density_cu / _nb3sn / _ss / _ge: constan
     case OSC2_MAT_SS: return 7800.0;
     case OSC2_MAT_AL: return 2700.0;
     case OSC2_MAT_RE123: return 6380.0;
+    case OSC2_MAT_MGB2: return 2570.0;                     /* magnesium_diboride.py density_mgb2 */
     case OSC2_MAT_NBTI: return 6160.0;                     /* niobium_titanium.py density_nbti */
     case OSC2_MAT_AG: return 10630.0;                       /* silver.py density_ag */
     case OSC2_MAT_HC276: return 8890.0;                    /* hastelloy_c276.py density_hc276 */
@@ -497,6 +509,9 @@ int osc2o_fit(int which, long n, const double *x, const double *y, const double 
         case 22: out[i] = k_sn60pb40(x[i]); break;
         case 23: out[i] = cp_sn60pb40(x[i]); break;
         case 25: out[i] = k_nbti(x[i]); break;
+        case 29: out[i] = k_mgb2(x[i], y[i]); break;
+        case 31: out[i] = mat_density((int)p1); break;
+        case 30: out[i] = cp_mgb2(x[i]); break;
         case 26: out[i] = cp_nbti(x[i], y[i], z[i], out[i]); break;   /* x = T, y = B, z = Tcs; out[] holds Tc on entry */
         case 27: out[i] = tc_nbti(x[i], p1, p2); break;                            /* x = B, p1 = Bc20m, p2 = Tc0m */
         case 24: out[i] = friction_simple((int)p1, x[i], y[i], z[i], p2); break;   /* p1 = IFRICTION, y = roughness, z = Dh, p2 = void fraction */
@@ -653,6 +668,7 @@ static void one_conductor(const osc2_topology *tp, const osc2_model *md, osc2o_o
                 case OSC2_MAT_RE123: cp_i[i] = cp_re123(T); k_i[i] = k_re123(T); break;
                 case OSC2_MAT_AG: cp_i[i] = cp_ag(T); k_i[i] = k_ag(T); break;
                 case OSC2_MAT_NBTI: cp_i[i] = cp_nbti(T, bg, tcs, tc); k_i[i] = k_nbti(T); break;
+                case OSC2_MAT_MGB2: cp_i[i] = cp_mgb2(T); k_i[i] = k_mgb2(T, bg); break;
                 case OSC2_MAT_HC276: cp_i[i] = cp_hc276(T); k_i[i] = k_hc276(T); break;
                 case OSC2_MAT_SN60PB40: cp_i[i] = cp_sn60pb40(T); k_i[i] = k_sn60pb40(T); break;
                 default: cp_i[i] = cp_ge(T); k_i[i] = k_ge(T); break;

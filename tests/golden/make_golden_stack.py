@@ -108,6 +108,21 @@ def main():
     out["nbti_bc20m_tc0m"] = np.array([bc20m, tc0m])
     out["k_nbti"] = thermal_conductivity_nbti(tn)
     out["cp_nbti"] = isobaric_specific_heat_nbti(tn.copy(), bn, tcsn, tcn)
+    # MgB2: conductivity (T, B) as strand_mixed_component.py calls it (default rrr), cp(T) incl. out-of-range zeros
+    from properties_of_materials.magnesium_diboride import isobaric_specific_heat_mgb2, thermal_conductivity_mgb2
+    tm = np.concatenate([rng.uniform(4.0, 40.0, 200), rng.uniform(40.0, 300.0, 96), [3.9, 4.0, 300.0, 310.0]])
+    bm = np.concatenate([rng.uniform(0.0, 6.0, 260), np.zeros(40)])
+    out["mgb2_t"], out["mgb2_b"] = tm, bm
+    out["k_mgb2"] = thermal_conductivity_mgb2(tm, bm)
+    out["cp_mgb2"] = isobaric_specific_heat_mgb2(tm)
+    # constant densities of every material id of include/opensc2_b200.h, in the order of its enum
+    import strand_mixed_component as SM
+    import jacket_component as JK
+    one = np.ones(1)
+    out["densities"] = np.array([SC.DENSITY_FUNC["cu"](one)[0], SM.DENSITY_FUNC["nb3sn"](one)[0], JK.DENSITY_FUNC["ss"](one)[0],
+                                 JK.DENSITY_FUNC["ge"](one)[0], SC.DENSITY_FUNC["al"](one)[0], SC.DENSITY_FUNC["re123"](one)[0],
+                                 SC.DENSITY_FUNC["ag"](one)[0], SC.DENSITY_FUNC["hc276"](one)[0], SC.DENSITY_FUNC["sn60pb40"](one)[0],
+                                 SM.DENSITY_FUNC["nbti"](one)[0], SM.DENSITY_FUNC["mgb2"](one)[0]])
     np.savez_compressed(os.path.join(HERE, "props_stack.npz"), **out)
     print("wrote props_stack.npz", {k: v.shape for k, v in out.items()})
 

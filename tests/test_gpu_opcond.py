@@ -398,10 +398,12 @@ def test_more_friction_laws_on_the_device(laws):
     assert rel(out["fl_gauss"], ref["fl_gauss"]) <= RTOL_FIT
 
 
-def test_niobium_titanium_strand_on_the_device():
-    """StrandMixedComponent with NbTi as superconductor (Tc from critical_temperature_nbti, cp from
-    isobaric_specific_heat_nbti with the current-sharing temperature of the sweep): K_P vs the oracle, which is
-    pinned to the reference fits (tests/test_props_oracle_golden.py)."""
+@pytest.mark.parametrize("sc", ["nbti", "mgb2"])
+def test_niobium_titanium_strand_on_the_device(sc):
+    """StrandMixedComponent with NbTi (Tc from critical_temperature_nbti, cp from isobaric_specific_heat_nbti with
+    the current-sharing temperature of the sweep) or MgB2 (conductivity of temperature and field, cp of
+    temperature) as superconductor: K_P vs the oracle, which is pinned to the reference fits
+    (tests/test_props_oracle_golden.py)."""
     import dataclasses
     from opensc2_b200 import model as Mdl
     from opensc2_b200.batch import BatchedStep
@@ -409,7 +411,7 @@ def test_niobium_titanium_strand_on_the_device():
 
     n, batch = 33, 19
     topo, model, tab, arr, sweep = _setup(True, n, batch)
-    strand = Mdl.SolidModel(Mdl.SOLID_STRAND_MIXED, (Mdl.MAT_CU_NIST, Mdl.MAT_NBTI), (1.6, 1.0), 2.6, rrr=120.0,
+    strand = Mdl.SolidModel(Mdl.SOLID_STRAND_MIXED, (Mdl.MAT_CU_NIST, Mdl.MAT_NBTI if sc == "nbti" else Mdl.MAT_MGB2), (1.6, 1.0), 2.6, rrr=120.0,
                             tc0m=9.03, bc20m=14.5, heated=True)
     model = dataclasses.replace(model, solids=(strand,) + model.solids[1:])
     with BatchedStep(topo, batch, n) as bs:

@@ -155,3 +155,18 @@ def test_more_steady_state_htc_correlations_against_the_reference_channel(corr):
     ref = g[f"htc_{corr}"]
     err = np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-300))
     assert err <= 2e-12, f"Flag_htc_steady_corr {corr}: {err:.3e}"
+
+
+def test_magnesium_diboride_and_all_densities_against_the_reference():
+    """MgB2 conductivity (T, B; the copper NIST form at rrr = 100, as strand_mixed_component.py calls it) and
+    cp(T) with its out-of-range zeros; the constant density of every material id."""
+    import os
+    from helpers import GOLDEN_DIR
+    g = np.load(os.path.join(GOLDEN_DIR, "props_stack.npz"))
+    for key, got in (("k_mgb2", O.fit("k_mgb2", g["mgb2_t"], g["mgb2_b"])), ("cp_mgb2", O.fit("cp_mgb2", g["mgb2_t"]))):
+        ref = g[key]
+        err = np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-300))
+        assert err <= 2e-12, f"{key}: {err:.3e}"
+        assert np.array_equal(got == 0.0, ref == 0.0)
+    for mat, rho in enumerate(g["densities"]):
+        assert O.fit("density", np.ones(1), p1=mat)[0] == rho, mat
