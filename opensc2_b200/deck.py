@@ -22,13 +22,15 @@ from typing import Dict, List, Optional, Tuple
 import numpy as np
 
 from . import xlsx
-from .model import (MAT_AL, MAT_CU_NIST, MAT_GE, MAT_MGB2, MAT_NB3SN, MAT_NBTI, MAT_RE123, MAT_SS, SOLID_JACKET, SOLID_STRAND_MIXED,
+from .model import (MAT_AG, MAT_AL, MAT_CU_NIST, MAT_GE, MAT_HC276, MAT_MGB2, MAT_NB3SN, MAT_NBTI, MAT_RE123, MAT_SN60PB40, MAT_SS,
+                    SOLID_STACK, SOLID_JACKET, SOLID_STRAND_MIXED,
                     SOLID_STRAND_STAB, Model, SolidModel, radiative_pair)
 from .problem import Topology
 
 _MATERIALS = {"cu": MAT_CU_NIST, "copper": MAT_CU_NIST, "nb3sn": MAT_NB3SN, "ss": MAT_SS, "steinless_steel": MAT_SS,
               "stainless_steel": MAT_SS, "ge": MAT_GE, "glass_epoxy": MAT_GE, "al": MAT_AL, "aluminium": MAT_AL,
-              "hts": MAT_RE123, "re123": MAT_RE123, "ybco": MAT_RE123, "nbti": MAT_NBTI, "mgb2": MAT_MGB2}
+              "hts": MAT_RE123, "re123": MAT_RE123, "ybco": MAT_RE123, "nbti": MAT_NBTI, "mgb2": MAT_MGB2,
+              "ag": MAT_AG, "silver": MAT_AG, "hc276": MAT_HC276, "sn60pb40": MAT_SN60PB40}
 
 
 @dataclass
@@ -62,6 +64,22 @@ def _get(d, *names, default=None):
         if n in d and d[n] is not None:
             return d[n]
     return default
+
+
+def stack_model(d, heated: bool = False):
+    """SolidModel of a HEAD-schema STACK sheet column (StackComponent.__reorganize_input, stack_component.py:216-
+    272): the `*material` entries that are not "none" are the tape layers, in sheet order; the non-zero
+    `*thickness` entries are their thicknesses; the stack is homogenised by thickness.  None when the column
+    carries no `*material` keys (then it is not a HEAD stack)."""
+    mats = [str(v).lower() for k, v in d.items() if str(k).endswith("material") and str(v).lower() != "none"]
+    thick = [float(v) for k, v in d.items() if str(k).endswith("thickness") and float(v) != 0.0]
+    if not mats:
+        return None
+    if len(mats) != len(thick):
+        raise ValueError(f"STACK: {len(mats)} tape materials but {len(thick)} non-zero layer thicknesses "
+                         "(the reference raises in StackComponent.__check_consistency)")
+    return SolidModel(SOLID_STACK, tuple(_material(m) for m in mats), tuple(thick), float(np.array(thick).sum()),
+                      rrr=float(d.get("RRR", 100.0)), heated=heated)
 
 
 def _material(name) -> int:
@@ -126,9 +144,11 @@ def load_deck(folder: str, conductor: int = 1, legacy_no_field: bool = True,
                             bc20m=float(_get(d, "Bc20m", default=0.0)), heated=heated)
             area = float(d["CROSSECTION"])
         elif kind in ("STR_SC", "STACK"):
-            if kind == "STR_SC":
-                notes.append(f"{ident}: legacy STR_SC restated as a single-material RE123 solid (SURVEY.md Appendix B)")
-            sm = SolidModel(SOLID_STRAND_STAB, (MAT_RE123,), (1.0,), 1.0, heated=heated)
+            sm = stack_model(d, heated) if kind == "STACK" else None
+            if sm is None:
+                if kind == "STR_SC":
+                    notes.append(f"{ident}: legacy STR_SC restated as a single-material RE123 solid (SURVEY.md Appendix B)")
+                sm = SolidModel(SOLID_STRAND_STAB, (MAT_RE123,), (1.0,), 1.0, heated=heated)
             area = float(d["CROSSECTION"])
         elif kind == "STR_STAB":
             mat = _material(_get(d, "stabilizer_material", "ISTABILIZER"))

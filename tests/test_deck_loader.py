@@ -68,3 +68,25 @@ def test_hand_written_case3_interfaces_match_the_deck():
         assert np.allclose(t[key], want[key], rtol=1e-3), key
     choices = [c[0] for c in SUMMARY["CASE_3_HTS_HVDC"]["model"]["ss"]]
     assert choices == [3, -1, 3, -1]               # two radiative gaps, two contacts
+
+
+def test_head_schema_stack_column_becomes_a_stack_solid():
+    """STACK sheet column of the HEAD schema -> SOLID_STACK with the layers in sheet order ("none" materials
+    and zero thicknesses dropped like StackComponent.__reorganize_input does)."""
+    from opensc2_b200 import model as M
+    from opensc2_b200.deck import stack_model
+
+    col = {"CROSSECTION": 4.8e-6, "RRR": 80.0, "Stack_width": 4e-3, "Tape_number": 12,
+           "HTS_material": "RE123", "HTS_thickness": 1.0e-6,
+           "Stabilizer_material": "Cu", "Stabilizer_thickness": 40.0e-6,
+           "Substrate_material": "HC276", "Substrate_thickness": 50.0e-6,
+           "Silver_material": "Ag", "Silver_thickness": 2.0e-6,
+           "Solder_material": "none", "Solder_thickness": 0.0}
+    sm = stack_model(col, heated=True)
+    assert sm.kind == M.SOLID_STACK and sm.heated and sm.rrr == 80.0
+    assert sm.materials == (M.MAT_RE123, M.MAT_CU_NIST, M.MAT_HC276, M.MAT_AG)
+    assert sm.weights == (1.0e-6, 40.0e-6, 50.0e-6, 2.0e-6)
+    assert sm.weight_sum == float(np.array(sm.weights).sum())
+    assert stack_model({"CROSSECTION": 1.0}) is None
+    with pytest.raises(ValueError):
+        stack_model({"HTS_material": "RE123", "HTS_thickness": 0.0})
