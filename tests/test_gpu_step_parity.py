@@ -241,3 +241,32 @@ def test_case2_singular_conductor_is_reported_by_the_d64_sweep():
     assert list(st) == [0, -(row + 1), 0]
     assert_bits(sv[0], ref["sysvar"][0], "conductor 0")
     assert_bits(sv[2], ref["sysvar"][2], "conductor 2")
+
+
+def test_case1_and_case2_handles_side_by_side():
+    """The mixed sweep of BASELINE configs[4] keeps one handle per topology on a GPU: a CASE_1 batch (register-
+    resident warp kernels) and a CASE_2 batch (CTA-per-conductor d = 64 sweeps) alive at the same time, stepped
+    alternately for three steps, each bit-identical to the oracle run on its own."""
+    from opensc2_b200.batch import BatchedStep
+    from oracle import oracle as O
+
+    t1, t2 = case1_topology(2), case2_topology()
+    a1 = synthetic_step_arrays(t1, 201, batch=48, seed=61, num_step=1, exact_squares=False)
+    a2 = synthetic_step_arrays(t2, 31, batch=6, seed=62, num_step=1, exact_squares=False)
+    h1, h2 = a1.copy(), a2.copy()
+    with BatchedStep(t1, 48, 201) as b1, BatchedStep(t2, 6, 31) as b2:
+        b1.upload_state(a1.sysvar, a1.syslod); b1.upload_step_inputs(a1)
+        b2.upload_state(a2.sysvar, a2.syslod); b2.upload_step_inputs(a2)
+        for k in range(1, 4):
+            b1.step(a1.dt, k)
+            b2.step(a2.dt, k)
+            for host, topo in ((h1, t1), (h2, t2)):
+                host.num_step = k
+                ref = O.step(topo, host)
+                host.sysvar, host.syslod = ref["sysvar"], ref["syslod"]
+        b1.synchronize(); b2.synchronize()
+        sv1, sl1, st1 = b1.download_state()
+        sv2, sl2, st2 = b2.download_state()
+    assert np.all(st1 == 0) and np.all(st2 == 0)
+    assert_bits(sv1, h1.sysvar, "CASE_1 sysvar"); assert_bits(sl1, h1.syslod, "CASE_1 syslod")
+    assert_bits(sv2, h2.sysvar, "CASE_2 sysvar"); assert_bits(sl2, h2.syslod, "CASE_2 syslod")
