@@ -38,8 +38,10 @@ typedef enum {
     OSC2_ERR_NO_DEVICE = -3,   /* no usable CUDA device: there is no CPU fallback */
     OSC2_ERR_SINGULAR = -4,    /* at least one conductor hit abs(pivot) <= 1e-20 (gredub/gbacsb, tsf:676,763) */
     OSC2_ERR_STATE = -5,       /* call order violated (e.g. step before upload) */
-    OSC2_ERR_RANGE = -6        /* a non-zero value below 2^-900 (or a divisor outside 2^+-100) met the fast
+    OSC2_ERR_RANGE = -6,       /* a non-zero value below 2^-900 (or a divisor outside 2^+-100) met the fast
                                   kernels' exactness guard; rerun with OSC2_FORCE_GENERIC=1 */
+    OSC2_ERR_TCS = -7          /* osc2_eval_tcs: Jop >= Jc(3.5 K) somewhere (scipy.optimize.bisect: "f(a) and f(b)
+                                  must have different signs", niobium3_tin.py:613) */
 } osc2_status;
 
 /* Uniform-across-the-batch description of the conductor; mirrors what step()
@@ -151,6 +153,8 @@ typedef struct {
     double ss_rad_den[OSC2_MAX_INTERFACES];
     double ss_rad_mlt[OSC2_MAX_INTERFACES];
     double ch_void_fraction[OSC2_MAX_CHANNELS]; /* Channel.inputs["VOID_FRACTION"] (bundle laws 204, 205, 206, 209) */
+    double sol_c0[OSC2_MAX_SOLIDS];             /* strand inputs["c0"]: scaling constant of Jc (A T / m^2), physical definition
+                                                   (strand_component.py:266-276); only read by osc2_eval_tcs */
 } osc2_model;
 
 /* Swept per-conductor scalars, batch leading. */
@@ -160,8 +164,11 @@ typedef struct {
     const double *q0;        /* [B][S]     Q0, W/m */
     const double *q_window;  /* [B][S][4]  first node, last node (heat0_where), TQBEG, TQEND */
     const double *tcs;       /* [B][S][E]  T_cur_sharing_min at the Gauss points (evaluated once at
-                                           step 0 by the caller, conductor.py:4615-4619); may be NULL
-                                           when no solid holds a superconductor */
+                                           step 0, conductor.py:4615-4619); NULL when no solid holds a
+                                           superconductor, or when the library computes it: osc2_eval_tcs */
+    const double *jop;       /* [B][S]     operating current density abs(op_current) / cross_section["sc"], A/m^2
+                                           (strand_component.py:266-276), the input of osc2_eval_tcs; may be NULL
+                                           (then tcs is the caller's) */
 } osc2_sweep;
 
 typedef struct osc2_context *osc2_handle;
@@ -194,11 +201,24 @@ int osc2_set_model(osc2_handle h, const osc2_model *model);
 int osc2_set_fluid_table(osc2_handle h, int fluid, int n_p, int n_t, double p_min, double p_step,
                          double t_min, double t_step, const double *props);
 int osc2_upload_sweep(osc2_handle h, const osc2_sweep *sweep);
+/* Current sharing temperature on the device (StrandComponent.eval_tcs, strand_component.py:266-349; Nb3Sn:
+ * current_sharing_temperature_nb3sn, properties_of_materials/niobium3_tin.py:493-623 -- the bisection of
+ * scipy.optimize.bisect(xtol = 1e-5, rtol = 4 eps) on Jc(T, B, eps) - Jop between 3.5 K and Tc(B, eps), iterate for
+ * iterate).  Fills T_cur_sharing_min at the Gauss points (what the Nb3Sn specific heat reads every step) and at the
+ * nodes (what save_properties prints) from sweep.b_field / eps / jop and model.sol_c0 / sol_tc0m / sol_bc20m for every
+ * StrandMixedComponent whose superconductor is Nb3Sn.  Called once, at step 0, like the reference does with
+ * TCS_EVALUATION False (conductor.py:4615-4619).  A conductor whose Jop is not below Jc(3.5 K) gets status
+ * OSC2_STATUS_TCS (the reference's bisect raises ValueError there). */
+int osc2_eval_tcs(osc2_handle h);
+/* tcs_gauss [B][S][E], tcs_nodal [B][S][N]; either may be NULL. */
+int osc2_download_tcs(osc2_handle h, double *tcs_gauss, double *tcs_nodal);
+/* Temperature margin min over the Gauss points of (T_cur_sharing_min - T) per conductor and solid, [B][S], of the
+ * state the LAST osc2_eval_operating_conditions / osc2_advance looked at (+inf for solids without a superconductor
+ * or before any evaluation): the quantity a temperature-margin sweep is run for. */
+int osc2_download_margin(osc2_handle h, double *margin);
 /* `time` = conductor.cond_time[-1] of the step about to be taken. */
 int osc2_eval_operating_conditions(osc2_handle h, double time);
-/* One full time step: osc2_eval_operating_conditions(time) + osc2_step(dt, num_step).
- * (OSC2_FUSED_OPCOND=1 selects an experimental kernel that fuses the property evaluation with the
- * element row records; it is bit-identical and, today, slower.) */
+/* One full time step: osc2_eval_operating_conditions(time) + osc2_step(dt, num_step). */
 int osc2_advance(osc2_handle h, double time, double dt, int num_step);
 /* Device -> host copy of the computed step inputs (parity tests); any member may be NULL. */
 int osc2_download_step_inputs(osc2_handle h, double *fl_gauss, double *fl_node, double *sol_gauss,
@@ -209,10 +229,12 @@ int osc2_download_step_inputs(osc2_handle h, double *fl_gauss, double *fl_node, 
  * LU (gredub) -> substitution (gbacsb) -> norms / EQTEIG.  Asynchronous. */
 int osc2_step(osc2_handle h, double dt, int num_step);
 
-/* Wait for the stream; returns OSC2_ERR_SINGULAR if any conductor is singular. */
+/* Wait for the stream; returns OSC2_ERR_SINGULAR if any conductor hit a singular pivot in ANY step since the
+ * state was uploaded (status is sticky: the first failing step is kept, like the reference's ValueError at that
+ * step; the state after it is meaningless).  osc2_upload_state starts it over. */
 int osc2_synchronize(osc2_handle h);
 
-/* Any pointer may be NULL.  status[b] = 0 or -(row+1) of the first tiny pivot. */
+/* Any pointer may be NULL.  status[b] = 0 or -(row+1) of the first tiny pivot of the first failing step. */
 int osc2_download_state(osc2_handle h, double *sysvar, double *syslod, int *status);
 /* norm_solution/norm_change/eqteig: [B][d]; k123: [B][3][nff][E]. */
 int osc2_download_diagnostics(osc2_handle h, double *norm_solution, double *norm_change,

@@ -18,7 +18,9 @@ OSC2_ERR_NO_DEVICE = -3
 OSC2_ERR_SINGULAR = -4
 OSC2_ERR_STATE = -5
 OSC2_ERR_RANGE = -6
+OSC2_ERR_TCS = -7
 OSC2_STATUS_RANGE = -2000000000
+OSC2_STATUS_TCS = -2000000001
 
 c_dp = C.POINTER(C.c_double)
 c_ip = C.POINTER(C.c_int)
@@ -79,11 +81,12 @@ class Osc2Model(C.Structure):
         ("ch_roughness", C.c_double * _CH),
         ("ss_rad_den", C.c_double * _IF), ("ss_rad_mlt", C.c_double * _IF),
         ("ch_void_fraction", C.c_double * _CH),
+        ("sol_c0", C.c_double * _SO),
     ]
 
 
 class Osc2Sweep(C.Structure):
-    _fields_ = [(n, c_dp) for n in ("b_field", "eps", "q0", "q_window", "tcs")]
+    _fields_ = [(n, c_dp) for n in ("b_field", "eps", "q0", "q_window", "tcs", "jop")]
 
 
 STEP_INPUT_FIELDS = tuple(n for n, _ in Osc2StepInputs._fields_[:-2])

@@ -48,6 +48,9 @@ def load() -> C.CDLL:
     L.osc2_upload_sweep.argtypes = [H, C.POINTER(Osc2Sweep)]
     L.osc2_eval_operating_conditions.argtypes = [H, C.c_double]
     L.osc2_advance.argtypes = [H, C.c_double, C.c_double, C.c_int]
+    L.osc2_eval_tcs.argtypes = [H]
+    L.osc2_download_tcs.argtypes = [H, c_dp, c_dp]
+    L.osc2_download_margin.argtypes = [H, c_dp]
     L.osc2_download_step_inputs.argtypes = [H] + [c_dp] * 8
     L.osc2_synchronize.argtypes = [H]
     L.osc2_download_state.argtypes = [H, c_dp, c_dp, c_ip]
@@ -67,7 +70,8 @@ def load() -> C.CDLL:
                  "osc2_synchronize", "osc2_download_state", "osc2_download_diagnostics", "osc2_set_capture",
                  "osc2_download_system", "osc2_set_profiling", "osc2_get_kernel_ms", "osc2_reset_kernel_ms",
                  "osc2_timer_start", "osc2_timer_stop", "osc2_set_model", "osc2_set_fluid_table", "osc2_upload_sweep",
-                 "osc2_eval_operating_conditions", "osc2_download_step_inputs", "osc2_advance"):
+                 "osc2_eval_operating_conditions", "osc2_download_step_inputs", "osc2_advance", "osc2_eval_tcs",
+                 "osc2_download_tcs", "osc2_download_margin"):
         getattr(L, name).restype = C.c_int
     _LIB = L
     return L
@@ -80,6 +84,7 @@ EXPORTED = (
     "osc2_set_profiling", "osc2_get_kernel_ms", "osc2_reset_kernel_ms", "osc2_timer_start",
     "osc2_timer_stop", "osc2_device_bytes", "osc2_selftest_division", "osc2_set_model", "osc2_set_fluid_table",
     "osc2_upload_sweep", "osc2_eval_operating_conditions", "osc2_download_step_inputs", "osc2_advance",
+    "osc2_eval_tcs", "osc2_download_tcs", "osc2_download_margin",
 )
 
 
@@ -89,6 +94,6 @@ def check(rc: int) -> None:
     text = load().osc2_last_error().decode("utf-8", "replace")
     if rc == -4:
         raise SingularMatrixError(text)
-    if rc == -1:
+    if rc in (-1, -7):          # -7: scipy.optimize.bisect's ValueError in the reference's Tcs evaluation
         raise ValueError(text)
     raise Osc2Error(rc, text)

@@ -104,8 +104,26 @@ class BatchedStep:
     def eval_operating_conditions(self, time: float):
         _lib.check(self._L.osc2_eval_operating_conditions(self._h, float(time)))
 
+    def eval_tcs(self):
+        """Current sharing temperature of the Nb3Sn strands on the device, once at step 0 (osc2_eval_tcs)."""
+        _lib.check(self._L.osc2_eval_tcs(self._h))
+
+    def download_tcs(self, nodal: bool = True):
+        """(tcs_gauss (B, S, E), tcs_nodal (B, S, N) or None)."""
+        S = self.topo.n_sol
+        g = np.empty((self.batch, S, self.n_nodes - 1))
+        nd = np.empty((self.batch, S, self.n_nodes)) if nodal else None
+        _lib.check(self._L.osc2_download_tcs(self._h, dptr(g), dptr(nd) if nd is not None else None))
+        return g, nd
+
+    def download_margin(self) -> np.ndarray:
+        """min over the Gauss points of (Tcs - T), (B, S), as of the last operating-condition evaluation."""
+        m = np.empty((self.batch, self.topo.n_sol))
+        _lib.check(self._L.osc2_download_margin(self._h, dptr(m)))
+        return m
+
     def advance(self, time: float, dt: float, num_step: int):
-        """Operating conditions at `time` + one step(); fused on the device where it fits."""
+        """Operating conditions at `time` + one step()."""
         _lib.check(self._L.osc2_advance(self._h, float(time), float(dt), int(num_step)))
 
     def download_step_inputs(self) -> Dict[str, np.ndarray]:

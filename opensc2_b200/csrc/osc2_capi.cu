@@ -14,7 +14,7 @@
 
 #include "step_launch.h"
 #include "props_kernels.cuh"
-#include "opcond_gauss_fused.cuh"
+#include "tcs_kernels.cuh"
 
 namespace {
 
@@ -57,11 +57,10 @@ struct osc2_context {
     size_t staging_doubles = 0;
     double *sysvar_a = nullptr, *sysvar_b = nullptr;
     bool have_state = false, have_inputs = false;
+    bool have_geometry = false;      // dz, fl_bc, contact perimeters, qsource: never computed on the device
+    bool have_peri_ss_nodal = false;
     bool capture = false, profiling = false;
     bool fast = false;               // register-resident kernels (step_kernels_fast.cuh)
-    bool fused_opcond = false;       // K_P + K_G in one kernel (opcond_gauss_fused.cuh), experimental
-    int fused_warps = 2;             // warps per CTA of the fused kernel
-    int fwd_mode = 0;                // K_F variant, see StepDev::fwd_split
     int max_smem = 0, sm_count = 0;
     std::vector<EventPair> pending, pool;
     double kernel_ms[OSC2_K_COUNT] = {0};
@@ -73,6 +72,8 @@ struct osc2_context {
     osc2_model *model_dev = nullptr;
     PropsDev q;
     bool have_model = false, have_sweep = false;
+    bool need_peri_ss_nodal = false; // some |ss_choice| == 3
+    double *tcs_nodal = nullptr;     // [S][N][B] (osc2_eval_tcs)
     bool have_table[OSC2_MAX_FLUIDS] = {false, false, false, false};
     int n_fluids_used = 0;
 
@@ -309,12 +310,6 @@ int osc2_create(const osc2_topology *topo, int batch, int n_nodes, int device, o
         h->fast = osc2_has_fast_path(h->d) && !(force && force[0] == '1');
     }
     h->NS = osc2_gm_slots(h->d, h->M, h->S, h->fast);
-    // experimental: bit-identical to K_P + K_G but slower today, off unless OSC2_FUSED_OPCOND=1
-    { const char *fo = getenv("OSC2_FUSED_OPCOND"); h->fused_opcond = (fo && fo[0] == '1'); }
-    { const char *fw = getenv("OSC2_FUSED_WARPS"); if (fw && atoi(fw) >= 1 && atoi(fw) <= 4) h->fused_warps = atoi(fw); }
-    // experimental: slower than the single-warp sweep today, off unless OSC2_FWD_SPLIT=1
-    { const char *sp = getenv("OSC2_FWD_SPLIT"); h->fwd_mode = (sp && sp[0] == '1') ? 1 : 0; }
-    { const char *sp = getenv("OSC2_FWD_MODE"); if (sp && sp[0] >= '0' && sp[0] <= '3') h->fwd_mode = sp[0] - '0'; }
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     h->max_smem = (int)prop.sharedMemPerBlockOptin;
@@ -329,7 +324,6 @@ int osc2_create(const osc2_topology *topo, int batch, int n_nodes, int device, o
     const size_t B = batch, E = h->E, N = h->N, M = h->M, S = h->S, d = h->d;
     StepDev &p = h->p;
     memset(&p, 0, sizeof p);
-    p.fwd_split = h->fwd_mode;
     p.B = batch; p.N = h->N; p.E = h->E; p.M = h->M; p.S = h->S; p.d = h->d; p.NS = h->NS;
     p.nff = topo->nff; p.nfs = topo->nfs; p.nss = topo->nss; p.nes = topo->nes;
     struct { const double **dst; size_t k; } ins[] = {
@@ -425,7 +419,12 @@ int osc2_upload_state(osc2_handle h, const double *sysvar, const double *syslod)
     if (!h) return fail(OSC2_ERR_INVALID, "handle is NULL");
     CK(cudaSetDevice(h->device));
     int rc = OSC2_OK;
-    if (sysvar) { rc = upload_transposed(h, sysvar, (double *)h->p.sysvar, h->total); if (rc) return rc; h->have_state = true; }
+    if (sysvar) {
+        rc = upload_transposed(h, sysvar, (double *)h->p.sysvar, h->total);
+        if (rc) return rc;
+        h->have_state = true;
+        CK(cudaMemsetAsync(h->p.status, 0, sizeof(int) * (size_t)h->B, h->stream));   // a new state: the sticky status starts over
+    }
     if (syslod) { rc = upload_transposed(h, syslod, h->p.syslod, h->total * 2); if (rc) return rc; }
     return OSC2_OK;
 }
@@ -449,16 +448,26 @@ int osc2_upload_step_inputs(osc2_handle h, const osc2_step_inputs *in)
     if (in->peri_ss_nodal && p.nss > 0) {
         int rc = upload_transposed(h, in->peri_ss_nodal, (double *)p.peri_ss_nodal, (size_t)p.nss * N);
         if (rc) return rc;
+        h->have_peri_ss_nodal = true;
     }
+    // what the device never computes: a first upload must bring all of it (later calls may refresh single arrays,
+    // e.g. the boundary values every step)
+    const void *geometry[] = {in->dz, in->fl_bc, in->peri_ff, in->peri_fs, in->peri_ss, in->peri_es, in->qsource};
+    const size_t geometry_k[] = {E, 6 * M, 2 * (size_t)p.nff * E, (size_t)p.nfs * E, (size_t)p.nss * E, (size_t)p.nes * E, N * S};
+    bool all_geometry = true;
+    for (int i = 0; i < 7; ++i) if (geometry_k[i] && !geometry[i]) all_geometry = false;
+    bool all_present = true;
     for (auto &x : a) {
         if (x.k == 0) continue;
-        if (!x.src && h->have_model) continue;   // computed on the device by osc2_eval_operating_conditions
-        if (!x.src) return fail(OSC2_ERR_INVALID, "step input %s is NULL", x.name);
+        if (!x.src) { all_present = false; continue; }
         int rc = upload_transposed(h, x.src, (double *)x.dst, x.k);
         if (rc) return rc;
     }
+    if (!all_present && !h->have_model)
+        return fail(OSC2_ERR_INVALID, "a step input is NULL and no model is set to compute it (osc2_set_model)");
     p.t_env = in->t_env;
-    h->have_inputs = true;
+    if (all_geometry) h->have_geometry = true;
+    if (all_present) h->have_inputs = true;
     return OSC2_OK;
 }
 
@@ -502,7 +511,11 @@ int osc2_set_model(osc2_handle h, const osc2_model *model)
         if (model->ss_choice[k] != 1 && model->ss_choice[k] != -1 && model->ss_choice[k] != 3 && model->ss_choice[k] != -3)
             return fail(OSC2_ERR_INVALID, "solid-solid interface %d: HTC_choice %d is not implemented on the device (1, -1, 3, -3)", k, model->ss_choice[k]);
     if (!h->model_dev) CK(cudaMalloc((void **)&h->model_dev, sizeof(osc2_model)));
+    CK(cudaStreamSynchronize(h->stream));    // kernels in flight on the (non-blocking) stream still read the old model
     CK(cudaMemcpy(h->model_dev, model, sizeof(osc2_model), cudaMemcpyHostToDevice));
+    h->need_peri_ss_nodal = false;
+    for (int k = 0; k < h->p.nss; ++k)
+        if (model->ss_choice[k] == 3 || model->ss_choice[k] == -3) h->need_peri_ss_nodal = true;
     if (!h->have_model) {
         memset(&h->q, 0, sizeof h->q);
         double *t = nullptr;
@@ -514,13 +527,18 @@ int osc2_set_model(osc2_handle h, const osc2_model *model)
         if (rc) return rc;
         h->q.tmin = t;
         t = nullptr;
-        rc = dev_alloc(h, &t, ((size_t)h->M * h->B + 1) / 2 + 1);
+        rc = dev_alloc(h, &t, ((size_t)(h->M > 0 ? h->M : 1) * h->B + 1) / 2 + 1);   // ints: max(M, 1) * B of them
         if (rc) return rc;
         h->q.cb_iters = (int *)t;
         double *c = nullptr;
         rc = dev_alloc(h, &c, 2 * (size_t)h->S);
         if (rc) return rc;
         h->q.sol_const = c;
+        t = nullptr;
+        rc = dev_alloc(h, &t, (size_t)h->S * h->B);
+        if (rc) return rc;
+        h->q.margin_key = (unsigned long long *)t;
+        CK(cudaMemsetAsync(t, 0xff, sizeof(double) * (size_t)h->S * h->B, h->stream));
     }
     if (h->S > 0) {
         osc2_model_consts_kernel<<<(h->S + 63) / 64, 64, 0, h->stream>>>(h->model_dev, h->S, h->q.sol_const);
@@ -528,26 +546,6 @@ int osc2_set_model(osc2_handle h, const osc2_model *model)
         CK(cudaStreamSynchronize(h->stream));
     }
     h->q.model = h->model_dev;
-    {   // greedy balance of the component items over the warps of the fused kernel by pow() count
-        static const int mat_cost[OSC2_MAT_COUNT] = {14, 9, 8, 8, 8, 4, 4, 4, 4, 8, 14};   // Cu, Nb3Sn, SS, glass-epoxy, Al, RE123, Ag, HC276, Sn60Pb40, NbTi, MgB2
-        const int n_items = h->M + h->S + 1;
-        std::vector<std::pair<int, int>> items;     // (cost, item)
-        for (int j = 0; j < h->M; ++j) items.push_back({2 + (model->ch_ifriction[j] == 124 ? 2 : 0), j});
-        for (int l = 0; l < h->S; ++l) {
-            int c = 1;
-            for (int i = 0; i < model->sol_nmat[l]; ++i) c += mat_cost[model->sol_mat[l][i]];
-            items.push_back({c, h->M + l});
-        }
-        items.push_back({1, n_items - 1});
-        std::sort(items.begin(), items.end(), [](const std::pair<int, int> &a, const std::pair<int, int> &b) { return a.first > b.first; });
-        std::vector<int> load(h->fused_warps, 0);
-        for (auto &it : items) {
-            int best = 0;
-            for (int w = 1; w < h->fused_warps; ++w) if (load[w] < load[best]) best = w;
-            load[best] += it.first;
-            h->q.item_owner[it.second] = (unsigned char)best;
-        }
-    }
     h->n_fluids_used = nf;
     h->have_model = true;
     return OSC2_OK;
@@ -568,6 +566,7 @@ int osc2_set_fluid_table(osc2_handle h, int fluid, int n_p, int n_t, double p_mi
         int rc = dev_alloc(h, &dev, n);
         if (rc) return rc;
     }
+    CK(cudaStreamSynchronize(h->stream));    // do not overwrite a table kernels in flight are reading
     CK(cudaMemcpy(dev, props, n * sizeof(double), cudaMemcpyHostToDevice));
     FluidTableDev &t = h->q.fluid[fluid];
     t.n_p = n_p; t.n_t = n_t; t.p_min = p_min; t.p_step = p_step; t.t_min = t_min; t.t_step = t_step; t.props = dev;
@@ -597,6 +596,7 @@ int osc2_upload_sweep(osc2_handle h, const osc2_sweep *sw)
     if (!rc) rc = upload_sweep_array(h, sw->q0, &h->q.q0, S);
     if (!rc) rc = upload_sweep_array(h, sw->q_window, &h->q.q_window, S * 4);
     if (!rc && sw->tcs) rc = upload_sweep_array(h, sw->tcs, &h->q.tcs, S * E);
+    if (!rc && sw->jop) rc = upload_sweep_array(h, sw->jop, &h->q.jop, S);
     if (rc) return rc;
     h->have_sweep = true;
     return OSC2_OK;
@@ -611,6 +611,11 @@ int osc2_eval_operating_conditions(osc2_handle h, double time)
         return fail(OSC2_ERR_STATE, "osc2_eval_operating_conditions needs osc2_set_model, osc2_upload_sweep and osc2_upload_state first");
     for (int f = 0; f < h->n_fluids_used; ++f)
         if (!h->have_table[f]) return fail(OSC2_ERR_STATE, "fluid table %d was not set", f);
+    if (!h->have_geometry)
+        return fail(OSC2_ERR_STATE, "dz, fl_bc, the contact perimeters and qsource are never computed on the device: "
+                    "upload them once with osc2_upload_step_inputs before osc2_eval_operating_conditions / osc2_advance");
+    if (h->need_peri_ss_nodal && !h->have_peri_ss_nodal)
+        return fail(OSC2_ERR_STATE, "a radiative solid-solid interface (HTC_choice +-3) needs peri_ss_nodal");
     CK(cudaSetDevice(h->device));
     h->q.time = time;
     { int rc = launch_tmax(h); if (rc) return rc; }
@@ -660,7 +665,8 @@ static int launch_tmax(osc2_context *h)
     CudaLauncher L{h};
     CK(cudaMemsetAsync(h->q.tmax, 0, sizeof(double) * (size_t)h->S * h->B, h->stream));
     CK(cudaMemsetAsync(h->q.tmin, 0x7f, sizeof(double) * (size_t)h->S * h->B, h->stream));   // a huge positive double
-    CK(cudaMemsetAsync(h->q.cb_iters, 0, sizeof(int) * (size_t)(h->M > 0 ? h->M : 1) * h->B, h->stream));
+    if (h->M > 0) CK(cudaMemsetAsync(h->q.cb_iters, 0, sizeof(int) * (size_t)h->M * h->B, h->stream));
+    if (h->q.margin_key) CK(cudaMemsetAsync(h->q.margin_key, 0xff, sizeof(unsigned long long) * (size_t)h->S * h->B, h->stream));
     const long long w = (long long)((h->E + 63) / 64) * h->B;
     L.launch(OSC2_K_PROPS, osc2_solid_tmax_kernel, (unsigned)((w + 127) / 128), 128u, (size_t)0,
              (const osc2_topology *)h->topo_dev, h->p, h->q);
@@ -670,32 +676,73 @@ static int launch_tmax(osc2_context *h)
 int osc2_advance(osc2_handle h, double time, double dt, int num_step)
 {
     if (!h) return fail(OSC2_ERR_INVALID, "handle is NULL");
-    if (!h->have_model || !h->have_sweep || !h->have_state)
-        return fail(OSC2_ERR_STATE, "osc2_advance needs osc2_set_model, osc2_upload_sweep and osc2_upload_state first");
-    const FusedSlots sl{h->M, h->S, h->p.nff, h->p.nfs, h->p.nss, h->p.nes, h->d};
-    const int n_warps = h->fused_warps;
-    const size_t smem = sl.smem_doubles(n_warps) * sizeof(double);
-    if (!h->fused_opcond || !h->fast || smem > 48 * 1024) {
-        int rc = osc2_eval_operating_conditions(h, time);
-        if (rc) return rc;
-        return run_step(h, dt, num_step, false);
-    }
-    for (int f = 0; f < h->n_fluids_used; ++f)
-        if (!h->have_table[f]) return fail(OSC2_ERR_STATE, "fluid table %d was not set", f);
-    if (!(dt > 0.0)) return fail(OSC2_ERR_INVALID, "time step must be positive");
-    if (num_step < 1) return fail(OSC2_ERR_INVALID, "num_step must be >= 1");
-    CK(cudaSetDevice(h->device));
-    h->q.time = time;
-    h->p.dt = dt;
-    h->p.num_step = num_step;
-    int rc = launch_tmax(h);
+    int rc = osc2_eval_operating_conditions(h, time);
     if (rc) return rc;
+    return run_step(h, dt, num_step, false);
+}
+
+int osc2_eval_tcs(osc2_handle h)
+{
+    if (!h) return fail(OSC2_ERR_INVALID, "handle is NULL");
+    if (!h->have_model || !h->have_sweep) return fail(OSC2_ERR_STATE, "osc2_eval_tcs needs osc2_set_model and osc2_upload_sweep first");
+    if (!h->q.jop) return fail(OSC2_ERR_STATE, "osc2_eval_tcs needs the operating current density (osc2_sweep.jop)");
+    CK(cudaSetDevice(h->device));
+    const size_t S = h->S, E = h->E, N = h->N, B = h->B;
+    if (!h->q.tcs) { double *t = nullptr; int rc = dev_alloc(h, &t, S * E * B); if (rc) return rc; h->q.tcs = t; }
+    if (!h->tcs_nodal) { int rc = dev_alloc(h, &h->tcs_nodal, S * N * B); if (rc) return rc; }
     CudaLauncher L{h};
-    const long long blocks = (long long)h->E * ((h->B + 31) / 32);
-    L.launch(OSC2_K_GAUSS, osc2_opcond_gauss_kernel, (unsigned)blocks, (unsigned)(32 * n_warps), smem, (const osc2_topology *)h->topo_dev,
-             h->p, h->q, h->capture ? 1 : 0);
-    h->have_inputs = true;
-    return run_step(h, dt, num_step, true);
+    const long long work = (long long)(N + E) * B;
+    L.launch(OSC2_K_PROPS, osc2_tcs_kernel, (unsigned)((work + 127) / 128), 128u, (size_t)0, h->p, h->q,
+             const_cast<double *>(h->q.tcs), h->tcs_nodal);
+    if (!h->launch_error.empty()) {
+        const int rc = fail(OSC2_ERR_CUDA, "%s", h->launch_error.c_str());
+        h->launch_error.clear();
+        return rc;
+    }
+    return OSC2_OK;
+}
+
+int osc2_download_tcs(osc2_handle h, double *tcs_gauss, double *tcs_nodal)
+{
+    if (!h) return fail(OSC2_ERR_INVALID, "handle is NULL");
+    CK(cudaSetDevice(h->device));
+    int rc;
+    if (tcs_gauss) {
+        if (!h->q.tcs) return fail(OSC2_ERR_STATE, "no current sharing temperature on the device (osc2_upload_sweep with tcs, or osc2_eval_tcs)");
+        rc = download_transposed(h, h->q.tcs, tcs_gauss, (size_t)h->S * h->E);
+        if (rc) return rc;
+    }
+    if (tcs_nodal) {
+        if (!h->tcs_nodal) return fail(OSC2_ERR_STATE, "nodal current sharing temperature needs osc2_eval_tcs");
+        rc = download_transposed(h, h->tcs_nodal, tcs_nodal, (size_t)h->S * h->N);
+        if (rc) return rc;
+    }
+    return OSC2_OK;
+}
+
+__global__ void osc2_margin_decode_kernel(const unsigned long long *key, double *out, long long n)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long k = key[i];
+    const unsigned long long u = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+    out[i] = (k == ~0ull) ? __longlong_as_double(0x7ff0000000000000ll) : __longlong_as_double((long long)u);
+}
+
+int osc2_download_margin(osc2_handle h, double *margin)
+{
+    if (!h || !margin) return fail(OSC2_ERR_INVALID, "NULL argument");
+    if (!h->q.margin_key) return fail(OSC2_ERR_STATE, "osc2_download_margin needs osc2_set_model first");
+    CK(cudaSetDevice(h->device));
+    const long long n = (long long)h->S * h->B;
+    if ((size_t)n > h->staging_doubles) return fail(OSC2_ERR_STATE, "staging buffer too small");
+    double *tmp = nullptr;
+    CK(cudaMallocAsync((void **)&tmp, sizeof(double) * (size_t)n, h->stream));
+    osc2_margin_decode_kernel<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(h->q.margin_key, tmp, n);
+    CK(cudaGetLastError());
+    int rc = download_transposed(h, tmp, margin, (size_t)h->S);
+    CK(cudaFreeAsync(tmp, h->stream));
+    return rc;
 }
 
 static int run_step(osc2_handle h, double dt, int num_step, bool records_ready)
@@ -734,6 +781,10 @@ int osc2_synchronize(osc2_handle h)
     CK(cudaSetDevice(h->device));
     CK(cudaMemcpyAsync(h->status_host, h->p.status, sizeof(int) * (size_t)h->B, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    for (int b = 0; b < h->B; ++b)
+        if (h->status_host[b] == OSC2_STATUS_TCS)
+            return fail(OSC2_ERR_TCS, "conductor %d of the batch: f(a) and f(b) must have different signs -- the operating "
+                        "current density is not below Jc(3.5 K) (current_sharing_temperature_nb3sn)", b);
     for (int b = 0; b < h->B; ++b)
         if (h->status_host[b] == OSC2_STATUS_RANGE)
             return fail(OSC2_ERR_RANGE, "conductor %d of the batch: a value left the range in which the fast kernels' "

@@ -14,6 +14,8 @@
 // status[b] value of a conductor whose numbers left the range in which the fast
 // kernels' division is verified exact (osc2_div.cuh); never produced by the generic path
 #define OSC2_STATUS_RANGE (-2000000000)
+// osc2_eval_tcs: Jop is not below Jc(3.5 K) (the reference's bisect raises ValueError)
+#define OSC2_STATUS_TCS (-2000000001)
 
 struct StepDev {
     int B, N, E, M, S, d, NS;
@@ -52,8 +54,6 @@ struct StepDev {
     const int *norm_prog;     // [n_prog]       >= 0: push leaf, -1: add the two on top
     double *norm_part;        // [n_leaves][3][d][B]
     int n_leaves, n_prog;
-    int fwd_split;            // K_F variant: 0 one warp per 32/LPC conductors, 1 assembler + eliminator warps
-                              // (step_kernels_split.cuh), 2 sixteen lanes per conductor (step_kernels_wide.cuh)
     // K_G: SMAT is staged per thread in shared memory; only the entries the topology can touch get a
     // slot (osc2_build_smap), every other (row, col) maps to one shared all-zero slot
     const unsigned char *smap; // [d*d] -> slot

@@ -28,13 +28,13 @@ struct PropsDev {
     const double *q0;        // [S][B]
     const double *q_window;  // [S][4][B]
     const double *tcs;       // [S][E][B] or nullptr
+    const double *jop;       // [S][B] operating current density (osc2_eval_tcs) or nullptr
+    unsigned long long *margin_key;   // [S][B] ordered key of min over the Gauss points of (Tcs - T), or nullptr
     double *tmax;            // [S][B] max Gauss temperature of each solid (whole-array branches)
     double *tmin;            // [S][B] min Gauss temperature (aluminium's whole-array range check)
     int *cb_iters;           // [M][B] array-wide Colebrook iteration count (IFRICTION 122)
     double *sol_const;       // [S][2] RRR-only constants of the copper fit: p7, rhoecu0(273 K)
     double time;
-    // fused K_PG: which warp of the CTA evaluates component item i (channels, then solids, then geometry)
-    unsigned char item_owner[OSC2_MAX_CHANNELS + OSC2_MAX_SOLIDS + 1];
 };
 
 namespace osc2p {
@@ -585,15 +585,23 @@ __global__ void osc2_solid_tmax_kernel(const osc2_topology *__restrict__ tp, Ste
         const int is = 3 * M + l;
         double prev = p.sysvar[((size_t)e0 * d + is) * B + b];
         double mx = 0.0, mn = __longlong_as_double(0x7ff0000000000000ll);
+        // temperature margin of the superconducting strands: min (Tcs - T) over the Gauss points
+        const bool want_margin = q.tcs && q.margin_key && q.model->sol_kind[l] == OSC2_SOLID_STRAND_MIXED;
+        double mg = __longlong_as_double(0x7ff0000000000000ll);
         for (int e = e0; e < e1; ++e) {
             const double nxt = p.sysvar[((size_t)(e + 1) * d + is) * B + b];
             const double tg = fabs(prev + nxt) / 2.0;
             if (tg > mx) mx = tg;
             if (tg < mn) mn = tg;
+            if (want_margin) { const double m = q.tcs[((size_t)l * p.E + e) * B + b] - tg; if (m < mg) mg = m; }
             prev = nxt;
         }
         atomicMax((unsigned long long *)(q.tmax + (size_t)l * B + b), (unsigned long long)__double_as_longlong(mx));
         atomicMin((unsigned long long *)(q.tmin + (size_t)l * B + b), (unsigned long long)__double_as_longlong(mn));
+        if (want_margin) {
+            const unsigned long long u = (unsigned long long)__double_as_longlong(mg);
+            atomicMin(q.margin_key + (size_t)l * B + b, (u >> 63) ? ~u : (u | 0x8000000000000000ull));
+        }
     }
     const osc2_model *md = q.model;
     for (int j = 0; j < M; ++j) {

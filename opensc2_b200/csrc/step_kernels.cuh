@@ -557,7 +557,7 @@ __global__ void osc2_forward_kernel(const osc2_topology *__restrict__ tp, StepDe
             const long long v = (long long)scratch[q];
             if (v >= 0 && (worst < 0 || v < worst)) worst = v;
         }
-        p.status[b] = (worst < 0) ? 0 : -(int)(worst + 1);
+        if (worst >= 0 && p.status[b] == 0) p.status[b] = -(int)(worst + 1);   // sticky: the first failing step is kept
     }
 }
 

@@ -628,7 +628,7 @@ __global__ void __launch_bounds__(256, 1) osc2_forward64_kernel(const osc2_topol
             const long long v = (long long)strip[q];
             if (v >= 0 && (worst < 0 || v < worst)) worst = v;
         }
-        p.status[b] = (worst < 0) ? 0 : -(int)(worst + 1);
+        if (worst >= 0 && p.status[b] == 0) p.status[b] = -(int)(worst + 1);   // sticky: the first failing step is kept
     }
 }
 

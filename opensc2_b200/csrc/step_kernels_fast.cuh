@@ -679,7 +679,8 @@ __global__ void osc2_forward_fast_kernel(const osc2_topology *__restrict__ tp, S
             range = range || (scratch[D + q] != 0.0);
         }
         // a singular pivot wins (the reference raises there); otherwise report the range problem
-        p.status[b] = (worst >= 0) ? -(int)(worst + 1) : (range ? OSC2_STATUS_RANGE : 0);
+        // sticky: the first failing step is kept (osc2_upload_state starts over)
+        if ((worst >= 0 || range) && p.status[b] == 0) p.status[b] = (worst >= 0) ? -(int)(worst + 1) : OSC2_STATUS_RANGE;
     }
 }
 

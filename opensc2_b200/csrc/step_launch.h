@@ -10,9 +10,6 @@
 
 #include "step_kernels.cuh"
 #include "step_kernels_fast.cuh"
-#include "step_kernels_split.cuh"
-#include "step_kernels_wide.cuh"
-#include "step_kernels_pipe.cuh"
 #include "step_kernels_d64.cuh"
 
 #include <cstdlib>
@@ -125,42 +122,10 @@ void osc2_run_fast_sweeps(Launcher &L, const osc2_topology *tp_dev, const StepDe
     // one warp per CTA: a batch of a few thousand conductors then still spreads
     // over all SMs (4096 conductors x 8 lanes = 1024 warps on 148 SMs)
     constexpr int cpb = 32 / LPC;
-    const unsigned grid = (unsigned)((p.B + cpb - 1) / cpb);
     const bool be = (theta == 1.0), cap = (p.cap_sysmat != nullptr);
     const size_t smem_f = (size_t)((be && D % 8 == 0) ? FastFwdSmem<D, true>::PER_COND : FastFwdSmem<D, false>::PER_COND) *
                           cpb * sizeof(double);
     const size_t smem_b = (size_t)(2 * D + 2) * cpb * sizeof(double);
-    if constexpr (D % 8 == 0) {
-        if (p.fwd_split == 3 && be && !cap) {      // two phases per round (step_kernels_pipe.cuh)
-            const size_t smem_p = (size_t)PipeFwdSmem<D>::PER_COND * cpb * sizeof(double);
-            bool fullp = false;
-            if constexpr (LPC == D) fullp = (p.B % cpb == 0);
-            if (fullp) {
-                if constexpr (LPC == D) L.launch(OSC2_K_FORWARD, osc2_forward_pipe_kernel<D, LPC, true>, grid, 32u, smem_p, tp_dev, p);
-            } else L.launch(OSC2_K_FORWARD, osc2_forward_pipe_kernel<D, LPC, false>, grid, 32u, smem_p, tp_dev, p);
-            L.launch(OSC2_K_BACKWARD, osc2_backward_fast_kernel<D, LPC>, grid, 32u, smem_b, p);
-            return;
-        }
-        if (p.fwd_split == 2 && be) {      // 16 lanes per conductor (step_kernels_wide.cuh)
-            constexpr int cpw = 32 / (2 * D);
-            const unsigned gridw = (unsigned)((p.B + cpw - 1) / cpw);
-            const size_t smem_w = (size_t)WideFwdSmem<D>::PER_COND * cpw * sizeof(double);
-            if (!cap) L.launch(OSC2_K_FORWARD, osc2_forward_wide_kernel<D, false>, gridw, 32u, smem_w, tp_dev, p);
-            else L.launch(OSC2_K_FORWARD, osc2_forward_wide_kernel<D, true>, gridw, 32u, smem_w, tp_dev, p);
-            L.launch(OSC2_K_BACKWARD, osc2_backward_fast_kernel<D, LPC>, grid, 32u, smem_b, p);
-            return;
-        }
-    }
-    if (p.fwd_split == 1) {
-        const bool closed = be && (D % 8 == 0);
-        const size_t smem_s = ((size_t)SplitFwdSmem<D>::per_cond(closed) * cpb + 2 * 32 * 2) * sizeof(double);
-        if (be && !cap) L.launch(OSC2_K_FORWARD, osc2_forward_split_kernel<D, LPC, true, false>, grid, 64u, smem_s, tp_dev, p);
-        else if (be) L.launch(OSC2_K_FORWARD, osc2_forward_split_kernel<D, LPC, true, true>, grid, 64u, smem_s, tp_dev, p);
-        else if (!cap) L.launch(OSC2_K_FORWARD, osc2_forward_split_kernel<D, LPC, false, false>, grid, 64u, smem_s, tp_dev, p);
-        else L.launch(OSC2_K_FORWARD, osc2_forward_split_kernel<D, LPC, false, true>, grid, 64u, smem_s, tp_dev, p);
-        L.launch(OSC2_K_BACKWARD, osc2_backward_fast_kernel<D, LPC>, grid, 32u, smem_b, p);
-        return;
-    }
     // warps per CTA of the two sweeps (experiment knob OSC2_SWEEP_WARPS, default 1): with 2, the two
     // 32-byte halves of a 64-byte DRAM burst are requested from the same SM
     static const int W = [] { const char *e = getenv("OSC2_SWEEP_WARPS"); return (e && e[0] == '2') ? 2 : 1; }();

@@ -120,7 +120,10 @@ def load_deck(folder: str, conductor: int = 1, legacy_no_field: bool = True,
     ch_area = tuple(float(chans[c]["CROSSECTION"]) for c in chan_ids)
     ch_dh = tuple(float(chans[c]["HYDIAMETER"]) for c in chan_ids)
     ch_forward = tuple(str(_get(chan_ops[c], "FLOWDIR", default="forward")).lower() == "forward" for c in chan_ids)
-    deck_intial = [abs(int(chan_ops[c]["INTIAL"])) for c in chan_ids]
+    deck_intial = [int(chan_ops[c]["INTIAL"]) for c in chan_ids]
+    if any(i not in (1, 2, 3) for i in deck_intial):
+        raise ValueError(f"INTIAL {deck_intial}: only 1, 2, 3 are implemented (negative flags read time-dependent "
+                         "boundary values from the EXTERNAL_FLOW workbook)")
     if intial_override is not None:
         notes.append(f"hydraulic boundary mode INTIAL {sorted(set(deck_intial))} of the deck replaced by {intial_override}")
     ch_intial = tuple(intial_override if intial_override is not None else i for i in deck_intial)
@@ -141,7 +144,8 @@ def load_deck(folder: str, conductor: int = 1, legacy_no_field: bool = True,
             ratio = float(d["STAB_NON_STAB"])
             sm = SolidModel(SOLID_STRAND_MIXED, (stab, sc), (ratio, 1.0), float(np.array([ratio, 1.0]).sum()),
                             rrr=float(_get(d, "RRR", default=100.0)), tc0m=float(_get(d, "Tc0m", default=0.0)),
-                            bc20m=float(_get(d, "Bc20m", default=0.0)), heated=heated)
+                            bc20m=float(_get(d, "Bc20m", default=0.0)), heated=heated,
+                            c0=float(_get(d, "c0", "C0", default=0.0)))
             area = float(d["CROSSECTION"])
         elif kind in ("STR_SC", "STACK"):
             sm = stack_model(d, heated) if kind == "STACK" else None

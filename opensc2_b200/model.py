@@ -37,6 +37,7 @@ class SolidModel:
     tc0m: float = 0.0
     bc20m: float = 0.0
     heated: bool = False                    # IQFUN == 1
+    c0: float = 0.0                         # inputs["c0"], Jc scaling constant (A T / m^2); read by osc2_eval_tcs only
 
 
 @dataclass(frozen=True)
@@ -70,6 +71,7 @@ class Model:
                 m.sol_mat[l][i], m.sol_weight[l][i] = mat, w
             m.sol_weight_sum[l], m.sol_rrr[l] = s.weight_sum, s.rrr
             m.sol_tc0m[l], m.sol_bc20m[l], m.sol_heated[l] = s.tc0m, s.bc20m, int(s.heated)
+            m.sol_c0[l] = s.c0
         for k, (c, h, mlt) in enumerate(self.fs):
             m.fs_choice[k], m.fs_htc[k], m.fs_mlt[k] = c, h, mlt
         for k, (c, h, mlt, th) in enumerate(self.ff):
@@ -106,11 +108,12 @@ class Sweep:
     q0: np.ndarray               # (B, S)     W/m
     q_window: np.ndarray         # (B, S, 4)  first node, last node, TQBEG, TQEND
     tcs: Optional[np.ndarray] = None   # (B, S, E)
+    jop: Optional[np.ndarray] = None   # (B, S) operating current density |I_op| / A_sc, A/m^2 (osc2_eval_tcs)
 
     def struct(self):
         keep = []
         s = Osc2Sweep()
-        for name in ("b_field", "eps", "q0", "q_window", "tcs"):
+        for name in ("b_field", "eps", "q0", "q_window", "tcs", "jop"):
             a = getattr(self, name)
             if a is None or a.size == 0:
                 setattr(s, name, None)
@@ -157,7 +160,7 @@ def case1_model(correlations: bool = False) -> Model:
     stab = 2.0846
     solids = (
         SolidModel(SOLID_STRAND_MIXED, (MAT_CU_NIST, MAT_NB3SN), (stab, 1.0), float(np.array([stab, 1.0]).sum()),
-                   rrr=197.71, tc0m=16.22, bc20m=32.35, heated=True),
+                   rrr=197.71, tc0m=16.22, bc20m=32.35, heated=True, c0=1.21508e11),
         SolidModel(SOLID_JACKET, (MAT_SS, MAT_GE), (3.0699e-4, 2.7966e-4), 3.0699e-4 + 2.7966e-4),
     )
     if correlations:

@@ -17,7 +17,8 @@ from typing import Optional, Sequence
 import numpy as np
 
 from .model import (FP_BETA, FP_CP, FP_CV, FP_H, FP_K, FP_KAPPA, FP_MU, FP_PRANDTL, FP_RHO, FP_SOUND, SOLID_JACKET,
-                    SOLID_STRAND_MIXED, FluidTable, Model, table_lookup)
+                    SOLID_STACK, SOLID_STRAND_MIXED, FluidTable, Model, table_lookup)
+from .correlations import channel_friction_factor
 from .problem import Topology
 
 CHAN_COLUMNS = (
@@ -32,26 +33,9 @@ _ALIAS_ORDER = (FP_BETA, FP_KAPPA, FP_PRANDTL, FP_MU, FP_H, FP_CP, FP_CV, FP_SOU
 
 
 def nodal_friction_factor(model: Model, topo: Topology, j: int, reynolds: np.ndarray) -> np.ndarray:
-    """`Channel.eval_friction_factor(reynolds, nodal=True)` (channel.py:1119-1138) for the flags on the device."""
-    re = np.fabs(reynolds)
-    flag = model.ch_ifriction[j]
-    if flag == -99:
-        total = np.ones(re.shape)
-    elif flag == 124:
-        f = np.array((0.316 * re ** -0.25) / 4.0)
-        f[re > 1e4] = 2.21 * re[re > 1e4] ** (-0.4) / 4.0
-        total = np.maximum(np.zeros(re.shape), f)
-    elif flag == 122:
-        rough, dh = (model.ch_roughness[j] if model.ch_roughness else 0.0), topo.ch_dh[j]
-        f = ((-1.8 * np.log10((rough / dh / 3.7) ** 1.11 + (6.9 / re))) ** -2) / 4.0
-        err, it = 10.0 * np.ones(re.shape), 0
-        while err.max() > 1e-5 and it < 100:
-            fn = ((-2.0 * np.log10((rough / dh / 3.7) + (2.51 / re / np.sqrt(f)))) ** -2) / 4.0
-            err, f, it = abs(f - fn), fn, it + 1
-        total = np.maximum(np.zeros(re.shape), f)
-    else:
-        raise ValueError(f"IFRICTION {flag} is not implemented")
-    return total * model.ch_friction_mult[j]
+    """`Channel.eval_friction_factor(reynolds, nodal=True)` (channel.py:1119-1138): every IFRICTION flag the
+    device accepts (`correlations.friction_factor`)."""
+    return channel_friction_factor(model, topo, j, reynolds)
 
 
 def channel_table(topo: Topology, model: Model, tab: FluidTable, j: int, zcoord, v, p, t) -> np.ndarray:
@@ -78,7 +62,7 @@ def save_properties(f_path: str, topo: Topology, model: Model, tables: Sequence[
     x = np.asarray(sysvar, dtype=np.float64).reshape(N, d)
     chan_ids = chan_ids or [f"CHAN_{j + 1}" for j in range(M)]
     if solid_ids is None:
-        names = {SOLID_STRAND_MIXED: "STR_MIX", SOLID_JACKET: "Z_JACKET"}
+        names = {SOLID_STRAND_MIXED: "STR_MIX", SOLID_JACKET: "Z_JACKET", SOLID_STACK: "STACK"}
         count, solid_ids = {}, []
         for s in model.solids:
             nm = names.get(s.kind, "STR_STAB")
@@ -97,7 +81,7 @@ def save_properties(f_path: str, topo: Topology, model: Model, tables: Sequence[
             a, header = np.stack([zcoord, temp], axis=1), "zcoord (m)\ttemperature (K)"
         else:
             bf = np.linspace(b_field[l, 0], b_field[l, 1], N)             # solid_component.py:383-388
-            if s.kind == SOLID_STRAND_MIXED:
+            if s.kind in (SOLID_STRAND_MIXED, SOLID_STACK):     # every strand that is not a stabiliser
                 tcs = np.zeros(N) if t_cur_sharing is None else t_cur_sharing[l]
                 a = np.stack([zcoord, temp, bf, tcs], axis=1)
                 header = "zcoord (m)\ttemperature (K)\tB_field (T)\tT_cur_sharing (K)"
@@ -153,7 +137,7 @@ def save_simulation_space(f_path: str, topo: Topology, model: Model, tables: Seq
     zg = (zcoord[:-1] + zcoord[1:]) / 2.0 if zcoord_gauss is None else zcoord_gauss
     chan_ids = chan_ids or [f"CHAN_{j + 1}" for j in range(M)]
     if solid_ids is None:
-        names = {SOLID_STRAND_MIXED: "STR_MIX", SOLID_JACKET: "Z_JACKET"}
+        names = {SOLID_STRAND_MIXED: "STR_MIX", SOLID_JACKET: "Z_JACKET", SOLID_STACK: "STACK"}
         count, solid_ids = {}, []
         for s in model.solids:
             nm = names.get(s.kind, "STR_STAB")
@@ -231,7 +215,7 @@ class TimeEvolutionWriter:
         self.ch_forward = list(ch_forward) if ch_forward is not None else [bool(f) for f in topo.ch_forward]
         self.chan_ids = list(chan_ids) if chan_ids else [f"CHAN_{j + 1}" for j in range(topo.n_ch)]
         if solid_ids is None:
-            names = {SOLID_STRAND_MIXED: "STR_MIX", SOLID_JACKET: "Z_JACKET"}
+            names = {SOLID_STRAND_MIXED: "STR_MIX", SOLID_JACKET: "Z_JACKET", SOLID_STACK: "STACK"}
             count, solid_ids = {}, []
             for s in model.solids:
                 nm = names.get(s.kind, "STR_STAB")

@@ -55,7 +55,7 @@ def topology_of(conductor) -> Topology:
         ch_area=tuple(float(f.channel.inputs["CROSSECTION"]) for f in fluids),
         ch_dh=tuple(float(f.channel.inputs["HYDIAMETER"]) for f in fluids),
         ch_forward=tuple(f.channel.flow_dir[0] == "forward" for f in fluids),
-        ch_intial=tuple(abs(int(f.coolant.operations["INTIAL"])) for f in fluids),
+        ch_intial=tuple(_positive_intial(f) for f in fluids),
         sol_area=tuple(float(s.inputs["CROSSECTION"]) for s in solids),
         sol_costeta=tuple(float(s.inputs["COSTETA"]) for s in solids),
         ff=tuple((fidx[id(i.comp_1)], fidx[id(i.comp_2)]) for i in itf.fluid_fluid),
@@ -67,6 +67,23 @@ def topology_of(conductor) -> Topology:
         delta_p_min=float(conductor.Delta_p_min), k_loc=float(conductor.k_loc),
         lambda_v=float(conductor.lambda_v), theta=float(conductor.theta_method), method=method,
     )
+
+
+def _positive_intial(f) -> int:
+    """INTIAL in {1, 2, 3}.  The negative flags make the reference read time-interpolated boundary values from the
+    EXTERNAL_FLOW workbook inside impose_pressure_drop / impose_inl_p_out_v / impose_inl_v_out_p
+    (fluid_component.py:255-565, `get_from_xlsx` branches) -- not implemented here, and not to be confused with
+    their positive twins, so they are refused."""
+    flag = int(f.coolant.operations["INTIAL"])
+    if flag not in (1, 2, 3):
+        raise ValueError(f"{f.identifier}: INTIAL = {flag}: only 1, 2, 3 are implemented (negative flags take their "
+                         "boundary values from the EXTERNAL_FLOW file at every step)")
+    return flag
+
+
+# boundary values each hydraulic mode reads (fluid_component.py:279-287, 383-391, 487-495 + the temperature rows)
+_BC_KEYS_READ = {1: ("PREINL", "PREOUT", "TEMINL", "TEMOUT"), 2: ("PREINL", "MDTOUT", "TEMINL", "TEMOUT"),
+                 3: ("MDTIN", "PREOUT", "TEMINL", "TEMOUT")}
 
 
 def pack(conductor, environment, qsource, num_step: int, topo: Topology) -> StepArrays:
@@ -94,7 +111,10 @@ def pack(conductor, environment, qsource, num_step: int, topo: Topology) -> Step
         op = f.coolant.operations
         for q, key in ((BC_PINL, "PREINL"), (BC_POUT, "PREOUT"), (BC_TINL, "TEMINL"), (BC_TOUT, "TEMOUT"),
                        (BC_MDTIN, "MDTIN"), (BC_MDTOUT, "MDTOUT")):
-            fl_bc[q, j] = op.get(key, 0.0) if hasattr(op, "get") else op[key]
+            if key in _BC_KEYS_READ[topo.ch_intial[j]]:
+                fl_bc[q, j] = op[key]                       # a missing key fails loudly (KeyError), like the reference
+            else:
+                fl_bc[q, j] = op[key] if key in op else 0.0   # never read in this mode
     sol_gauss = np.empty((N_SOL_GAUSS, S, E))
     sol_q = np.zeros((2, S, E, 2))
     for l, s in enumerate(solids):

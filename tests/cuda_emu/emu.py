@@ -20,7 +20,7 @@ class StepDev(C.Structure):
                             "sysvar", "sysvar_new", "syslod", "gm", "k123", "spill",
                             "norm_solution", "norm_change", "eqteig")] + [
         ("status", c_ip), ("cap_sysmat", c_dp), ("cap_known", c_dp),
-        ("norm_leaf", c_ip), ("norm_prog", c_ip), ("norm_part", c_dp), ("n_leaves", C.c_int), ("n_prog", C.c_int), ("fwd_split", C.c_int), ("smap", C.c_void_p), ("s_slots", C.c_int)]
+        ("norm_leaf", c_ip), ("norm_prog", c_ip), ("norm_part", c_dp), ("n_leaves", C.c_int), ("n_prog", C.c_int), ("smap", C.c_void_p), ("s_slots", C.c_int)]
 
 
 _LIB = None
@@ -81,7 +81,7 @@ def emu_step(topo, arr, capture=False, fast=None, split=True):
     }
     for k, a in outs.items():
         setattr(p, k, a.ctypes.data_as(c_dp))
-    status = np.full(B, 12345, dtype=np.int32)
+    status = np.zeros(B, dtype=np.int32)      # sticky on the device: a step only writes a failure
     p.status = status.ctypes.data_as(c_ip)
     if capture:
         outs["cap_sysmat"] = np.zeros((4 * d - 1, total, B))

@@ -13,7 +13,7 @@ extern "C" int osc2_emu_step(const osc2_topology *tp, const StepDev *p, int fast
     std::vector<double> part(leaves.size() / 2 * 3 * (size_t)q.d * q.B, std::nan(""));
     q.norm_leaf = leaves.data(); q.norm_prog = prog.data(); q.norm_part = part.data();
     q.n_leaves = (int)(leaves.size() / 2); q.n_prog = (int)prog.size();
-    q.fwd_split = split;
+    (void)split;
     std::vector<unsigned char> smap;
     q.s_slots = osc2_build_smap(*tp, smap);
     q.smap = smap.data();

@@ -141,42 +141,6 @@ def test_model_validation_rejects_unimplemented_flags():
             bs.set_model(bad, [synthetic_helium_table()])
 
 
-@pytest.mark.parametrize("correlations", [False, True, "radiative"])
-@pytest.mark.parametrize("batch", [9, 70])
-def test_fused_advance_is_bit_identical_to_separate_kernels(correlations, batch, monkeypatch):
-    """osc2_advance: the fused K_PG kernel (properties -> row records in shared memory) against the
-    separate K_P + K_G launches.  Same device arithmetic, so states, SYSLOD history, norms and the
-    materialised coefficient arrays must agree bit for bit (ragged last tile of 32 included)."""
-    from opensc2_b200.batch import BatchedStep
-
-    import dataclasses
-
-    n, dt = 37, 0.1
-    topo, model, tab, _arr, sweep = _setup(correlations is True, n, batch, seed=21)
-    arr = consistent_initial_state(topo, model, tab, n, batch, seed=21, dt=dt)
-    if correlations == "radiative":      # a constant radiative exchange (-3) on the strand-jacket interface
-        model = dataclasses.replace(model, ss=((-3, 7.0, 1.5, 0.0, 0.0, 0.0),))
-        arr.peri_ss_nodal = np.full((batch, 1, n), 0.03)
-        arr.sysvar.reshape(batch, n, topo.ndf)[:, :, -1] += 3.0
-    results = {}
-    for fused in ("0", "1"):
-        monkeypatch.setenv("OSC2_FUSED_OPCOND", fused)
-        with BatchedStep(topo, batch, n) as bs:
-            bs.set_model(model, [tab])
-            bs.upload_sweep(sweep)
-            bs.upload_state(arr.sysvar, arr.syslod)
-            bs.upload_geometry(arr)
-            bs.set_capture(True)                         # also materialises the coefficient arrays
-            for k in range(1, 5):
-                bs.advance(9.8 + k * dt, dt, k)
-            bs.synchronize()
-            sv, sl, st = bs.download_state()
-            results[fused] = dict(sysvar=sv, syslod=sl, status=st, **bs.download_diagnostics(), **bs.download_step_inputs())
-    for key, v in results["0"].items():
-        assert_bits(results["1"][key], v, key)
-    assert np.all(results["1"]["status"] == 0)
-
-
 def test_case2_flavoured_model_colebrook_aluminium_generic_kernels():
     """d = 9 (generic shared-memory kernels): IFRICTION 122 with its array-wide iteration count,
     124, Nusselt 1 / 212, aluminium + copper stabilisers, SS jacket, Kapitza-limited HTCs.
@@ -298,17 +262,15 @@ def test_full_size_mesh_batch_order_invariance():
     assert_bits(outs[0][1], outs[1][1], "norm_change")
 
 
-@pytest.mark.parametrize("fused", ["0", "1"])
-def test_case3_flavoured_model_radiative_exchange(fused, monkeypatch):
+def test_case3_flavoured_model_radiative_exchange():
     """d = 7: radiation between two jackets (HTC_choice 3, nodal HTC, explicit source on both solids), a
     constant contact, convection to the environment; K_P vs oracle (sources bit-exact) and two chained
-    steps.  The fused K_PG kernel does not apply to d = 7 (generic path), so both settings must agree."""
+    steps."""
     from opensc2_b200.batch import BatchedStep
     from opensc2_b200.model import case3_mini_model
     from opensc2_b200.problem import case3_mini_topology
     from oracle import oracle as O
 
-    monkeypatch.setenv("OSC2_FUSED_OPCOND", fused)
     n, batch, dt = 21, 5, 0.1
     topo, model, tab = case3_mini_topology(), case3_mini_model(), synthetic_helium_table()
     arr = consistent_initial_state(topo, model, tab, n, batch, seed=6, dt=dt)

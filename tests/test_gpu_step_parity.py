@@ -58,25 +58,6 @@ def test_batch_matches_oracle(label, topo, n, batch):
         assert_bits(out[key], ref[key], f"{label}:{key}")
 
 
-@pytest.mark.parametrize("mode", ["1", "2", "3"])
-@pytest.mark.parametrize("intial,n,batch", [(1, 37, 64), (3, 21, 10)])
-def test_experimental_forward_sweeps_are_bit_exact(mode, intial, n, batch, monkeypatch):
-    """The opt-in K_F variants (OSC2_FWD_MODE: 1 split warps, 2 sixteen lanes, 3 node-pipelined) produce
-    the bits of the oracle, full and ragged warps."""
-    from opensc2_b200.batch import BatchedStep
-    from oracle import oracle as O
-
-    monkeypatch.setenv("OSC2_FWD_MODE", mode)
-    topo = case1_topology(intial)
-    arr = synthetic_step_arrays(topo, n, batch=batch, seed=100 + n, exact_squares=False)
-    with BatchedStep(topo, batch, n) as bs:
-        out = bs.run(arr)
-    ref = O.step(topo, arr)
-    assert np.all(out["status"] == 0)
-    for key in KEYS:
-        assert_bits(out[key], ref[key], f"mode{mode}:{key}")
-
-
 def test_chained_steps_match_oracle():
     """Five consecutive steps (state and SYSLOD history carried on the device)."""
     from opensc2_b200.batch import BatchedStep

@@ -27,7 +27,7 @@ def _batched(arr):
 @pytest.mark.parametrize("name", ["case1_pdrop_n21", "case1_pinl_vout_first_step_n17",
                                   "case1_vinl_pout_cn_refined_n12", "case1_min_mesh_n4",
                                   "case3_backward_n15", "case3_rectangular_env_n9"])
-@pytest.mark.parametrize("fast,split", [(False, 0), (True, 0), (True, 1), (True, 2)])
+@pytest.mark.parametrize("fast,split", [(False, 0), (True, 0)])
 def test_emulated_kernels_match_reference_fixture(name, fast, split):
     topo, arr, ref = load_golden(name)
     out = emu.emu_step(topo, _batched(arr), capture=True, fast=fast, split=split)
@@ -36,55 +36,6 @@ def test_emulated_kernels_match_reference_fixture(name, fast, split):
     assert_bits(out["known"][0], ref["known"], f"{name}:known")
     for key in KEYS:
         assert_bits(out[key][0], ref[key], f"{name}:{key}")
-
-
-@pytest.mark.parametrize("name", ["case1_pdrop_n21", "case1_pinl_vout_first_step_n17", "case1_min_mesh_n4"])
-def test_emulated_pipelined_sweep_matches_reference_fixture(name):
-    """OSC2_FWD_MODE=3 (step_kernels_pipe.cuh: rounds of node n and of node n+1 merged), no capture."""
-    topo, arr, ref = load_golden(name)
-    out = emu.emu_step(topo, _batched(arr), fast=True, split=3)
-    assert out["status"][0] == 0
-    for key in KEYS:
-        assert_bits(out[key][0], ref[key], f"{name}:{key}")
-
-
-@pytest.mark.parametrize("intial,n,batch", [(1, 9, 8), (2, 7, 6), (3, 23, 5)])
-def test_emulated_pipelined_sweep_batches(intial, n, batch):
-    """Full and ragged warps, every boundary-condition mode, against the oracle."""
-    topo = case1_topology(intial)
-    arr = synthetic_step_arrays(topo, n, batch=batch, seed=40 + n)
-    out = emu.emu_step(topo, arr, fast=True, split=3)
-    ref = O.step(topo, arr)
-    assert np.all(out["status"] == 0)
-    for key in KEYS:
-        assert_bits(out[key], ref[key], key)
-
-
-def test_emulated_batch_ragged_tail():
-    """B not a multiple of the conductors-per-warp; every slot matches the oracle."""
-    topo = case1_topology(2)
-    arr = synthetic_step_arrays(topo, 7, batch=6, seed=5)
-    assert np.array_equal(emu.emu_step(topo, arr, fast=False)["sysvar"], emu.emu_step(topo, arr, fast=True)["sysvar"])
-    out = emu.emu_step(topo, arr)
-    ref = O.step(topo, arr)
-    assert np.all(out["status"] == 0)
-    for key in KEYS:
-        assert_bits(out[key], ref[key], key)
-
-
-def test_emulated_case2_sixty_four_lanes():
-    topo, arr, ref = load_golden("case2_first_step_n5")
-    out = emu.emu_step(topo, _batched(arr))
-    for key in KEYS:
-        assert_bits(out[key][0], ref[key], key)
-
-
-def test_emulated_singular_status():
-    from helpers import singular_case
-
-    topo, arr = singular_case()
-    out = emu.emu_step(topo, arr)
-    assert list(out["status"]) == [0, -9]
 
 
 @pytest.mark.parametrize("n", [129, 201, 300, 1100])
