@@ -49,6 +49,48 @@ class Deck:
     solid_ops: List[Dict[str, object]]     # per solid: BISS, BOSS, EPS, IQFUN, Q0, XQBEG, XQEND, TQBEG, TQEND, INTIAL, TEMINL, TEMOUT
     peri: Dict[str, np.ndarray]            # constant contact perimeters per interface list: ff (2, nff), fs, ss, es
     notes: List[str] = field(default_factory=list)
+    solid_inputs: List[Dict[str, object]] = field(default_factory=list)   # raw input-sheet column of every solid
+    ss_view_factor: List[float] = field(default_factory=list)             # per solid-solid interface
+
+
+def deck_to_dict(d: "Deck") -> dict:
+    """Plain-data image of a Deck (JSON-able): lets a parsed deck travel without its workbooks."""
+    import dataclasses
+
+    def clean(x):
+        if isinstance(x, dict):
+            return {k: clean(v) for k, v in x.items()}
+        if isinstance(x, (list, tuple)):
+            return [clean(v) for v in x]
+        if isinstance(x, np.ndarray):
+            return x.tolist()
+        if isinstance(x, float) and x == float("inf"):
+            return "inf"
+        if isinstance(x, (np.floating, np.integer)):
+            return x.item()
+        return x
+
+    return clean({"topology": dataclasses.asdict(d.topology), "model": dataclasses.asdict(d.model), "chan_ids": d.chan_ids,
+                  "solid_ids": d.solid_ids, "length": d.length, "n_elems": d.n_elems, "mesh": d.mesh, "t_env": d.t_env,
+                  "fl_bc": d.fl_bc, "solid_ops": d.solid_ops, "peri": d.peri,
+                  "transient": {k: v for k, v in d.transient.items() if isinstance(v, (int, float, str))}, "notes": d.notes,
+                  "solid_inputs": d.solid_inputs, "ss_view_factor": d.ss_view_factor})
+
+
+def deck_from_dict(x: dict, folder: str = "") -> "Deck":
+    def tup(v):
+        return tuple(tup(i) for i in v) if isinstance(v, list) else (float("inf") if v == "inf" else v)
+
+    t = {k: tup(v) for k, v in x["topology"].items()}
+    m = dict(x["model"])
+    solids = tuple(SolidModel(**{k: tup(v) for k, v in s.items()}) for s in m.pop("solids"))
+    model = Model(solids=solids, **{k: tup(v) for k, v in m.items()})
+    peri = {k: np.array(v, dtype=np.float64).reshape((2, -1) if k == "ff" else (-1,)) for k, v in x["peri"].items()}
+    return Deck(folder=folder, topology=Topology(**t), model=model, chan_ids=list(x["chan_ids"]), solid_ids=list(x["solid_ids"]),
+                length=float(x["length"]), n_elems=int(x["n_elems"]), mesh=dict(x.get("mesh", {})), transient=dict(x["transient"]),
+                t_env=float(x["t_env"]), fl_bc=np.array(x["fl_bc"], dtype=np.float64), solid_ops=list(x["solid_ops"]), peri=peri,
+                notes=list(x.get("notes", [])), solid_inputs=list(x.get("solid_inputs", [])),
+                ss_view_factor=list(x.get("ss_view_factor", [])))
 
 
 def _objects(sheet_rows, kind):
@@ -193,6 +235,7 @@ def load_deck(folder: str, conductor: int = 1, legacy_no_field: bool = True,
     ff, fs, ss, es = [], [], [], []
     m_fs, m_ff, m_ss, m_ss_rad, m_es = [], [], [], [], []
     p_ff, p_fs, p_ss, p_es = [], [], [], []
+    v_ss: List[float] = []
     phi_conv = float(_get(cin, "Phi_conv", default=1.0))
     for j, a in enumerate(chan_ids):
         for l, b in enumerate(solid_ids):
@@ -209,7 +252,7 @@ def load_deck(folder: str, conductor: int = 1, legacy_no_field: bool = True,
             b = solid_ids[l2]
             if abs(at(flag, a, b)) == 1:
                 ch = int(at(choice, a, b))
-                ss.append((l, l2)); p_ss.append(at(perim, a, b))
+                ss.append((l, l2)); p_ss.append(at(perim, a, b)); v_ss.append(at(view, a, b))
                 m_ss.append((ch, at(htc, a, b), at(mlt, a, b, 1.0), at(thick, a, b), at(thick, b, a), at(rcont, a, b)))
                 if ch == 3:
                     da, db = solids[l][2], solids[l2][2]
@@ -253,4 +296,5 @@ def load_deck(folder: str, conductor: int = 1, legacy_no_field: bool = True,
     return Deck(folder=folder, topology=topo, model=model, chan_ids=chan_ids, solid_ids=solid_ids,
                 length=float(_get(cin, "ZLENGTH", "XLENGTH")), n_elems=int(grid["NELEMS"]),
                 mesh={k: float(v) for k, v in grid.items() if isinstance(v, float)}, transient=transient,
-                t_env=float(env.get("Temperature", 300.0)), fl_bc=fl_bc, solid_ops=solid_ops, peri=peri, notes=notes)
+                t_env=float(env.get("Temperature", 300.0)), fl_bc=fl_bc, solid_ops=solid_ops, peri=peri, notes=notes,
+                solid_inputs=[dict(sd[2]) for sd in solids], ss_view_factor=v_ss)

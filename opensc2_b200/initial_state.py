@@ -237,12 +237,30 @@ class InitialState:
     rho: np.ndarray          # (M, N) nodal coolant density at t = 0
 
 
-def initial_state(deck, tables: Sequence[FluidTable], zcoord: np.ndarray, fl_bc: np.ndarray | None = None) -> InitialState:
-    """Deck -> initial state of ONE conductor; `fl_bc` overrides the deck's boundary values (sweeps)."""
+def initial_state(deck, tables: Sequence[FluidTable], zcoord: np.ndarray, fl_bc: np.ndarray | None = None,
+                  legacy_intial2: bool = False) -> InitialState:
+    """Deck -> initial state of ONE conductor; `fl_bc` overrides the deck's boundary values (sweeps).
+
+    `legacy_intial2`: the shipped TDD_examples decks say INTIAL = 2 in an older meaning -- inlet pressure, inlet
+    temperature and mass flow are known, gen_flow computes the OUTLET pressure, and the transient then imposes inlet
+    mass flow + that outlet pressure (HEAD's INTIAL = 3 rows).  Evidence: golden CASE_3 CHAN_2 keeps p(outlet) =
+    260 115.741 Pa = what gen_flow's INTIAL = 2 branch yields from PREINL = 3.0e5 Pa with CoolProp-exact nitrogen
+    properties (profiles/r2_coolant_table_validation.txt), while PREOUT of the deck is 2.6e5.  With the flag, the flow
+    is generated with HEAD's INTIAL = 2 branch (MDTOUT := MDTIN) and everything after it uses INTIAL = 3."""
+    from dataclasses import replace
+
     topo, model = deck.topology, deck.model
     bc0 = deck.fl_bc if fl_bc is None else fl_bc
     peri_open = deck.peri["ff"][0] if len(topo.ff) else np.zeros(0)
-    bc = gen_flow(topo, model, tables, bc0, deck.length, peri_open)
+    if legacy_intial2:
+        if any(i != 3 for i in topo.ch_intial):
+            raise ValueError("legacy_intial2 expects the deck loaded with intial_override=3")
+        bc0 = np.array(bc0, dtype=np.float64, copy=True)
+        bc0[BC_MDTOUT] = bc0[BC_MDTIN]
+        bc = gen_flow(replace(topo, ch_intial=(2,) * topo.n_ch), model, tables, bc0, deck.length, peri_open)
+        bc[BC_MDTOUT] = bc[BC_MDTIN]                # signed like MDTIN from here on
+    else:
+        bc = gen_flow(topo, model, tables, bc0, deck.length, peri_open)
     v, p, t, rho = coolant_initial_state(topo, model, tables, bc, zcoord, deck.length)
     ts = solid_initial_temperature(topo, deck.solid_ops, deck.peri["fs"], t, zcoord, deck.length)
     return InitialState(zcoord=zcoord, fl_bc=bc, sysvar=pack_sysvar(v, p, t, ts), rho=rho)

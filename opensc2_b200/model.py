@@ -259,6 +259,33 @@ def synthetic_helium_table(n_p: int = 65, n_t: int = 129) -> FluidTable:
     return FluidTable(float(p[0]), float(p[1] - p[0]), float(t[0]), float(t[1] - t[0]), props)
 
 
+def helium_gas_table(n_p: int = 65, n_t: int = 161, p_range=(0.5e5, 4.0e5), t_range=(20.0, 60.0)) -> FluidTable:
+    """Stand-in for gaseous helium around 30 K / 1-2.5 bar (CASE_3 CHAN_1): ideal gas with a constant second virial
+    coefficient, cp = 5/2 R, power-law viscosity, constant Prandtl number, anchored on the values the reference's
+    golden CASE_3 CHAN_1.tsv prints at 30 K (mu 4.675e-6 Pa s, Pr 0.723, h 160 370 J/kg).  NOT CoolProp: within about
+    1 % of real helium here, which is all a solver test needs -- both sides of every parity test read the same table."""
+    rs = 8.3144598 / 4.002602e-3
+    p = np.linspace(p_range[0], p_range[1], n_p)
+    t = np.linspace(t_range[0], t_range[1], n_t)
+    P, T = np.meshgrid(p, t, indexing="ij")
+    bvir = 2.4e-6 / 4.002602e-3                   # m^3/kg, B(30 K) ~ +2.4 cm^3/mol
+    rho = P / (rs * T + bvir * P)                 # v = R T / p + B
+    cp, cv = 2.5 * rs * np.ones_like(T), 1.5 * rs * np.ones_like(T)
+    mu = 4.675e-6 * (T / 30.0) ** 0.6286
+    props = np.empty((OSC2_N_FLUID_PROPS, n_p, n_t))
+    props[FP_BETA] = (rs / P) * rho               # (1/v) (dv/dT)_p
+    props[FP_KAPPA] = (rs * T / P ** 2) * rho     # -(1/v) (dv/dp)_T
+    props[FP_PRANDTL] = 0.723
+    props[FP_RHO] = rho
+    props[FP_MU] = mu
+    props[FP_H] = cp * T + bvir * P + 4580.0
+    props[FP_CP] = cp
+    props[FP_CV] = cv
+    props[FP_SOUND] = np.sqrt(cp / cv * rs * T) * (1.0 + bvir * rho)
+    props[FP_K] = mu * cp / 0.723
+    return FluidTable(float(p[0]), float(p[1] - p[0]), float(t[0]), float(t[1] - t[0]), props)
+
+
 def synthetic_sweep(topo, model: Model, n_nodes: int, batch: int, seed: int = 20261019, length: float = 10.0,
                     with_tcs: bool = True) -> Sweep:
     """Swept scalars of SURVEY.md 8(d): Q0 ~ U[50, 1000] W/m on x in [1, 3] m for t in [10, 20] s,

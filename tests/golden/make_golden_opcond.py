@@ -38,7 +38,12 @@ ALIAS_TO_PROP = {"isobaric_expansion_coefficient": FP_BETA, "isothermal_compress
                  "Cvmass": FP_CV, "speed_of_sound": FP_SOUND, "conductivity": FP_K}
 
 
-def reference_operating_conditions(topo, model, tab, sweep, sysvar, n_nodes, time, b=0, length=10.0, peri_ss_nodal=None):
+def reference_operating_conditions(topo, model, tab, sweep, sysvar, n_nodes, time, b=0, length=10.0, peri_ss_nodal=None,
+                                   tables=None, fluid_names=None, zcoord=None, solid_inputs=None, ss_view_factor=None):
+    """`tables` / `fluid_names`: one table per fluid index of `model.ch_fluid` and the name the reference passes to
+    PropsSI (default: the single table `tab`, helium); `zcoord`: mesh (default uniform over `length`);
+    `solid_inputs` / `ss_view_factor`: raw deck columns of the solids (jacket emissivities and perimeters) and the view
+    factor of every solid-solid interface, for radiative interfaces of a real deck (default: CASE3_MINI_JACKETS)."""
     H._import_reference()
     import coolant as coolant_mod
     from channel import Channel
@@ -48,8 +53,12 @@ def reference_operating_conditions(topo, model, tab, sweep, sysvar, n_nodes, tim
     from strand_mixed_component import StrandMixedComponent
     from strand_stabilizer_component import StrandStabilizerComponent
 
+    tables = [tab] if tables is None else list(tables)
+    fluid_names = ["He"] * len(tables) if fluid_names is None else list(fluid_names)
+    by_name = {nm: t for nm, t in zip(fluid_names, tables)}
+
     def props_si(alias, _t, temperature, _p, pressure, _fluid):
-        return table_lookup(tab, ALIAS_TO_PROP[alias], pressure, temperature)
+        return table_lookup(by_name[_fluid], ALIAS_TO_PROP[alias], pressure, temperature)
 
     coolant_mod.PropsSI = props_si
     # the reference pins scipy == 1.8.0 (requirements.txt), whose CODATA-2018 table gives
@@ -65,7 +74,7 @@ def reference_operating_conditions(topo, model, tab, sweep, sysvar, n_nodes, tim
                    total_speed_of_sound="speed_of_sound", total_thermal_conductivity="conductivity")
     M, S, d, N = topo.n_ch, topo.n_sol, topo.ndf, n_nodes
     x = sysvar[b].reshape(N, d)
-    zcoord = np.linspace(0.0, length, N)
+    zcoord = np.linspace(0.0, length, N) if zcoord is None else np.asarray(zcoord, dtype=np.float64)
 
     cond = object.__new__(Conductor)
     cond.identifier = "CONDUCTOR_1"
@@ -82,7 +91,7 @@ def reference_operating_conditions(topo, model, tab, sweep, sysvar, n_nodes, tim
     for j in range(M):
         f = types.SimpleNamespace(identifier=f"CHAN_{j + 1}")
         co = object.__new__(Coolant)
-        co.type = "He"
+        co.type = fluid_names[model.ch_fluid[j]]
         co.inputs = {"CROSSECTION": topo.ch_area[j], "HYDIAMETER": topo.ch_dh[j]}
         co.dict_node_pt = {"velocity": x[:, j].copy(), "pressure": x[:, M + j].copy(), "temperature": x[:, 2 * M + j].copy()}
         co.dict_Gauss_pt = {}
@@ -202,14 +211,22 @@ def reference_operating_conditions(topo, model, tab, sweep, sysvar, n_nodes, tim
     jackets_all = [s for s in solids if s.name == "Z_JACKET"]
     has_rad = any(abs(c[0]) == 3 for c in model.ss)
     if has_rad:
-        jk = CASE3_MINI_JACKETS
-        for i, s in enumerate(jackets_all[:2]):
-            s.inputs.update(Emissivity=jk["emissivity"][i], Outer_perimeter=jk["outer_perimeter"][i],
-                            Inner_perimeter=jk["inner_perimeter"][i])
+        if solid_inputs is None:
+            jk = CASE3_MINI_JACKETS
+            for i, s in enumerate(jackets_all[:2]):
+                s.inputs.update(Emissivity=jk["emissivity"][i], Outer_perimeter=jk["outer_perimeter"][i],
+                                Inner_perimeter=jk["inner_perimeter"][i])
+        else:
+            for l, s in enumerate(solids):
+                if s.name == "Z_JACKET":
+                    s.inputs.update(Emissivity=float(solid_inputs[l].get("Emissivity", 0.0)),
+                                    Outer_perimeter=float(solid_inputs[l].get("Outer_perimeter", 1.0)),
+                                    Inner_perimeter=float(solid_inputs[l].get("Inner_perimeter", 0.5)))
         cond.dict_df_coupling["contact_perimeter"] = frame(0.0)
         for k, (la, lb) in enumerate(topo.ss):
             if abs(model.ss[k][0]) == 3:
-                view.at[solids[la].identifier, solids[lb].identifier] = jk["view_factor"]
+                view.at[solids[la].identifier, solids[lb].identifier] = (CASE3_MINI_JACKETS["view_factor"] if ss_view_factor is None
+                                                                         else ss_view_factor[k])
         cond.dict_interf_peri = {"sol_sol": {"nodal": {
             f"{solids[la].identifier}_{solids[lb].identifier}": peri_ss_nodal[b, k].copy() for k, (la, lb) in enumerate(topo.ss)}}}
         for s in jackets_all:                      # conductor.py:2759-2770

@@ -1,0 +1,42 @@
+"""CPU side of the transient pins: the host pipeline (deck image -> mesh -> gen_flow -> initial state -> sweep ->
+geometry) and the oracle's time loop against the snapshots the UNMODIFIED reference functions produced over the whole
+transient (tests/golden/ref_transient.py).  The device runs the same comparison in tests/test_gpu_transients.py."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import GOLDEN_DIR
+from transient_common import deck_of, field_drift, legacy_of, oracle_transient, sweep_kwargs, tables_of
+
+
+@pytest.mark.parametrize("tag,n_steps", [("case1", 1000), ("case1_current", 300), ("case3", 2000)])
+def test_oracle_loop_follows_the_reference_loop(tag, n_steps):
+    from opensc2_b200.runner import TransientSetup
+
+    z = np.load(os.path.join(GOLDEN_DIR, f"transient_{tag}.npz"))
+    deck = deck_of(tag)
+    tr = TransientSetup(deck, tables_of(tag), 1, legacy_intial2=legacy_of(tag), **sweep_kwargs(tag))
+    topo, M, N = deck.topology, deck.topology.n_ch, tr.zcoord.shape[0]
+    assert np.array_equal(tr.zcoord, z["zcoord"]) and np.array_equal(tr.fl_bc[0], z["fl_bc"])
+    assert np.array_equal(tr.sysvar0[0], z["sysvar"][0])
+    steps = [int(s) for s in z["steps"]]
+    assert steps[-1] == n_steps
+    snaps = oracle_transient(tr, n_steps, tcs=z["tcs"] if "tcs" in z.files else None, snapshot_every=steps[1] - steps[0])
+    worst_v = worst_pt = 0.0
+    for i, k in enumerate(steps[1:], start=1):
+        e = field_drift(snaps[k][0], z["sysvar"][i], N, topo)
+        worst_v, worst_pt = max(worst_v, e[:M].max()), max(worst_pt, e[M:].max())
+    assert worst_v <= 1e-6 and worst_pt <= 1e-6, (worst_v, worst_pt)   # measured: 2e-7 / 3.3e-7 (case1_current, during the slug)
+
+
+def test_the_transients_do_something():
+    """Sanity of the fixtures themselves: CASE_1's slug heats the strand by > 1 K at t = 20 s and the conductor is back
+    within 0.05 K of its start at t = 100 s; CASE_3's nitrogen channel warms up along the (backward) flow."""
+    z = np.load(os.path.join(GOLDEN_DIR, "transient_case1.npz"))
+    x = z["sysvar"].reshape(len(z["steps"]), 201, 8)
+    i20 = list(z["steps"]).index(200)
+    assert x[i20, :, 6].max() - x[0, :, 6].max() > 1.0 and abs(x[-1, :, 6].max() - x[0, :, 6].max()) < 0.05
+    z3 = np.load(os.path.join(GOLDEN_DIR, "transient_case3.npz"))
+    x3 = z3["sysvar"].reshape(len(z3["steps"]), 201, 13)
+    assert x3[-1, 0, 5] > x3[-1, -1, 5] + 5.0        # N2 (channel 2, T index 2M+1 = 5) enters at x = L, leaves warmer at x = 0
