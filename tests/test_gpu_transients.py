@@ -59,6 +59,15 @@ def test_transient_matches_the_reference_loop(tag):
     if res.margin_min is not None:
         sc = [l for l, s in enumerate(deck.model.solids) if s.kind == 0]
         assert np.all(np.isfinite(res.margin_min[:, sc]))
+    if tag == "case3":
+        # the device's end state against the reference's own SHIPPED result (TDD_examples/CASE_3/Solution/*.tsv):
+        # everything the (CoolProp-validated) nitrogen loop determines, tolerance 1e-5
+        from test_transient_host import CASE3_NITROGEN_SIDE, GOLDEN_TSV_TOL, golden_fields
+
+        x, gold = res.sysvar[0].reshape(N, topo.ndf), golden_fields("case3", deck)
+        worst = max(float(np.max(np.abs(x[:, q] / gold[q] - 1.0))) for q in CASE3_NITROGEN_SIDE)
+        _report("case3_vs_shipped_golden_tsv", [(steps[-1], worst, worst)])
+        assert worst <= GOLDEN_TSV_TOL
 
 
 def test_case2_transient_matches_the_oracle_loop():
@@ -127,7 +136,7 @@ def test_margin_diagnostic_is_the_minimum_of_tcs_minus_temperature():
     q0 = np.linspace(100.0, 900.0, 5)
     with Transient(deck, tables, 5, q0=q0, b_field=np.tile([5.0, 5.5], (5, 1)), i_op=np.linspace(10e3, 40e3, 5)) as tr:
         N, d, M = tr.zcoord.shape[0], deck.topology.ndf, deck.topology.n_ch
-        res = tr.run(max_steps=130, track_margin=True)
+        res = tr.run(max_steps=260, track_margin=True)          # t = 26 s: the slug (10-20 s) is over, the strand cools
         tcs_g, _ = tr.bs.download_tcs()
         tr.bs.eval_operating_conditions(tr.time[-1] + 0.1)         # margin of the FINAL state
         m = tr.bs.download_margin()
@@ -135,5 +144,5 @@ def test_margin_diagnostic_is_the_minimum_of_tcs_minus_temperature():
     tg = np.abs(x[:, :-1] + x[:, 1:]) / 2.0
     assert np.array_equal(m[:, 0], np.min(tcs_g[:, 0] - tg, axis=1))
     assert np.all(np.isinf(m[:, 1]))                                # the jacket holds no superconductor
-    assert np.all(res.margin_min[:, 0] <= m[:, 0] + 1e-12)          # the slug (10-20 s: steps 100-130) ate into the margin
+    assert np.all(res.margin_min[:, 0] < m[:, 0])                   # the slug ate into the margin, which has recovered since
     assert np.all(np.diff(res.margin_min[:, 0]) < 0)                # more current and more power: less margin
