@@ -325,6 +325,8 @@ int osc2_create(const osc2_topology *topo, int batch, int n_nodes, int device, o
     StepDev &p = h->p;
     memset(&p, 0, sizeof p);
     p.B = batch; p.N = h->N; p.E = h->E; p.M = h->M; p.S = h->S; p.d = h->d; p.NS = h->NS;
+    p.cpw = h->fast ? osc2_fast_cpw(h->d) : 1;
+    p.NT = h->fast ? (int)osc2_fast_tiles(h->d, batch) : batch;
     p.nff = topo->nff; p.nfs = topo->nfs; p.nss = topo->nss; p.nes = topo->nes;
     struct { const double **dst; size_t k; } ins[] = {
         {&p.dz, E}, {&p.fl_gauss, 9 * M * E}, {&p.fl_node, 4 * M}, {&p.fl_bc, 6 * M},
@@ -348,9 +350,9 @@ int osc2_create(const osc2_topology *topo, int batch, int n_nodes, int device, o
     rc = dev_alloc(h, &h->sysvar_a, h->total * B);
     if (!rc) rc = dev_alloc(h, &h->sysvar_b, h->total * B);
     if (!rc) rc = dev_alloc(h, &p.syslod, h->total * 2 * B);
-    if (!rc) rc = dev_alloc(h, &p.gm, E * (size_t)h->NS * B);
+    if (!rc) rc = dev_alloc(h, &p.gm, osc2_gm_doubles(h->d, h->M, h->S, h->fast, E, B));
     if (!rc) rc = dev_alloc(h, &p.k123, k123 * B);
-    if (!rc) rc = dev_alloc(h, &p.spill, N * d * (2 * d + 2) * B);
+    if (!rc) rc = dev_alloc(h, &p.spill, osc2_spill_doubles(h->d, h->fast, N, B));
     if (!rc) rc = dev_alloc(h, &p.norm_solution, d * B);
     if (!rc) rc = dev_alloc(h, &p.norm_change, d * B);
     if (!rc) rc = dev_alloc(h, &p.eqteig, d * B);

@@ -58,6 +58,13 @@ struct StepDev {
     // slot (osc2_build_smap), every other (row, col) maps to one shared all-zero slot
     const unsigned char *smap; // [d*d] -> slot
     int s_slots;              // number of slots incl. the zero slot
+    // fast path (step_kernels_fast.cuh / step_kernels_tile.cuh): `gm` and `spill` are TILED by warp -- a tile is the
+    // cpw = 32 / LPC conductors one warp of the sweeps owns, NT = ceil(B / cpw) tiles:
+    //   gm    [E][NT][d + 9 fields][32 lanes]      lane = row * cpw + (b % cpw)
+    //   spill [N][NT][2d + 2 fields][32 lanes]
+    // so that everything a warp needs for one node is ONE contiguous block (4352 / 4608 bytes at d = 8) that a
+    // single bulk copy (cp.async.bulk, TMA) moves
+    int cpw, NT;
 };
 
 // Slot map of one element's Gauss-point record in `gm`:

@@ -20,19 +20,25 @@
 #include "step_kernels.cuh"
 #include "osc2_div.cuh"
 
-// Row record r of one element in `gm` (fast path): D + 9 doubles.
+// Row record r of one element in `gm` (fast path): D + 9 fields.  The records are tiled by warp
+// (osc2_dev.h: StepDev::cpw): field f of row r of conductor b lives at double
+//   ((e * NT + b / cpw) * (D + 9) + f) * 32 + r * cpw + b % cpw
+// the methods below return the offset inside the (element, tile) block, without the b % cpw part.
 struct GmSlots2 {
-    int d, M, S;
+    int d, M, S, cpw;
     __host__ __device__ int width() const { return d + 9; }
-    __host__ __device__ int sd(int r, int c) const { return r * (d + 9) + c; }      // S[r][c]*dz/3
-    __host__ __device__ int kb(int r) const { return r * (d + 9) + d; }             // K[r]/dz
-    __host__ __device__ int md(int r) const { return r * (d + 9) + d + 1; }         // dz/3*M[r]
-    __host__ __device__ int mo(int r) const { return r * (d + 9) + d + 2; }         // dz/6*M[r]
-    __host__ __device__ int ahd(int r) const { return r * (d + 9) + d + 3; }        // A[r][r]/2
-    __host__ __device__ int aho(int r) const { return r * (d + 9) + d + 4; }        // A[r][offcol(r)]/2
-    __host__ __device__ int lod(int r, int which) const { return r * (d + 9) + d + 5 + which; }
-    __host__ __device__ int count() const { return d * (d + 9); }
+    __host__ __device__ int at(int r, int f) const { return f * 32 + r * cpw; }
+    __host__ __device__ int sd(int r, int c) const { return at(r, c); }             // S[r][c]*dz/3
+    __host__ __device__ int kb(int r) const { return at(r, d); }                    // K[r]/dz
+    __host__ __device__ int md(int r) const { return at(r, d + 1); }                // dz/3*M[r]
+    __host__ __device__ int mo(int r) const { return at(r, d + 2); }                // dz/6*M[r]
+    __host__ __device__ int ahd(int r) const { return at(r, d + 3); }               // A[r][r]/2
+    __host__ __device__ int aho(int r) const { return at(r, d + 4); }               // A[r][offcol(r)]/2
+    __host__ __device__ int lod(int r, int which) const { return at(r, d + 5 + which); }
+    __host__ __device__ int block() const { return (d + 9) * 32; }                  // doubles of one (element, tile)
 };
+// doubles of one (node, tile) block of `spill`
+__host__ __device__ inline int osc2_spill_block(int d) { return (2 * d + 2) * 32; }
 enum { LOD_UP = 0, LOD_LO = 1, LOD_UP_PREV = 2, LOD_LO_PREV = 3 };
 
 // ---------------------------------------------------------------------------
@@ -49,15 +55,15 @@ __global__ void osc2_gauss2_kernel(const osc2_topology *__restrict__ tp, StepDev
     const size_t b = (size_t)(idx % p.B);
     const int e = (int)(idx / p.B);
     const int M = p.M, Sn = p.S, d = p.d, E = p.E;
-    const GmSlots2 sl{d, M, Sn};
-    double *g = p.gm + ((size_t)e * p.NS) * B + b;
+    const GmSlots2 sl{d, M, Sn, p.cpw};
+    double *g = p.gm + ((size_t)e * p.NT + b / p.cpw) * sl.block() + b % p.cpw;
     static_assert(SMEM_S, "the fast path always stages SMAT in shared memory");
     double *Sb = sm_dyn + threadIdx.x;
     const size_t Ss = blockDim.x;
     const unsigned char *__restrict__ smap = p.smap;
 #define SM_(r, c) Sb[(size_t)smap[(r) * d + (c)] * Ss]
 #define FG(q, j) p.fl_gauss[((((size_t)(q) * M + (j)) * E) + e) * B + b]
-#define GOUT(slot) g[(size_t)(slot) * B]
+#define GOUT(slot) g[slot]
     for (int i = 0; i < p.s_slots; ++i) Sb[(size_t)i * Ss] = 0.0;
     const double dz = p.dz[(size_t)e * B + b];
     const double alpha = 0.0;
@@ -281,12 +287,17 @@ __global__ void osc2_forward_fast_kernel(const osc2_topology *__restrict__ tp, S
     auto fld = [Bu](auto *ptr, const int k) {
         return (decltype(ptr))((const char *)ptr + (unsigned long long)Bu * (unsigned)(8 * k));
     };
-    const int cpb = blockDim.x / LPC;
-    const int grp = threadIdx.x / LPC, r = threadIdx.x % LPC;
+    // lane = row * CPW + conductor of the tile (the layout of the tiled records, osc2_dev.h)
+    constexpr int CPW = 32 / LPC;
+    const int cpb = (blockDim.x / 32) * CPW;
+    const int lane_ = threadIdx.x & 31;
+    const int grp = (threadIdx.x >> 5) * CPW + lane_ % CPW, r = lane_ / CPW;
     const long long b_ll = (long long)blockIdx.x * cpb + grp;
     const bool act = FULL || ((b_ll < (long long)p.B) && (r < D));
     const size_t b = act ? (size_t)b_ll : 0;
     const int rr_ = (FULL || r < D) ? r : 0;
+    const size_t tile_ = (size_t)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);    // < NT by the launch geometry
+    auto tfld = [](auto *ptr, const int k) { return ptr + 32 * k; };                     // field k of a tiled record
     const long long Total = (long long)D * N;
     constexpr int Half = 2 * D;
     const double theta = tp->theta, omt = 1.0 - tp->theta;
@@ -353,22 +364,22 @@ __global__ void osc2_forward_fast_kernel(const osc2_topology *__restrict__ tp, S
     };
     enum { PF_SDR = D, PF_SDO, PF_KB, PF_MD, PF_MO, PF_AHD, PF_AHO, PF_LODU, PF_LODL, PF_X, PF_SL0, PF_SL1 };
     static_assert(PF_SL1 + 1 == SM::PF_FIELDS, "prefetch slot layout");
-    const size_t gstep = (size_t)p.NS * B;                       // one element further
-    const double *gptr = p.gm + (size_t)rr_ * RW * B + b;        // row record of element 0
-    const size_t off_r = (size_t)rr_ * B, off_o = (size_t)(aoffcol >= 0 ? aoffcol : 0) * B;
+    const size_t gstep = (size_t)p.NT * RW * 32;                 // one element further
+    const double *gptr = p.gm + tile_ * (RW * 32) + rr_ * CPW + lane_ % CPW;    // row record of element 0
+    const size_t off_r = (size_t)rr_ * 32, off_o = (size_t)(aoffcol >= 0 ? aoffcol : 0) * 32;
     const size_t xstep = (size_t)D * B;
     const double *xptr = p.sysvar + (size_t)rr_ * B + b;                 // x[node][r]
     double *lodptr = p.syslod + (size_t)rr_ * 2 * B + b;                 // SYSLOD[node][r][0]
-    double *spptr = p.spill + (size_t)rr_ * (2 * D + 2) * B + b;         // spill[node][r][0]
+    double *spptr = p.spill + tile_ * (PW * 32) + rr_ * CPW + lane_ % CPW;      // spill[node][tile][0][lane]
     // start the copies node m needs: element m, x[m+1], SYSLOD[m] (g, xq, lq point at them)
     auto prefetch = [&](const int m, const double *g, const double *xq, const double *lq) {
         if (m < N - 1) {
 #pragma unroll
-            for (int c = 0; c < D; ++c) osc2_async_copy8(pre + c, fld(g, c));
+            for (int c = 0; c < D; ++c) osc2_async_copy8(pre + c, tfld(g, c));
             osc2_async_copy8(pre + PF_SDR, g + off_r);
             osc2_async_copy8(pre + PF_SDO, g + off_o);
 #pragma unroll
-            for (int q = 0; q < 7; ++q) osc2_async_copy8(pre + PF_KB + q, fld(g, D + q));
+            for (int q = 0; q < 7; ++q) osc2_async_copy8(pre + PF_KB + q, tfld(g, D + q));
             osc2_async_copy8(pre + PF_X, xq);
         }
         if (m < N) {
@@ -390,11 +401,11 @@ __global__ void osc2_forward_fast_kernel(const osc2_topology *__restrict__ tp, S
     double x_pre = 0.0, sl0_pre = 0.0, sl1_pre = 0.0;
     auto load_elem = [&](const double *g, Elem &el) {
 #pragma unroll
-        for (int c = 0; c < D; ++c) el.sd[c] = *fld(g, c);
+        for (int c = 0; c < D; ++c) el.sd[c] = *tfld(g, c);
         el.sdr = g[off_r];
         el.sdo = g[off_o];
-        el.kb = *fld(g, D + 0); el.md = *fld(g, D + 1); el.mo = *fld(g, D + 2); el.ahd = *fld(g, D + 3);
-        el.aho = *fld(g, D + 4); el.lodu = *fld(g, D + 5); el.lodl = *fld(g, D + 6);
+        el.kb = *tfld(g, D + 0); el.md = *tfld(g, D + 1); el.mo = *tfld(g, D + 2); el.ahd = *tfld(g, D + 3);
+        el.aho = *tfld(g, D + 4); el.lodu = *tfld(g, D + 5); el.lodl = *tfld(g, D + 6);
     };
     if (act) {
         load_elem(gptr, eB);
@@ -433,8 +444,8 @@ __global__ void osc2_forward_fast_kernel(const osc2_topology *__restrict__ tp, S
             // SYSLOD (smc:1165-1318); fluid rows carry zero loads
             if (shift) { sl1 = sl0; sl0 = 0.0; }
             // (the previous-step halves exist at the first step only: read in place, not prefetched)
-            if (hasL) { sl0 += A.lodl; if (first) sl1 += *fld(gptr - gstep, D + 8); }
-            if (hasR) { sl0 += Bv.lodu; if (first) sl1 += *fld(gptr, D + 7); }
+            if (hasL) { sl0 += A.lodl; if (first) sl1 += *tfld(gptr - gstep, D + 8); }
+            if (hasR) { sl0 += Bv.lodu; if (first) sl1 += *tfld(gptr, D + 7); }
             lodptr[0] = sl0;
             *fld(lodptr, 1) = sl1;
 
@@ -646,11 +657,11 @@ __global__ void osc2_forward_fast_kernel(const osc2_topology *__restrict__ tp, S
             if (tiny && bad_row < 0) bad_row = i_row;
             div_span = osc2_umax(div_span, tiny ? 0u : osc2_abs_hi(my_rcp.b) - OSC2_HI_DIV_LO);
 #pragma unroll
-            for (int c = 0; c < D; ++c) *fld(spptr, c) = rowD[c];
+            for (int c = 0; c < D; ++c) *tfld(spptr, c) = rowD[c];
 #pragma unroll
-            for (int c = 0; c < D; ++c) *fld(spptr, D + c) = rowU[c];
-            *fld(spptr, 2 * D) = rhs;
-            *fld(spptr, 2 * D + 1) = my_rcp.y;
+            for (int c = 0; c < D; ++c) *tfld(spptr, D + c) = rowU[c];
+            *tfld(spptr, 2 * D) = rhs;
+            *tfld(spptr, 2 * D + 1) = my_rcp.y;
             xm = x0; x0 = xp;       // rotate the old solution
             if (hasR) { const Elem t = A; A = Bv; Bv = t; }   // left <- right, right <- the prefetched element
         }
@@ -658,7 +669,7 @@ __global__ void osc2_forward_fast_kernel(const osc2_topology *__restrict__ tp, S
         gptr += gstep;
         xptr += xstep;
         lodptr += 2 * xstep;
-        spptr += (size_t)D * (2 * D + 2) * B;
+        spptr += (size_t)p.NT * (PW * 32);
     };
     // (one body for all interior nodes: a two-node body that alternates the register sets saves the
     //  copy of the element record but doubles the loop to 50 KB of code, and instruction-cache
@@ -703,14 +714,19 @@ __global__ void osc2_backward_fast_kernel(StepDev p)
 {
     const int N = p.N;
     const size_t B = (size_t)p.B;
-    const int cpb = blockDim.x / LPC;
-    const int grp = threadIdx.x / LPC, r = threadIdx.x % LPC;
+    constexpr int CPW = 32 / LPC;
+    const int cpb = (blockDim.x / 32) * CPW;
+    const int lane_ = threadIdx.x & 31;
+    const int grp = (threadIdx.x >> 5) * CPW + lane_ % CPW, r = lane_ / CPW;    // lane = row * CPW + conductor of the tile
     const long long b_ll = (long long)blockIdx.x * cpb + grp;
     const bool act = (b_ll < (long long)p.B) && (r < D);
     const size_t b = act ? (size_t)b_ll : 0;
-    const int lane0 = (threadIdx.x & 31) - r;            // first lane of this conductor's group
+    const int lane0 = lane_ % CPW;                       // lane of row 0 of this conductor; row rr sits at lane0 + rr * CPW
 
     constexpr int W = 2 * D + 2;      // D' | U | rhs | 1/pivot
+    const size_t tile_ = (size_t)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+    const size_t sstep = (size_t)p.NT * (W * 32);        // one node further in the tiled spill
+    const double *spbase = p.spill + tile_ * (W * 32) + lane_;
     int range_flag = 0;
     // factor rows of the current node and of the two nodes below it: a node takes ~2500 cycles, about
     // one DRAM round trip under load, so a one-node prefetch still left 0.6 of them exposed (ncu)
@@ -720,13 +736,13 @@ __global__ void osc2_backward_fast_kernel(StepDev p)
 #pragma unroll
     for (int c = 0; c < D; ++c) { xc[c] = 0.0; xn[c] = 0.0; }
     if (act) {
-        const double *sp = p.spill + (((size_t)(N - 1) * D + r) * W) * B + b;
+        const double *sp = spbase + (size_t)(N - 1) * sstep;
 #pragma unroll
-        for (int c = 0; c < W; ++c) fn[c] = sp[(size_t)c * B];
+        for (int c = 0; c < W; ++c) fn[c] = sp[32 * c];
         if (N > 1) {
-            const double *sq = p.spill + (((size_t)(N - 2) * D + r) * W) * B + b;
+            const double *sq = spbase + (size_t)(N - 2) * sstep;
 #pragma unroll
-            for (int c = 0; c < W; ++c) fnn[c] = sq[(size_t)c * B];
+            for (int c = 0; c < W; ++c) fnn[c] = sq[32 * c];
         }
     } else {
         fn[r < D ? r : 0] = 1.0;      // idle lanes divide by 1
@@ -738,9 +754,9 @@ __global__ void osc2_backward_fast_kernel(StepDev p)
 #pragma unroll
         for (int c = 0; c < W; ++c) { f[c] = fn[c]; fn[c] = fnn[c]; }
         if (act && n > 1) {
-            const double *sp = p.spill + (((size_t)(n - 2) * D + r) * W) * B + b;
+            const double *sp = spbase + (size_t)(n - 2) * sstep;
 #pragma unroll
-            for (int c = 0; c < W; ++c) fnn[c] = sp[(size_t)c * B];
+            for (int c = 0; c < W; ++c) fnn[c] = sp[32 * c];
         }
         // products with the already known node n+1 are off the dependency chain
         double pu[D];
@@ -760,7 +776,7 @@ __global__ void osc2_backward_fast_kernel(StepDev p)
             int flag = 0;
             const double x = osc2_div_flag(q, osc2_rcp_make(f[rr], f[2 * D + 1]), flag);
             if (r == rr) { mine = x; range_flag |= flag; }
-            xc[rr] = osc2_bcast(x, lane0 + rr);
+            xc[rr] = osc2_bcast(x, lane0 + rr * CPW);
         }
         if (act) p.sysvar_new[((size_t)n * D + r) * B + b] = mine;
 #pragma unroll

@@ -10,6 +10,7 @@
 
 #include "step_kernels.cuh"
 #include "step_kernels_fast.cuh"
+#include "step_kernels_tile.cuh"
 #include "step_kernels_d64.cuh"
 
 #include <cstdlib>
@@ -75,12 +76,26 @@ struct Osc2LaunchPlan {
 // NODOFS values with a register-resident instantiation (CASE_1: 8, CASE_3: 13).
 inline bool osc2_has_fast_path(int d) { return d == 4 || d == 8 || d == 13; }
 
-// number of doubles of one element record in `gm` for the chosen path
+// number of doubles of one element record in `gm` per conductor (generic path; the fast path tiles, below)
 inline int osc2_gm_slots(int d, int M, int S, bool fast)
 {
-    if (fast) { const GmSlots2 s{d, M, S}; return s.count(); }
+    if (fast) return d * (d + 9);
     const GmSlots s{d, M, S};
     return s.count();
+}
+
+// fast path: conductors per warp of the sweeps, tiles of the batch, sizes of the tiled buffers (osc2_dev.h)
+inline int osc2_fast_cpw(int d) { return 32 / (d <= 8 ? 8 : 16); }
+inline long long osc2_fast_tiles(int d, long long B) { const int c = osc2_fast_cpw(d); return (B + c - 1) / c; }
+inline size_t osc2_gm_doubles(int d, int M, int S, bool fast, size_t E, size_t B)
+{
+    if (fast) return E * (size_t)osc2_fast_tiles(d, (long long)B) * (size_t)(d + 9) * 32;
+    return E * (size_t)osc2_gm_slots(d, M, S, false) * B;
+}
+inline size_t osc2_spill_doubles(int d, bool fast, size_t N, size_t B)
+{
+    if (fast) return N * (size_t)osc2_fast_tiles(d, (long long)B) * (size_t)(2 * d + 2) * 32;
+    return N * (size_t)d * (2 * d + 2) * B;
 }
 
 inline int osc2_pick_lpc(int d)
@@ -126,9 +141,19 @@ void osc2_run_fast_sweeps(Launcher &L, const osc2_topology *tp_dev, const StepDe
     const size_t smem_f = (size_t)((be && D % 8 == 0) ? FastFwdSmem<D, true>::PER_COND : FastFwdSmem<D, false>::PER_COND) *
                           cpb * sizeof(double);
     const size_t smem_b = (size_t)(2 * D + 2) * cpb * sizeof(double);
-    // warps per CTA of the two sweeps (experiment knob OSC2_SWEEP_WARPS, default 1): with 2, the two
-    // 32-byte halves of a 64-byte DRAM burst are requested from the same SM
-    static const int W = [] { const char *e = getenv("OSC2_SWEEP_WARPS"); return (e && e[0] == '2') ? 2 : 1; }();
+    if constexpr (D % 8 == 0 && LPC == D) {
+        // Backward Euler, no capture: tiled records by TMA bulk copies + node-pipelined rounds (step_kernels_tile.cuh);
+        // OSC2_FWD_TILE=0 keeps the round-1 kernel (same bits) for A/B timing
+        static const bool tile_on = [] { const char *e = getenv("OSC2_FWD_TILE"); return !(e && e[0] == '0'); }();
+        if (be && !cap && tile_on) {
+            const unsigned nt = (unsigned)((p.B + cpb - 1) / cpb);
+            if (p.B % cpb == 0) L.launch(OSC2_K_FORWARD, osc2_forward_tile_kernel<D, LPC, true>, nt, 32u, TileFwdSmem<D, LPC>::BYTES, tp_dev, p);
+            else L.launch(OSC2_K_FORWARD, osc2_forward_tile_kernel<D, LPC, false>, nt, 32u, TileFwdSmem<D, LPC>::BYTES, tp_dev, p);
+            L.launch(OSC2_K_BACKWARD, osc2_backward_tile_kernel<D, LPC>, nt, 32u, TileBwdSmem<D, LPC>::BYTES, p);
+            return;
+        }
+    }
+    constexpr int W = 1;     // one warp per CTA
     const unsigned blk = 32u * W, gridW = (unsigned)((p.B + cpb * W - 1) / (cpb * W));
     bool full = false;       // every lane of every warp owns a row: the kernel drops its lane predicates
     if constexpr (LPC == D) full = be && !cap && (p.B % (cpb * W) == 0);

@@ -55,6 +55,7 @@ inline bool emu_any(bool pred)
 }
 
 #define OSC2_DYN_SMEM(name) double *name = emu_dyn_smem
+#define OSC2_DYN_SMEM_ALIGNED(name) double *name = emu_dyn_smem
 
 inline void __syncthreads() { emu_block_barrier->arrive_and_wait(); }
 inline void __syncwarp() { emu_warp_barrier->arrive_and_wait(); }

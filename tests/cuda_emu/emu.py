@@ -20,7 +20,7 @@ class StepDev(C.Structure):
                             "sysvar", "sysvar_new", "syslod", "gm", "k123", "spill",
                             "norm_solution", "norm_change", "eqteig")] + [
         ("status", c_ip), ("cap_sysmat", c_dp), ("cap_known", c_dp),
-        ("norm_leaf", c_ip), ("norm_prog", c_ip), ("norm_part", c_dp), ("n_leaves", C.c_int), ("n_prog", C.c_int), ("smap", C.c_void_p), ("s_slots", C.c_int)]
+        ("norm_leaf", c_ip), ("norm_prog", c_ip), ("norm_part", c_dp), ("n_leaves", C.c_int), ("n_prog", C.c_int), ("smap", C.c_void_p), ("s_slots", C.c_int), ("cpw", C.c_int), ("NT", C.c_int)]
 
 
 _LIB = None
@@ -38,6 +38,10 @@ def lib():
             subprocess.run(["g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-ffp-contract=off", "-pthread",
                             "-o", so, os.path.join(HERE, "emu_step.cpp")], check=True)
         _LIB = C.CDLL(so)
+        _LIB.osc2_emu_gm_doubles.restype = C.c_longlong
+        _LIB.osc2_emu_gm_doubles.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_longlong]
+        _LIB.osc2_emu_spill_doubles.restype = C.c_longlong
+        _LIB.osc2_emu_spill_doubles.argtypes = [C.c_int, C.c_int, C.c_longlong, C.c_longlong]
         assert _LIB.osc2_emu_sizeof_stepdev() == C.sizeof(StepDev)
         assert _LIB.osc2_emu_sizeof_topology() == C.sizeof(Osc2Topology)
     return _LIB
@@ -45,7 +49,7 @@ def lib():
 
 def to_dev(a):
     """[B][...] -> [...][B] contiguous (the device layout)."""
-    return np.ascontiguousarray(np.moveaxis(np.asarray(a, dtype=np.float64), 0, -1))
+    return np.array(np.moveaxis(np.asarray(a, dtype=np.float64), 0, -1), order="C", copy=True)   # never a view: the kernels write SYSLOD in place
 
 
 def from_dev(a):
@@ -75,8 +79,9 @@ def emu_step(topo, arr, capture=False, fast=None, split=True):
         keep[name] = a
         setattr(p, name, a.ctypes.data_as(c_dp))
     outs = {
-        "sysvar_new": np.full((total, B), np.nan), "gm": np.full((E, NS, B), np.nan),
-        "k123": np.zeros((3, max(p.nff, 1), E, B)), "spill": np.full((N, d, 2 * d + 2, B), np.nan),
+        "sysvar_new": np.full((total, B), np.nan),
+        "gm": np.full(L.osc2_emu_gm_doubles(d, M, S, int(fast), E, B), np.nan),
+        "k123": np.zeros((3, max(p.nff, 1), E, B)), "spill": np.full(L.osc2_emu_spill_doubles(d, int(fast), N, B), np.nan),
         "norm_solution": np.zeros((d, B)), "norm_change": np.zeros((d, B)), "eqteig": np.zeros((d, B)),
     }
     for k, a in outs.items():

@@ -14,6 +14,8 @@ extern "C" int osc2_emu_step(const osc2_topology *tp, const StepDev *p, int fast
     q.norm_leaf = leaves.data(); q.norm_prog = prog.data(); q.norm_part = part.data();
     q.n_leaves = (int)(leaves.size() / 2); q.n_prog = (int)prog.size();
     (void)split;
+    q.cpw = fast ? osc2_fast_cpw(q.d) : 1;
+    q.NT = fast ? (int)osc2_fast_tiles(q.d, q.B) : q.B;
     std::vector<unsigned char> smap;
     q.s_slots = osc2_build_smap(*tp, smap);
     q.smap = smap.data();
@@ -22,6 +24,8 @@ extern "C" int osc2_emu_step(const osc2_topology *tp, const StepDev *p, int fast
 }
 extern "C" int osc2_emu_has_fast(int d) { return osc2_has_fast_path(d) ? 1 : 0; }
 extern "C" int osc2_emu_gm_slots(int d, int M, int S, int fast) { return osc2_gm_slots(d, M, S, fast != 0); }
+extern "C" long long osc2_emu_gm_doubles(int d, int M, int S, int fast, long long E, long long B) { return (long long)osc2_gm_doubles(d, M, S, fast != 0, (size_t)E, (size_t)B); }
+extern "C" long long osc2_emu_spill_doubles(int d, int fast, long long N, long long B) { return (long long)osc2_spill_doubles(d, fast != 0, (size_t)N, (size_t)B); }
 
 extern "C" int osc2_emu_transpose(const double *in, double *out, long long rows, long long cols)
 {

@@ -100,3 +100,32 @@ def test_emulated_d64_flag_synchronised_rounds():
     res = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, OSC2_D64_SYNC="flags"),
                          capture_output=True, text=True, timeout=600)
     assert res.returncode == 0 and "bits-equal" in res.stdout, res.stdout + res.stderr
+
+
+@pytest.mark.parametrize("intial,n,batch,num_step", [(1, 9, 8, 2), (2, 7, 6, 2), (3, 23, 5, 3), (1, 4, 4, 1), (3, 5, 13, 1), (2, 40, 1, 2)])
+def test_emulated_tile_sweep_batches(intial, n, batch, num_step):
+    """step_kernels_tile.cuh (tiled records through bulk copies, node-pipelined rounds): full and ragged tiles, every
+    boundary-condition mode, first step, the minimum mesh (3 elements in a ring of 3 stages), against the oracle."""
+    topo = case1_topology(intial)
+    arr = synthetic_step_arrays(topo, n, batch=batch, seed=40 + n, num_step=num_step)
+    out = emu.emu_step(topo, arr, fast=True)
+    ref = O.step(topo, arr)
+    assert np.all(out["status"] == 0)
+    for key in KEYS:
+        assert_bits(out[key], ref[key], key)
+
+
+def test_emulated_tile_sweep_reports_a_singular_conductor():
+    topo = case1_topology(1)
+    arr = synthetic_step_arrays(topo, 9, batch=6, seed=3)
+    # conductor 4: the jacket without mass term and without thermal contact -- its Neumann diffusion rows
+    # [1 -1], [-1/2 1 -1/2], ..., [-1 1] eliminate to an exact zero pivot in the last node (tsf:763-786)
+    arr.sol_gauss[4, 1, 1] = 0.0
+    arr.sol_gauss[4, 2, 1] = 100.0
+    arr.htc_fs[4, 1], arr.htc_ss[4], arr.htc_es[4] = 0.0, 0.0, 0.0
+    arr.sol_q[4, :, 1] = 0.0
+    out = emu.emu_step(topo, arr, fast=True)
+    ref = O.step(topo, arr)
+    assert list(out["status"]) == list(ref["status"]) and ref["status"][4] != 0
+    ok = np.array([0, 1, 2, 3, 5])
+    assert_bits(out["sysvar"][ok], ref["sysvar"][ok], "the conductors next to the singular one")
