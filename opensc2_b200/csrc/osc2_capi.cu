@@ -74,6 +74,7 @@ struct osc2_context {
     bool have_model = false, have_sweep = false;
     bool need_peri_ss_nodal = false; // some |ss_choice| == 3
     double *tcs_nodal = nullptr;     // [S][N][B] (osc2_eval_tcs)
+    double *margin_out = nullptr;    // [S][B] decoded temperature margins (osc2_download_margin)
     bool have_table[OSC2_MAX_FLUIDS] = {false, false, false, false};
     int n_fluids_used = 0;
 
@@ -540,6 +541,8 @@ int osc2_set_model(osc2_handle h, const osc2_model *model)
         rc = dev_alloc(h, &t, (size_t)h->S * h->B);
         if (rc) return rc;
         h->q.margin_key = (unsigned long long *)t;
+        rc = dev_alloc(h, &h->margin_out, (size_t)h->S * h->B);
+        if (rc) return rc;
         CK(cudaMemsetAsync(t, 0xff, sizeof(double) * (size_t)h->S * h->B, h->stream));
     }
     if (h->S > 0) {
@@ -738,13 +741,9 @@ int osc2_download_margin(osc2_handle h, double *margin)
     CK(cudaSetDevice(h->device));
     const long long n = (long long)h->S * h->B;
     if ((size_t)n > h->staging_doubles) return fail(OSC2_ERR_STATE, "staging buffer too small");
-    double *tmp = nullptr;
-    CK(cudaMallocAsync((void **)&tmp, sizeof(double) * (size_t)n, h->stream));
-    osc2_margin_decode_kernel<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(h->q.margin_key, tmp, n);
+    osc2_margin_decode_kernel<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(h->q.margin_key, h->margin_out, n);
     CK(cudaGetLastError());
-    int rc = download_transposed(h, tmp, margin, (size_t)h->S);
-    CK(cudaFreeAsync(tmp, h->stream));
-    return rc;
+    return download_transposed(h, h->margin_out, margin, (size_t)h->S);
 }
 
 static int run_step(osc2_handle h, double dt, int num_step, bool records_ready)

@@ -43,13 +43,15 @@ def step_geometry(deck, zcoord: np.ndarray, batch: int, fl_bc: np.ndarray) -> St
     if nff:
         peri_ff[:] = deck.peri["ff"][None, :, :, None]
     z = np.zeros
+    # the coefficient arrays K_P computes on the device (and the state, kept elsewhere) are one-conductor placeholders:
+    # at 4096 x 10 001 nodes they would be 20 GB of zeros on the host
     arr = StepArrays(
-        dz=dz, fl_gauss=z((batch, 9, M, E)), fl_node=z((batch, 4, M)), fl_bc=np.array(fl_bc, dtype=np.float64),
-        sol_gauss=z((batch, 3, S, E)), sol_q=z((batch, 2, S, E, 2)), peri_ff=peri_ff, htc_ff=z((batch, 2, nff, E)),
-        peri_fs=(deck.peri["fs"][None, :, None] * ones) if nfs else z((batch, 0, E)), htc_fs=z((batch, nfs, E)),
-        peri_ss=(deck.peri["ss"][None, :, None] * ones) if nss else z((batch, 0, E)), htc_ss=z((batch, nss, E)),
-        peri_es=(deck.peri["es"][None, :, None] * ones) if nes else z((batch, 0, E)), htc_es=z((batch, nes, 3, E)),
-        qsource=z((batch, N, S)), sysvar=z((batch, N * topo.ndf)), syslod=z((batch, N * topo.ndf, 2)),
+        dz=dz, fl_gauss=z((1, 9, M, E)), fl_node=z((1, 4, M)), fl_bc=np.array(fl_bc, dtype=np.float64),
+        sol_gauss=z((1, 3, S, E)), sol_q=z((1, 2, S, E, 2)), peri_ff=peri_ff, htc_ff=z((1, 2, nff, E)),
+        peri_fs=(deck.peri["fs"][None, :, None] * ones) if nfs else z((batch, 0, E)), htc_fs=z((1, nfs, E)),
+        peri_ss=(deck.peri["ss"][None, :, None] * ones) if nss else z((batch, 0, E)), htc_ss=z((1, nss, E)),
+        peri_es=(deck.peri["es"][None, :, None] * ones) if nes else z((batch, 0, E)), htc_es=z((1, nes, 3, E)),
+        qsource=z((batch, N, S)), sysvar=z((1, N * topo.ndf)), syslod=z((1, N * topo.ndf, 2)),
         t_env=deck.t_env, dt=float(deck.transient.get("STPMIN", 0.1)), num_step=1)
     if any(abs(c[0]) == 3 for c in deck.model.ss):
         arr.peri_ss_nodal = deck.peri["ss"][None, :, None] * np.ones((batch, 1, N))
@@ -148,7 +150,7 @@ class Transient(TransientSetup):
         self.bs = BatchedStep(topo, self.batch, N, device=device)
         self.bs.set_model(deck.model, self.tables)
         self.bs.upload_sweep(self.sweep)
-        self.bs.upload_state(self.sysvar0, np.zeros((self.batch, N * topo.ndf, 2)))
+        self.bs.upload_state(self.sysvar0, None)          # SYSLOD starts at zero on the device (osc2_create)
         self.bs.upload_geometry(self.geometry)
         if self.has_sc:
             self.bs.eval_tcs()                     # once, at step 0 (conductor.py:4615-4619)

@@ -25,22 +25,32 @@ def test_header_symbols_are_exported():
 
 
 def test_ctypes_structs_match_header_layout():
-    """sizeof of the ctypes mirrors equals what the C compiler lays out."""
+    """sizeof AND the offset of every member of the four ctypes mirrors equal what the C compiler lays out
+    (osc2_topology, osc2_step_inputs, osc2_model, osc2_sweep)."""
     import subprocess
     import tempfile
 
-    from opensc2_b200._abi import Osc2StepInputs, Osc2Topology
+    from opensc2_b200._abi import Osc2Model, Osc2StepInputs, Osc2Sweep, Osc2Topology
 
-    src = ('#include <stdio.h>\n#include "opensc2_b200.h"\n'
-           'int main(void){printf("%zu %zu\\n", sizeof(osc2_topology), sizeof(osc2_step_inputs));return 0;}\n')
+    mirrors = (("osc2_topology", Osc2Topology), ("osc2_step_inputs", Osc2StepInputs), ("osc2_model", Osc2Model),
+               ("osc2_sweep", Osc2Sweep))
+    lines = []
+    for cname, cls in mirrors:
+        lines.append(f'printf("%zu\\n", sizeof({cname}));')
+        for fname, _t in cls._fields_:
+            lines.append(f'printf("%zu\\n", offsetof({cname}, {fname}));')
+    src = ('#include <stdio.h>\n#include <stddef.h>\n#include "opensc2_b200.h"\nint main(void){' + "".join(lines) + "return 0;}\n")
     with tempfile.TemporaryDirectory() as td:
         c = os.path.join(td, "s.c")
         open(c, "w").write(src)
         exe = os.path.join(td, "s")
         subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe], check=True)
-        a, b = map(int, subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split())
-    assert a == C.sizeof(Osc2Topology)
-    assert b == C.sizeof(Osc2StepInputs)
+        got = list(map(int, subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()))
+    want = []
+    for _cname, cls in mirrors:
+        want.append(C.sizeof(cls))
+        want += [getattr(cls, fname).offset for fname, _t in cls._fields_]
+    assert got == want
 
 
 def test_version_and_error_text():
