@@ -622,13 +622,11 @@ __global__ void osc2_solid_tmax_kernel(const osc2_topology *__restrict__ tp, Ste
     }
 }
 
-__global__ void __launch_bounds__(128, 6) osc2_opcond_kernel(const osc2_topology *__restrict__ tp, StepDev p, PropsDev q)
+// body for element e of conductor b
+__device__ __forceinline__ void osc2_opcond_body(const osc2_topology *__restrict__ tp, const StepDev &p, const PropsDev &q, const int e,
+                                                 const size_t b)
 {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long long)p.E * p.B) return;
     const size_t B = (size_t)p.B;
-    const size_t b = (size_t)(idx % p.B);
-    const int e = (int)(idx / p.B);
     const int M = p.M, S = p.S, d = p.d, E = p.E, N = p.N;
     const osc2_model *md = q.model;
     const double *x0 = p.sysvar + ((size_t)e * d) * B + b;          // node e
@@ -803,4 +801,11 @@ __global__ void __launch_bounds__(128, 6) osc2_opcond_kernel(const osc2_topology
         hes[(((size_t)k * 3 + 1) * E + e) * B + b] = 0.0;
         hes[(((size_t)k * 3 + 2) * E + e) * B + b] = 0.0;
     }
+}
+
+__global__ void __launch_bounds__(128, 6) osc2_opcond_kernel(const osc2_topology *__restrict__ tp, StepDev p, PropsDev q)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)p.E * p.B) return;
+    osc2_opcond_body(tp, p, q, (int)(idx / p.B), (size_t)(idx % p.B));
 }

@@ -45,15 +45,12 @@ enum { LOD_UP = 0, LOD_LO = 1, LOD_UP_PREV = 2, LOD_LO_PREV = 3 };
 // K_G2: same statement order as osc2_gauss_kernel for SMAT, then converts the
 // Gauss-point values into the element-matrix values (smc:1015-1216).
 // ---------------------------------------------------------------------------
+// body for element e of conductor b; sm_dyn: s_slots * blockDim.x doubles of shared memory
 template <bool SMEM_S>
-__global__ void osc2_gauss2_kernel(const osc2_topology *__restrict__ tp, StepDev p)
+__device__ __forceinline__ void osc2_gauss2_body(const osc2_topology *__restrict__ tp, const StepDev &p, double *sm_dyn, const int e,
+                                                 const size_t b)
 {
-    OSC2_DYN_SMEM(sm_dyn);
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long long)p.E * p.B) return;
     const size_t B = (size_t)p.B;
-    const size_t b = (size_t)(idx % p.B);
-    const int e = (int)(idx / p.B);
     const int M = p.M, Sn = p.S, d = p.d, E = p.E;
     const GmSlots2 sl{d, M, Sn, p.cpw};
     double *g = p.gm + ((size_t)e * p.NT + b / p.cpw) * sl.block() + b % p.cpw;
@@ -215,6 +212,15 @@ __global__ void osc2_gauss2_kernel(const osc2_topology *__restrict__ tp, StepDev
 #undef SM_
 #undef FG
 #undef GOUT
+}
+
+template <bool SMEM_S>
+__global__ void osc2_gauss2_kernel(const osc2_topology *__restrict__ tp, StepDev p)
+{
+    OSC2_DYN_SMEM(sm_dyn);
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)p.E * p.B) return;
+    osc2_gauss2_body<SMEM_S>(tp, p, sm_dyn, (int)(idx / p.B), (size_t)(idx % p.B));
 }
 
 // max(m, |v|) as one compare and one select (a NaN never wins, as in `if (|v| > m) m = |v|`)
