@@ -368,6 +368,18 @@ int osc2_create(const osc2_topology *topo, int batch, int n_nodes, int device, o
             CK(cudaMemcpy(qm, map.data(), map.size(), cudaMemcpyHostToDevice));
             p.smap = (const unsigned char *)qm;
             p.s_slots = slots;
+            if (h->fast) {   // inverse map for K_G's final pass; the constant zeros of `gm` are written once, here
+                std::vector<unsigned char> inv((size_t)slots, 0);
+                for (size_t i = 0; i < map.size(); ++i) if (map[i]) inv[map[i]] = (unsigned char)i;
+                double *qi = nullptr;
+                rc = dev_alloc(h, &qi, inv.size() / 8 + 1);
+                if (!rc) {
+                    CK(cudaMemcpy(qi, inv.data(), inv.size(), cudaMemcpyHostToDevice));
+                    p.sinv = (const unsigned char *)qi;
+                    CK(cudaMemset(p.gm, 0, osc2_gm_doubles(h->d, h->M, h->S, true, E, B) * sizeof(double)));
+                    p.gm_prezeroed = 1;
+                }
+            }
         }
     }
     if (!rc) {   // numpy pairwise-sum tree of the N nodal values of one equation (norms)

@@ -65,6 +65,10 @@ struct StepDev {
     // so that everything a warp needs for one node is ONE contiguous block (4352 / 4608 bytes at d = 8) that a
     // single bulk copy (cp.async.bulk, TMA) moves
     int cpw, NT;
+    // K_G (fast path): slot -> row * d + column, the inverse of `smap`; gm_prezeroed: `gm` was zeroed at creation
+    // and K_G leaves the fields that are +0 for every element of this topology alone
+    const unsigned char *sinv;
+    int gm_prezeroed;
 };
 
 // Slot map of one element's Gauss-point record in `gm`:

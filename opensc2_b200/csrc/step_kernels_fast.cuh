@@ -41,6 +41,16 @@ struct GmSlots2 {
 __host__ __device__ inline int osc2_spill_block(int d) { return (2 * d + 2) * 32; }
 enum { LOD_UP = 0, LOD_LO = 1, LOD_UP_PREV = 2, LOD_LO_PREV = 3 };
 
+// request the line that holds *ptr from DRAM into L2 (no register, no completion to wait for)
+__device__ __forceinline__ void osc2_prefetch_l2(const void *ptr)
+{
+#ifndef OSC2_EMU
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+#else
+    (void)ptr;
+#endif
+}
+
 // ---------------------------------------------------------------------------
 // K_G2: same statement order as osc2_gauss_kernel for SMAT, then converts the
 // Gauss-point values into the element-matrix values (smc:1015-1216).
@@ -58,9 +68,28 @@ __device__ __forceinline__ void osc2_gauss2_body(const osc2_topology *__restrict
     double *Sb = sm_dyn + threadIdx.x;
     const size_t Ss = blockDim.x;
     const unsigned char *__restrict__ smap = p.smap;
+    // `gm` was zeroed when the handle was created and nothing but this kernel writes it: fields that are +0 for
+    // every element of this topology (SMAT entries no statement can touch, the load halves of the fluid rows,
+    // the advection entries of the solid rows) are not written again -- 440 of the 1088 bytes of a CASE_1 record
+    const bool skipz = p.gm_prezeroed != 0;
 #define SM_(r, c) Sb[(size_t)smap[(r) * d + (c)] * Ss]
 #define FG(q, j) p.fl_gauss[((((size_t)(q) * M + (j)) * E) + e) * B + b]
 #define GOUT(slot) g[slot]
+    // The kernel is bound by load latency (ncu: 67 % of the stall samples wait for global loads that sit inside
+    // loops with run-time trip counts, 6 warps per scheduler): every input of this (element, conductor) is
+    // requested from L2 up front, the loads below then hit L2
+    {
+        const size_t EB = (size_t)E * B, eb = (size_t)e * B + b;
+        osc2_prefetch_l2(p.dz + eb);
+        for (int q = 0; q < 9 * M; ++q) osc2_prefetch_l2(p.fl_gauss + (size_t)q * EB + eb);
+        for (int q = 0; q < 2 * p.nff; ++q) { osc2_prefetch_l2(p.peri_ff + (size_t)q * EB + eb); osc2_prefetch_l2(p.htc_ff + (size_t)q * EB + eb); }
+        for (int q = 0; q < p.nfs; ++q) { osc2_prefetch_l2(p.peri_fs + (size_t)q * EB + eb); osc2_prefetch_l2(p.htc_fs + (size_t)q * EB + eb); }
+        for (int q = 0; q < p.nss; ++q) { osc2_prefetch_l2(p.peri_ss + (size_t)q * EB + eb); osc2_prefetch_l2(p.htc_ss + (size_t)q * EB + eb); }
+        for (int q = 0; q < p.nes; ++q) { osc2_prefetch_l2(p.peri_es + (size_t)q * EB + eb); osc2_prefetch_l2(p.htc_es + (size_t)q * 3 * EB + eb); }
+        for (int q = 0; q < 3 * Sn; ++q) osc2_prefetch_l2(p.sol_gauss + (size_t)q * EB + eb);
+        for (int q = 0; q < 2 * Sn; ++q) { osc2_prefetch_l2(p.sol_q + ((size_t)q * E + e) * 2 * B + b); osc2_prefetch_l2(p.sol_q + ((size_t)q * E + e) * 2 * B + B + b); }
+        for (int l = 0; l < 2 * Sn; ++l) osc2_prefetch_l2(p.qsource + ((size_t)e * Sn + l) * B + b);
+    }
     for (int i = 0; i < p.s_slots; ++i) Sb[(size_t)i * Ss] = 0.0;
     const double dz = p.dz[(size_t)e * B + b];
     const double alpha = 0.0;
@@ -80,7 +109,7 @@ __device__ __forceinline__ void osc2_gauss2_body(const osc2_topology *__restrict
             GOUT(sl.kb(row)) = kb;
             GOUT(sl.md(row)) = cdiag;              // MMAT = 1 on the fluid equations
             GOUT(sl.mo(row)) = coff;
-            for (int w = 0; w < 4; ++w) GOUT(sl.lod(row, w)) = 0.0;
+            if (!skipz) for (int w = 0; w < 4; ++w) GOUT(sl.lod(row, w)) = 0.0;
         }
         const double svv = 2.0 * FG(FL_F, j) * fabs(v) / tp->ch_dh[j];
         SM_(iv, iv) = svv;
@@ -168,8 +197,7 @@ __device__ __forceinline__ void osc2_gauss2_body(const osc2_topology *__restrict
         GOUT(sl.md(is)) = cdiag * mm;
         GOUT(sl.mo(is)) = coff * mm;
         GOUT(sl.kb(is)) = (A * kk / cs) / dz;
-        GOUT(sl.ahd(is)) = 0.0;
-        GOUT(sl.aho(is)) = 0.0;
+        if (!skipz) { GOUT(sl.ahd(is)) = 0.0; GOUT(sl.aho(is)) = 0.0; }
         const size_t q1 = ((((size_t)0 * Sn + l) * E + e) * 2) * B + b;
         const size_t q2 = ((((size_t)1 * Sn + l) * E + e) * 2) * B + b;
         const double qs0 = p.qsource[((size_t)e * Sn + l) * B + b];
@@ -204,11 +232,20 @@ __device__ __forceinline__ void osc2_gauss2_body(const osc2_topology *__restrict
     // S * dz / 3 (smc:1126-1163): 3 is a shared divisor, so its reciprocal is refined once (bit-identical
     // quotients, osc2_div.cuh); entries the topology cannot touch are +0 and need no arithmetic at all
     const Osc2Rcp r3 = osc2_rcp_prepare(3.0);
-    for (int r = 0; r < d; ++r)
-        for (int c = 0; c < d; ++c) {
-            const int slot = smap[r * d + c];
-            GOUT(sl.sd(r, c)) = slot ? osc2_div(Sb[(size_t)slot * Ss] * dz, r3) : 0.0;
+    if (skipz) {
+        // slot -> (row, column) of the entries the topology can touch (osc2_build_smap, inverted on the host)
+        const unsigned char *__restrict__ sinv = p.sinv;
+        for (int slot = 1; slot < p.s_slots; ++slot) {
+            const int rc = sinv[slot], r = rc / d, c = rc - r * d;
+            GOUT(sl.sd(r, c)) = osc2_div(Sb[(size_t)slot * Ss] * dz, r3);
         }
+    } else {
+        for (int r = 0; r < d; ++r)
+            for (int c = 0; c < d; ++c) {
+                const int slot = smap[r * d + c];
+                GOUT(sl.sd(r, c)) = slot ? osc2_div(Sb[(size_t)slot * Ss] * dz, r3) : 0.0;
+            }
+    }
 #undef SM_
 #undef FG
 #undef GOUT

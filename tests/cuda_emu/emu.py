@@ -20,7 +20,8 @@ class StepDev(C.Structure):
                             "sysvar", "sysvar_new", "syslod", "gm", "k123", "spill",
                             "norm_solution", "norm_change", "eqteig")] + [
         ("status", c_ip), ("cap_sysmat", c_dp), ("cap_known", c_dp),
-        ("norm_leaf", c_ip), ("norm_prog", c_ip), ("norm_part", c_dp), ("n_leaves", C.c_int), ("n_prog", C.c_int), ("smap", C.c_void_p), ("s_slots", C.c_int), ("cpw", C.c_int), ("NT", C.c_int)]
+        ("norm_leaf", c_ip), ("norm_prog", c_ip), ("norm_part", c_dp), ("n_leaves", C.c_int), ("n_prog", C.c_int), ("smap", C.c_void_p), ("s_slots", C.c_int), ("cpw", C.c_int), ("NT", C.c_int),
+        ("sinv", C.c_void_p), ("gm_prezeroed", C.c_int)]
 
 
 _LIB = None
@@ -80,7 +81,8 @@ def emu_step(topo, arr, capture=False, fast=None, split=True):
         setattr(p, name, a.ctypes.data_as(c_dp))
     outs = {
         "sysvar_new": np.full((total, B), np.nan),
-        "gm": np.full(L.osc2_emu_gm_doubles(d, M, S, int(fast), E, B), np.nan),
+        # fast path: zeroed once like osc2_create does (K_G skips the fields that are +0 for the whole topology)
+        "gm": (np.zeros if fast else (lambda n: np.full(n, np.nan)))(L.osc2_emu_gm_doubles(d, M, S, int(fast), E, B)),
         "k123": np.zeros((3, max(p.nff, 1), E, B)), "spill": np.full(L.osc2_emu_spill_doubles(d, int(fast), N, B), np.nan),
         "norm_solution": np.zeros((d, B)), "norm_change": np.zeros((d, B)), "eqteig": np.zeros((d, B)),
     }
