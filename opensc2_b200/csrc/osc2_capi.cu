@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "step_launch.h"
+#include <cmath>
 #include "props_kernels.cuh"
 #include "tcs_kernels.cuh"
 
@@ -282,6 +283,8 @@ int osc2_device_count(void)
     return n;
 }
 
+static int osc2_upload_math_tables();
+
 int osc2_create(const osc2_topology *topo, int batch, int n_nodes, int device, osc2_handle *out)
 {
     if (!out) return fail(OSC2_ERR_INVALID, "out handle is NULL");
@@ -315,6 +318,7 @@ int osc2_create(const osc2_topology *topo, int batch, int n_nodes, int device, o
     CK(cudaGetDeviceProperties(&prop, device));
     h->max_smem = (int)prop.sharedMemPerBlockOptin;
     h->sm_count = prop.multiProcessorCount;
+    { const int trc = osc2_upload_math_tables(); if (trc) return trc; }
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&h->t0));
     CK(cudaEventCreate(&h->t1));
@@ -369,13 +373,14 @@ int osc2_create(const osc2_topology *topo, int batch, int n_nodes, int device, o
             p.smap = (const unsigned char *)qm;
             p.s_slots = slots;
             if (h->fast) {   // inverse map for K_G's final pass; the constant zeros of `gm` are written once, here
-                std::vector<unsigned char> inv((size_t)slots, 0);
-                for (size_t i = 0; i < map.size(); ++i) if (map[i]) inv[map[i]] = (unsigned char)i;
+                std::vector<unsigned short> inv((size_t)slots, 0);
+                for (size_t i = 0; i < map.size(); ++i)
+                    if (map[i]) inv[map[i]] = (unsigned short)((i % h->d) * 32 + (i / h->d) * p.cpw);
                 double *qi = nullptr;
-                rc = dev_alloc(h, &qi, inv.size() / 8 + 1);
+                rc = dev_alloc(h, &qi, inv.size() / 4 + 1);
                 if (!rc) {
-                    CK(cudaMemcpy(qi, inv.data(), inv.size(), cudaMemcpyHostToDevice));
-                    p.sinv = (const unsigned char *)qi;
+                    CK(cudaMemcpy(qi, inv.data(), inv.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
+                    p.sinv = (const unsigned short *)qi;
                     CK(cudaMemset(p.gm, 0, osc2_gm_doubles(h->d, h->M, h->S, true, E, B) * sizeof(double)));
                     p.gm_prezeroed = 1;
                 }
@@ -408,6 +413,22 @@ int osc2_create(const osc2_topology *topo, int batch, int n_nodes, int device, o
     CK(cudaStreamSynchronize(h->stream));
     guard.h = nullptr;
     *out = h;
+    return OSC2_OK;
+}
+
+// tables of the device exp / log (props_kernels.cuh), rounded from long double; written to the current device
+static int osc2_upload_math_tables()
+{
+    double lt[128][2], et[64];
+    for (int i = 0; i < 128; ++i) {
+        const long double c = 1.0L + (i + 0.5L) / 128.0L;
+        const double rc = (double)(1.0L / c);
+        lt[i][0] = rc;
+        lt[i][1] = (double)(-logl((long double)rc));      // log of the value m is really divided by
+    }
+    for (int k = 0; k < 64; ++k) et[k] = (double)powl(2.0L, k / 64.0L);
+    CK(cudaMemcpyToSymbol(osc2p::osc2_log_table, lt, sizeof lt));
+    CK(cudaMemcpyToSymbol(osc2p::osc2_exp_table, et, sizeof et));
     return OSC2_OK;
 }
 
@@ -550,6 +571,10 @@ int osc2_set_model(osc2_handle h, const osc2_model *model)
         if (rc) return rc;
         h->q.sol_const = c;
         t = nullptr;
+        rc = dev_alloc(h, &t, 2 * (size_t)(h->M > 0 ? h->M : 1) * h->E * h->B);
+        if (rc) return rc;
+        h->q.ch_scratch = t;
+        t = nullptr;
         rc = dev_alloc(h, &t, (size_t)h->S * h->B);
         if (rc) return rc;
         h->q.margin_key = (unsigned long long *)t;
@@ -638,7 +663,12 @@ int osc2_eval_operating_conditions(osc2_handle h, double time)
     { int rc = launch_tmax(h); if (rc) return rc; }
     CudaLauncher L{h};
     const long long work = (long long)h->E * h->B;
-    L.launch(OSC2_K_PROPS, osc2_opcond_kernel, (unsigned)((work + 127) / 128), 128u, (size_t)0,
+    if (h->M > 0)
+        L.launch(OSC2_K_PROPS, osc2_opcond_coolant_kernel, (unsigned)((work * h->M + 127) / 128), 128u, (size_t)0,
+                 (const osc2_topology *)h->topo_dev, h->p, h->q);
+    if (h->S > 0)
+        L.launch(OSC2_K_PROPS, osc2_opcond_solid_kernel, (unsigned)((work * h->S + 127) / 128), 128u, (size_t)0, h->p, h->q);
+    L.launch(OSC2_K_PROPS, osc2_opcond_interface_kernel, (unsigned)((work + 127) / 128), 128u, (size_t)0,
              (const osc2_topology *)h->topo_dev, h->p, h->q);
     if (!h->launch_error.empty()) {
         const int rc = fail(OSC2_ERR_CUDA, "%s", h->launch_error.c_str());

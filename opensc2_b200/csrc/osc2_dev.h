@@ -65,9 +65,10 @@ struct StepDev {
     // so that everything a warp needs for one node is ONE contiguous block (4352 / 4608 bytes at d = 8) that a
     // single bulk copy (cp.async.bulk, TMA) moves
     int cpw, NT;
-    // K_G (fast path): slot -> row * d + column, the inverse of `smap`; gm_prezeroed: `gm` was zeroed at creation
-    // and K_G leaves the fields that are +0 for every element of this topology alone
-    const unsigned char *sinv;
+    // K_G (fast path): slot -> offset of S[row][column] inside the tiled record (column * 32 + row * cpw), the inverse
+    // of `smap`; gm_prezeroed: `gm` was zeroed at creation and K_G leaves the fields that are +0 for every element of
+    // this topology alone
+    const unsigned short *sinv;
     int gm_prezeroed;
 };
 

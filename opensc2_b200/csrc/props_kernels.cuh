@@ -12,6 +12,7 @@
 #pragma once
 
 #include "osc2_dev.h"
+#include "osc2_div.cuh"
 
 struct FluidTableDev {
     int n_p, n_t;
@@ -34,6 +35,7 @@ struct PropsDev {
     double *tmin;            // [S][B] min Gauss temperature (aluminium's whole-array range check)
     int *cb_iters;           // [M][B] array-wide Colebrook iteration count (IFRICTION 122)
     double *sol_const;       // [S][2] RRR-only constants of the copper fit: p7, rhoecu0(273 K)
+    double *ch_scratch;      // [2][M][E][B] coolant kernel -> interface kernel: Nu k / Dh, k rho cp
     double time;
 };
 
@@ -48,18 +50,87 @@ __device__ __forceinline__ double quart(double x) { const double y = x * x; retu
 // a few 1e-15 of the correctly rounded power (the fits' stated tolerance is 2e-12) at a third of pw()'s cost
 // (ONE copy of each: inlined, the ~45 expansions of exp/log made the kernel 150 KB of code, and ncu
 // showed 3 stall cycles per issued instruction waiting for the instruction cache)
-__device__ __noinline__ double pw(double x, double y) { return exp(y * log(x)); }
-__device__ __noinline__ double pw10(double y) { return exp(y * 2.302585092994046); }
+//
+// exp and log here are table-driven (ncu, round 2: the 42 pw() calls of a CASE_1 element were 40 % of K_P's
+// instructions, ~80 each with the CUDA library's exp and log):
+//   log x, x = 2^e m:  m / c_i = 1 + r with c_i the centre of the 1/128-wide interval of m, |r| < 2^-8;
+//                      log x = e ln2 + log c_i + (r - r^2/2 + ... - r^6/6)           table: 1/c_i, log c_i
+//   exp z:             z = k ln2/64 + r, |r| <= ln2/128; exp z = 2^(k/64) (1 + r + ... + r^5/120)   table: 2^(k/64)
+// Measured against long double over x in [1e-8, 1e12], y in [-10, 52] (tools/pw_accuracy.c): x^y within 2.5e-13
+// relative where exp(y log x) with the library functions is within 1.3e-13 -- both errors are the rounding of
+// y log x amplified by |y log x| (up to 600 in that sweep; below 40 in every fit here, i.e. < 2e-14), inside the
+// stated 2e-12 of the fits.  Arguments outside the normal positive range (Re = 0 ...) take the library functions.
+// The tables are written once per device by osc2_upload_math_tables().
+__device__ double2 osc2_log_table[128];      // 1 / c_i (rounded), -log of that rounded value
+__device__ double osc2_exp_table[64];        // 2^(k / 64)
+__device__ __noinline__ double slow_log(double x) { return log(x); }
+__device__ __noinline__ double slow_exp(double z) { return exp(z); }
+__device__ __forceinline__ double flog(double x)
+{
+    const int hi = __double2hiint(x), lo = __double2loint(x);
+    if ((unsigned)(hi - 0x00100000) >= 0x7fe00000u) return slow_log(x);          // zero, negative, subnormal, inf, NaN
+    const int e = (hi >> 20) - 1023, i = (hi >> 13) & 127;
+    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
+    const double2 t = osc2_log_table[i];
+    const double r = __fma_rn(m, t.x, -1.0);
+    double pl = __fma_rn(r, -1.0 / 6, 1.0 / 5);
+    pl = __fma_rn(r, pl, -0.25);
+    pl = __fma_rn(r, pl, 1.0 / 3);
+    pl = __fma_rn(r, pl, -0.5);
+    const double l1 = __fma_rn(__dmul_rn(r, r), pl, r);
+    const double ed = (double)e;
+    const double sum = __fma_rn(ed, 0x1.62e42fefa38p-1, t.y);                // ln2 high part: 42 bits, e * high is exact
+    return __dadd_rn(__dadd_rn(sum, l1), __dmul_rn(ed, 0x1.ef35793c7673p-45));
+}
+__device__ __forceinline__ double fexp(double z)
+{
+    if (!(fabs(z) < 700.0)) return slow_exp(z);
+    const double tk = __fma_rn(z, 64.0 / 0.6931471805599453094172321, 0x1.8p52);   // round to nearest integer
+    const double kd = __dadd_rn(tk, -0x1.8p52);
+    const int k = __double2loint(tk);
+    double r = __fma_rn(-kd, 0x1.62e42fefa38p-7, z);                         // ln2 / 64, high and low part
+    r = __fma_rn(-kd, 0x1.ef35793c7673p-51, r);
+    double pe = __fma_rn(r, 1.0 / 120, 1.0 / 24);
+    pe = __fma_rn(r, pe, 1.0 / 6);
+    pe = __fma_rn(r, pe, 0.5);
+    const double q = __fma_rn(__dmul_rn(r, r), pe, r);
+    const double T = osc2_exp_table[k & 63];
+    const double v = __fma_rn(T, q, T);
+    return __hiloint2double(__double2hiint(v) + ((k >> 6) << 20), __double2loint(v));
+}
+__device__ __noinline__ double pw(double x, double y) { return fexp(y * flog(x)); }
+__device__ __noinline__ double pw10(double y) { return fexp(y * 2.302585092994046); }
+// four independent powers in one body: the instruction streams interleave (a single pw() is one dependent chain of
+// ~25 FP64 operations, and K_P's solid kernel has only 4 warps per scheduler to hide it with)
+struct Pw4 { double a, b, c, d; };
+__device__ __noinline__ Pw4 pw4(double x0, double y0, double x1, double y1, double x2, double y2, double x3, double y3)
+{
+    Pw4 o;
+    const double l0 = flog(x0), l1 = flog(x1), l2 = flog(x2), l3 = flog(x3);
+    o.a = fexp(y0 * l0); o.b = fexp(y1 * l1); o.c = fexp(y2 * l2); o.d = fexp(y3 * l3);
+    return o;
+}
+// exp(y0 L), exp(y1 L), exp(y2 L2) for logarithms already taken (the copper fits raise t to three powers)
+struct Pw3 { double a, b, c; };
+__device__ __noinline__ Pw3 exp3(double z0, double z1, double z2)
+{
+    Pw3 o;
+    o.a = fexp(z0); o.b = fexp(z1); o.c = fexp(z2);
+    return o;
+}
 
 // copper.py:221-275
-__device__ __noinline__ double rhoecu0(double t, double rrr)
+// lt = log(t) (shared with k_cu: one logarithm feeds every power of t; log(50 / t) = log 50 - log t)
+__device__ __forceinline__ double rhoecu0_l(double lt, double rrr)
 {
-    const double P0 = 1.553e-8, P1 = 1.171e-17, P2 = 4.49, P3 = 3.841e10, P4 = 1.14, P5 = 50, P6 = 6.428, P7 = 0.4531;
+    const double P0 = 1.553e-8, P1 = 1.171e-17, P2 = 4.49, P3 = 3.841e10, P4 = 1.14, P6 = 6.428, P7 = 0.4531;
     const double rho0 = P0 / rrr;
-    const double rhoi = (P1 * pw(t, P2)) / (1.0 + P1 * P3 * pw(t, P2 - P4) * exp(-pw(P5 / t, P6)));
+    const Pw3 e = exp3(P2 * lt, (P2 - P4) * lt, P6 * (3.9120230054281460586 - lt));
+    const double rhoi = (P1 * e.a) / (1.0 + P1 * P3 * e.b * fexp(-e.c));
     const double rhoi0 = P7 * rhoi * rho0 / (rhoi + rho0);
     return rho0 + rhoi + rhoi0;
 }
+__device__ __noinline__ double rhoecu0(double t, double rrr) { return rhoecu0_l(flog(t), rrr); }
 // copper.py:140-217, with rhoecu0(t, rrr) and rhoecu0(273, rrr) passed in (evaluated once)
 __device__ inline double rhoecu(double t, double b, double rrr, double rho_t, double rho_273)
 {
@@ -67,7 +138,7 @@ __device__ inline double rhoecu(double t, double b, double rrr, double rho_t, do
     double ccc = 0.0;
     if (b > 0) {
         const double xxx = rho_273 / rho_t * b;
-        const double L = log10(xxx);
+        const double L = flog(xxx) * 0.43429448190325182765;
         double aaa = 0.0;
         aaa = aaa + -2.662 * 1.0;
         aaa = aaa + 0.3168 * L;
@@ -83,18 +154,20 @@ __device__ inline double rhoecu(double t, double b, double rrr, double rho_t, do
 __device__ __noinline__ double k_cu(double t, double b, double rrr, double p7, double rho_273)
 {
     const double beta = 0.634 / rrr;
-    const double P1 = 1.754e-8, P2 = 2.763, P3 = 1102, P4 = -0.165, P5 = 70, P6 = 1.756;
+    const double P1 = 1.754e-8, P2 = 2.763, P3 = 1102, P4 = -0.165, P6 = 1.756;     // P5 = 70
     const double W0 = beta / t;
-    const double Wi = (P1 * pw(t, P2)) / (1 + (P1 * P3 * pw(t, P2 + P4) * exp(-pw(P5 / t, P6))));
+    const double lt = flog(t);
+    const Pw3 e = exp3(P2 * lt, (P2 + P4) * lt, P6 * (4.2484952420493593784 - lt));     // log(P5 / t) = log 70 - log t
+    const double Wi = (P1 * e.a) / (1 + (P1 * P3 * e.b * fexp(-e.c)));
     const double Wi0 = p7 * Wi * W0 / (Wi + W0);
-    const double rho_t = rhoecu0(t, rrr);
+    const double rho_t = rhoecu0_l(lt, rrr);
     return 1.0 / (Wi + W0 + Wi0) * rho_t / rhoecu(t, b, rrr, rho_t, rho_273);
 }
 // copper.py:75-136
 __device__ __noinline__ double cp_cu(double t)
 {
     if (!(t >= 4 && t <= 300)) return 0.0;
-    const double L = log10(t);
+    const double L = flog(t) * 0.43429448190325182765;
     const double L2 = sq(L), L3 = L2 * L, L4 = L2 * L2;
     return pw10(-1.91844 + -0.15973 * L + 8.61013 * L2 + -18.996 * L3 + 21.9661 * L4
                          + -12.7328 * (L4 * L) + 3.54322 * (L3 * L3) + -0.3797 * (L4 * L3));
@@ -162,8 +235,9 @@ __device__ __noinline__ double cp_nb3sn(double T, double TCS, double TC, double 
 __device__ __noinline__ double four_term(double T, double C0, double C1, double C2, double C3, double s0, double s1,
                                    double s2, double s3, double n0, double n1, double n2, double n3)
 {
-    return C0 * T / pw(s0 + T, n0) + C1 * sq(T) / pw(s1 + T, n1) + C2 * cube(T) / pw(s2 + T, n2)
-           + C3 * quart(T) / pw(s3 + T, n3);
+    // x / (s + T)^n as x (s + T)^-n: four FP64 divisions (~40 instructions each) less, one rounding apart
+    const Pw4 w = pw4(s0 + T, -n0, s1 + T, -n1, s2 + T, -n2, s3 + T, -n3);
+    return C0 * T * w.a + C1 * sq(T) * w.b + C2 * cube(T) * w.c + C3 * quart(T) * w.d;
 }
 // stainless_steel.py:5-38
 __device__ inline double k_ss(double t)
@@ -525,15 +599,17 @@ __device__ __noinline__ double nusselt_more(int corr, double re, double pr, doub
 struct Cell { int off; double a, b; int n_t; };
 __device__ inline Cell locate(const FluidTableDev &tab, double p, double t)
 {
-    double fp = floor((p - tab.p_min) / tab.p_step), ft = floor((t - tab.t_min) / tab.t_step);
+    // two quotients per axis share their divisor: exact division through one refined reciprocal (osc2_div.cuh)
+    const Osc2Rcp rps = osc2_rcp_prepare(tab.p_step), rts = osc2_rcp_prepare(tab.t_step);
+    double fp = floor(osc2_div(p - tab.p_min, rps)), ft = floor(osc2_div(t - tab.t_min, rts));
     if (!(fp >= 0.0)) fp = 0.0;
     if (fp > (double)(tab.n_p - 2)) fp = (double)(tab.n_p - 2);
     if (!(ft >= 0.0)) ft = 0.0;
     if (ft > (double)(tab.n_t - 2)) ft = (double)(tab.n_t - 2);
     Cell c;
     c.off = (int)fp * tab.n_t + (int)ft;
-    c.a = (p - (tab.p_min + fp * tab.p_step)) / tab.p_step;
-    c.b = (t - (tab.t_min + ft * tab.t_step)) / tab.t_step;
+    c.a = osc2_div(p - (tab.p_min + fp * tab.p_step), rps);
+    c.b = osc2_div(t - (tab.t_min + ft * tab.t_step), rts);
     c.n_t = tab.n_t;
     return c;
 }
@@ -553,6 +629,19 @@ __device__ inline double linspace_at(double start, double stop, int N, int i)
     const double step = delta / div;
     if (step == 0.0) return ((double)i / div) * delta + start;
     return (double)i * step + start;
+}
+
+// |linspace[i] + linspace[i + 1]| / 2 with the step's division done once
+__device__ inline double linspace_mid(double start, double stop, int N, int i)
+{
+    const double div = (double)(N - 1), delta = stop - start;
+    const double step = delta / div;
+    double a, b;
+    if (step == 0.0) { a = ((double)i / div) * delta + start; b = ((double)(i + 1) / div) * delta + start; }
+    else { a = (double)i * step + start; b = (double)(i + 1) * step + start; }
+    if (N > 1 && i == N - 1) a = stop;
+    if (N > 1 && i + 1 == N - 1) b = stop;
+    return fabs(a + b) / 2.0;
 }
 
 }  // namespace osc2p
@@ -622,108 +711,145 @@ __global__ void osc2_solid_tmax_kernel(const osc2_topology *__restrict__ tp, Ste
     }
 }
 
-// body for element e of conductor b
-__device__ __forceinline__ void osc2_opcond_body(const osc2_topology *__restrict__ tp, const StepDev &p, const PropsDev &q, const int e,
-                                                 const size_t b)
+// ---------------------------------------------------------------------------
+// K_P as three kernels:
+//   osc2_opcond_coolant_kernel     thread per (channel, element, conductor)   tables, Re, Nu, friction
+//   osc2_opcond_solid_kernel       thread per (solid, element, conductor)     Tc, material fits, heat source
+//   osc2_opcond_interface_kernel   thread per (element, conductor)            radiative exchange, HTCs
+// The steady-state coefficient Nu k / Dh and k rho cp of a channel travel to the interface kernel through
+// `ch_scratch` [2][M][E][B].  (Round 1 had one kernel; the split by itself changed nothing -- 14.57 vs 14.59 ms --
+// but the solid part now takes its own register budget: 80 registers / 6 CTAs per SM, 12.7 -> 11.7 ms.)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) osc2_opcond_coolant_kernel(const osc2_topology *__restrict__ tp, StepDev p, PropsDev q)
 {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long EB = (long long)p.E * p.B;
+    if (idx >= EB * p.M) return;
+    const int j = (int)(idx / EB);
+    const long long rem = idx - (long long)j * EB;
+    const int e = (int)(rem / p.B);
+    const size_t b = (size_t)(rem % p.B);
+    const size_t B = (size_t)p.B;
+    const int M = p.M, d = p.d, E = p.E, N = p.N;
+    const osc2_model *md = q.model;
+    const double *x0 = p.sysvar + ((size_t)e * d) * B + b;
+    const double *x1 = x0 + (size_t)d * B;
+    double *fg = const_cast<double *>(p.fl_gauss);
+    const FluidTableDev &tab = q.fluid[md->ch_fluid[j]];
+    const double v = (x0[(size_t)j * B] + x1[(size_t)j * B]) / 2.0;
+    const double pr = (x0[(size_t)(M + j) * B] + x1[(size_t)(M + j) * B]) / 2.0;
+    const double T = (x0[(size_t)(2 * M + j) * B] + x1[(size_t)(2 * M + j) * B]) / 2.0;
+    const osc2p::Cell c = osc2p::locate(tab, pr, T);
+    const double rho = osc2p::lookup(tab, c, OSC2_FP_RHO), mu = osc2p::lookup(tab, c, OSC2_FP_MU);
+    const double cv = osc2p::lookup(tab, c, OSC2_FP_CV), kk = osc2p::lookup(tab, c, OSC2_FP_K);
+    const double re = fabs(tp->ch_dh[j] * v * rho / mu);
+    const double grun = osc2p::lookup(tab, c, OSC2_FP_BETA) / osc2p::lookup(tab, c, OSC2_FP_KAPPA) / cv / rho;
+    const int hcorr = md->ch_htc_corr[j];
+    const double nu = (hcorr == 212) ? osc2p::nusselt_212(re)
+                      : (hcorr == 1) ? osc2p::nusselt_1(re, osc2p::lookup(tab, c, OSC2_FP_PRANDTL))
+                                     : osc2p::nusselt_more(hcorr, re, osc2p::lookup(tab, c, OSC2_FP_PRANDTL), tp->ch_dh[j]);
+    const double ftot = osc2p::friction_total(md, tp, j, re, q.cb_iters[(size_t)j * B + b]);
+#define FGW(qq) fg[((((size_t)(qq) * M + j) * E) + e) * B + b]
+    FGW(0) = v; FGW(1) = pr; FGW(2) = T; FGW(3) = rho;
+    FGW(4) = osc2p::lookup(tab, c, OSC2_FP_SOUND);
+    FGW(5) = grun;
+    FGW(6) = osc2p::lookup(tab, c, OSC2_FP_H);
+    FGW(7) = cv;
+    FGW(8) = ftot;
+#undef FGW
+    q.ch_scratch[(((size_t)0 * M + j) * E + e) * B + b] = nu * kk / tp->ch_dh[j];
+    q.ch_scratch[(((size_t)1 * M + j) * E + e) * B + b] = kk * rho * osc2p::lookup(tab, c, OSC2_FP_CP);   // k rho cp of the transient HTC
+    if (e == 0) {   // nodal values the boundary rows look at
+        double *fn = const_cast<double *>(p.fl_node);
+        const double *xl = p.sysvar + ((size_t)(N - 1) * d) * B + b;
+        fn[((size_t)0 * M + j) * B + b] = x0[(size_t)j * B];
+        fn[((size_t)1 * M + j) * B + b] = xl[(size_t)j * B];
+        const osc2p::Cell cf = osc2p::locate(tab, x0[(size_t)(M + j) * B], x0[(size_t)(2 * M + j) * B]);
+        const osc2p::Cell cl = osc2p::locate(tab, xl[(size_t)(M + j) * B], xl[(size_t)(2 * M + j) * B]);
+        fn[((size_t)2 * M + j) * B + b] = osc2p::lookup(tab, cf, OSC2_FP_RHO);
+        fn[((size_t)3 * M + j) * B + b] = osc2p::lookup(tab, cl, OSC2_FP_RHO);
+    }
+}
+
+__global__ void __launch_bounds__(128, 6) osc2_opcond_solid_kernel(StepDev p, PropsDev q)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long EB = (long long)p.E * p.B;
+    if (idx >= EB * p.S) return;
+    const int l = (int)(idx / EB);
+    const long long rem = idx - (long long)l * EB;
+    const int e = (int)(rem / p.B);
+    const size_t b = (size_t)(rem % p.B);
     const size_t B = (size_t)p.B;
     const int M = p.M, S = p.S, d = p.d, E = p.E, N = p.N;
     const osc2_model *md = q.model;
-    const double *x0 = p.sysvar + ((size_t)e * d) * B + b;          // node e
-    const double *x1 = x0 + (size_t)d * B;                          // node e + 1
-    double *fg = const_cast<double *>(p.fl_gauss);
+    const double *x0 = p.sysvar + ((size_t)e * d) * B + b;
+    const double *x1 = x0 + (size_t)d * B;
     double *sg = const_cast<double *>(p.sol_gauss);
-    double tf[OSC2_MAX_CHANNELS], hst[OSC2_MAX_CHANNELS], rcp[OSC2_MAX_CHANNELS];
-
-    for (int j = 0; j < M; ++j) {
-        const FluidTableDev &tab = q.fluid[md->ch_fluid[j]];
-        const double v = (x0[(size_t)j * B] + x1[(size_t)j * B]) / 2.0;
-        const double pr = (x0[(size_t)(M + j) * B] + x1[(size_t)(M + j) * B]) / 2.0;
-        const double T = (x0[(size_t)(2 * M + j) * B] + x1[(size_t)(2 * M + j) * B]) / 2.0;
-        const osc2p::Cell c = osc2p::locate(tab, pr, T);
-        const double rho = osc2p::lookup(tab, c, OSC2_FP_RHO), mu = osc2p::lookup(tab, c, OSC2_FP_MU);
-        const double cv = osc2p::lookup(tab, c, OSC2_FP_CV), kk = osc2p::lookup(tab, c, OSC2_FP_K);
-        const double re = fabs(tp->ch_dh[j] * v * rho / mu);
-        const double grun = osc2p::lookup(tab, c, OSC2_FP_BETA) / osc2p::lookup(tab, c, OSC2_FP_KAPPA) / cv / rho;
-        const int hcorr = md->ch_htc_corr[j];
-        const double nu = (hcorr == 212) ? osc2p::nusselt_212(re)
-                          : (hcorr == 1) ? osc2p::nusselt_1(re, osc2p::lookup(tab, c, OSC2_FP_PRANDTL))
-                                         : osc2p::nusselt_more(hcorr, re, osc2p::lookup(tab, c, OSC2_FP_PRANDTL), tp->ch_dh[j]);
-        const double ftot = osc2p::friction_total(md, tp, j, re, q.cb_iters[(size_t)j * B + b]);
-#define FGW(qq) fg[((((size_t)(qq) * M + j) * E) + e) * B + b]
-        FGW(0) = v; FGW(1) = pr; FGW(2) = T; FGW(3) = rho;
-        FGW(4) = osc2p::lookup(tab, c, OSC2_FP_SOUND);
-        FGW(5) = grun;
-        FGW(6) = osc2p::lookup(tab, c, OSC2_FP_H);
-        FGW(7) = cv;
-        FGW(8) = ftot;
-#undef FGW
-        tf[j] = T;
-        hst[j] = nu * kk / tp->ch_dh[j];
-        rcp[j] = kk * rho * osc2p::lookup(tab, c, OSC2_FP_CP);     // k * rho * cp of the transient HTC
-        if (e == 0) {   // nodal values the boundary rows look at
-            double *fn = const_cast<double *>(p.fl_node);
-            const double *xl = p.sysvar + ((size_t)(N - 1) * d) * B + b;
-            fn[((size_t)0 * M + j) * B + b] = x0[(size_t)j * B];
-            fn[((size_t)1 * M + j) * B + b] = xl[(size_t)j * B];
-            const osc2p::Cell cf = osc2p::locate(tab, x0[(size_t)(M + j) * B], x0[(size_t)(2 * M + j) * B]);
-            const osc2p::Cell cl = osc2p::locate(tab, xl[(size_t)(M + j) * B], xl[(size_t)(2 * M + j) * B]);
-            fn[((size_t)2 * M + j) * B + b] = osc2p::lookup(tab, cf, OSC2_FP_RHO);
-            fn[((size_t)3 * M + j) * B + b] = osc2p::lookup(tab, cl, OSC2_FP_RHO);
-        }
-    }
-
     double *sqv = const_cast<double *>(p.sol_q);
-    for (int l = 0; l < S; ++l) {
-        const int is = 3 * M + l;
-        const double T = fabs(x0[(size_t)is * B] + x1[(size_t)is * B]) / 2.0;
-        const double biss = q.b_field[((size_t)l * 2 + 0) * B + b], boss = q.b_field[((size_t)l * 2 + 1) * B + b];
-        const double bg = fabs(osc2p::linspace_at(biss, boss, N, e) + osc2p::linspace_at(biss, boss, N, e + 1)) / 2.0;
-        const int nmat = md->sol_nmat[l];
-        const int kind = md->sol_kind[l];
-        double tc = 0.0, tcs = 0.0;
-        if (kind == OSC2_SOLID_STRAND_MIXED) {
-            const double eps = q.eps[(size_t)l * B + b];
-            // strand_component.py:191-246: Tc by superconducting_material (a StrandMixedComponent has two
-            // materials, stabiliser and superconductor)
-            tc = (md->sol_mat[l][0] == OSC2_MAT_NBTI || md->sol_mat[l][nmat - 1] == OSC2_MAT_NBTI)
-                     ? osc2p::tc_nbti(bg, md->sol_bc20m[l], md->sol_tc0m[l])
-                 : osc2p::tc_nb3sn(bg, (eps + eps) / 2.0, md->sol_tc0m[l], md->sol_bc20m[l]);
-            tcs = q.tcs ? q.tcs[((size_t)l * E + e) * B + b] : 0.0;
-        }
-        const double tmax = q.tmax[(size_t)l * B + b], tmin = q.tmin[(size_t)l * B + b];
-        double nsum = 0.0, cps = 0.0, ksum = 0.0, rho1 = 0.0, cp1 = 0.0, k1 = 0.0;
-        for (int i = 0; i < nmat; ++i) {
-            const int mat = md->sol_mat[l][i];
-            const double w = md->sol_weight[l][i];
-            const double rho_i = osc2p::mat_density(mat);
-            double cp_i, k_i;
-            osc2p::material_cp_k(mat, T, bg, tcs, tc, tmin, tmax, md->sol_rrr[l], md->sol_tc0m[l], q.sol_const[2 * l],
-                                 q.sol_const[2 * l + 1], cp_i, k_i);
-            const double num = rho_i * w;
-            if (i == 0) { nsum = num; cps = cp_i * num; ksum = k_i * w; rho1 = rho_i; cp1 = cp_i; k1 = k_i; }
-            else { nsum = nsum + num; cps = cps + cp_i * num; ksum = ksum + k_i * w; }
-        }
-        double rho, cp, kk;
-        if ((kind == OSC2_SOLID_JACKET && nmat == 1) || kind == OSC2_SOLID_STRAND_STAB) { rho = rho1; cp = cp1; kk = k1; }
-        else { rho = nsum / md->sol_weight_sum[l]; cp = cps / nsum; kk = ksum / md->sol_weight_sum[l]; }
-        sg[(((size_t)0 * S + l) * E + e) * B + b] = rho;
-        sg[(((size_t)1 * S + l) * E + e) * B + b] = cp;
-        sg[(((size_t)2 * S + l) * E + e) * B + b] = kk;
-        // square-wave external heating
-        const double n0 = q.q_window[((size_t)l * 4 + 0) * B + b], n1 = q.q_window[((size_t)l * 4 + 1) * B + b];
-        const double tb = q.q_window[((size_t)l * 4 + 2) * B + b], te = q.q_window[((size_t)l * 4 + 3) * B + b];
-        const double q0 = q.q0[(size_t)l * B + b];
-        const bool on_now = md->sol_heated[l] && q.time >= tb && q.time <= te;
-        const bool on_t0 = md->sol_heated[l] && 0.0 >= tb && 0.0 <= te;
-        for (int side = 0; side < 2; ++side) {
-            const int node = e + side;
-            const bool in = node >= (int)n0 && node <= (int)n1;
-            sqv[(((((size_t)side * S + l) * E + e) * 2) + 0) * B + b] = (on_now && in) ? q0 : 0.0;
-            sqv[(((((size_t)side * S + l) * E + e) * 2) + 1) * B + b] = (on_t0 && in) ? q0 : 0.0;
-        }
+    const int is = 3 * M + l;
+    const double T = fabs(x0[(size_t)is * B] + x1[(size_t)is * B]) / 2.0;
+    const double biss = q.b_field[((size_t)l * 2 + 0) * B + b], boss = q.b_field[((size_t)l * 2 + 1) * B + b];
+    const double bg = osc2p::linspace_mid(biss, boss, N, e);
+    const int nmat = md->sol_nmat[l];
+    const int kind = md->sol_kind[l];
+    double tc = 0.0, tcs = 0.0;
+    if (kind == OSC2_SOLID_STRAND_MIXED) {
+        const double eps = q.eps[(size_t)l * B + b];
+        tc = (md->sol_mat[l][0] == OSC2_MAT_NBTI || md->sol_mat[l][nmat - 1] == OSC2_MAT_NBTI)
+                 ? osc2p::tc_nbti(bg, md->sol_bc20m[l], md->sol_tc0m[l])
+             : osc2p::tc_nb3sn(bg, (eps + eps) / 2.0, md->sol_tc0m[l], md->sol_bc20m[l]);
+        tcs = q.tcs ? q.tcs[((size_t)l * E + e) * B + b] : 0.0;
     }
+    const double tmax = q.tmax[(size_t)l * B + b], tmin = q.tmin[(size_t)l * B + b];
+    double nsum = 0.0, cps = 0.0, ksum = 0.0, rho1 = 0.0, cp1 = 0.0, k1 = 0.0;
+    for (int i = 0; i < nmat; ++i) {
+        const int mat = md->sol_mat[l][i];
+        const double w = md->sol_weight[l][i];
+        const double rho_i = osc2p::mat_density(mat);
+        double cp_i, k_i;
+        osc2p::material_cp_k(mat, T, bg, tcs, tc, tmin, tmax, md->sol_rrr[l], md->sol_tc0m[l], q.sol_const[2 * l],
+                             q.sol_const[2 * l + 1], cp_i, k_i);
+        const double num = rho_i * w;
+        if (i == 0) { nsum = num; cps = cp_i * num; ksum = k_i * w; rho1 = rho_i; cp1 = cp_i; k1 = k_i; }
+        else { nsum = nsum + num; cps = cps + cp_i * num; ksum = ksum + k_i * w; }
+    }
+    double rho, cp, kk;
+    if ((kind == OSC2_SOLID_JACKET && nmat == 1) || kind == OSC2_SOLID_STRAND_STAB) { rho = rho1; cp = cp1; kk = k1; }
+    else { rho = nsum / md->sol_weight_sum[l]; cp = cps / nsum; kk = ksum / md->sol_weight_sum[l]; }
+    sg[(((size_t)0 * S + l) * E + e) * B + b] = rho;
+    sg[(((size_t)1 * S + l) * E + e) * B + b] = cp;
+    sg[(((size_t)2 * S + l) * E + e) * B + b] = kk;
+    // square-wave external heating
+    const double n0 = q.q_window[((size_t)l * 4 + 0) * B + b], n1 = q.q_window[((size_t)l * 4 + 1) * B + b];
+    const double tb = q.q_window[((size_t)l * 4 + 2) * B + b], te = q.q_window[((size_t)l * 4 + 3) * B + b];
+    const double q0 = q.q0[(size_t)l * B + b];
+    const bool on_now = md->sol_heated[l] && q.time >= tb && q.time <= te;
+    const bool on_t0 = md->sol_heated[l] && 0.0 >= tb && 0.0 <= te;
+    for (int side = 0; side < 2; ++side) {
+        const int node = e + side;
+        const bool in = node >= (int)n0 && node <= (int)n1;
+        sqv[(((((size_t)side * S + l) * E + e) * 2) + 0) * B + b] = (on_now && in) ? q0 : 0.0;
+        sqv[(((((size_t)side * S + l) * E + e) * 2) + 1) * B + b] = (on_t0 && in) ? q0 : 0.0;
+    }
+}
 
+__global__ void __launch_bounds__(128) osc2_opcond_interface_kernel(const osc2_topology *__restrict__ tp, StepDev p, PropsDev q)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)p.E * p.B) return;
+    const int e = (int)(idx / p.B);
+    const size_t b = (size_t)(idx % p.B);
+    const size_t B = (size_t)p.B;
+    const int M = p.M, S = p.S, d = p.d, E = p.E, N = p.N;
+    const osc2_model *md = q.model;
+    const double *x0 = p.sysvar + ((size_t)e * d) * B + b;
+    const double *x1 = x0 + (size_t)d * B;
+    const double *sg = p.sol_gauss;
+    double *sqv = const_cast<double *>(p.sol_q);
+#define TF(j) ((x0[(size_t)(2 * M + (j)) * B] + x1[(size_t)(2 * M + (j)) * B]) / 2.0)
+#define HST(j) q.ch_scratch[(((size_t)0 * M + (j)) * E + e) * B + b]
+#define RCP(j) q.ch_scratch[(((size_t)1 * M + (j)) * E + e) * B + b]
     // radiative exchange between jackets (HTC_choice +-3): explicit, evaluated at the two NODES of the element
     // from the nodal temperatures and added to the heat sources of both solids, interface by interface
     // (jacket_component.py:174-232, conductor.py:5161-5228, 4558-4579)
@@ -740,23 +866,21 @@ __device__ __forceinline__ void osc2_opcond_body(const osc2_topology *__restrict
             sqv[(((((size_t)side * S + c) * E + e) * 2) + 0) * B + b] += ph * (Ta - Tc);
         }
     }
-
-    // interface heat transfer coefficients
     double *hfs = const_cast<double *>(p.htc_fs);
     for (int k = 0; k < p.nfs; ++k) {
         const int j = tp->fs[k][0], l = tp->fs[k][1];
         double h;
         if (md->fs_choice[k] == 2) {
             const int is = 3 * M + l;
-            const double Ts = fabs(x0[(size_t)is * B] + x1[(size_t)is * B]) / 2.0, Tf = tf[j];
+            const double Ts = fabs(x0[(size_t)is * B] + x1[(size_t)is * B]) / 2.0, Tf = TF(j);
             const double hK = 200.0 * (Ts + Tf) * (osc2p::sq(Ts) + osc2p::sq(Tf));
             const double tqbeg = q.q_window[((size_t)l * 4 + 2) * B + b];
             double full = 0.0;
             if (q.time > tqbeg) {
-                const double htr = sqrt(rcp[j] / (3.141592653589793 * (q.time - tqbeg)));
+                const double htr = sqrt(RCP(j) / (3.141592653589793 * (q.time - tqbeg)));
                 full = (hK * htr) / (hK + htr);
             }
-            h = fmax(hst[j] * md->fs_mlt[k], full);
+            h = fmax(HST(j) * md->fs_mlt[k], full);
         } else {
             h = md->fs_htc[k] * md->fs_mlt[k];
         }
@@ -767,9 +891,9 @@ __device__ __forceinline__ void osc2_opcond_body(const osc2_topology *__restrict
         const int ja = tp->ff[k][0], jb = tp->ff[k][1];
         double ho, hc;
         if (md->ff_choice[k] == 2) {
-            const double h1 = hst[ja], h2 = hst[jb];
+            const double h1 = HST(ja), h2 = HST(jb);
             ho = md->ff_mlt[k] * h1 * h2 / (h1 + h2);
-            const double cond = osc2p::k_ss((tf[ja] + tf[jb]) / 2);
+            const double cond = osc2p::k_ss((TF(ja) + TF(jb)) / 2);
             const double rwall = md->ff_thick[k] / cond;
             hc = md->ff_mlt[k] / (1 / h1 + 1 / h2 + rwall);
         } else {
@@ -801,11 +925,7 @@ __device__ __forceinline__ void osc2_opcond_body(const osc2_topology *__restrict
         hes[(((size_t)k * 3 + 1) * E + e) * B + b] = 0.0;
         hes[(((size_t)k * 3 + 2) * E + e) * B + b] = 0.0;
     }
-}
-
-__global__ void __launch_bounds__(128, 6) osc2_opcond_kernel(const osc2_topology *__restrict__ tp, StepDev p, PropsDev q)
-{
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long long)p.E * p.B) return;
-    osc2_opcond_body(tp, p, q, (int)(idx / p.B), (size_t)(idx % p.B));
+#undef TF
+#undef HST
+#undef RCP
 }

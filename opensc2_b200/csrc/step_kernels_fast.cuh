@@ -56,23 +56,23 @@ __device__ __forceinline__ void osc2_prefetch_l2(const void *ptr)
 // Gauss-point values into the element-matrix values (smc:1015-1216).
 // ---------------------------------------------------------------------------
 // body for element e of conductor b; sm_dyn: s_slots * blockDim.x doubles of shared memory
-template <bool SMEM_S>
-__device__ __forceinline__ void osc2_gauss2_body(const osc2_topology *__restrict__ tp, const StepDev &p, double *sm_dyn, const int e,
-                                                 const size_t b)
+// `g`: the record of (element e, conductor b) without the lane offset of the row -- in `gm` (K_G) or in a consumer's
+// shared-memory ring (INREC: the producer warps of osc2_forward_fused_kernel); Sb, Ss: per-thread SMAT staging
+// column and its stride (unused with INREC, where SMAT is accumulated in the record itself)
+template <bool SMEM_S, bool INREC>
+__device__ __forceinline__ void osc2_gauss2_body(const osc2_topology *__restrict__ tp, const StepDev &p, double *g, double *Sb,
+                                                 const size_t Ss, const int e, const size_t b)
 {
     const size_t B = (size_t)p.B;
     const int M = p.M, Sn = p.S, d = p.d, E = p.E;
     const GmSlots2 sl{d, M, Sn, p.cpw};
-    double *g = p.gm + ((size_t)e * p.NT + b / p.cpw) * sl.block() + b % p.cpw;
     static_assert(SMEM_S, "the fast path always stages SMAT in shared memory");
-    double *Sb = sm_dyn + threadIdx.x;
-    const size_t Ss = blockDim.x;
     const unsigned char *__restrict__ smap = p.smap;
     // `gm` was zeroed when the handle was created and nothing but this kernel writes it: fields that are +0 for
     // every element of this topology (SMAT entries no statement can touch, the load halves of the fluid rows,
     // the advection entries of the solid rows) are not written again -- 440 of the 1088 bytes of a CASE_1 record
-    const bool skipz = p.gm_prezeroed != 0;
-#define SM_(r, c) Sb[(size_t)smap[(r) * d + (c)] * Ss]
+    const bool skipz = INREC || p.gm_prezeroed != 0;
+#define SM_(r, c) (*(INREC ? &g[(c) * 32 + (r) * sl.cpw] : &Sb[(size_t)smap[(r) * d + (c)] * Ss]))
 #define FG(q, j) p.fl_gauss[((((size_t)(q) * M + (j)) * E) + e) * B + b]
 #define GOUT(slot) g[slot]
     // The kernel is bound by load latency (ncu: 67 % of the stall samples wait for global loads that sit inside
@@ -80,17 +80,20 @@ __device__ __forceinline__ void osc2_gauss2_body(const osc2_topology *__restrict
     // requested from L2 up front, the loads below then hit L2
     {
         const size_t EB = (size_t)E * B, eb = (size_t)e * B + b;
+        // `n` lines, `stride` doubles apart (running pointers: a 64-bit multiply per address costs three instructions)
+        auto run = [](const double *q0, int n, size_t stride) { for (int i = 0; i < n; ++i, q0 += stride) osc2_prefetch_l2(q0); };
         osc2_prefetch_l2(p.dz + eb);
-        for (int q = 0; q < 9 * M; ++q) osc2_prefetch_l2(p.fl_gauss + (size_t)q * EB + eb);
-        for (int q = 0; q < 2 * p.nff; ++q) { osc2_prefetch_l2(p.peri_ff + (size_t)q * EB + eb); osc2_prefetch_l2(p.htc_ff + (size_t)q * EB + eb); }
-        for (int q = 0; q < p.nfs; ++q) { osc2_prefetch_l2(p.peri_fs + (size_t)q * EB + eb); osc2_prefetch_l2(p.htc_fs + (size_t)q * EB + eb); }
-        for (int q = 0; q < p.nss; ++q) { osc2_prefetch_l2(p.peri_ss + (size_t)q * EB + eb); osc2_prefetch_l2(p.htc_ss + (size_t)q * EB + eb); }
-        for (int q = 0; q < p.nes; ++q) { osc2_prefetch_l2(p.peri_es + (size_t)q * EB + eb); osc2_prefetch_l2(p.htc_es + (size_t)q * 3 * EB + eb); }
-        for (int q = 0; q < 3 * Sn; ++q) osc2_prefetch_l2(p.sol_gauss + (size_t)q * EB + eb);
-        for (int q = 0; q < 2 * Sn; ++q) { osc2_prefetch_l2(p.sol_q + ((size_t)q * E + e) * 2 * B + b); osc2_prefetch_l2(p.sol_q + ((size_t)q * E + e) * 2 * B + B + b); }
-        for (int l = 0; l < 2 * Sn; ++l) osc2_prefetch_l2(p.qsource + ((size_t)e * Sn + l) * B + b);
+        run(p.fl_gauss + eb, 9 * M, EB);
+        run(p.peri_ff + eb, 2 * p.nff, EB); run(p.htc_ff + eb, 2 * p.nff, EB);
+        run(p.peri_fs + eb, p.nfs, EB); run(p.htc_fs + eb, p.nfs, EB);
+        run(p.peri_ss + eb, p.nss, EB); run(p.htc_ss + eb, p.nss, EB);
+        run(p.peri_es + eb, p.nes, EB); run(p.htc_es + eb, p.nes, 3 * EB);
+        run(p.sol_gauss + eb, 3 * Sn, EB);
+        run(p.sol_q + (size_t)e * 2 * B + b, 2 * Sn, 2 * EB); run(p.sol_q + (size_t)e * 2 * B + B + b, 2 * Sn, 2 * EB);
+        run(p.qsource + (size_t)e * Sn * B + b, 2 * Sn, B);
     }
-    for (int i = 0; i < p.s_slots; ++i) Sb[(size_t)i * Ss] = 0.0;
+    if (INREC) { for (int slot = 1; slot < p.s_slots; ++slot) g[p.sinv[slot]] = 0.0; }
+    else for (int i = 0; i < p.s_slots; ++i) Sb[(size_t)i * Ss] = 0.0;
     const double dz = p.dz[(size_t)e * B + b];
     const double alpha = 0.0;
     const double cdiag = dz * (1. / 3. + alpha), coff = dz * (1. / 6. - alpha);
@@ -233,12 +236,11 @@ __device__ __forceinline__ void osc2_gauss2_body(const osc2_topology *__restrict
     // quotients, osc2_div.cuh); entries the topology cannot touch are +0 and need no arithmetic at all
     const Osc2Rcp r3 = osc2_rcp_prepare(3.0);
     if (skipz) {
-        // slot -> (row, column) of the entries the topology can touch (osc2_build_smap, inverted on the host)
-        const unsigned char *__restrict__ sinv = p.sinv;
-        for (int slot = 1; slot < p.s_slots; ++slot) {
-            const int rc = sinv[slot], r = rc / d, c = rc - r * d;
-            GOUT(sl.sd(r, c)) = osc2_div(Sb[(size_t)slot * Ss] * dz, r3);
-        }
+        // slot -> offset of S[r][c] in the record, for the entries the topology can touch (osc2_build_smap, inverted
+        // on the host: a division by the run-time d here cost 27 instructions per entry)
+        const unsigned short *__restrict__ sinv = p.sinv;
+        if (INREC) { for (int slot = 1; slot < p.s_slots; ++slot) { double *q = g + sinv[slot]; *q = osc2_div(*q * dz, r3); } }
+        else for (int slot = 1; slot < p.s_slots; ++slot) GOUT(sinv[slot]) = osc2_div(Sb[(size_t)slot * Ss] * dz, r3);
     } else {
         for (int r = 0; r < d; ++r)
             for (int c = 0; c < d; ++c) {
@@ -257,7 +259,10 @@ __global__ void osc2_gauss2_kernel(const osc2_topology *__restrict__ tp, StepDev
     OSC2_DYN_SMEM(sm_dyn);
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)p.E * p.B) return;
-    osc2_gauss2_body<SMEM_S>(tp, p, sm_dyn, (int)(idx / p.B), (size_t)(idx % p.B));
+    const int e = (int)(idx / p.B);
+    const size_t b = (size_t)(idx % p.B);
+    double *g = p.gm + ((size_t)e * p.NT + b / p.cpw) * ((size_t)(p.d + 9) * 32) + b % p.cpw;
+    osc2_gauss2_body<SMEM_S, false>(tp, p, g, sm_dyn + threadIdx.x, blockDim.x, e, b);
 }
 
 // max(m, |v|) as one compare and one select (a NaN never wins, as in `if (|v| > m) m = |v|`)

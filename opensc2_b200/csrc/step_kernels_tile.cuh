@@ -32,6 +32,19 @@ inline void osc2_bulk_store(void *dst, const void *src, unsigned bytes) { std::m
 inline void osc2_bulk_store_wait_read() {}
 inline void osc2_bulk_store_wait_all() {}
 inline void osc2_fence_async_smem() {}
+// CTA-scope mbarrier between warps (fused kernel): 16 bytes of shared memory per barrier
+struct EmuMbar { std::atomic<unsigned> pending, phase; unsigned count, pad; };
+inline void osc2_cbar_init(void *bar, unsigned count) { auto *m = new (bar) EmuMbar; m->pending.store(count); m->phase.store(0); m->count = count; }
+inline void osc2_cbar_arrive(void *bar)
+{
+    auto *m = (EmuMbar *)bar;
+    if (m->pending.fetch_sub(1, std::memory_order_acq_rel) == 1) { m->pending.store(m->count); m->phase.fetch_add(1, std::memory_order_release); }
+}
+inline void osc2_cbar_wait(void *bar, unsigned parity)
+{
+    auto *m = (EmuMbar *)bar;
+    while ((m->phase.load(std::memory_order_acquire) & 1u) == parity) std::this_thread::yield();
+}
 #else
 __device__ __forceinline__ unsigned osc2_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void osc2_mbar_init(unsigned long long *bar, unsigned count)
@@ -70,6 +83,13 @@ __device__ __forceinline__ void osc2_bulk_store(void *dst, const void *src, unsi
 }
 __device__ __forceinline__ void osc2_bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void osc2_bulk_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// CTA-scope mbarrier between warps (fused kernel): arrive has release, the wait acquire semantics
+__device__ __forceinline__ void osc2_cbar_init(void *bar, unsigned count) { osc2_mbar_init((unsigned long long *)bar, count); }
+__device__ __forceinline__ void osc2_cbar_arrive(void *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(osc2_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void osc2_cbar_wait(void *bar, unsigned parity) { osc2_mbar_wait((unsigned long long *)bar, parity); }
 // generic-proxy writes to shared memory -> visible to the async proxy (the bulk store engine)
 __device__ __forceinline__ void osc2_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 #endif
@@ -92,21 +112,33 @@ struct TileFwdSmem {
     static constexpr size_t BYTES = (size_t)DOUBLES * sizeof(double);
 };
 
-template <int D, int LPC, bool FULL>
-__global__ void __launch_bounds__(32) osc2_forward_tile_kernel(const osc2_topology *__restrict__ tp, StepDev p)
+// Where one warp of the forward sweep finds its shared memory.  FUSED (step_kernels_fused.cuh): the element records
+// are not copied in from `gm` but written into the ring by a producer warp of the same CTA; `full` / `empty` are the
+// mbarriers of the ring stages (16 bytes apart), shared by the consumer warps one producer serves.
+struct TileFwdCtx {
+    double *rec;                 // [NST][NF][32] ring of element records
+    double *stg;                 // [PW][32] factor rows of one node on their way out
+    double *pub;                 // [CPW][PUBC] published pivot rows
+    unsigned long long *bars;    // !FUSED: the NST mbarriers of the bulk loads
+    double *full, *empty;        // FUSED
+    size_t tile;
+    bool tile_valid;             // FUSED: a CTA covers 8 tiles, the last CTA may own tiles past the batch
+};
+
+template <int D, int LPC, bool FULL, bool FUSED, int NST>
+__device__ __forceinline__ void osc2_forward_tile_body(const osc2_topology *__restrict__ tp, const StepDev &p, const TileFwdCtx &cx)
 {
     static_assert(D % 8 == 0, "closed-form Known: D % 8 == 0");
     static_assert(!FULL || LPC == D, "FULL: every lane owns a row");
-    OSC2_DYN_SMEM_ALIGNED(sm_dyn);
     using SM = TileFwdSmem<D, LPC>;
-    constexpr int CPW = SM::CPW, PW = SM::PW, NF = SM::NF, NST = SM::NST;
+    constexpr int CPW = SM::CPW, PW = SM::PW;
     const int M = p.M, N = p.N;
     const size_t B = (size_t)p.B;
     const int lane = threadIdx.x & 31;
     const int r = lane / CPW, bb = lane % CPW;
-    const size_t tile = blockIdx.x;
+    const size_t tile = cx.tile;
     const long long b_ll = (long long)tile * CPW + bb;
-    const bool act = FULL || ((b_ll < (long long)p.B) && (r < D));
+    const bool act = FULL || ((b_ll < (long long)p.B) && (r < D) && (!FUSED || cx.tile_valid));
     const size_t b = act ? (size_t)b_ll : 0;
     const int rr_ = (FULL || r < D) ? r : 0;
     const Osc2Rcp rdt = osc2_rcp_prepare(p.dt);
@@ -114,10 +146,10 @@ __global__ void __launch_bounds__(32) osc2_forward_tile_kernel(const osc2_topolo
     const bool shift = (p.num_step > 1);
     unsigned div_span = osc2_abs_hi(p.dt) - OSC2_HI_DIV_LO;     // divisor range: dt, then every pivot
 
-    double *rec = sm_dyn;                                        // [NST][NF][32]
-    double *stg = rec + NST * SM::REC;                           // [PW][32]
-    double *pub = stg + SM::STG + (size_t)bb * SM::PUBC;         // this conductor's [D][PW]
-    unsigned long long *bars = (unsigned long long *)(sm_dyn + NST * SM::REC + SM::STG + CPW * SM::PUBC);
+    double *rec = cx.rec;                                        // [NST][NF][32]
+    double *stg = cx.stg;                                        // [PW][32]
+    double *pub = cx.pub + (size_t)bb * SM::PUBC;                // this conductor's [D][PW]
+    unsigned long long *bars = cx.bars;
 
     // column of the off-diagonal AMAT entry of this row (smc:62-101)
     int kind = 3, j = 0, aoffcol = -1;
@@ -165,22 +197,30 @@ __global__ void __launch_bounds__(32) osc2_forward_tile_kernel(const osc2_topolo
     double *sptile = p.spill + tile * SM::STG;                   // factor rows of node 0 of this tile
     const size_t sstep = (size_t)p.NT * SM::STG;
     auto issue = [&](const int e) {                              // lane 0: start the copy of element e (stage e % NST is free)
-        if (lane == 0 && e < N - 1) {
+        if (!FUSED && lane == 0 && e < N - 1) {
             const int s = e % NST;
             osc2_mbar_expect_tx(bars + s, (unsigned)(SM::REC * sizeof(double)));
             osc2_bulk_load(rec + (size_t)s * SM::REC, gtile + (size_t)e * gstep, (unsigned)(SM::REC * sizeof(double)), bars + s);
         }
     };
     auto arrived = [&](const int e) {                            // every lane: element e is in its stage
-        if (e < N - 1) osc2_mbar_wait(bars + e % NST, (unsigned)((e / NST) & 1));
+        if (e < N - 1) {
+            if (FUSED) osc2_cbar_wait(cx.full + 2 * (e % NST), (unsigned)((e / NST) & 1));
+            else osc2_mbar_wait(bars + e % NST, (unsigned)((e / NST) & 1));
+        }
     };
-    if (lane == 0) {
-        for (int s = 0; s < NST; ++s) osc2_mbar_init(bars + s, 1);
-        osc2_mbar_init_fence();
+    auto release = [&](const int e) {                            // every lane: this lane has read element e for the last time
+        if (FUSED && e >= 0 && e < N - 1) osc2_cbar_arrive(cx.empty + 2 * (e % NST));
+    };
+    if (!FUSED) {
+        if (lane == 0) {
+            for (int s = 0; s < NST; ++s) osc2_mbar_init(bars + s, 1);
+            osc2_mbar_init_fence();
+        }
+        __syncwarp();
+        issue(0);
+        issue(1);
     }
-    __syncwarp();
-    issue(0);
-    issue(1);
 
     // per-lane field offsets inside a record
     const int f_own = lane;                                      // field f of this lane: rec[f * 32 + lane]
@@ -359,7 +399,7 @@ __global__ void __launch_bounds__(32) osc2_forward_tile_kernel(const osc2_topolo
         }
         osc2_fence_async_smem();
         __syncwarp();
-        if (lane == 0) osc2_bulk_store(sptile + (size_t)n * sstep, stg, (unsigned)(SM::STG * sizeof(double)));
+        if (lane == 0 && (!FUSED || cx.tile_valid)) osc2_bulk_store(sptile + (size_t)n * sstep, stg, (unsigned)(SM::STG * sizeof(double)));
     };
 
     double cL[D], cD[D], cU[D], crhs = 0.0;       // node under elimination (cL: node 0 has no L block)
@@ -372,6 +412,7 @@ __global__ void __launch_bounds__(32) osc2_forward_tile_kernel(const osc2_topolo
     }
     arrived(0);
     construct(std::false_type(), std::true_type(), 0, cL, cD, cU, crhs);
+    release(-1);
     // one step of the pipeline: row of node n+1, then the rounds of node n
     auto stage = [&](auto HR, const int n) {
         // element n+2 goes where element n-1 was: its last readers (the construction of node n) are past the
@@ -379,6 +420,7 @@ __global__ void __launch_bounds__(32) osc2_forward_tile_kernel(const osc2_topolo
         issue(n + 2);
         arrived(n + 1);
         construct(std::true_type(), HR, n + 1, nL, nD, nU, nrhs);
+        release(n);                                  // element n was the left neighbour of node n + 1
         eliminate(std::true_type(), n, cD, cU, crhs, nL, nD, nrhs);
 #pragma unroll
         for (int c = 0; c < D; ++c) { cD[c] = nD[c]; cU[c] = nU[c]; }
@@ -389,7 +431,7 @@ __global__ void __launch_bounds__(32) osc2_forward_tile_kernel(const osc2_topolo
     eliminate(std::false_type(), N - 1, cD, cU, crhs, nL, nD, nrhs);
     if (lane == 0) osc2_bulk_store_wait_all();
     __syncwarp();
-    double *scratch = sm_dyn;
+    double *scratch = rec;                          // every element has been consumed
     if (r < D) { scratch[lane] = (double)bad_row; scratch[32 + lane] = (div_span >= OSC2_HI_DIV_SPAN) ? 1.0 : 0.0; }
     __syncwarp();
     if (act && r == 0) {
@@ -403,6 +445,22 @@ __global__ void __launch_bounds__(32) osc2_forward_tile_kernel(const osc2_topolo
         // a singular pivot wins (the reference raises there); otherwise report the range problem; sticky
         if ((worst >= 0 || range) && p.status[b] == 0) p.status[b] = (worst >= 0) ? -(int)(worst + 1) : OSC2_STATUS_RANGE;
     }
+}
+
+template <int D, int LPC, bool FULL>
+__global__ void __launch_bounds__(32) osc2_forward_tile_kernel(const osc2_topology *__restrict__ tp, StepDev p)
+{
+    OSC2_DYN_SMEM_ALIGNED(sm_dyn);
+    using SM = TileFwdSmem<D, LPC>;
+    TileFwdCtx cx;
+    cx.rec = sm_dyn;
+    cx.stg = cx.rec + SM::NST * SM::REC;
+    cx.pub = cx.stg + SM::STG;
+    cx.bars = (unsigned long long *)(sm_dyn + SM::NST * SM::REC + SM::STG + SM::CPW * SM::PUBC);
+    cx.full = cx.empty = nullptr;
+    cx.tile = blockIdx.x;
+    cx.tile_valid = true;
+    osc2_forward_tile_body<D, LPC, FULL, false, SM::NST>(tp, p, cx);
 }
 
 // ---------------------------------------------------------------------------

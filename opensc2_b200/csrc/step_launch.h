@@ -11,6 +11,9 @@
 #include "step_kernels.cuh"
 #include "step_kernels_fast.cuh"
 #include "step_kernels_tile.cuh"
+#ifdef OSC2_WITH_FUSED_GF          // experiments/step_kernels_fused.cuh: K_G inside K_F (bit-exact, 3x slower: DESIGN.md 5)
+#include "../../experiments/step_kernels_fused.cuh"
+#endif
 #include "step_kernels_d64.cuh"
 
 #include <cstdlib>
@@ -131,8 +134,21 @@ inline Osc2LaunchPlan osc2_make_plan(int d, int batch, size_t max_smem, int sm_c
     return pl;
 }
 
+// experiment (-DOSC2_WITH_FUSED_GF and OSC2_FUSED=1): K_G inside the forward sweep, experiments/step_kernels_fused.cuh
+template <class Launcher>
+bool osc2_use_fused(Launcher &L, const StepDev &p, double theta)
+{
+#ifdef OSC2_WITH_FUSED_GF
+    static const bool on = [] { const char *e = getenv("OSC2_FUSED"); return e && e[0] == '1'; }();
+    return on && p.d == 8 && theta == 1.0 && p.cap_sysmat == nullptr && p.sinv != nullptr && FusedFwdSmem<8, 8>::BYTES <= L.max_smem();
+#else
+    (void)L; (void)p; (void)theta;
+    return false;
+#endif
+}
+
 template <int D, int LPC, class Launcher>
-void osc2_run_fast_sweeps(Launcher &L, const osc2_topology *tp_dev, const StepDev &p, double theta)
+void osc2_run_fast_sweeps(Launcher &L, const osc2_topology *tp_dev, const StepDev &p, double theta, bool fused = false)
 {
     // one warp per CTA: a batch of a few thousand conductors then still spreads
     // over all SMs (4096 conductors x 8 lanes = 1024 warps on 148 SMs)
@@ -147,6 +163,19 @@ void osc2_run_fast_sweeps(Launcher &L, const osc2_topology *tp_dev, const StepDe
         static const bool tile_on = [] { const char *e = getenv("OSC2_FWD_TILE"); return !(e && e[0] == '0'); }();
         if (be && !cap && tile_on) {
             const unsigned nt = (unsigned)((p.B + cpb - 1) / cpb);
+#ifdef OSC2_WITH_FUSED_GF
+            if constexpr (D == 8) {
+                if (fused) {
+                    using FS = FusedFwdSmem<D, LPC>;
+                    const unsigned nc = (nt + FS::NCW - 1) / FS::NCW;
+                    if (p.B % (cpb * FS::NCW) == 0) L.launch(OSC2_K_FORWARD, osc2_forward_fused_kernel<D, LPC, true>, nc, 32u * (FS::NCW + FS::NPW), FS::BYTES, tp_dev, p);
+                    else L.launch(OSC2_K_FORWARD, osc2_forward_fused_kernel<D, LPC, false>, nc, 32u * (FS::NCW + FS::NPW), FS::BYTES, tp_dev, p);
+                    L.launch(OSC2_K_BACKWARD, osc2_backward_tile_kernel<D, LPC>, nt, 32u, TileBwdSmem<D, LPC>::BYTES, p);
+                    return;
+                }
+            }
+#endif
+            (void)fused;
             if (p.B % cpb == 0) L.launch(OSC2_K_FORWARD, osc2_forward_tile_kernel<D, LPC, true>, nt, 32u, TileFwdSmem<D, LPC>::BYTES, tp_dev, p);
             else L.launch(OSC2_K_FORWARD, osc2_forward_tile_kernel<D, LPC, false>, nt, 32u, TileFwdSmem<D, LPC>::BYTES, tp_dev, p);
             L.launch(OSC2_K_BACKWARD, osc2_backward_tile_kernel<D, LPC>, nt, 32u, TileBwdSmem<D, LPC>::BYTES, p);
@@ -177,12 +206,13 @@ void osc2_run_step(Launcher &L, const osc2_topology *tp_dev, const StepDev &p, b
     if (fast) {
         const long long work = (long long)p.E * p.B;
         const unsigned grid = (unsigned)((work + pl.gauss_block - 1) / pl.gauss_block);
-        if (!records_ready)
+        const bool fused = !records_ready && osc2_use_fused(L, p, theta);
+        if (!records_ready && !fused)
             L.launch(OSC2_K_GAUSS, osc2_gauss2_kernel<true>, grid, pl.gauss_block,
                      (size_t)p.s_slots * sizeof(double) * pl.gauss_block, tp_dev, p);
         switch (p.d) {
         case 4: osc2_run_fast_sweeps<4, 8>(L, tp_dev, p, theta); break;
-        case 8: osc2_run_fast_sweeps<8, 8>(L, tp_dev, p, theta); break;
+        case 8: osc2_run_fast_sweeps<8, 8>(L, tp_dev, p, theta, fused); break;
         default: osc2_run_fast_sweeps<13, 16>(L, tp_dev, p, theta); break;
         }
         {

@@ -25,6 +25,7 @@ class StepDev(C.Structure):
 
 
 _LIB = None
+last_launches = 0
 
 
 def lib():
@@ -95,7 +96,8 @@ def emu_step(topo, arr, capture=False, fast=None, split=True):
         outs["cap_known"] = np.zeros((total, B))
         p.cap_sysmat = outs["cap_sysmat"].ctypes.data_as(c_dp)
         p.cap_known = outs["cap_known"].ctypes.data_as(c_dp)
-    L.osc2_emu_step(C.byref(t), C.byref(p), int(fast), int(split))
+    global last_launches
+    last_launches = L.osc2_emu_step(C.byref(t), C.byref(p), int(fast), int(split))   # kernels launched (4 on the fused path)
     res = {
         "sysvar": from_dev(outs["sysvar_new"]), "syslod": from_dev(keep["syslod"]),
         "k123": from_dev(outs["k123"])[:, :, :p.nff], "norm_solution": from_dev(outs["norm_solution"]),

@@ -19,8 +19,8 @@ extern "C" int osc2_emu_step(const osc2_topology *tp, const StepDev *p, int fast
     std::vector<unsigned char> smap;
     q.s_slots = osc2_build_smap(*tp, smap);
     q.smap = smap.data();
-    std::vector<unsigned char> sinv((size_t)(q.s_slots > 0 ? q.s_slots : 1), 0);
-    for (size_t i = 0; i < smap.size(); ++i) if (smap[i]) sinv[smap[i]] = (unsigned char)i;
+    std::vector<unsigned short> sinv((size_t)(q.s_slots > 0 ? q.s_slots : 1), 0);
+    for (size_t i = 0; i < smap.size(); ++i) if (smap[i]) sinv[smap[i]] = (unsigned short)((i % q.d) * 32 + (i / q.d) * q.cpw);
     q.sinv = sinv.data();
     q.gm_prezeroed = fast ? 1 : 0;      // emu.py hands over a zeroed `gm` on the fast path, as osc2_create does
     osc2_run_step(L, tp, q, fast != 0, tp->theta);
