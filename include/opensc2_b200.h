@@ -216,6 +216,17 @@ int osc2_download_tcs(osc2_handle h, double *tcs_gauss, double *tcs_nodal);
  * state the LAST osc2_eval_operating_conditions / osc2_advance looked at (+inf for solids without a superconductor
  * or before any evaluation): the quantity a temperature-margin sweep is run for. */
 int osc2_download_margin(osc2_handle h, double *margin);
+/* Nodal coolant pass on the CURRENT state (after a step: the new solution) -- what the reference evaluates for its
+ * outputs with FluidComponent._eval_properties_nodal_gauss(nodal = True) and
+ * _compute_density_and_mass_flow_rates (coolant.py:134-263) and Channel.eval_friction_factor(nodal = True)
+ * (channel.py:1119-1138).  osc2_download_nodal_properties: chan [OSC2_N_NODAL = 14][B][M][N] = total_density,
+ * isobaric_expansion_coefficient, isothermal_compressibility, Prandtl, total_dynamic_viscosity, total_enthalpy,
+ * total_isobaric_specific_heat, total_isochoric_specific_heat, total_speed_of_sound, total_thermal_conductivity,
+ * Reynolds, Gruneisen, mass_flow_rate, friction_factor (the property columns of save_properties' channel files,
+ * utility_functions/output.py:8-92).  The device buffer (14 M N B doubles) is allocated by the first call. */
+#define OSC2_N_NODAL_PROPS 14
+int osc2_eval_nodal_properties(osc2_handle h);
+int osc2_download_nodal_properties(osc2_handle h, double *chan);
 /* `time` = conductor.cond_time[-1] of the step about to be taken. */
 int osc2_eval_operating_conditions(osc2_handle h, double time);
 /* One full time step: osc2_eval_operating_conditions(time) + osc2_step(dt, num_step). */

@@ -51,6 +51,8 @@ def load() -> C.CDLL:
     L.osc2_eval_tcs.argtypes = [H]
     L.osc2_download_tcs.argtypes = [H, c_dp, c_dp]
     L.osc2_download_margin.argtypes = [H, c_dp]
+    L.osc2_eval_nodal_properties.argtypes = [H]
+    L.osc2_download_nodal_properties.argtypes = [H, c_dp]
     L.osc2_download_step_inputs.argtypes = [H] + [c_dp] * 8
     L.osc2_synchronize.argtypes = [H]
     L.osc2_download_state.argtypes = [H, c_dp, c_dp, c_ip]
@@ -71,7 +73,8 @@ def load() -> C.CDLL:
                  "osc2_download_system", "osc2_set_profiling", "osc2_get_kernel_ms", "osc2_reset_kernel_ms",
                  "osc2_timer_start", "osc2_timer_stop", "osc2_set_model", "osc2_set_fluid_table", "osc2_upload_sweep",
                  "osc2_eval_operating_conditions", "osc2_download_step_inputs", "osc2_advance", "osc2_eval_tcs",
-                 "osc2_download_tcs", "osc2_download_margin"):
+                 "osc2_download_tcs", "osc2_download_margin", "osc2_eval_nodal_properties",
+                 "osc2_download_nodal_properties"):
         getattr(L, name).restype = C.c_int
     _LIB = L
     return L
@@ -84,7 +87,8 @@ EXPORTED = (
     "osc2_set_profiling", "osc2_get_kernel_ms", "osc2_reset_kernel_ms", "osc2_timer_start",
     "osc2_timer_stop", "osc2_device_bytes", "osc2_selftest_division", "osc2_set_model", "osc2_set_fluid_table",
     "osc2_upload_sweep", "osc2_eval_operating_conditions", "osc2_download_step_inputs", "osc2_advance",
-    "osc2_eval_tcs", "osc2_download_tcs", "osc2_download_margin",
+    "osc2_eval_tcs", "osc2_download_tcs", "osc2_download_margin", "osc2_eval_nodal_properties",
+    "osc2_download_nodal_properties",
 )
 
 

@@ -122,6 +122,20 @@ class BatchedStep:
         _lib.check(self._L.osc2_download_margin(self._h, dptr(m)))
         return m
 
+    NODAL_COLUMNS = ("total_density", "isobaric_expansion_coefficient", "isothermal_compressibility", "Prandtl",
+                     "total_dynamic_viscosity", "total_enthalpy", "total_isobaric_specific_heat",
+                     "total_isochoric_specific_heat", "total_speed_of_sound", "total_thermal_conductivity", "Reynolds",
+                     "Gruneisen", "mass_flow_rate", "friction_factor")
+
+    def nodal_properties(self) -> Dict[str, np.ndarray]:
+        """Nodal coolant pass on the current device state (coolant.py:134-263 with nodal = True, post-step density and
+        mass flow rate, nodal friction factor): {column name: (B, M, N)}, the property columns of save_properties'
+        channel files."""
+        _lib.check(self._L.osc2_eval_nodal_properties(self._h))
+        a = np.empty((len(self.NODAL_COLUMNS), self.batch, self.topo.n_ch, self.n_nodes))
+        _lib.check(self._L.osc2_download_nodal_properties(self._h, dptr(a)))
+        return {k: a[i] for i, k in enumerate(self.NODAL_COLUMNS)}
+
     def advance(self, time: float, dt: float, num_step: int):
         """Operating conditions at `time` + one step()."""
         _lib.check(self._L.osc2_advance(self._h, float(time), float(dt), int(num_step)))

@@ -56,6 +56,8 @@ struct osc2_context {
     size_t bytes = 0;
     double *staging = nullptr;       // [max array] for layout changes
     size_t staging_doubles = 0;
+    double *nodal = nullptr;         // [OSC2_N_NODAL][M][N][B], allocated by the first osc2_eval_nodal_properties
+    int *cb_nodal = nullptr;         // [M][B] array-wide Colebrook iteration count of the nodal pass
     double *sysvar_a = nullptr, *sysvar_b = nullptr;
     bool have_state = false, have_inputs = false;
     bool have_geometry = false;      // dz, fl_bc, contact perimeters, qsource: never computed on the device
@@ -745,6 +747,44 @@ int osc2_eval_tcs(osc2_handle h)
         const int rc = fail(OSC2_ERR_CUDA, "%s", h->launch_error.c_str());
         h->launch_error.clear();
         return rc;
+    }
+    return OSC2_OK;
+}
+
+int osc2_eval_nodal_properties(osc2_handle h)
+{
+    if (!h) return fail(OSC2_ERR_INVALID, "handle is NULL");
+    if (!h->have_model || !h->have_state) return fail(OSC2_ERR_STATE, "osc2_eval_nodal_properties needs osc2_set_model and a state first");
+    for (int f = 0; f < h->n_fluids_used; ++f)
+        if (!h->have_table[f]) return fail(OSC2_ERR_STATE, "fluid table %d was not set", f);
+    if (h->M == 0) return OSC2_OK;
+    CK(cudaSetDevice(h->device));
+    const size_t M = h->M, N = h->N, B = h->B;
+    if (!h->nodal) { int rc = dev_alloc(h, &h->nodal, (size_t)OSC2_N_NODAL * M * N * B); if (rc) return rc; }
+    if (!h->cb_nodal) { double *t = nullptr; int rc = dev_alloc(h, &t, (M * B + 1) / 2 + 1); if (rc) return rc; h->cb_nodal = (int *)t; }
+    CK(cudaMemsetAsync(h->cb_nodal, 0, sizeof(int) * M * B, h->stream));
+    CudaLauncher L{h};
+    const long long work = (long long)(M * N * B);
+    for (int pass = 0; pass < 2; ++pass)
+        L.launch(OSC2_K_PROPS, osc2_nodal_coolant_kernel, (unsigned)((work + 127) / 128), 128u, (size_t)0,
+                 (const osc2_topology *)h->topo_dev, h->p, h->q, h->nodal, h->cb_nodal, pass);
+    if (!h->launch_error.empty()) {
+        const int rc = fail(OSC2_ERR_CUDA, "%s", h->launch_error.c_str());
+        h->launch_error.clear();
+        return rc;
+    }
+    return OSC2_OK;
+}
+
+int osc2_download_nodal_properties(osc2_handle h, double *chan)
+{
+    if (!h || !chan) return fail(OSC2_ERR_INVALID, "NULL argument");
+    if (!h->nodal) return fail(OSC2_ERR_STATE, "osc2_eval_nodal_properties first");
+    CK(cudaSetDevice(h->device));
+    const size_t K = (size_t)h->M * h->N;
+    for (int q = 0; q < OSC2_N_NODAL; ++q) {
+        int rc = download_transposed(h, h->nodal + (size_t)q * K * h->B, chan + (size_t)q * K * h->B, K);
+        if (rc) return rc;
     }
     return OSC2_OK;
 }

@@ -929,3 +929,57 @@ __global__ void __launch_bounds__(128) osc2_opcond_interface_kernel(const osc2_t
 #undef HST
 #undef RCP
 }
+
+// ---------------------------------------------------------------------------
+// Nodal coolant pass after a step (what the reference does for its outputs: FluidComponent
+// _eval_properties_nodal_gauss(nodal = True) + _compute_density_and_mass_flow_rates, coolant.py:134-263;
+// Channel.eval_friction_factor(nodal = True), channel.py:1119-1138).  Thread per (channel, node, conductor);
+// `out` is [OSC2_N_NODAL][M][N][B]: total_density, the nine other table properties in the order of the alias
+// table (simulation.py:89-100), Reynolds, Gruneisen, mass_flow_rate, friction_factor -- columns 4 and 6..18 of
+// save_properties' channel file.  Pass 0 writes everything but the friction factor and, for IFRICTION 122,
+// takes the array-wide Colebrook iteration count; pass 1 writes the friction factor.
+// ---------------------------------------------------------------------------
+#define OSC2_N_NODAL 14
+__global__ void __launch_bounds__(128) osc2_nodal_coolant_kernel(const osc2_topology *__restrict__ tp, StepDev p, PropsDev q,
+                                                                 double *__restrict__ out, int *__restrict__ cb_nodal, const int pass)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long NB = (long long)p.N * p.B;
+    if (idx >= NB * p.M) return;
+    const int j = (int)(idx / NB);
+    const long long rem = idx - (long long)j * NB;
+    const int n = (int)(rem / p.B);
+    const size_t b = (size_t)(rem % p.B);
+    const size_t B = (size_t)p.B;
+    const int M = p.M, d = p.d, N = p.N;
+    const osc2_model *md = q.model;
+    const size_t plane = (size_t)M * N * B, at = ((size_t)j * N + n) * B + b;
+    if (pass == 1) {
+        out[13 * plane + at] = osc2p::friction_total(md, tp, j, out[10 * plane + at], cb_nodal[(size_t)j * B + b]);
+        return;
+    }
+    const double *x = p.sysvar + ((size_t)n * d) * B + b;
+    const FluidTableDev &tab = q.fluid[md->ch_fluid[j]];
+    const double v = x[(size_t)j * B], pr = x[(size_t)(M + j) * B], T = x[(size_t)(2 * M + j) * B];
+    const osc2p::Cell c = osc2p::locate(tab, pr, T);
+    const double rho = osc2p::lookup(tab, c, OSC2_FP_RHO), mu = osc2p::lookup(tab, c, OSC2_FP_MU);
+    const double beta = osc2p::lookup(tab, c, OSC2_FP_BETA), kappa = osc2p::lookup(tab, c, OSC2_FP_KAPPA);
+    const double cv = osc2p::lookup(tab, c, OSC2_FP_CV);
+    const double re = fabs(tp->ch_dh[j] * v * rho / mu);
+    out[0 * plane + at] = rho;
+    out[1 * plane + at] = beta;
+    out[2 * plane + at] = kappa;
+    out[3 * plane + at] = osc2p::lookup(tab, c, OSC2_FP_PRANDTL);
+    out[4 * plane + at] = mu;
+    out[5 * plane + at] = osc2p::lookup(tab, c, OSC2_FP_H);
+    out[6 * plane + at] = osc2p::lookup(tab, c, OSC2_FP_CP);
+    out[7 * plane + at] = cv;
+    out[8 * plane + at] = osc2p::lookup(tab, c, OSC2_FP_SOUND);
+    out[9 * plane + at] = osc2p::lookup(tab, c, OSC2_FP_K);
+    out[10 * plane + at] = re;
+    out[11 * plane + at] = beta / kappa / cv / rho;
+    out[12 * plane + at] = tp->ch_area[j] * v * rho;
+    if (md->ch_ifriction[j] == 122)
+        atomicMax(cb_nodal + (size_t)j * B + b, osc2p::colebrook_count(re, md->ch_roughness[j], tp->ch_dh[j]));
+}
+

@@ -41,6 +41,15 @@ struct GmSlots2 {
 __host__ __device__ inline int osc2_spill_block(int d) { return (2 * d + 2) * 32; }
 enum { LOD_UP = 0, LOD_LO = 1, LOD_UP_PREV = 2, LOD_LO_PREV = 3 };
 
+// read-only input of this launch through the non-coherent path: such loads may be hoisted over the stores of the
+// kernel and issued in batches (with plain loads every one of K_G's ~50 input loads was waited for on its own,
+// ~660 cycles each: the compiler cannot prove that the record stores do not alias the inputs)
+#ifdef OSC2_EMU
+#define OSC2_LDG(ptr) (*(ptr))
+#else
+#define OSC2_LDG(ptr) __ldg(ptr)
+#endif
+
 // request the line that holds *ptr from DRAM into L2 (no register, no completion to wait for)
 __device__ __forceinline__ void osc2_prefetch_l2(const void *ptr)
 {
@@ -73,7 +82,7 @@ __device__ __forceinline__ void osc2_gauss2_body(const osc2_topology *__restrict
     // the advection entries of the solid rows) are not written again -- 440 of the 1088 bytes of a CASE_1 record
     const bool skipz = INREC || p.gm_prezeroed != 0;
 #define SM_(r, c) (*(INREC ? &g[(c) * 32 + (r) * sl.cpw] : &Sb[(size_t)smap[(r) * d + (c)] * Ss]))
-#define FG(q, j) p.fl_gauss[((((size_t)(q) * M + (j)) * E) + e) * B + b]
+#define FG(q, j) OSC2_LDG(p.fl_gauss + ((((size_t)(q) * M + (j)) * E) + e) * B + b)
 #define GOUT(slot) g[slot]
     // The kernel is bound by load latency (ncu: 67 % of the stall samples wait for global loads that sit inside
     // loops with run-time trip counts, 6 warps per scheduler): every input of this (element, conductor) is
@@ -94,7 +103,7 @@ __device__ __forceinline__ void osc2_gauss2_body(const osc2_topology *__restrict
     }
     if (INREC) { for (int slot = 1; slot < p.s_slots; ++slot) g[p.sinv[slot]] = 0.0; }
     else for (int i = 0; i < p.s_slots; ++i) Sb[(size_t)i * Ss] = 0.0;
-    const double dz = p.dz[(size_t)e * B + b];
+    const double dz = OSC2_LDG(p.dz + ((size_t)e * B + b));
     const double alpha = 0.0;
     const double cdiag = dz * (1. / 3. + alpha), coff = dz * (1. / 6. - alpha);
 
@@ -126,8 +135,8 @@ __device__ __forceinline__ void osc2_gauss2_body(const osc2_topology *__restrict
         if (delta_p < tp->delta_p_min) delta_p = tp->delta_p_min;
         const int cu = (pb < pa) ? ca : cb;
         const double vel = FG(FL_V, cu);
-        const double peri_o = p.peri_ff[(((size_t)0 * p.nff + k) * E + e) * B + b];
-        const double peri_c = p.peri_ff[(((size_t)1 * p.nff + k) * E + e) * B + b];
+        const double peri_o = OSC2_LDG(p.peri_ff + ((((size_t)0 * p.nff + k) * E + e) * B + b));
+        const double peri_c = OSC2_LDG(p.peri_ff + ((((size_t)1 * p.nff + k) * E + e) * B + b));
         const double K1 = peri_o * sqrt(2. * FG(FL_RHO, cu) / (tp->k_loc * delta_p));
         const double K2 = K1 * tp->lambda_v * vel;
         const double vl = vel * tp->lambda_v;
@@ -135,8 +144,8 @@ __device__ __forceinline__ void osc2_gauss2_body(const osc2_topology *__restrict
         p.k123[(((size_t)0 * p.nff + k) * E + e) * B + b] = K1;
         p.k123[(((size_t)1 * p.nff + k) * E + e) * B + b] = K2;
         p.k123[(((size_t)2 * p.nff + k) * E + e) * B + b] = K3;
-        const double coef_htc = peri_o * p.htc_ff[(((size_t)0 * p.nff + k) * E + e) * B + b]
-                              + peri_c * p.htc_ff[(((size_t)1 * p.nff + k) * E + e) * B + b];
+        const double coef_htc = peri_o * OSC2_LDG(p.htc_ff + ((((size_t)0 * p.nff + k) * E + e) * B + b))
+                              + peri_c * OSC2_LDG(p.htc_ff + ((((size_t)1 * p.nff + k) * E + e) * B + b));
         for (int side = 0; side < 2; ++side) {
             const int c1 = side ? cb : ca, c2 = side ? ca : cb;
             const int v1 = c1, p1 = M + c1, t1 = 2 * M + c1, p2 = M + c2, t2 = 2 * M + c2;
@@ -167,7 +176,7 @@ __device__ __forceinline__ void osc2_gauss2_body(const osc2_topology *__restrict
         const int ip = M + j, it = 2 * M + j, is = 3 * M + l;
         const double A = tp->ch_area[j];
         const double cga = FG(FL_GRUN, j) / A;
-        const double coef_htc = p.peri_fs[((size_t)k * E + e) * B + b] * p.htc_fs[((size_t)k * E + e) * B + b];
+        const double coef_htc = OSC2_LDG(p.peri_fs + (((size_t)k * E + e) * B + b)) * OSC2_LDG(p.htc_fs + (((size_t)k * E + e) * B + b));
         const double s_pj_tj = cga * coef_htc;
         SM_(ip, it) += s_pj_tj;
         SM_(ip, is) = -s_pj_tj;
@@ -182,7 +191,7 @@ __device__ __forceinline__ void osc2_gauss2_body(const osc2_topology *__restrict
     const double dz_6 = dz / 6.;
     for (int k = 0; k < p.nss; ++k) {
         const int a = 3 * M + tp->ss[k][0], c = 3 * M + tp->ss[k][1];
-        const double coef = p.peri_ss[((size_t)k * E + e) * B + b] * p.htc_ss[((size_t)k * E + e) * B + b];
+        const double coef = OSC2_LDG(p.peri_ss + (((size_t)k * E + e) * B + b)) * OSC2_LDG(p.htc_ss + (((size_t)k * E + e) * B + b));
         SM_(a, a) += coef;
         SM_(a, c) = -coef;
         SM_(c, c) += coef;
@@ -193,9 +202,9 @@ __device__ __forceinline__ void osc2_gauss2_body(const osc2_topology *__restrict
     for (int l = 0; l < Sn; ++l) {
         const int is = 3 * M + l;
         const double A = tp->sol_area[l], cs = tp->sol_costeta[l];
-        const double rho = p.sol_gauss[(((size_t)0 * Sn + l) * E + e) * B + b];
-        const double cp = p.sol_gauss[(((size_t)1 * Sn + l) * E + e) * B + b];
-        const double kk = p.sol_gauss[(((size_t)2 * Sn + l) * E + e) * B + b];
+        const double rho = OSC2_LDG(p.sol_gauss + ((((size_t)0 * Sn + l) * E + e) * B + b));
+        const double cp = OSC2_LDG(p.sol_gauss + ((((size_t)1 * Sn + l) * E + e) * B + b));
+        const double kk = OSC2_LDG(p.sol_gauss + ((((size_t)2 * Sn + l) * E + e) * B + b));
         const double mm = A * rho * cp / cs;
         GOUT(sl.md(is)) = cdiag * mm;
         GOUT(sl.mo(is)) = coff * mm;
@@ -203,19 +212,19 @@ __device__ __forceinline__ void osc2_gauss2_body(const osc2_topology *__restrict
         if (!skipz) { GOUT(sl.ahd(is)) = 0.0; GOUT(sl.aho(is)) = 0.0; }
         const size_t q1 = ((((size_t)0 * Sn + l) * E + e) * 2) * B + b;
         const size_t q2 = ((((size_t)1 * Sn + l) * E + e) * 2) * B + b;
-        const double qs0 = p.qsource[((size_t)e * Sn + l) * B + b];
-        const double qs1 = p.qsource[((size_t)(e + 1) * Sn + l) * B + b];
-        double sv0 = p.sol_q[q1] - qs0, sv1 = p.sol_q[q2] - qs1;
-        double sp0 = first ? p.sol_q[q1 + B] - qs0 : 0.0, sp1 = first ? p.sol_q[q2 + B] - qs1 : 0.0;
+        const double qs0 = OSC2_LDG(p.qsource + (((size_t)e * Sn + l) * B + b));
+        const double qs1 = OSC2_LDG(p.qsource + (((size_t)(e + 1) * Sn + l) * B + b));
+        double sv0 = OSC2_LDG(p.sol_q + (q1)) - qs0, sv1 = OSC2_LDG(p.sol_q + (q2)) - qs1;
+        double sp0 = first ? OSC2_LDG(p.sol_q + (q1 + B)) - qs0 : 0.0, sp1 = first ? OSC2_LDG(p.sol_q + (q2 + B)) - qs1 : 0.0;
         for (int k = 0; k < p.nes; ++k) {
             if (tp->es[k] != l) continue;
-            const double h0 = p.htc_es[(((size_t)k * 3 + 0) * E + e) * B + b];
-            const double peri = p.peri_es[((size_t)k * E + e) * B + b];
+            const double h0 = OSC2_LDG(p.htc_es + ((((size_t)k * 3 + 0) * E + e) * B + b));
+            const double peri = OSC2_LDG(p.peri_es + (((size_t)k * E + e) * B + b));
             const bool rect = tp->es_choice2[k] && tp->is_rectangular;
             double coef_htc;
             if (rect) {
-                const double h1 = p.htc_es[(((size_t)k * 3 + 1) * E + e) * B + b];
-                const double h2 = p.htc_es[(((size_t)k * 3 + 2) * E + e) * B + b];
+                const double h1 = OSC2_LDG(p.htc_es + ((((size_t)k * 3 + 1) * E + e) * B + b));
+                const double h2 = OSC2_LDG(p.htc_es + ((((size_t)k * 3 + 2) * E + e) * B + b));
                 coef_htc = 2. * tp->height * h0 + tp->width * (h1 + h2);
             } else {
                 coef_htc = h0 * peri;

@@ -415,3 +415,35 @@ def test_more_steady_state_htc_correlations_on_the_device(corrs):
     if 211 in corrs:      # (the other three only move the lower limit, which this flow does not reach)
         base = O.operating_conditions(topo, dataclasses.replace(model, ch_htc_corr=(1, 1)), [tab], sweep, arr.sysvar, n, 12.0)
         assert np.max(np.abs(base["htc_fs"] - ref["htc_fs"])) > 0.0
+
+
+@pytest.mark.parametrize("colebrook", [False, True])
+def test_nodal_coolant_pass_matches_the_host_writer(colebrook):
+    """osc2_eval_nodal_properties (post-step density, mass flow rate, the nodal property columns and the nodal
+    friction factor, coolant.py:134-263 with nodal = True) against opensc2_b200.output.channel_table, the host code
+    pinned byte for byte to files written by the reference's save_properties (tests/test_output_writer.py): table
+    columns, Reynolds, Gruneisen and mass flow rate bit-exact, the friction factor within RTOL_FIT."""
+    import dataclasses
+
+    from opensc2_b200.batch import BatchedStep
+    from opensc2_b200.output import channel_table
+
+    n, batch = 41, 9
+    topo, model, tab, arr, sweep = _setup(True, n, batch, seed=11)
+    if colebrook:        # IFRICTION 122: the iteration count is the maximum over the nodes of one channel
+        model = dataclasses.replace(model, ch_ifriction=(122,) * topo.n_ch, ch_roughness=(2.0e-6,) * topo.n_ch)
+    with BatchedStep(topo, batch, n) as bs:
+        bs.set_model(model, [tab])
+        bs.upload_sweep(sweep)
+        bs.upload_state(arr.sysvar, arr.syslod)
+        out = bs.nodal_properties()
+    z = np.linspace(0.0, 10.0, n)
+    x = arr.sysvar.reshape(batch, n, topo.ndf)
+    M = topo.n_ch
+    for b in range(batch):
+        for j in range(M):
+            ref = channel_table(topo, model, tab, j, z, x[b, :, j].copy(), x[b, :, M + j].copy(), x[b, :, 2 * M + j].copy())
+            assert_bits(out["total_density"][b, j], ref[:, 3], "total_density")
+            for i, name in enumerate(BatchedStep.NODAL_COLUMNS[1:13]):
+                assert_bits(out[name][b, j], ref[:, 5 + i], name)
+            assert rel(out["friction_factor"][b, j], ref[:, 17]) <= RTOL_FIT
