@@ -70,7 +70,7 @@ __device__ __forceinline__ void osc2_prefetch_l2(const void *ptr)
 // column and its stride (unused with INREC, where SMAT is accumulated in the record itself)
 template <bool SMEM_S, bool INREC>
 __device__ __forceinline__ void osc2_gauss2_body(const osc2_topology *__restrict__ tp, const StepDev &p, double *g, double *Sb,
-                                                 const size_t Ss, const int e, const size_t b)
+                                                 const size_t Ss, const int e, const size_t b, const unsigned short *sinv_in = nullptr)
 {
     const size_t B = (size_t)p.B;
     const int M = p.M, Sn = p.S, d = p.d, E = p.E;
@@ -247,7 +247,7 @@ __device__ __forceinline__ void osc2_gauss2_body(const osc2_topology *__restrict
     if (skipz) {
         // slot -> offset of S[r][c] in the record, for the entries the topology can touch (osc2_build_smap, inverted
         // on the host: a division by the run-time d here cost 27 instructions per entry)
-        const unsigned short *__restrict__ sinv = p.sinv;
+        const unsigned short *__restrict__ sinv = sinv_in ? sinv_in : p.sinv;
         if (INREC) { for (int slot = 1; slot < p.s_slots; ++slot) { double *q = g + sinv[slot]; *q = osc2_div(*q * dz, r3); } }
         else for (int slot = 1; slot < p.s_slots; ++slot) GOUT(sinv[slot]) = osc2_div(Sb[(size_t)slot * Ss] * dz, r3);
     } else {
@@ -267,11 +267,18 @@ __global__ void osc2_gauss2_kernel(const osc2_topology *__restrict__ tp, StepDev
 {
     OSC2_DYN_SMEM(sm_dyn);
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    // slot -> record offset table next to the staging columns (its loads from global memory, one per touched entry in
+    // the final pass and each waited for, were 17 % of the kernel's stall samples)
+    unsigned short *sinv_s = (unsigned short *)(sm_dyn + (size_t)p.s_slots * blockDim.x);
+    if (p.gm_prezeroed) {
+        for (int i = threadIdx.x; i < p.s_slots; i += blockDim.x) sinv_s[i] = p.sinv[i];
+        __syncthreads();
+    }
     if (idx >= (long long)p.E * p.B) return;
     const int e = (int)(idx / p.B);
     const size_t b = (size_t)(idx % p.B);
     double *g = p.gm + ((size_t)e * p.NT + b / p.cpw) * ((size_t)(p.d + 9) * 32) + b % p.cpw;
-    osc2_gauss2_body<SMEM_S, false>(tp, p, g, sm_dyn + threadIdx.x, blockDim.x, e, b);
+    osc2_gauss2_body<SMEM_S, false>(tp, p, g, sm_dyn + threadIdx.x, blockDim.x, e, b, p.gm_prezeroed ? sinv_s : nullptr);
 }
 
 // max(m, |v|) as one compare and one select (a NaN never wins, as in `if (|v| > m) m = |v|`)

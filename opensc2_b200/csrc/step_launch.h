@@ -209,7 +209,7 @@ void osc2_run_step(Launcher &L, const osc2_topology *tp_dev, const StepDev &p, b
         const bool fused = !records_ready && osc2_use_fused(L, p, theta);
         if (!records_ready && !fused)
             L.launch(OSC2_K_GAUSS, osc2_gauss2_kernel<true>, grid, pl.gauss_block,
-                     (size_t)p.s_slots * sizeof(double) * pl.gauss_block, tp_dev, p);
+                     (size_t)p.s_slots * sizeof(double) * pl.gauss_block + (((size_t)p.s_slots * 2 + 15) / 16) * 16, tp_dev, p);
         switch (p.d) {
         case 4: osc2_run_fast_sweeps<4, 8>(L, tp_dev, p, theta); break;
         case 8: osc2_run_fast_sweeps<8, 8>(L, tp_dev, p, theta, fused); break;

@@ -24,17 +24,22 @@ def main():
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, un, data = rows[0], rows[1], rows[2:]
     col = {h: i for i, h in enumerate(hdr)}
-    out = {}
+    out, seen = {}, set()
     for r in data:
         name = r[col["Kernel Name"]]
         fam = next((f for key, f in FAMILY if key in name), None)
-        if fam is None or fam in out:
+        short = name.split("(")[0]
+        if fam is None or short in seen:          # one launch of every distinct kernel; a family may have several kernels
             continue
+        seen.add(short)
         tot = 0.0
         for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
             tot += float(r[col[key]].replace(",", "")) * TO_BYTES.get(un[col[key]], 1.0)
-        out[fam] = {"name": name.split("(")[0], "dram_bytes_per_unit": tot / units,
-                    "duration_ms_under_ncu": float(r[col["gpu__time_duration.sum"]].replace(",", ""))}
+        ms = float(r[col["gpu__time_duration.sum"]].replace(",", ""))
+        e = out.setdefault(fam, {"name": "", "dram_bytes_per_unit": 0.0, "duration_ms_under_ncu": 0.0})
+        e["name"] = (e["name"] + " + " if e["name"] else "") + short
+        e["dram_bytes_per_unit"] += tot / units
+        e["duration_ms_under_ncu"] += ms
     j = {"report": os.path.basename(rep), "units_per_launch": units, "csrc_sha1": csrc_hash(), "kernels": out}
     with open(os.path.join(ROOT, "profiles", "ncu_traffic.json"), "w") as f:
         json.dump(j, f, indent=1)
