@@ -11,13 +11,17 @@ writers (utility_functions/output.py).  Reference: `Channel.eval_friction_factor
                            CICC hole (:782-795); their "laminar" slot calls the same method, which writes the
                            TURBULENT array, so laminar stays 0 and total = max(0, turbulent)
 * 204 / 205, 206 / 209     Katheder and Darcy-Forchheimer bundle laws
-Every total is multiplied by FRICTION_MULTIPLIER.
+* 113 / 114 / 115 / 118    hole laws (:447-496, 636-648; the closing statement of 113 has no effect)
+* 200-203, 207, 210        bundle laws (:799-866, 939-963, 1015-1037)
+* 211                      HTS current-lead bundle (:1039-1066): laminar slot stays 0, FRICTION_MULTIPLIER forced to 1
+Every total is multiplied by FRICTION_MULTIPLIER.  Not built: 100-109 (Newton iteration on the hole geometry), 116 / 117 /
+119 / 120 (rectangular / triangular duct inputs), 123 (fails in the reference on arrays), 208 (raises in the reference).
 """
 from __future__ import annotations
 
 import numpy as np
 
-SUPPORTED_IFRICTION = (-99, 110, 111, 112, 121, 122, 124, 204, 205, 206, 209)
+SUPPORTED_IFRICTION = (-99, 110, 111, 112, 113, 114, 115, 118, 121, 122, 124, 200, 201, 202, 203, 204, 205, 206, 207, 209, 210, 211)
 
 
 def _laminar(re: np.ndarray) -> np.ndarray:
@@ -32,7 +36,7 @@ def _haaland(re, rough, dh):
 
 
 def friction_factor(ifriction: int, multiplier: float, reynolds, dh: float, roughness: float = 0.0,
-                    void_fraction: float = 0.0) -> np.ndarray:
+                    void_fraction: float = 0.0, area: float = 0.0) -> np.ndarray:
     """Total friction factor (Fanning) of one channel for an array of Reynolds numbers."""
     re = np.fabs(np.atleast_1d(np.asarray(reynolds, dtype=np.float64)))
     flag = int(ifriction)
@@ -75,6 +79,54 @@ def friction_factor(ifriction: int, multiplier: float, reynolds, dh: float, roug
             kk = c0 * void_fraction ** 3.0 / (1 - void_fraction) ** 2.0
             turb = dh ** 2.0 * void_fraction / 2.0 / kk / re + (dh * void_fraction ** 2.0) / 2.0 * jj
         total = np.maximum(_laminar(re), turb)
+    elif flag in (113, 114, 115, 118, 200, 201, 202, 203, 207, 210, 211):
+        turb = np.zeros(re.shape)
+        if flag == 113:
+            corr = (dh + 2 * 1e-3) / dh
+            ind = re / corr < 1.5e5
+            turb[ind] = 3.160 * (re[ind] / corr) ** -0.249
+            ind = re / corr >= 1.5e5
+            turb[ind] = 0.216 * (re[ind] / corr) ** -0.024
+        elif flag == 114:
+            turb = 0.0958 * re ** -0.181
+        elif flag == 115:
+            corr = 3.18e-3 / dh
+            turb = 0.25 * 0.3164 * (re / corr) ** -0.25 / corr
+        elif flag == 118:
+            turb = 0.1687 / 4.0 * re ** -0.1129
+        elif flag == 200:
+            doutct = dh + 2 * 1e-3
+            turb = (2.46 * (re / dh * 0.25e-3) ** -0.52 * dh / 0.25e-3
+                    * (area / (0.3 * (39.8e-3 ** 2 - doutct ** 2) * 0.25 * np.pi)) ** 2 / 4.0)
+        elif flag == 201:
+            turb = (0.0231 + 19.5 / (re / (6.0 / 5.0)) ** 0.7953) / (void_fraction ** 0.742) / 4.0
+        elif flag == 202:
+            turb = 6.1 * re ** -0.51 / 4.0
+        elif flag == 203:
+            turb = 0.4335 * re ** -0.263
+        elif flag == 207:
+            ind = (re >= 2e3) & (re < 4e3)
+            turb[ind] = 2.6471e-3 * re[ind] ** 0.3279 / 4.0
+            ind = (re >= 4e3) & (re < 3e4)
+            turb[ind] = 0.3194 * re[ind] ** -0.25 / 4.0
+            ind = re >= 3e4
+            turb[ind] = 1.0 / (1.8 * np.log10(re[ind]) / np.log10(10.0) - 1.64) ** 2 / 4.0
+        elif flag == 210:
+            ind = re < 1.5e3
+            turb[ind] = 47.65 * re[ind] ** -0.885 / 4.0
+            ind = (re >= 1.5e3) & (re <= 2e5)
+            turb[ind] = 1.093 * re[ind] ** -0.338 / 4.0
+            turb[re > 2e5] = 0.0377 / 4.0
+        else:
+            ind = re < 1e3
+            turb[ind] = 194.002 * re[ind] ** -0.52 / 4.0
+            ind = (re >= 1e3) & (re < 2e3)
+            turb[ind] = 4.8563 + 4.87e-4 * re[ind] / 4.0
+            ind = re >= 2e3
+            turb[ind] = 14.5148 * re[ind] ** -0.12 / 4.0
+        total = np.maximum(np.zeros(re.shape) if flag == 211 else _laminar(re), turb)
+        if flag == 211:
+            multiplier = 1.0
     else:
         raise ValueError(f"IFRICTION {flag} is not implemented (device flags: {SUPPORTED_IFRICTION})")
     return total * multiplier
@@ -84,4 +136,4 @@ def channel_friction_factor(model, topo, j: int, reynolds) -> np.ndarray:
     """`friction_factor` for channel j of a (Model, Topology) pair."""
     return friction_factor(model.ch_ifriction[j], model.ch_friction_mult[j], reynolds, topo.ch_dh[j],
                            model.ch_roughness[j] if model.ch_roughness else 0.0,
-                           model.ch_void_fraction[j] if model.ch_void_fraction else 0.0)
+                           model.ch_void_fraction[j] if model.ch_void_fraction else 0.0, topo.ch_area[j])

@@ -520,9 +520,12 @@ int osc2_set_model(osc2_handle h, const osc2_model *model)
         if (model->ch_fluid[j] + 1 > nf) nf = model->ch_fluid[j] + 1;
         {
             const int ifr = model->ch_ifriction[j];
-            if (ifr != -99 && ifr != 124 && ifr != 122 && ifr != 110 && ifr != 111 && ifr != 112 && ifr != 121 && ifr != 204 &&
-                ifr != 205 && ifr != 206 && ifr != 209)
-                return fail(OSC2_ERR_INVALID, "channel %d: IFRICTION %d is not implemented on the device (-99, 110, 111, 112, 121, 122, 124, 204, 205, 206, 209)", j, ifr);
+            static const int known[] = {-99, 110, 111, 112, 113, 114, 115, 118, 121, 122, 124, 200, 201, 202, 203, 204, 205, 206, 207, 209, 210, 211};
+            bool ok = false;
+            for (int v : known) ok = ok || (ifr == v);
+            if (!ok)
+                return fail(OSC2_ERR_INVALID, "channel %d: IFRICTION %d is not implemented on the device (-99, 110-115, 118, 121, 122, 124, 200-207, 209-211; "
+                            "208 raises in the reference, 123 fails there on arrays, 100-109 / 116 / 117 / 119 / 120 are not built)", j, ifr);
         }
         {
             const int hc = model->ch_htc_corr[j];

@@ -474,12 +474,46 @@ __device__ inline int colebrook_count(double re, double rough, double dh)
     }
     return it;
 }
+// turbulent slot of the hole laws 113 / 114 / 115 / 118 (channel.py:447-496, 636-648; the closing statement of 113 has
+// no effect and is not applied) and of the bundle laws 200 / 201 / 202 / 203 / 207 / 210 / 211 (:799-866, 939-963,
+// 1015-1066); re > 0 on entry.  211: the laminar slot stays 0 and the multiplier is forced to 1 (friction_total)
+__device__ __noinline__ double friction_more(int ifr, double re, double dh, double vf, double area)
+{
+    double turb = 0.0;
+    if (ifr == 113) {
+        const double corr = (dh + 2 * 1e-3) / dh, x = re / corr;
+        if (x < 1.5e5) turb = 3.160 * pw(x, -0.249);
+        if (x >= 1.5e5) turb = 0.216 * pw(x, -0.024);
+    } else if (ifr == 114) turb = 0.0958 * pw(re, -0.181);
+    else if (ifr == 115) { const double corr = 3.18e-3 / dh; turb = 0.25 * 0.3164 * pw(re / corr, -0.25) / corr; }
+    else if (ifr == 118) turb = 0.1687 / 4.0 * pw(re, -0.1129);
+    else if (ifr == 200) {
+        const double doutct = dh + 2 * 1e-3;
+        turb = 2.46 * pw(re / dh * 0.25e-3, -0.52) * dh / 0.25e-3 * sq(area / (0.3 * (sq(39.8e-3) - sq(doutct)) * 0.25 * 3.141592653589793)) / 4.0;
+    } else if (ifr == 201) turb = (0.0231 + 19.5 / pw(re / (6.0 / 5.0), 0.7953)) / pw(vf, 0.742) / 4.0;
+    else if (ifr == 202) turb = 6.1 * pw(re, -0.51) / 4.0;
+    else if (ifr == 203) turb = 0.4335 * pw(re, -0.263);
+    else if (ifr == 207) {
+        if (re >= 2e3 && re < 4e3) turb = 2.6471e-3 * pw(re, 0.3279) / 4.0;
+        if (re >= 4e3 && re < 3e4) turb = 0.3194 * pw(re, -0.25) / 4.0;
+        if (re >= 3e4) { const double x = 1.8 * log10(re) / 1.0 - 1.64; turb = 1.0 / (x * x) / 4.0; }
+    } else if (ifr == 210) {
+        if (re < 1.5e3) turb = 47.65 * pw(re, -0.885) / 4.0;
+        if (re >= 1.5e3 && re <= 2e5) turb = 1.093 * pw(re, -0.338) / 4.0;
+        if (re > 2e5) turb = 0.0377 / 4.0;
+    } else if (ifr == 211) {
+        if (re < 1e3) turb = 194.002 * pw(re, -0.52) / 4.0;
+        if (re >= 1e3 && re < 2e3) turb = 4.8563 + 4.87e-4 * re / 4.0;
+        if (re >= 2e3) turb = 14.5148 * pw(re, -0.12) / 4.0;
+    }
+    return turb;
+}
 // total friction factor of channel j (channel.py:1119-1138)
 // IFRICTION 110 (Blasius), 111 (Bhatti-Shah), 112 (LHC magnets recipe), 121 (Haaland), 204 / 205 (Katheder), 206 / 209
 // (Darcy-Forchheimer porous medium): channel.py:392-438, 700-717, katheder_correlation_bundle, _eval_jj_and_kk;
 // total = max(laminar, turbulent) with the general laminar correlation 16/Re (channel.py:284-299, 1104-1115);
 // for 121 the laminar slot calls the Haaland method again, which writes the turbulent array: laminar stays 0
-__device__ __noinline__ double friction_simple(int ifr, double re, double rough, double dh, double vf)
+__device__ __noinline__ double friction_simple(int ifr, double re, double rough, double dh, double vf, double area)
 {
     re = fabs(re);
     double turb = 0.0, lam = 0.0;
@@ -495,6 +529,7 @@ __device__ __noinline__ double friction_simple(int ifr, double re, double rough,
     }
     else if (ifr == 110) turb = (0.316 * pw(re, -0.25)) / 4.0;
     else if (ifr == 111) turb = 0.00128 + 0.1143 * pw(fmax(re, 4000.0), -0.311);
+    else if (ifr != 112) return fmax(friction_more(ifr, re, dh, vf, area), ifr == 211 ? 0.0 : lam);
     else {
         if (re <= 2.0e3) turb = 64 / re / 4.0;
         if (re > 2.0e3 && re < 4.0e3) turb = 2.6471e-3 * pw(re, 0.3279) / 4.0;
@@ -509,14 +544,14 @@ __device__ inline double friction_total(const osc2_model *md, const osc2_topolog
     const int ifr = md->ch_ifriction[j];
     if (ifr == 124) f = friction_124(re);
     else if (ifr != -99 && ifr != 122)      // 110, 111, 112, 121, 204, 205, 206, 209 (validated by osc2_set_model)
-        f = friction_simple(ifr, re, md->ch_roughness[j], tp->ch_dh[j], md->ch_void_fraction[j]);
+        f = friction_simple(ifr, re, md->ch_roughness[j], tp->ch_dh[j], md->ch_void_fraction[j], tp->ch_area[j]);
     else if (md->ch_ifriction[j] == 122) {
         const double rough = md->ch_roughness[j], dh = tp->ch_dh[j];
         f = haaland(fabs(re), rough, dh);
         for (int it = 0; it < cb_iters; ++it) f = colebrook_step(fabs(re), f, rough, dh);
         f = fmax(0.0, f);
     }
-    return f * md->ch_friction_mult[j];
+    return f * (ifr == 211 ? 1.0 : md->ch_friction_mult[j]);      // hts_cl_correlation_bundle sets FRICTION_MULTIPLIER = 1
 }
 // HTC["sol_sol"]["rad"] of interface k at one node: choice 3 = _inner_radiative_htc (conductor.py:5428-5443,
 // symmetric in the two temperatures; the denominator is prepared on the host), -3 = constant

@@ -43,7 +43,7 @@ class SolidModel:
 @dataclass(frozen=True)
 class Model:
     ch_fluid: Tuple[int, ...]
-    ch_ifriction: Tuple[int, ...]           # -99 | 110 | 111 | 112 | 121 | 122 | 124 | 204 | 205 | 206 | 209
+    ch_ifriction: Tuple[int, ...]           # correlations.SUPPORTED_IFRICTION (-99, 110-115, 118, 121, 122, 124, 200-207, 209-211)
     ch_friction_mult: Tuple[float, ...]
     ch_htc_corr: Tuple[int, ...]            # 1 | 119 | 120 | 121 | 211 | 212
     solids: Tuple[SolidModel, ...]

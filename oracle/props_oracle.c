@@ -377,7 +377,7 @@ static double friction_laminar(double re) { return re >= 1.0e-5 ? 16.0 / re : 0.
  * (channel.py:1104-1115).  110-112: laminar slot = general_laminar_correlation.  121: the laminar slot calls
  * haaland_equation again, which writes the TURBULENT array, so laminar stays 0.  112 assigns by masks that
  * leave Re = 2e3 < . , Re = 4e3 exactly at the initial 0 of the turbulent array. */
-static double friction_simple(int ifr, double re, double rough, double dh, double vf)
+static double friction_simple(int ifr, double re, double rough, double dh, double vf, double area)
 {
     re = fabs(re);
     double turb = 0.0, lam = 0.0;
@@ -404,6 +404,50 @@ static double friction_simple(int ifr, double re, double rough, double dh, doubl
         lam = friction_laminar(re);
         break;
     }
+    /* hole laws 113 (memorandum_bessette_iter_cs_spiral_hole_y2015, channel.py:447-468: its closing statement
+     * `turbulent / 4.0 / corr_diam ** 5` has no effect and is not applied), 114 (:470-480), 115 (:482-496), 118 (:636-648);
+     * corr_diam of _eval_correction_diameter_hole (:305-319, tthick = 1e-3) */
+    case 113: {
+        const double corr = (dh + 2 * 1e-3) / dh, x = re / corr;
+        if (x < 1.5e5) turb = 3.160 * pow(x, -0.249);
+        if (x >= 1.5e5) turb = 0.216 * pow(x, -0.024);
+        lam = friction_laminar(re);
+        break;
+    }
+    case 114: turb = 0.0958 * pow(re, -0.181); lam = friction_laminar(re); break;
+    case 115: { const double corr = 3.18e-3 / dh; turb = 0.25 * 0.3164 * pow(re / corr, -0.25) / corr; lam = friction_laminar(re); break; }
+    case 118: turb = 0.1687 / 4.0 * pow(re, -0.1129); lam = friction_laminar(re); break;
+    /* bundle laws 200 (tronza_iter_tf_correlation_bundle, :799-822), 201 (Nicollet, :824-840), 202 (Wanner, :842-853),
+     * 203 (KSTAR, :855-866), 207 (LHC Poncet, :939-963: nothing assigned below Re 2e3), 210 (DEMO TF HTS, :1015-1037) */
+    case 200: {
+        const double doutct = dh + 2 * 1e-3;
+        turb = 2.46 * pow(re / dh * 0.25e-3, -0.52) * dh / 0.25e-3
+               * pow(area / (0.3 * (pow(39.8e-3, 2.0) - pow(doutct, 2.0)) * 0.25 * 3.141592653589793), 2.0) / 4.0;
+        lam = friction_laminar(re);
+        break;
+    }
+    case 201: turb = (0.0231 + 19.5 / pow(re / (6.0 / 5.0), 0.7953)) / pow(vf, 0.742) / 4.0; lam = friction_laminar(re); break;
+    case 202: turb = 6.1 * pow(re, -0.51) / 4.0; lam = friction_laminar(re); break;
+    case 203: turb = 0.4335 * pow(re, -0.263); lam = friction_laminar(re); break;
+    case 207:
+        if (re >= 2e3 && re < 4e3) turb = 2.6471e-3 * pow(re, 0.3279) / 4.0;
+        if (re >= 4e3 && re < 3e4) turb = 0.3194 * pow(re, -0.25) / 4.0;
+        if (re >= 3e4) turb = 1.0 / pow(1.8 * log10(re) / log10(10.0) - 1.64, 2.0) / 4.0;
+        lam = friction_laminar(re);
+        break;
+    case 210:
+        if (re < 1.5e3) turb = 47.65 * pow(re, -0.885) / 4.0;
+        if (re >= 1.5e3 && re <= 2e5) turb = 1.093 * pow(re, -0.338) / 4.0;
+        if (re > 2e5) turb = 0.0377 / 4.0;
+        lam = friction_laminar(re);
+        break;
+    /* 211 (hts_cl_correlation_bundle, :1039-1066): the laminar slot calls the same method, which writes the
+     * turbulent array (laminar stays 0), and the method sets FRICTION_MULTIPLIER to 1 (applied by the caller) */
+    case 211:
+        if (re < 1e3) turb = 194.002 * pow(re, -0.52) / 4.0;
+        if (re >= 1e3 && re < 2e3) turb = 4.8563 + 4.87e-4 * re / 4.0;
+        if (re >= 2e3) turb = 14.5148 * pow(re, -0.12) / 4.0;
+        break;
     default: break;
     }
     return fmax(lam, turb);
@@ -514,7 +558,7 @@ int osc2o_fit(int which, long n, const double *x, const double *y, const double 
         case 30: out[i] = cp_mgb2(x[i]); break;
         case 26: out[i] = cp_nbti(x[i], y[i], z[i], out[i]); break;   /* x = T, y = B, z = Tcs; out[] holds Tc on entry */
         case 27: out[i] = tc_nbti(x[i], p1, p2); break;                            /* x = B, p1 = Bc20m, p2 = Tc0m */
-        case 24: out[i] = friction_simple((int)p1, x[i], y[i], z[i], p2); break;   /* p1 = IFRICTION, y = roughness, z = Dh, p2 = void fraction */
+        case 24: out[i] = friction_simple((int)p1, x[i], y[i], z[i], p2, y[i]); break;   /* p1 = IFRICTION, y = roughness (IFRICTION 200: CROSSECTION), z = Dh, p2 = void fraction */
         default: return -1;
         }
     }
@@ -599,9 +643,9 @@ static void one_conductor(const osc2_topology *tp, const osc2_model *md, osc2o_o
             /* channel.py:1119-1138 (IFRICTION 122 is array-wide: filled in after this loop) */
             const int ifr = md->ch_ifriction[j];
             const double ftot = ((ifr == 124) ? friction_124(re)
-                                 : (ifr == 110 || ifr == 111 || ifr == 112 || ifr == 121 || ifr == 204 || ifr == 205 || ifr == 206 || ifr == 209)
-                                     ? friction_simple(ifr, re, md->ch_roughness[j], tp->ch_dh[j], md->ch_void_fraction[j])
-                                 : 1.0) * md->ch_friction_mult[j];
+                                 : (ifr != -99 && ifr != 122)
+                                     ? friction_simple(ifr, re, md->ch_roughness[j], tp->ch_dh[j], md->ch_void_fraction[j], tp->ch_area[j])
+                                 : 1.0) * (ifr == 211 ? 1.0 : md->ch_friction_mult[j]);
             rey[e] = re;
             fg[((size_t)0 * M + j) * E + e] = v;
             fg[((size_t)1 * M + j) * E + e] = p;

@@ -1,7 +1,7 @@
 """Generate tests/golden/props_stack.npz by running the UNMODIFIED reference: the silver, Hastelloy C276 and
 Sn60Pb40 fits (properties_of_materials/) and the StackComponent homogenisers (stack_component.py:398-476) on
-a bare StackComponent object (its constructor needs openpyxl); and the friction laws IFRICTION 110, 111, 112,
-121, 204, 205, 206, 209 through Channel.eval_friction_factor on a bare object wired like Channel.__init__ (channel.py:43-169).
+a bare StackComponent object (its constructor needs openpyxl); and the friction laws IFRICTION 110-115, 118,
+121, 200-207, 209-211 through Channel.eval_friction_factor on a bare object wired like Channel.__init__ (channel.py:43-169).
 
 Build-container only (needs /root/reference):  python tests/golden/make_golden_stack.py
 """
@@ -67,13 +67,26 @@ def main():
               204: ("general_laminar_correlation", "katheder_correlation_bundle"),
               205: ("general_laminar_correlation", "katheder_correlation_bundle"),
               206: ("general_laminar_correlation", "darcy_forcheimer_porus_medium_correlation_bundle"),
-              209: ("general_laminar_correlation", "darcy_forcheimer_porus_medium_correlation_bundle")}
+              209: ("general_laminar_correlation", "darcy_forcheimer_porus_medium_correlation_bundle"),
+              113: ("general_laminar_correlation", "memorandum_bessette_iter_cs_spiral_hole_y2015"),
+              114: ("general_laminar_correlation", "csi_hole_ls_best_fit_icec_hole_y2016"),
+              115: ("general_laminar_correlation", "tronza_iter_tf_hole_correlation"),
+              118: ("general_laminar_correlation", "flat_spiral_from_cfd_hole"),
+              200: ("general_laminar_correlation", "tronza_iter_tf_correlation_bundle"),
+              201: ("general_laminar_correlation", "nicollet_general_correlation_bundle"),
+              202: ("general_laminar_correlation", "wanner_correlation_bundle"),
+              203: ("general_laminar_correlation", "kstar_correlation_bundle"),
+              207: ("general_laminar_correlation", "lhc_poncet_correlation_bundle"),
+              210: ("general_laminar_correlation", "demo_tf_hts_correlation_bundle"),
+              211: ("hts_cl_correlation_bundle", "hts_cl_correlation_bundle")}
+    out["crossection"] = np.array(3.7e-4)
     out["void_fraction"] = np.array(0.33)
     for ifr, (lam, turb) in wiring.items():
         ch = types.SimpleNamespace()
-        for name in ("_quantities_initialization", "_eval_total_friction_factor_max", "eval_friction_factor", "_eval_jj_and_kk", lam, turb):
+        for name in ("_quantities_initialization", "_eval_total_friction_factor_max", "eval_friction_factor", "_eval_jj_and_kk",
+                     "_eval_correction_diameter_hole", lam, turb):
             setattr(ch, name, types.MethodType(getattr(Channel, name), ch))
-        ch.inputs = {"FRICTION_MULTIPLIER": 0.02, "HYDIAMETER": 2.499e-3, "Roughness": 2.0e-6, "IFRICTION": ifr, "VOID_FRACTION": 0.33}
+        ch.inputs = {"FRICTION_MULTIPLIER": 0.02, "HYDIAMETER": 2.499e-3, "Roughness": 2.0e-6, "IFRICTION": ifr, "VOID_FRACTION": 0.33, "CROSSECTION": 3.7e-4}
         ch.dict_friction_factor = {True: {"laminar": None, "turbulent": None, "total": 0.0}}
         ch.laminar_friction_factor_correlation = getattr(ch, lam)
         ch.turbulent_friction_factor_correlation = getattr(ch, turb)
