@@ -122,10 +122,14 @@ struct TileFwdCtx {
     unsigned long long *bars;    // !FUSED: the NST mbarriers of the bulk loads
     double *full, *empty;        // FUSED
     size_t tile;
-    bool tile_valid;             // FUSED: a CTA covers 8 tiles, the last CTA may own tiles past the batch
+    bool tile_valid;             // a CTA that covers several tiles may own tiles past the batch
+    // split roles (osc2_forward_split_kernel): scaled rows handed from the assembler warp to the eliminator warp
+    double *hand;                // [2][3 D + 1][32]
+    double *hfull, *hempty;      // mbarriers of the two hand-over slots, 16 bytes apart
 };
+enum { OSC2_ROLE_BOTH = 0, OSC2_ROLE_ASM = 1, OSC2_ROLE_ELIM = 2 };
 
-template <int D, int LPC, bool FULL, bool FUSED, int NST>
+template <int D, int LPC, bool FULL, bool FUSED, int NST, int ROLE = OSC2_ROLE_BOTH>
 __device__ __forceinline__ void osc2_forward_tile_body(const osc2_topology *__restrict__ tp, const StepDev &p, const TileFwdCtx &cx)
 {
     static_assert(D % 8 == 0, "closed-form Known: D % 8 == 0");
@@ -138,7 +142,7 @@ __device__ __forceinline__ void osc2_forward_tile_body(const osc2_topology *__re
     const int r = lane / CPW, bb = lane % CPW;
     const size_t tile = cx.tile;
     const long long b_ll = (long long)tile * CPW + bb;
-    const bool act = FULL || ((b_ll < (long long)p.B) && (r < D) && (!FUSED || cx.tile_valid));
+    const bool act = FULL || ((b_ll < (long long)p.B) && (r < D) && cx.tile_valid);
     const size_t b = act ? (size_t)b_ll : 0;
     const int rr_ = (FULL || r < D) ? r : 0;
     const Osc2Rcp rdt = osc2_rcp_prepare(p.dt);
@@ -212,12 +216,14 @@ __device__ __forceinline__ void osc2_forward_tile_body(const osc2_topology *__re
     auto release = [&](const int e) {                            // every lane: this lane has read element e for the last time
         if (FUSED && e >= 0 && e < N - 1) osc2_cbar_arrive(cx.empty + 2 * (e % NST));
     };
-    if (!FUSED) {
-        if (lane == 0) {
-            for (int s = 0; s < NST; ++s) osc2_mbar_init(bars + s, 1);
-            osc2_mbar_init_fence();
+    if (!FUSED && ROLE != OSC2_ROLE_ELIM) {
+        if (ROLE == OSC2_ROLE_BOTH) {          // split roles: the kernel initialises every barrier before the roles part
+            if (lane == 0) {
+                for (int s = 0; s < NST; ++s) osc2_mbar_init(bars + s, 1);
+                osc2_mbar_init_fence();
+            }
+            __syncwarp();
         }
-        __syncwarp();
         issue(0);
         issue(1);
     }
@@ -338,6 +344,8 @@ __device__ __forceinline__ void osc2_forward_tile_body(const osc2_topology *__re
         const long long i_row = (long long)n * D + r;
         Osc2Rcp my_rcp = osc2_rcp_make(1.0, 1.0);
         Osc2Rcp nxt = osc2_rcp_prepare(cD[0]);          // every lane; lane k's is the one that gets published
+        // (publishing row k + 1 inside round k, ahead of the updates of the next node's row, was tried: the longer live
+        // ranges cost 255 registers and spills -- 36.9 instead of 28.9 ms)
 #pragma unroll
         for (int k = 0; k < D; ++k) {
             if (act && r == k) {
@@ -380,15 +388,29 @@ __device__ __forceinline__ void osc2_forward_tile_body(const osc2_topology *__re
             }
         }
         // the staging block is free once the bulk store of node n-1 has READ it
-        if (lane == 0) osc2_bulk_store_wait_read();
-        __syncwarp();
+        if (ROLE != OSC2_ROLE_ELIM) {
+            if (lane == 0) osc2_bulk_store_wait_read();
+            __syncwarp();
+        }
         if (act) {
             // this lane's pivot: singular (tsf:676-682) or outside the exact range of the division
             const bool tiny = fabs(my_rcp.b) <= OSC2_TINY_PIVOT;
             if (tiny && bad_row < 0) bad_row = i_row;
             div_span = osc2_umax(div_span, tiny ? 0u : osc2_abs_hi(my_rcp.b) - OSC2_HI_DIV_LO);
         }
-        {
+        if (ROLE == OSC2_ROLE_ELIM) {
+            // split roles: no staging block (its shared memory went to the hand-over slots); a warp-wide store of one
+            // field is 256 contiguous bytes of the tiled `spill`
+            if (cx.tile_valid) {
+                double *sq = sptile + (size_t)n * sstep + lane;
+#pragma unroll
+                for (int c = 0; c < D; ++c) sq[c * 32] = cD[c];
+#pragma unroll
+                for (int c = 0; c < D; ++c) sq[(D + c) * 32] = cU[c];
+                sq[2 * D * 32] = crhs;
+                sq[(2 * D + 1) * 32] = my_rcp.y;
+            }
+        } else {
             double *sq = stg + lane;
 #pragma unroll
             for (int c = 0; c < D; ++c) sq[c * 32] = cD[c];
@@ -396,42 +418,96 @@ __device__ __forceinline__ void osc2_forward_tile_body(const osc2_topology *__re
             for (int c = 0; c < D; ++c) sq[(D + c) * 32] = cU[c];
             sq[2 * D * 32] = crhs;
             sq[(2 * D + 1) * 32] = my_rcp.y;
+            osc2_fence_async_smem();
+            __syncwarp();
+            if (lane == 0 && cx.tile_valid) osc2_bulk_store(sptile + (size_t)n * sstep, stg, (unsigned)(SM::STG * sizeof(double)));
         }
-        osc2_fence_async_smem();
-        __syncwarp();
-        if (lane == 0 && (!FUSED || cx.tile_valid)) osc2_bulk_store(sptile + (size_t)n * sstep, stg, (unsigned)(SM::STG * sizeof(double)));
     };
 
     double cL[D], cD[D], cU[D], crhs = 0.0;       // node under elimination (cL: node 0 has no L block)
     double nL[D], nD[D], nU[D], nrhs = 0.0;       // node n+1
-    if (act) {
+    constexpr int HREC = (3 * D + 1) * 32;        // doubles of one hand-over slot: L | D | U | rhs, lane innermost
+    if (ROLE != OSC2_ROLE_ELIM && act) {
         x0 = xptr[0];
         x_pre = xptr[xstep];
         sl0_pre = lodptr[0];
         sl1_pre = lodptr[B];
     }
-    arrived(0);
-    construct(std::false_type(), std::true_type(), 0, cL, cD, cU, crhs);
-    release(-1);
-    // one step of the pipeline: row of node n+1, then the rounds of node n
-    auto stage = [&](auto HR, const int n) {
-        // element n+2 goes where element n-1 was: its last readers (the construction of node n) are past the
-        // __syncwarp()s of the rounds that followed
-        issue(n + 2);
-        arrived(n + 1);
-        construct(std::true_type(), HR, n + 1, nL, nD, nU, nrhs);
-        release(n);                                  // element n was the left neighbour of node n + 1
-        eliminate(std::true_type(), n, cD, cU, crhs, nL, nD, nrhs);
+    if constexpr (ROLE == OSC2_ROLE_BOTH) {
+        arrived(0);
+        construct(std::false_type(), std::true_type(), 0, cL, cD, cU, crhs);
+        release(-1);
+        // one step of the pipeline: row of node n+1, then the rounds of node n
+        auto stage = [&](auto HR, const int n) {
+            // element n+2 goes where element n-1 was: its last readers (the construction of node n) are past the
+            // __syncwarp()s of the rounds that followed
+            issue(n + 2);
+            arrived(n + 1);
+            construct(std::true_type(), HR, n + 1, nL, nD, nU, nrhs);
+            release(n);                                  // element n was the left neighbour of node n + 1
+            eliminate(std::true_type(), n, cD, cU, crhs, nL, nD, nrhs);
 #pragma unroll
-        for (int c = 0; c < D; ++c) { cD[c] = nD[c]; cU[c] = nU[c]; }
-        crhs = nrhs;
-    };
-    for (int n = 0; n < N - 2; ++n) stage(std::true_type(), n);
-    stage(std::false_type(), N - 2);
-    eliminate(std::false_type(), N - 1, cD, cU, crhs, nL, nD, nrhs);
-    if (lane == 0) osc2_bulk_store_wait_all();
-    __syncwarp();
-    double *scratch = rec;                          // every element has been consumed
+            for (int c = 0; c < D; ++c) { cD[c] = nD[c]; cU[c] = nU[c]; }
+            crhs = nrhs;
+        };
+        for (int n = 0; n < N - 2; ++n) stage(std::true_type(), n);
+        stage(std::false_type(), N - 2);
+        eliminate(std::false_type(), N - 1, cD, cU, crhs, nL, nD, nrhs);
+        if (lane == 0) osc2_bulk_store_wait_all();
+        __syncwarp();
+    } else if constexpr (ROLE == OSC2_ROLE_ASM) {
+        // ---- assembler warp: the scaled row of node m into hand-over slot m % 2, up to two nodes ahead of the eliminator.
+        //      Every lane writes and (in the eliminator warp) reads its own row only ----------------------------------
+        auto hand_over = [&](const int m, const double (&rowL)[D], const double (&rowD)[D], const double (&rowU)[D], const double rhs) {
+            const int s = m & 1;
+            if (m >= 2) osc2_cbar_wait(cx.hempty + 2 * s, (unsigned)(((m >> 1) - 1) & 1));
+            double *h = cx.hand + (size_t)s * HREC + lane;
+#pragma unroll
+            for (int c = 0; c < D; ++c) { h[c * 32] = rowL[c]; h[(D + c) * 32] = rowD[c]; h[(2 * D + c) * 32] = rowU[c]; }
+            h[3 * D * 32] = rhs;
+            osc2_cbar_arrive(cx.hfull + 2 * s);
+        };
+        arrived(0);
+        construct(std::false_type(), std::true_type(), 0, cL, cD, cU, crhs);
+        hand_over(0, cL, cD, cU, crhs);
+        for (int m = 1; m < N - 1; ++m) {
+            __syncwarp();                                // every lane is past its reads of element m - 2
+            issue(m + 1);
+            arrived(m);
+            construct(std::true_type(), std::true_type(), m, nL, nD, nU, nrhs);
+            hand_over(m, nL, nD, nU, nrhs);
+        }
+        construct(std::true_type(), std::false_type(), N - 1, nL, nD, nU, nrhs);
+        hand_over(N - 1, nL, nD, nU, nrhs);
+        return;
+    } else {
+        // ---- eliminator warp ----------------------------------------------------------------------------------------
+        auto take = [&](const int m) { osc2_cbar_wait(cx.hfull + 2 * (m & 1), (unsigned)((m >> 1) & 1)); };
+        {
+            take(0);
+            const double *h = cx.hand + lane;
+#pragma unroll
+            for (int c = 0; c < D; ++c) { cD[c] = h[(D + c) * 32]; cU[c] = h[(2 * D + c) * 32]; }
+            crhs = h[3 * D * 32];
+            osc2_cbar_arrive(cx.hempty);
+        }
+        for (int n = 0; n < N - 1; ++n) {
+            const int s = (n + 1) & 1;
+            take(n + 1);
+            const double *h = cx.hand + (size_t)s * HREC + lane;
+#pragma unroll
+            for (int c = 0; c < D; ++c) { nL[c] = h[c * 32]; nD[c] = h[(D + c) * 32]; }
+            nrhs = h[3 * D * 32];
+            eliminate(std::true_type(), n, cD, cU, crhs, nL, nD, nrhs);
+#pragma unroll
+            for (int c = 0; c < D; ++c) { cD[c] = nD[c]; cU[c] = h[(2 * D + c) * 32]; }     // the U block is untouched by node n's pivots
+            crhs = nrhs;
+            osc2_cbar_arrive(cx.hempty + 2 * s);
+        }
+        eliminate(std::false_type(), N - 1, cD, cU, crhs, nL, nD, nrhs);
+        __syncwarp();
+    }
+    double *scratch = (ROLE == OSC2_ROLE_ELIM) ? cx.hand : rec;     // every element / row has been consumed
     if (r < D) { scratch[lane] = (double)bad_row; scratch[32 + lane] = (div_span >= OSC2_HI_DIV_SPAN) ? 1.0 : 0.0; }
     __syncwarp();
     if (act && r == 0) {
@@ -457,10 +533,87 @@ __global__ void __launch_bounds__(32) osc2_forward_tile_kernel(const osc2_topolo
     cx.stg = cx.rec + SM::NST * SM::REC;
     cx.pub = cx.stg + SM::STG;
     cx.bars = (unsigned long long *)(sm_dyn + SM::NST * SM::REC + SM::STG + SM::CPW * SM::PUBC);
-    cx.full = cx.empty = nullptr;
+    cx.full = cx.empty = cx.hand = cx.hfull = cx.hempty = nullptr;
     cx.tile = blockIdx.x;
     cx.tile_valid = true;
     osc2_forward_tile_body<D, LPC, FULL, false, SM::NST>(tp, p, cx);
+}
+
+// ---------------------------------------------------------------------------
+// K_F with split roles.  The forward sweep of a tile is two instruction streams with a one-way dependence: building
+// and scaling the row of node m (tables of selects, the range keys, 75 quotients: ~550 instructions, no dependence
+// on the elimination) and the eight pivot rounds (~930 instructions, the serial chain).  In
+// osc2_forward_tile_kernel one warp runs both, and with 200 registers per thread only two such warps fit a
+// scheduler -- which then issues on half of its cycles.  Here an ASSEMBLER warp builds the rows one or two nodes
+// ahead and hands them over through two shared-memory slots, an ELIMINATOR warp runs the pivot rounds: four warps
+// per scheduler instead of two for the same 4096 conductors.  One CTA per SM: 7 tiles = 7 eliminators (warps 0..6)
+// + 7 assemblers (warps 8..14), 147 CTAs for 4096 conductors; setmaxnreg moves registers from the assembler
+// warpgroups (120) to the eliminator warpgroups (136): 8 * 136 + 8 * 120 = 16 * 128 (152 / 104 and 144 / 112 spill in
+// the assembler: 34.6 and 31.8 ms; 128 / 128: 29.2 ms; 136 / 120: 28.0 ms).  Shared memory per tile: record
+// ring 3 x 4352 B (TMA, assembler) + hand-over 2 x 6400 B + pivot rows 4672 B; the factor rows leave by plain
+// coalesced stores.  Same arithmetic, same bits.
+// ---------------------------------------------------------------------------
+template <int R> __device__ __forceinline__ void osc2_setmaxnreg_inc()
+{
+#ifndef OSC2_EMU
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R));
+#endif
+}
+template <int R> __device__ __forceinline__ void osc2_setmaxnreg_dec()
+{
+#ifndef OSC2_EMU
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R));
+#endif
+}
+
+template <int D, int LPC>
+struct SplitFwdSmem {
+    using T = TileFwdSmem<D, LPC>;
+    static constexpr int TILES = 7;                        // per CTA: 7 x 30.5 KB of the 227 KB
+    static constexpr int NST = 3;                          // record ring
+    static constexpr int HREC = (3 * D + 1) * 32;          // one hand-over slot
+    static constexpr int PER_TILE = NST * T::REC + 2 * HREC + T::CPW * T::PUBC;
+    static constexpr int BAR = 16;                         // doubles per tile: ring barriers (8 bytes each) in 0..3, hand-over
+                                                           // full x 2 at 4 and 6, empty x 2 at 8 and 10 (16 bytes each)
+    static constexpr int OFF_BAR = TILES * PER_TILE;
+    static constexpr int DOUBLES = OFF_BAR + TILES * BAR;
+    static constexpr size_t BYTES = (size_t)DOUBLES * sizeof(double);
+    static_assert(PER_TILE % 2 == 0 && T::REC % 2 == 0, "16-byte alignment of the bulk-copy destinations");
+};
+
+template <int D, int LPC, bool FULL, int RE = 136>       // RE: registers of an eliminator thread; an assembler thread gets 256 - RE
+__global__ void __launch_bounds__(512, 1) osc2_forward_split_kernel(const osc2_topology *__restrict__ tp, StepDev p)
+{
+    OSC2_DYN_SMEM_ALIGNED(sm_dyn);
+    using SM = SplitFwdSmem<D, LPC>;
+    using T = TileFwdSmem<D, LPC>;
+    const int warp = threadIdx.x >> 5;
+    if (threadIdx.x < SM::TILES) {
+        double *bar = sm_dyn + SM::OFF_BAR + (size_t)threadIdx.x * SM::BAR;
+        for (int s = 0; s < SM::NST; ++s) osc2_mbar_init((unsigned long long *)bar + s, 1);
+        for (int s = 0; s < 4; ++s) osc2_cbar_init(bar + 4 + 2 * s, 32);
+        osc2_mbar_init_fence();
+    }
+    __syncthreads();
+    const int role = (warp < 8) ? OSC2_ROLE_ELIM : OSC2_ROLE_ASM;
+    const int t = warp & 7;
+    if (RE > 128) { if (role == OSC2_ROLE_ELIM) osc2_setmaxnreg_inc<RE>(); else osc2_setmaxnreg_dec<256 - RE>(); }
+    if (t >= SM::TILES || (size_t)blockIdx.x * SM::TILES + t >= (size_t)p.NT) return;     // the barriers are per tile
+    double *base = sm_dyn + (size_t)t * SM::PER_TILE;
+    double *bar = sm_dyn + SM::OFF_BAR + (size_t)t * SM::BAR;
+    TileFwdCtx cx;
+    cx.rec = base;
+    cx.hand = base + SM::NST * T::REC;
+    cx.pub = cx.hand + 2 * SM::HREC;
+    cx.stg = nullptr;
+    cx.bars = (unsigned long long *)bar;
+    cx.full = cx.empty = nullptr;
+    cx.hfull = bar + 4;
+    cx.hempty = bar + 8;
+    cx.tile = (size_t)blockIdx.x * SM::TILES + t;
+    cx.tile_valid = true;
+    if (role == OSC2_ROLE_ELIM) osc2_forward_tile_body<D, LPC, FULL, false, SM::NST, OSC2_ROLE_ELIM>(tp, p, cx);
+    else osc2_forward_tile_body<D, LPC, FULL, false, SM::NST, OSC2_ROLE_ASM>(tp, p, cx);
 }
 
 // ---------------------------------------------------------------------------

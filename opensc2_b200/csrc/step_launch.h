@@ -163,6 +163,17 @@ void osc2_run_fast_sweeps(Launcher &L, const osc2_topology *tp_dev, const StepDe
         static const bool tile_on = [] { const char *e = getenv("OSC2_FWD_TILE"); return !(e && e[0] == '0'); }();
         if (be && !cap && tile_on) {
             const unsigned nt = (unsigned)((p.B + cpb - 1) / cpb);
+            // assembler / eliminator warps (osc2_forward_split_kernel) when a CTA's 209 KB of shared memory are there;
+            // OSC2_FWD_SPLIT=0 keeps the one-warp-per-tile kernel (same bits) for A/B timing
+            static const bool split_on = [] { const char *e = getenv("OSC2_FWD_SPLIT"); return !(e && e[0] == '0'); }();
+            if (split_on && SplitFwdSmem<D, LPC>::BYTES <= L.max_smem()) {
+                using SS = SplitFwdSmem<D, LPC>;
+                const unsigned nc = (nt + SS::TILES - 1) / SS::TILES;
+                if (p.B % cpb != 0) L.launch(OSC2_K_FORWARD, osc2_forward_split_kernel<D, LPC, false>, nc, 512u, SS::BYTES, tp_dev, p);
+                else L.launch(OSC2_K_FORWARD, osc2_forward_split_kernel<D, LPC, true>, nc, 512u, SS::BYTES, tp_dev, p);
+                L.launch(OSC2_K_BACKWARD, osc2_backward_tile_kernel<D, LPC>, nt, 32u, TileBwdSmem<D, LPC>::BYTES, p);
+                return;
+            }
 #ifdef OSC2_WITH_FUSED_GF
             if constexpr (D == 8) {
                 if (fused) {
