@@ -66,16 +66,40 @@ def b_alg(d: int) -> int:
     return 8 * (3 * d * (4 * d - 1) + 6 * d)
 
 
+def touched_smat_entries(topo) -> int:
+    """Entries of the d x d source Jacobian a statement of K_G can write (osc2_build_smap, step_launch.h)."""
+    M = topo.n_ch
+    e = set()
+    for j in range(M):
+        e |= {(j, j), (M + j, j), (2 * M + j, j)}
+    for (a, b) in topo.ff:
+        for c1, c2 in ((a, b), (b, a)):
+            v1, p1, t1, p2, t2 = c1, M + c1, 2 * M + c1, M + c2, 2 * M + c2
+            e |= {(v1, p1), (v1, p2), (p1, p1), (p1, p2), (p1, t1), (p1, t2), (t1, p1), (t1, p2), (t1, t1), (t1, t2)}
+    for (j, l) in topo.fs:
+        ip, it, is_ = M + j, 2 * M + j, 3 * M + l
+        e |= {(ip, it), (ip, is_), (it, it), (it, is_), (is_, is_), (is_, it)}
+    for (a, c) in topo.ss:
+        a, c = 3 * M + a, 3 * M + c
+        e |= {(a, a), (a, c), (c, c), (c, a)}
+    for l in topo.es:
+        e.add((3 * M + l, 3 * M + l))
+    return len(e)
+
+
 def kernel_alg_bytes(topo):
-    """Per-unit algorithmic bytes of each kernel (DESIGN.md section 4)."""
+    """Per-unit algorithmic bytes of each kernel (DESIGN.md section 5)."""
     d, M, S = topo.ndf, topo.n_ch, topo.n_sol
     nff, nfs, nss, nes = len(topo.ff), len(topo.fs), len(topo.ss), len(topo.es)
     rec = d * (d + 9)
+    # record fields K_G writes every step: the ones that are +0 for every element of the topology (untouched SMAT
+    # entries, load halves of the fluid rows, advection entries of the solid rows) were written once, at creation
+    rec_written = rec - ((d * d - touched_smat_entries(topo)) + 4 * 3 * M + 2 * S)
     coef = 1 + 9 * M + 3 * S + 4 * S + 4 * nff + 2 * nfs + 2 * nss + 4 * nes     # per element, K_G inputs
     computed = 9 * M + 3 * S + 4 * S + 2 * nff + nfs + nss + 3 * nes              # per element, K_P outputs
     return {
         "props": 8 * (d + S + computed),                    # per element: state, Tcs in; coefficients out
-        "gauss": 8 * (coef + S + rec + 3 * nff),            # per element: coefficients, qsource in; row records, K1..K3 out
+        "gauss": 8 * (coef + S + rec_written + 3 * nff),    # per element: coefficients, qsource in; row records, K1..K3 out
         "forward": 8 * (rec + d + 4 * d + d * (2 * d + 2)),  # per node: record, x_old, SYSLOD in/out, factors out
         "backward": 8 * (d * (2 * d + 2) + d),              # per node: factors in, x out
         "norms": 8 * d,                                      # per node: x in

@@ -107,6 +107,35 @@ def test_full_size_mesh_linearity_property():
         assert np.max(np.abs(ax - known) / scale) < 1e-9
 
 
+@pytest.mark.parametrize("batch", [8, 29])
+def test_full_size_mesh_matches_the_oracle_bit_for_bit(batch):
+    """BASELINE mesh size per conductor (10 001 nodes) through the production sweeps (split-role K_F, tiled K_B),
+    a full and a ragged set of tiles, two chained steps: every output equals the oracle's bits."""
+    from opensc2_b200.batch import BatchedStep
+    from oracle import oracle as O
+
+    topo = case1_topology(1)
+    n = 10001
+    arr = synthetic_step_arrays(topo, n, batch=batch, seed=7, num_step=1)
+    host = arr.copy()
+    with BatchedStep(topo, batch, n) as bs:
+        bs.upload_state(arr.sysvar, arr.syslod)
+        bs.upload_step_inputs(arr)
+        for k in (1, 2):
+            bs.step(arr.dt, k)
+            host.num_step = k
+            ref = O.step(topo, host, n_threads=8) if "n_threads" in O.step.__code__.co_varnames else O.step(topo, host)
+            host.sysvar, host.syslod = ref["sysvar"], ref["syslod"]
+        bs.synchronize()
+        sv, sl, st = bs.download_state()
+        diag = bs.download_diagnostics()
+    assert np.all(st == 0)
+    assert_bits(sv, host.sysvar, "sysvar, 10 001 nodes")
+    assert_bits(sl, host.syslod, "syslod, 10 001 nodes")
+    for key in ("norm_solution", "norm_change", "eqteig"):
+        assert_bits(diag[key], ref[key], key)
+
+
 def test_too_few_nodes_is_rejected():
     from opensc2_b200.batch import BatchedStep
 
