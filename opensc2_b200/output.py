@@ -38,8 +38,17 @@ def nodal_friction_factor(model: Model, topo: Topology, j: int, reynolds: np.nda
     return channel_friction_factor(model, topo, j, reynolds)
 
 
-def channel_table(topo: Topology, model: Model, tab: FluidTable, j: int, zcoord, v, p, t) -> np.ndarray:
-    """(N, 18) array of one channel's file."""
+NODAL_COLUMNS = ("total_density", "isobaric_expansion_coefficient", "isothermal_compressibility", "Prandtl",
+                 "total_dynamic_viscosity", "total_enthalpy", "total_isobaric_specific_heat", "total_isochoric_specific_heat",
+                 "total_speed_of_sound", "total_thermal_conductivity", "Reynolds", "Gruneisen", "mass_flow_rate",
+                 "friction_factor")         # BatchedStep.nodal_properties(): the device's nodal coolant pass
+
+
+def channel_table(topo: Topology, model: Model, tab: FluidTable, j: int, zcoord, v, p, t, nodal=None) -> np.ndarray:
+    """(N, 18) array of one channel's file.  `nodal`: {column: (M, N)} of this conductor from the device's nodal pass
+    (osc2_eval_nodal_properties); without it the columns are evaluated here with the same table lookup."""
+    if nodal is not None:
+        return np.stack([zcoord, p, t, nodal["total_density"][j], v] + [nodal[k][j] for k in NODAL_COLUMNS[1:]], axis=1)
     rho = table_lookup(tab, FP_RHO, p, t)
     cols = [zcoord, p, t, rho, v] + [table_lookup(tab, q, p, t) for q in _ALIAS_ORDER]
     mu, beta, kappa, cv = cols[8], cols[5], cols[6], cols[11]
@@ -52,11 +61,13 @@ def channel_table(topo: Topology, model: Model, tab: FluidTable, j: int, zcoord,
 
 def save_properties(f_path: str, topo: Topology, model: Model, tables: Sequence[FluidTable], zcoord: np.ndarray,
                     sysvar: np.ndarray, b_field: np.ndarray, t_cur_sharing: Optional[np.ndarray] = None,
-                    chan_ids: Optional[Sequence[str]] = None, solid_ids: Optional[Sequence[str]] = None) -> None:
+                    chan_ids: Optional[Sequence[str]] = None, solid_ids: Optional[Sequence[str]] = None,
+                    nodal=None) -> None:
     """Write `<identifier>.tsv` for every component of ONE conductor.
 
     sysvar: (N*d,) state; b_field: (S, 2) BISS, BOSS; t_cur_sharing: (S, N) nodal current sharing
-    temperature of the superconducting strands (rows of other solids are ignored)."""
+    temperature of the superconducting strands (rows of other solids are ignored); nodal: this conductor's
+    {column: (M, N)} from the device's nodal coolant pass (optional, see channel_table)."""
     M, S, d = topo.n_ch, topo.n_sol, topo.ndf
     N = zcoord.shape[0]
     x = np.asarray(sysvar, dtype=np.float64).reshape(N, d)
@@ -72,7 +83,7 @@ def save_properties(f_path: str, topo: Topology, model: Model, tables: Sequence[
     header_chan = "\t".join(f"{n} {u}" for n, u in CHAN_COLUMNS)
     for j in range(M):
         a = channel_table(topo, model, tables[model.ch_fluid[j]], j, zcoord, x[:, j].copy(), x[:, M + j].copy(),
-                          x[:, 2 * M + j].copy())
+                          x[:, 2 * M + j].copy(), nodal)
         with open(os.path.join(f_path, f"{chan_ids[j]}.tsv"), "w") as w:
             np.savetxt(w, a, delimiter="\t", header=header_chan, comments="")
     for l, s in enumerate(model.solids):

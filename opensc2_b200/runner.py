@@ -111,6 +111,7 @@ class TransientResult:
     snapshots: Dict[int, np.ndarray] = field(default_factory=dict)   # step -> (B, N*d)
     margin_min: Optional[np.ndarray] = None  # (B, S) min over the run of min_x (Tcs - T)
     tcs_nodal: Optional[np.ndarray] = None   # (B, S, N)
+    nodal: Optional[Dict[str, np.ndarray]] = None   # run(want_nodal=True): {column: (B, M, N)}, the device's nodal coolant pass
 
 
 class TransientSetup:
@@ -179,7 +180,9 @@ class Transient(TransientSetup):
         return float(self._get_time_step(self))
 
     def run(self, t_end: Optional[float] = None, max_steps: Optional[int] = None, snapshot_every: int = 0,
-            track_margin: bool = False, on_step: Optional[Callable] = None) -> TransientResult:
+            track_margin: bool = False, on_step: Optional[Callable] = None, want_nodal: bool = False) -> TransientResult:
+        """want_nodal: also run the device's nodal coolant pass on the final state (post-step density, mass flow rate,
+        the property columns of save_properties; 14 M N doubles per conductor come back to the host)."""
         tr = self.deck.transient
         t_end = float(tr["TEND"]) if t_end is None else float(t_end)
         stpmin = float(tr["STPMIN"])
@@ -204,8 +207,11 @@ class Transient(TransientSetup):
         self.bs.synchronize()                      # raises like the reference on a singular system
         sv, _, st = self.bs.download_state(want_syslod=False)
         tcs_nodal = self.bs.download_tcs()[1] if self.has_sc else None
+        # post-step density, mass flow rate and the nodal property columns of the final state, on the device
+        # (coolant.py:226-263; what save_properties prints)
+        nodal = self.bs.nodal_properties() if (want_nodal and self.deck.topology.n_ch > 0) else None
         return TransientResult(time=list(self.time), sysvar=sv, status=st, snapshots=snaps, margin_min=margin,
-                               tcs_nodal=tcs_nodal)
+                               tcs_nodal=tcs_nodal, nodal=nodal)
 
     def save_solution(self, folder: str, result: TransientResult, conductors: Optional[Sequence[int]] = None):
         """Solution/*.tsv per conductor, the reference's save_properties layout (output.py)."""
@@ -217,4 +223,5 @@ class Transient(TransientSetup):
             save_properties(os.path.join(folder, f"conductor_{b}") if self.batch > 1 else folder, self.deck.topology,
                             self.deck.model, self.tables, self.zcoord, result.sysvar[b], self.sweep.b_field[b],
                             None if result.tcs_nodal is None else result.tcs_nodal[b],
-                            chan_ids=self.deck.chan_ids, solid_ids=self.deck.solid_ids)
+                            chan_ids=self.deck.chan_ids, solid_ids=self.deck.solid_ids,
+                            nodal=None if result.nodal is None else {k: v[b] for k, v in result.nodal.items()})

@@ -146,3 +146,25 @@ def test_margin_diagnostic_is_the_minimum_of_tcs_minus_temperature():
     assert np.all(np.isinf(m[:, 1]))                                # the jacket holds no superconductor
     assert np.all(res.margin_min[:, 0] < m[:, 0])                   # the slug ate into the margin, which has recovered since
     assert np.all(np.diff(res.margin_min[:, 0]) < 0)                # more current and more power: less margin
+
+
+def test_solution_files_from_the_device_nodal_pass(tmp_path):
+    """Transient.save_solution with run(want_nodal=True): the channel files are written from the device's nodal coolant
+    pass (osc2_eval_nodal_properties) and equal the ones the host writer computes from the downloaded state -- every
+    column to the last bit except the friction factor (2e-12: powers by the device's exp / log)."""
+    from opensc2_b200.runner import Transient
+
+    deck, tables = deck_of("case1"), tables_of("case1")
+    with Transient(deck, tables, 3, legacy_intial2=legacy_of("case1"), q0=np.array([200.0, 500.0, 900.0])) as tr:
+        res = tr.run(max_steps=12, want_nodal=True)
+        assert res.nodal is not None and res.nodal["mass_flow_rate"].shape == (3, deck.topology.n_ch, tr.zcoord.shape[0])
+        tr.save_solution(str(tmp_path / "dev"), res)
+        host = type(res)(time=res.time, sysvar=res.sysvar, status=res.status, tcs_nodal=res.tcs_nodal)
+        tr.save_solution(str(tmp_path / "host"), host)
+    for b in range(3):
+        for ch in deck.chan_ids:
+            a = np.loadtxt(tmp_path / "dev" / f"conductor_{b}" / f"{ch}.tsv", skiprows=1)
+            c = np.loadtxt(tmp_path / "host" / f"conductor_{b}" / f"{ch}.tsv", skiprows=1)
+            assert a.shape == c.shape and a.shape[1] == 18
+            assert np.array_equal(a[:, :17], c[:, :17])
+            assert np.max(np.abs(a[:, 17] / c[:, 17] - 1.0)) <= 2e-12
