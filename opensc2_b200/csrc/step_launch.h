@@ -14,6 +14,9 @@
 #ifdef OSC2_WITH_FUSED_GF          // experiments/step_kernels_fused.cuh: K_G inside K_F (bit-exact, 3x slower: DESIGN.md 5)
 #include "../../experiments/step_kernels_fused.cuh"
 #endif
+#ifdef OSC2_WITH_SPLIT_ROLES       // experiments/step_kernels_split_roles.cuh: assembler + eliminator warps per tile
+#include "../../experiments/step_kernels_split_roles.cuh"
+#endif
 #include "step_kernels_d64.cuh"
 
 #include <cstdlib>
@@ -163,9 +166,9 @@ void osc2_run_fast_sweeps(Launcher &L, const osc2_topology *tp_dev, const StepDe
         static const bool tile_on = [] { const char *e = getenv("OSC2_FWD_TILE"); return !(e && e[0] == '0'); }();
         if (be && !cap && tile_on) {
             const unsigned nt = (unsigned)((p.B + cpb - 1) / cpb);
-            // assembler / eliminator warps (osc2_forward_split_kernel) when a CTA's 209 KB of shared memory are there;
-            // OSC2_FWD_SPLIT=0 keeps the one-warp-per-tile kernel (same bits) for A/B timing
-            static const bool split_on = [] { const char *e = getenv("OSC2_FWD_SPLIT"); return !(e && e[0] == '0'); }();
+#ifdef OSC2_WITH_SPLIT_ROLES
+            // experiment: assembler / eliminator warps (experiments/step_kernels_split_roles.cuh), OSC2_FWD_SPLIT=1
+            static const bool split_on = [] { const char *e = getenv("OSC2_FWD_SPLIT"); return e && e[0] == '1'; }();
             if (split_on && SplitFwdSmem<D, LPC>::BYTES <= L.max_smem()) {
                 using SS = SplitFwdSmem<D, LPC>;
                 const unsigned nc = (nt + SS::TILES - 1) / SS::TILES;
@@ -174,6 +177,7 @@ void osc2_run_fast_sweeps(Launcher &L, const osc2_topology *tp_dev, const StepDe
                 L.launch(OSC2_K_BACKWARD, osc2_backward_tile_kernel<D, LPC>, nt, 32u, TileBwdSmem<D, LPC>::BYTES, p);
                 return;
             }
+#endif
 #ifdef OSC2_WITH_FUSED_GF
             if constexpr (D == 8) {
                 if (fused) {

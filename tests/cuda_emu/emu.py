@@ -36,8 +36,13 @@ def lib():
         csrc = os.path.join(ROOT, "opensc2_b200", "csrc")
         srcs += [os.path.join(csrc, f) for f in sorted(os.listdir(csrc)) if f.endswith((".cuh", ".h"))]
         srcs += [os.path.join(ROOT, "include", "opensc2_b200.h")]
+        exp = os.path.join(ROOT, "experiments")
+        srcs += [os.path.join(exp, f) for f in ("step_kernels_split_roles.cuh", "step_kernels_fused.cuh")]
         if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+            # the two kernel experiments that are not in the product build are compiled in here, so that their logic stays
+            # checked (selected by OSC2_FWD_SPLIT=1 / OSC2_FUSED=1, read once per process)
             subprocess.run(["g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-ffp-contract=off", "-pthread",
+                            "-DOSC2_WITH_SPLIT_ROLES", "-DOSC2_WITH_FUSED_GF",
                             "-o", so, os.path.join(HERE, "emu_step.cpp")], check=True)
         _LIB = C.CDLL(so)
         _LIB.osc2_emu_gm_doubles.restype = C.c_longlong

@@ -129,3 +129,34 @@ def test_emulated_tile_sweep_reports_a_singular_conductor():
     assert list(out["status"]) == list(ref["status"]) and ref["status"][4] != 0
     ok = np.array([0, 1, 2, 3, 5])
     assert_bits(out["sysvar"][ok], ref["sysvar"][ok], "the conductors next to the singular one")
+
+
+@pytest.mark.parametrize("switch", ["OSC2_FWD_SPLIT", "OSC2_FUSED"])
+def test_emulated_forward_sweep_experiments_stay_bit_exact(switch):
+    """experiments/step_kernels_split_roles.cuh (assembler + eliminator warps per tile, hand-over through mbarriers) and
+    experiments/step_kernels_fused.cuh (K_G as producer warps inside K_F): not in the product build (both measured slower,
+    DESIGN.md 5), compiled into the emulator library so that their logic stays verified.  The switch is read once per
+    process, hence the child."""
+    import os, subprocess, sys, textwrap
+    here = os.path.dirname(os.path.abspath(__file__))
+    code = textwrap.dedent(f"""
+        import sys, numpy as np
+        sys.path[:0] = [{here!r}, {os.path.dirname(here)!r}]
+        from cuda_emu import emu
+        from opensc2_b200.problem import case1_topology, synthetic_step_arrays
+        from oracle import oracle as O
+        for intial, n, batch, ns in ((1, 9, 8, 2), (2, 23, 37, 3), (3, 5, 29, 1)):
+            topo = case1_topology(intial)
+            arr = synthetic_step_arrays(topo, n, batch=batch, seed=40 + n, num_step=ns)
+            out = emu.emu_step(topo, arr, fast=True)
+            ref = O.step(topo, arr)
+            for key in ("sysvar", "syslod", "k123", "norm_solution", "norm_change", "eqteig"):
+                assert np.array_equal(out[key], ref[key]), key
+            assert np.all(out["status"] == 0)
+        print("bits-equal", emu.last_launches)
+    """)
+    res = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **{switch: "1"}), capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0 and "bits-equal" in res.stdout, res.stdout + res.stderr
+    if switch == "OSC2_FUSED":
+        assert res.stdout.split()[-1] == "4"          # K_GF + K_B + two norm kernels: K_G's launch is gone
+
