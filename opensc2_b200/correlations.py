@@ -14,14 +14,19 @@ writers (utility_functions/output.py).  Reference: `Channel.eval_friction_factor
 * 113 / 114 / 115 / 118    hole laws (:447-496, 636-648; the closing statement of 113 has no effect)
 * 200-203, 207, 210        bundle laws (:799-866, 939-963, 1015-1037)
 * 211                      HTS current-lead bundle (:1039-1066): laminar slot stays 0, FRICTION_MULTIPLIER forced to 1
-Every total is multiplied by FRICTION_MULTIPLIER.  Not built: 100-109 (Newton iteration on the hole geometry), 116 / 117 /
-119 / 120 (rectangular / triangular duct inputs), 123 (fails in the reference on arrays), 208 (raises in the reference).
+* 100 / 101                ITER spiral holes (:321-347)
+* 102-109                  hole laws by fixed-point iteration on the whole array (:190-222, 349-390); 106 interpolates
+                           between laminar and turbulent (:1068-1101), the others take the maximum
+* 120                      triangular duct (:650-662, 688-698), total by interpolation
+Every total is multiplied by FRICTION_MULTIPLIER.  Not built: 116 / 117 / 119 (need the duct sides SIDE1 / SIDE2, which the
+model does not carry), 123 (fails in the reference on arrays), 208 (raises in the reference).
 """
 from __future__ import annotations
 
 import numpy as np
 
-SUPPORTED_IFRICTION = (-99, 110, 111, 112, 113, 114, 115, 118, 121, 122, 124, 200, 201, 202, 203, 204, 205, 206, 207, 209, 210, 211)
+SUPPORTED_IFRICTION = (-99, 100, 101, 102, 103, 104, 105, 106, 107, 108, 109, 110, 111, 112, 113, 114, 115, 118, 120, 121, 122, 124,
+                       200, 201, 202, 203, 204, 205, 206, 207, 209, 210, 211)
 
 
 def _laminar(re: np.ndarray) -> np.ndarray:
@@ -31,13 +36,34 @@ def _laminar(re: np.ndarray) -> np.ndarray:
     return lam
 
 
+def _total_llimt(re, lam, turb, l_lim_t):
+    """_eval_total_friction_factor_L_lim_T (channel.py:1068-1101); l_lim_t is what the caller really passes (see friction_factor)."""
+    tot = np.zeros(re.shape)
+    ind = re <= 2.0e3
+    tot[ind] = lam[ind]
+    ind = (re > 2.0e3) & (re < l_lim_t)
+    tot[ind] = (re[ind] - 2000.0) / (l_lim_t - 2000.0) * (turb[ind] - lam[ind]) + lam[ind]
+    ind = re >= l_lim_t
+    tot[ind] = turb[ind]
+    return tot
+
+
 def _haaland(re, rough, dh):
     return ((-1.8 * np.log10((rough / dh / 3.7) ** 1.11 + (6.9 / re))) ** -2) / 4.0
 
 
 def friction_factor(ifriction: int, multiplier: float, reynolds, dh: float, roughness: float = 0.0,
-                    void_fraction: float = 0.0, area: float = 0.0) -> np.ndarray:
-    """Total friction factor (Fanning) of one channel for an array of Reynolds numbers."""
+                    void_fraction: float = 0.0, area: float = 0.0, nodal=True) -> np.ndarray:
+    """Total friction factor (Fanning) of one channel for an array of Reynolds numbers.
+
+    nodal: the reference's `nodal` argument (True: nodal pass, False: Gauss points, None: gen_flow).  It only matters
+    for the interpolated totals (106, 120): `eval_friction_factor` passes it positionally into the L_lim_T parameter of
+    `_eval_total_friction_factor_L_lim_T` (channel.py:1068-1138), so L_lim_T is 1, 0 or -- in gen_flow -- None, where the
+    reference raises TypeError."""
+    if int(ifriction) in (106, 120) and nodal is None:
+        raise TypeError(f"IFRICTION {int(ifriction)} in gen_flow: '>=' not supported between instances of 'float' and "
+                        "'NoneType' (the reference compares the Reynolds number with L_lim_T = nodal = None)")
+    llim = 1.0 if nodal else 0.0
     re = np.fabs(np.atleast_1d(np.asarray(reynolds, dtype=np.float64)))
     flag = int(ifriction)
     if flag == -99:
@@ -79,6 +105,29 @@ def friction_factor(ifriction: int, multiplier: float, reynolds, dh: float, roug
             kk = c0 * void_fraction ** 3.0 / (1 - void_fraction) ** 2.0
             turb = dh ** 2.0 * void_fraction / 2.0 / kk / re + (dh * void_fraction ** 2.0) / 2.0 * jj
         total = np.maximum(_laminar(re), turb)
+    elif flag in (100, 101):
+        aa, bb = (0.45, -0.034) if flag == 100 else (0.36, -0.038)
+        corr = (dh + 2 * 1e-3) / dh
+        total = np.maximum(_laminar(re), (aa * (re / corr) ** bb) / 4.0 / (corr ** 5.0))
+    elif 102 <= flag <= 109:
+        fit64 = flag in (102, 106, 107)
+        aa, bb, cc = (6.4, 0.1717, -0.3428) if fit64 else (11.88, 0.039, -0.299)
+        gg = {103: 3.0e-3, 104: 1.5e-3, 106: 2.0e-3, 108: 2.40e-3, 109: 5.30e-3}.get(flag, 3.05e-3)
+        tt = 1.5e-3 if flag == 104 else 1e-3
+        goverh, hp, hd2 = gg / tt, tt / dh * re, 2.0 * tt / dh
+        turb = 1e-2 * np.ones(re.shape)
+        err, it = 10 * np.ones(re.shape), 0
+        with np.errstate(all="ignore"):
+            while np.max(err) >= 1e-2 and it < 1000:
+                old = turb
+                hpiu = hp * np.sqrt(0.5 * turb)
+                rhpiu = aa * hpiu ** bb * goverh ** cc
+                turb = 2.0 / (rhpiu - 2.5 * np.log10(hd2) - 3.75) ** 2
+                err, it = np.fabs((turb - old) / turb), it + 1
+        total = _total_llimt(re, _laminar(re), turb, llim) if flag == 106 else np.maximum(_laminar(re), turb)
+    elif flag == 120:
+        with np.errstate(all="ignore"):
+            total = _total_llimt(re, 13.33 / np.minimum(re, 2000), 0.00128 + 0.1143 * np.maximum(re, 4000) ** -0.311, llim)
     elif flag in (113, 114, 115, 118, 200, 201, 202, 203, 207, 210, 211):
         turb = np.zeros(re.shape)
         if flag == 113:
@@ -132,8 +181,8 @@ def friction_factor(ifriction: int, multiplier: float, reynolds, dh: float, roug
     return total * multiplier
 
 
-def channel_friction_factor(model, topo, j: int, reynolds) -> np.ndarray:
+def channel_friction_factor(model, topo, j: int, reynolds, nodal=True) -> np.ndarray:
     """`friction_factor` for channel j of a (Model, Topology) pair."""
     return friction_factor(model.ch_ifriction[j], model.ch_friction_mult[j], reynolds, topo.ch_dh[j],
                            model.ch_roughness[j] if model.ch_roughness else 0.0,
-                           model.ch_void_fraction[j] if model.ch_void_fraction else 0.0, topo.ch_area[j])
+                           model.ch_void_fraction[j] if model.ch_void_fraction else 0.0, topo.ch_area[j], nodal)

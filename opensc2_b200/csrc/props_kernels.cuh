@@ -474,13 +474,81 @@ __device__ inline int colebrook_count(double re, double rough, double dh)
     }
     return it;
 }
+// IFRICTION 102..109: turbulent_friction_with_newton_hole + _eval_ft_newton (channel.py:190-222, 349-390): the fixed-point
+// iteration f <- 2 / (a (hp sqrt(f/2))^b (g/h)^c - 2.5 log10(2 h / Dh) - 3.75)^2 from f = 1e-2, run on the WHOLE array
+// until the largest relative change is below 1e-2 -- like Colebrook's, an array-wide iteration count
+struct HoleCoeff { double aa, bb, cc, gg, tt; };
+__device__ inline HoleCoeff hole_coeff(int ifr)
+{
+    const bool fit64 = (ifr == 102 || ifr == 106 || ifr == 107);      // "coefficient for 7/9 mm spiral"
+    HoleCoeff c;
+    c.aa = fit64 ? 6.4 : 11.88; c.bb = fit64 ? 0.1717 : 0.039; c.cc = fit64 ? -0.3428 : -0.299;
+    c.gg = ifr == 103 ? 3.0e-3 : ifr == 104 ? 1.5e-3 : ifr == 106 ? 2.0e-3 : ifr == 108 ? 2.40e-3 : ifr == 109 ? 5.30e-3 : 3.05e-3;
+    c.tt = ifr == 104 ? 1.5e-3 : 1e-3;
+    return c;
+}
+__device__ inline double hole_step(const HoleCoeff &c, double re, double f, double dh)
+{
+    const double goverh = c.gg / c.tt, hp = c.tt / dh * re, hd2 = 2.0 * c.tt / dh;
+    const double hpiu = hp * sqrt(0.5 * f);
+    const double rhpiu = c.aa * pw(hpiu, c.bb) * pw(goverh, c.cc);
+    const double x = rhpiu - 2.5 * log10(hd2) - 3.75;
+    return 2.0 / (x * x);
+}
+__device__ __noinline__ int hole_count(int ifr, double re, double dh)
+{
+    const HoleCoeff c = hole_coeff(ifr);
+    double f = 1e-2, err = 10.0;
+    int it = 0;
+    while (err >= 1e-2 && it < 1000) {
+        const double fn = hole_step(c, re, f, dh);
+        err = fabs((fn - f) / fn);
+        f = fn;
+        ++it;
+    }
+    return it;
+}
+__device__ __noinline__ double hole_friction(int ifr, double re, double dh, int iters)
+{
+    const HoleCoeff c = hole_coeff(ifr);
+    double f = 1e-2;
+    for (int it = 0; it < iters; ++it) f = hole_step(c, re, f, dh);
+    return f;
+}
+// _eval_total_friction_factor_L_lim_T (channel.py:1068-1101): laminar up to Re 2000, turbulent from L_lim_T, linear in Re in
+// between (a NaN Reynolds number leaves the initial 0).  Observable quirk: eval_friction_factor (:1119-1138) calls it as
+// total_friction_factor_correlation(reynolds, nodal), so `nodal` lands in the L_lim_T parameter -- L_lim_T is True = 1 in
+// the nodal pass and False = 0 at the Gauss points, never its default 4e3: the total is the turbulent factor from Re = 1
+// (nodes) / for every Re (Gauss points), and the laminar one only below
+__device__ inline double total_llimt(double re, double lam, double turb, double llim)
+{
+    double tot = 0.0;
+    if (re <= 2.0e3) tot = lam;
+    if (re > 2.0e3 && re < llim) tot = (re - 2000.0) / (llim - 2000.0) * (turb - lam) + lam;
+    if (re >= llim) tot = turb;
+    return tot;
+}
+// array-wide iteration count of channel j's friction law, this element's contribution (0: the law has none)
+__device__ inline int friction_iter_count(const osc2_model *md, const osc2_topology *tp, int j, double re)
+{
+    const int ifr = md->ch_ifriction[j];
+    if (ifr == 122) return colebrook_count(re, md->ch_roughness[j], tp->ch_dh[j]);
+    if (ifr >= 102 && ifr <= 109) return hole_count(ifr, re, tp->ch_dh[j]);
+    return 0;
+}
+__device__ inline bool friction_iterates(int ifr) { return ifr == 122 || (ifr >= 102 && ifr <= 109); }
 // turbulent slot of the hole laws 113 / 114 / 115 / 118 (channel.py:447-496, 636-648; the closing statement of 113 has
 // no effect and is not applied) and of the bundle laws 200 / 201 / 202 / 203 / 207 / 210 / 211 (:799-866, 939-963,
 // 1015-1066); re > 0 on entry.  211: the laminar slot stays 0 and the multiplier is forced to 1 (friction_total)
 __device__ __noinline__ double friction_more(int ifr, double re, double dh, double vf, double area)
 {
     double turb = 0.0;
-    if (ifr == 113) {
+    if (ifr == 100 || ifr == 101) {          // iter_conductor_hole (channel.py:321-347)
+        const double aa = ifr == 100 ? 0.45 : 0.36, bb = ifr == 100 ? -0.034 : -0.038, corr = (dh + 2 * 1e-3) / dh;
+        turb = (aa * pw(re / corr, bb)) / 4.0 / pw(corr, 5.0);
+    } else if (ifr == 120) {                 // duct_demo_common_memo_turbulent_flow_hole (:650-662)
+        turb = 0.00128 + 0.1143 * pw(fmax(re, 4000.0), -0.311);
+    } else if (ifr == 113) {
         const double corr = (dh + 2 * 1e-3) / dh, x = re / corr;
         if (x < 1.5e5) turb = 3.160 * pw(x, -0.249);
         if (x >= 1.5e5) turb = 0.216 * pw(x, -0.024);
@@ -513,7 +581,7 @@ __device__ __noinline__ double friction_more(int ifr, double re, double dh, doub
 // (Darcy-Forchheimer porous medium): channel.py:392-438, 700-717, katheder_correlation_bundle, _eval_jj_and_kk;
 // total = max(laminar, turbulent) with the general laminar correlation 16/Re (channel.py:284-299, 1104-1115);
 // for 121 the laminar slot calls the Haaland method again, which writes the turbulent array: laminar stays 0
-__device__ __noinline__ double friction_simple(int ifr, double re, double rough, double dh, double vf, double area)
+__device__ __noinline__ double friction_simple(int ifr, double re, double rough, double dh, double vf, double area, double llim)
 {
     re = fabs(re);
     double turb = 0.0, lam = 0.0;
@@ -529,6 +597,8 @@ __device__ __noinline__ double friction_simple(int ifr, double re, double rough,
     }
     else if (ifr == 110) turb = (0.316 * pw(re, -0.25)) / 4.0;
     else if (ifr == 111) turb = 0.00128 + 0.1143 * pw(fmax(re, 4000.0), -0.311);
+    else if (ifr == 120)      // triangular duct: laminar 13.33 / min(Re, 2000) (:688-698), total by interpolation
+        return total_llimt(re, 13.33 / fmin(re, 2000.0), friction_more(ifr, re, dh, vf, area), llim);
     else if (ifr != 112) return fmax(friction_more(ifr, re, dh, vf, area), ifr == 211 ? 0.0 : lam);
     else {
         if (re <= 2.0e3) turb = 64 / re / 4.0;
@@ -538,13 +608,20 @@ __device__ __noinline__ double friction_simple(int ifr, double re, double rough,
     }
     return fmax(lam, turb);
 }
-__device__ inline double friction_total(const osc2_model *md, const osc2_topology *tp, int j, double re, int cb_iters)
+// nodal: evaluated in the nodal pass (true) or at the Gauss points (false) -- only the interpolated totals care (total_llimt)
+__device__ inline double friction_total(const osc2_model *md, const osc2_topology *tp, int j, double re, int cb_iters, bool nodal)
 {
+    const double llim = nodal ? 1.0 : 0.0;
     double f = 1.0;
     const int ifr = md->ch_ifriction[j];
     if (ifr == 124) f = friction_124(re);
-    else if (ifr != -99 && ifr != 122)      // 110, 111, 112, 121, 204, 205, 206, 209 (validated by osc2_set_model)
-        f = friction_simple(ifr, re, md->ch_roughness[j], tp->ch_dh[j], md->ch_void_fraction[j], tp->ch_area[j]);
+    else if (ifr >= 102 && ifr <= 109) {    // Newton hole laws: 106 interpolates, the others take the maximum
+        const double ra = fabs(re), lam = ra >= 1.0e-5 ? 16.0 / ra : 0.0;
+        const double turb = hole_friction(ifr, ra, tp->ch_dh[j], cb_iters);
+        f = (ifr == 106) ? total_llimt(ra, lam, turb, llim) : fmax(lam, turb);
+    }
+    else if (ifr != -99 && ifr != 122)      // the closed-form laws (validated by osc2_set_model)
+        f = friction_simple(ifr, re, md->ch_roughness[j], tp->ch_dh[j], md->ch_void_fraction[j], tp->ch_area[j], llim);
     else if (md->ch_ifriction[j] == 122) {
         const double rough = md->ch_roughness[j], dh = tp->ch_dh[j];
         f = haaland(fabs(re), rough, dh);
@@ -729,7 +806,7 @@ __global__ void osc2_solid_tmax_kernel(const osc2_topology *__restrict__ tp, Ste
     }
     const osc2_model *md = q.model;
     for (int j = 0; j < M; ++j) {
-        if (md->ch_ifriction[j] != 122) continue;
+        if (!osc2p::friction_iterates(md->ch_ifriction[j])) continue;
         const FluidTableDev &tab = q.fluid[md->ch_fluid[j]];
         int worst = 0;
         for (int e = e0; e < e1; ++e) {
@@ -739,7 +816,7 @@ __global__ void osc2_solid_tmax_kernel(const osc2_topology *__restrict__ tp, Ste
             const double T = (x0[(size_t)(2 * M + j) * B] + x1[(size_t)(2 * M + j) * B]) / 2.0;
             const osc2p::Cell cl = osc2p::locate(tab, pr, T);
             const double re = fabs(tp->ch_dh[j] * v * osc2p::lookup(tab, cl, OSC2_FP_RHO) / osc2p::lookup(tab, cl, OSC2_FP_MU));
-            const int it = osc2p::colebrook_count(re, md->ch_roughness[j], tp->ch_dh[j]);
+            const int it = osc2p::friction_iter_count(md, tp, j, re);
             if (it > worst) worst = it;
         }
         atomicMax(q.cb_iters + (size_t)j * B + b, worst);
@@ -755,7 +832,7 @@ __global__ void osc2_solid_tmax_kernel(const osc2_topology *__restrict__ tp, Ste
 // `ch_scratch` [2][M][E][B].  (Round 1 had one kernel; the split by itself changed nothing -- 14.57 vs 14.59 ms --
 // but the solid part now takes its own register budget: 80 registers / 6 CTAs per SM, 12.7 -> 11.7 ms.)
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) osc2_opcond_coolant_kernel(const osc2_topology *__restrict__ tp, StepDev p, PropsDev q)
+__global__ void __launch_bounds__(128, 5) osc2_opcond_coolant_kernel(const osc2_topology *__restrict__ tp, StepDev p, PropsDev q)
 {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long EB = (long long)p.E * p.B;
@@ -783,7 +860,7 @@ __global__ void __launch_bounds__(128) osc2_opcond_coolant_kernel(const osc2_top
     const double nu = (hcorr == 212) ? osc2p::nusselt_212(re)
                       : (hcorr == 1) ? osc2p::nusselt_1(re, osc2p::lookup(tab, c, OSC2_FP_PRANDTL))
                                      : osc2p::nusselt_more(hcorr, re, osc2p::lookup(tab, c, OSC2_FP_PRANDTL), tp->ch_dh[j]);
-    const double ftot = osc2p::friction_total(md, tp, j, re, q.cb_iters[(size_t)j * B + b]);
+    const double ftot = osc2p::friction_total(md, tp, j, re, q.cb_iters[(size_t)j * B + b], false);
 #define FGW(qq) fg[((((size_t)(qq) * M + j) * E) + e) * B + b]
     FGW(0) = v; FGW(1) = pr; FGW(2) = T; FGW(3) = rho;
     FGW(4) = osc2p::lookup(tab, c, OSC2_FP_SOUND);
@@ -990,7 +1067,7 @@ __global__ void __launch_bounds__(128) osc2_nodal_coolant_kernel(const osc2_topo
     const osc2_model *md = q.model;
     const size_t plane = (size_t)M * N * B, at = ((size_t)j * N + n) * B + b;
     if (pass == 1) {
-        out[13 * plane + at] = osc2p::friction_total(md, tp, j, out[10 * plane + at], cb_nodal[(size_t)j * B + b]);
+        out[13 * plane + at] = osc2p::friction_total(md, tp, j, out[10 * plane + at], cb_nodal[(size_t)j * B + b], true);
         return;
     }
     const double *x = p.sysvar + ((size_t)n * d) * B + b;
@@ -1014,7 +1091,7 @@ __global__ void __launch_bounds__(128) osc2_nodal_coolant_kernel(const osc2_topo
     out[10 * plane + at] = re;
     out[11 * plane + at] = beta / kappa / cv / rho;
     out[12 * plane + at] = tp->ch_area[j] * v * rho;
-    if (md->ch_ifriction[j] == 122)
-        atomicMax(cb_nodal + (size_t)j * B + b, osc2p::colebrook_count(re, md->ch_roughness[j], tp->ch_dh[j]));
+    if (osc2p::friction_iterates(md->ch_ifriction[j]))
+        atomicMax(cb_nodal + (size_t)j * B + b, osc2p::friction_iter_count(md, tp, j, re));
 }
 

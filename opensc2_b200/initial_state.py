@@ -35,7 +35,7 @@ def _rho_mu(tab: FluidTable, p: float, t: float):
 
 
 def _friction(model, topo, j, re) -> float:
-    return float(channel_friction_factor(model, topo, j, np.array([re]))[0])
+    return float(channel_friction_factor(model, topo, j, np.array([re]), nodal=None)[0])      # gen_flow: nodal = None
 
 
 def hydraulic_groups(topo: Topology, peri_ff_open: np.ndarray) -> (List[List[int]], List[int]):

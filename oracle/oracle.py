@@ -169,7 +169,8 @@ def pairwise_sum(a, stride: int = 1) -> float:
 FITS = {"k_cu": 0, "cp_cu": 1, "k_nb3sn": 2, "cp_nb3sn": 3, "tc_nb3sn": 4, "k_ss": 5, "cp_ss": 6, "k_ge": 7,
         "cp_ge": 8, "friction_124": 9, "nusselt_1": 10, "nusselt_212": 11, "rhoe_cu": 12,
         "k_al": 13, "cp_al": 14, "k_re123": 15, "cp_re123": 16, "friction_122": 17,
-        "k_ag": 18, "cp_ag": 19, "k_hc276": 20, "cp_hc276": 21, "k_sn60pb40": 22, "cp_sn60pb40": 23, "friction_simple": 24, "k_nbti": 25, "cp_nbti": 26, "tc_nbti": 27, "nusselt_more": 28, "k_mgb2": 29, "cp_mgb2": 30, "density": 31}
+        "k_ag": 18, "cp_ag": 19, "k_hc276": 20, "cp_hc276": 21, "k_sn60pb40": 22, "cp_sn60pb40": 23, "friction_simple": 24, "k_nbti": 25, "cp_nbti": 26, "tc_nbti": 27, "nusselt_more": 28, "k_mgb2": 29, "cp_mgb2": 30, "density": 31,
+        "friction_hole_newton": 32}
 
 
 def fit(name, x, y=None, z=None, p1=0.0, p2=0.0, out_init=None):

@@ -373,11 +373,54 @@ static double friction_124(double re)
 }
 /* general_laminar_correlation channel.py:284-299: 16/Re where Re >= 1e-5, else the initial 0 */
 static double friction_laminar(double re) { return re >= 1.0e-5 ? 16.0 / re : 0.0; }
+/* _eval_total_friction_factor_L_lim_T (channel.py:1068-1101).  Observable quirk: eval_friction_factor (:1119-1138) calls
+ * self.total_friction_factor_correlation(reynolds, nodal), so `nodal` binds to the L_lim_T parameter: llim = True = 1 in the
+ * nodal pass, False = 0 at the Gauss points (never the default 4e3). */
+static double total_llimt(double re, double lam, double turb, double llim)
+{
+    double tot = 0.0;
+    if (re <= 2.0e3) tot = lam;
+    if (re > 2.0e3 && re < llim) tot = (re - 2000.0) / (llim - 2000.0) * (turb - lam) + lam;
+    if (re >= llim) tot = turb;
+    return tot;
+}
+/* IFRICTION 102..109: turbulent_friction_with_newton_hole + _eval_ft_newton (channel.py:190-222, 349-390).  The loop runs
+ * on the WHOLE array until the largest relative change is below 1e-2; re[] >= 0, tot[] out (total friction factor before
+ * the multiplier: max(laminar, turbulent), 106: interpolation); returns the iteration count. */
+static int newton_hole_array(const double *re, double *tot, long n, int ifr, double dh, double llim)
+{
+    const int fit64 = (ifr == 102 || ifr == 106 || ifr == 107);
+    const double aa = fit64 ? 6.4 : 11.88, bb = fit64 ? 0.1717 : 0.039, cc = fit64 ? -0.3428 : -0.299;
+    const double gg = ifr == 103 ? 3.0e-3 : ifr == 104 ? 1.5e-3 : ifr == 106 ? 2.0e-3 : ifr == 108 ? 2.40e-3 : ifr == 109 ? 5.30e-3 : 3.05e-3;
+    const double tt = ifr == 104 ? 1.5e-3 : 1e-3;
+    const double goverh = gg / tt, hd2 = 2.0 * tt / dh;
+    for (long i = 0; i < n; ++i) tot[i] = 1e-2;
+    int it = 0;
+    double errmax = 10.0;
+    while (errmax >= 1e-2 && it < 1000) {
+        errmax = 0.0;
+        for (long i = 0; i < n; ++i) {
+            const double hp = tt / dh * re[i];
+            const double hpiu = hp * sqrt(0.5 * tot[i]);
+            const double rhpiu = aa * pow(hpiu, bb) * pow(goverh, cc);
+            const double fn = 2.0 / pow(rhpiu - 2.5 * log10(hd2) - 3.75, 2.0);
+            const double err = fabs((fn - tot[i]) / fn);
+            if (err > errmax || err != err) errmax = err;
+            tot[i] = fn;
+        }
+        ++it;
+    }
+    for (long i = 0; i < n; ++i) {
+        const double lam = friction_laminar(re[i]);
+        tot[i] = (ifr == 106) ? total_llimt(re[i], lam, tot[i], llim) : fmax(lam, tot[i]);
+    }
+    return it;
+}
 /* IFRICTION 110, 111, 112, 121 (channel.py:392-401, 403-413, 415-438, 700-717): total = max(laminar, turbulent)
  * (channel.py:1104-1115).  110-112: laminar slot = general_laminar_correlation.  121: the laminar slot calls
  * haaland_equation again, which writes the TURBULENT array, so laminar stays 0.  112 assigns by masks that
  * leave Re = 2e3 < . , Re = 4e3 exactly at the initial 0 of the turbulent array. */
-static double friction_simple(int ifr, double re, double rough, double dh, double vf, double area)
+static double friction_simple(int ifr, double re, double rough, double dh, double vf, double area, double llim)
 {
     re = fabs(re);
     double turb = 0.0, lam = 0.0;
@@ -404,6 +447,16 @@ static double friction_simple(int ifr, double re, double rough, double dh, doubl
         lam = friction_laminar(re);
         break;
     }
+    /* iter_conductor_hole (100, 101), channel.py:321-347 */
+    case 100: case 101: {
+        const double aa = ifr == 100 ? 0.45 : 0.36, bb = ifr == 100 ? -0.034 : -0.038, corr = (dh + 2 * 1e-3) / dh;
+        turb = (aa * pow(re / corr, bb)) / 4.0 / pow(corr, 5.0);
+        lam = friction_laminar(re);
+        break;
+    }
+    /* 120: triangular duct, laminar 13.33 / min(Re, 2000) (:688-698), turbulent :650-662, total by interpolation (:1068-1101) */
+    case 120:
+        return total_llimt(re, 13.33 / fmin(re, 2000.0), 0.00128 + 0.1143 * pow(fmax(re, 4000.0), -0.311), llim);
     /* hole laws 113 (memorandum_bessette_iter_cs_spiral_hole_y2015, channel.py:447-468: its closing statement
      * `turbulent / 4.0 / corr_diam ** 5` has no effect and is not applied), 114 (:470-480), 115 (:482-496), 118 (:636-648);
      * corr_diam of _eval_correction_diameter_hole (:305-319, tthick = 1e-3) */
@@ -513,6 +566,15 @@ static double nusselt_212(double re) { return 0.42 * pow(re, 0.3); }
 
 int osc2o_fit(int which, long n, const double *x, const double *y, const double *z, double p1, double p2, double *out)
 {
+    if (which == 32) {          /* friction_hole_newton: x = Reynolds (whole array), p1 = IFRICTION, p2 = Dh */
+        double *ra = (double *)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+        if (!ra) return -1;
+        for (long i = 0; i < n; ++i) ra[i] = fabs(x[i]);
+        newton_hole_array(ra, out, n, (int)p1, p2, 1.0);      /* nodal pass: L_lim_T = True */
+        free(ra);
+        (void)y; (void)z;
+        return 0;
+    }
     double tmax = 0.0, tmin = 0.0;
     if (which == 6 || which == 13 || which == 14) {
         tmax = tmin = x[0];
@@ -558,7 +620,7 @@ int osc2o_fit(int which, long n, const double *x, const double *y, const double 
         case 30: out[i] = cp_mgb2(x[i]); break;
         case 26: out[i] = cp_nbti(x[i], y[i], z[i], out[i]); break;   /* x = T, y = B, z = Tcs; out[] holds Tc on entry */
         case 27: out[i] = tc_nbti(x[i], p1, p2); break;                            /* x = B, p1 = Bc20m, p2 = Tc0m */
-        case 24: out[i] = friction_simple((int)p1, x[i], y[i], z[i], p2, y[i]); break;   /* p1 = IFRICTION, y = roughness (IFRICTION 200: CROSSECTION), z = Dh, p2 = void fraction */
+        case 24: out[i] = friction_simple((int)p1, x[i], y[i], z[i], p2, y[i], 1.0); break;   /* nodal pass: L_lim_T = True; */   /* p1 = IFRICTION, y = roughness (IFRICTION 200: CROSSECTION), z = Dh, p2 = void fraction */
         default: return -1;
         }
     }
@@ -643,8 +705,8 @@ static void one_conductor(const osc2_topology *tp, const osc2_model *md, osc2o_o
             /* channel.py:1119-1138 (IFRICTION 122 is array-wide: filled in after this loop) */
             const int ifr = md->ch_ifriction[j];
             const double ftot = ((ifr == 124) ? friction_124(re)
-                                 : (ifr != -99 && ifr != 122)
-                                     ? friction_simple(ifr, re, md->ch_roughness[j], tp->ch_dh[j], md->ch_void_fraction[j], tp->ch_area[j])
+                                 : (ifr != -99 && ifr != 122 && !(ifr >= 102 && ifr <= 109))
+                                     ? friction_simple(ifr, re, md->ch_roughness[j], tp->ch_dh[j], md->ch_void_fraction[j], tp->ch_area[j], 0.0)
                                  : 1.0) * (ifr == 211 ? 1.0 : md->ch_friction_mult[j]);
             rey[e] = re;
             fg[((size_t)0 * M + j) * E + e] = v;
@@ -661,6 +723,10 @@ static void one_conductor(const osc2_topology *tp, const osc2_model *md, osc2o_o
             kf[(size_t)j * E + e] = f[OSC2_FP_K];
             rf[(size_t)j * E + e] = f[OSC2_FP_RHO];
             cpf[(size_t)j * E + e] = f[OSC2_FP_CP];
+        }
+        if (md->ch_ifriction[j] >= 102 && md->ch_ifriction[j] <= 109) {
+            newton_hole_array(rey, rey + E, E, md->ch_ifriction[j], tp->ch_dh[j], 0.0);      /* Gauss points: L_lim_T = False */
+            for (int e = 0; e < E; ++e) fg[((size_t)8 * M + j) * E + e] = rey[E + e] * md->ch_friction_mult[j];
         }
         if (md->ch_ifriction[j] == 122) {      /* total = max(laminar = 0, turbulent) * multiplier */
             colebrook_array(rey, rey + E, E, md->ch_roughness[j], tp->ch_dh[j]);

@@ -1,7 +1,7 @@
 """Generate tests/golden/props_stack.npz by running the UNMODIFIED reference: the silver, Hastelloy C276 and
 Sn60Pb40 fits (properties_of_materials/) and the StackComponent homogenisers (stack_component.py:398-476) on
-a bare StackComponent object (its constructor needs openpyxl); and the friction laws IFRICTION 110-115, 118,
-121, 200-207, 209-211 through Channel.eval_friction_factor on a bare object wired like Channel.__init__ (channel.py:43-169).
+a bare StackComponent object (its constructor needs openpyxl); and the friction laws IFRICTION 100-115, 118,
+120, 121, 200-207, 209-211 through Channel.eval_friction_factor on a bare object wired like Channel.__init__ (channel.py:43-169).
 
 Build-container only (needs /root/reference):  python tests/golden/make_golden_stack.py
 """
@@ -78,21 +78,36 @@ def main():
               203: ("general_laminar_correlation", "kstar_correlation_bundle"),
               207: ("general_laminar_correlation", "lhc_poncet_correlation_bundle"),
               210: ("general_laminar_correlation", "demo_tf_hts_correlation_bundle"),
-              211: ("hts_cl_correlation_bundle", "hts_cl_correlation_bundle")}
+              211: ("hts_cl_correlation_bundle", "hts_cl_correlation_bundle"),
+              100: ("general_laminar_correlation", "iter_conductor_hole"),
+              101: ("general_laminar_correlation", "iter_conductor_hole"),
+              120: ("triangular_duct_demo_common_memo_laminar_flow_hole", "duct_demo_common_memo_turbulent_flow_hole")}
+    wiring.update({k: ("general_laminar_correlation", "turbulent_friction_with_newton_hole") for k in range(102, 110)})
     out["crossection"] = np.array(3.7e-4)
     out["void_fraction"] = np.array(0.33)
+    rng2 = np.random.default_rng(20261020)           # its own generator: the vectors drawn further down stay what they were
+    out["re_regular"] = np.concatenate([rng2.uniform(1.0e3, 4.0e3, 60), rng2.uniform(4.0e3, 1.0e6, 140)]) * np.where(rng2.uniform(size=200) < 0.2, -1.0, 1.0)
     for ifr, (lam, turb) in wiring.items():
         ch = types.SimpleNamespace()
-        for name in ("_quantities_initialization", "_eval_total_friction_factor_max", "eval_friction_factor", "_eval_jj_and_kk",
-                     "_eval_correction_diameter_hole", lam, turb):
+        for name in ("_quantities_initialization", "_eval_total_friction_factor_max", "_eval_total_friction_factor_L_lim_T",
+                     "eval_friction_factor", "_eval_jj_and_kk", "_eval_correction_diameter_hole", "_eval_ft_newton", lam, turb):
             setattr(ch, name, types.MethodType(getattr(Channel, name), ch))
         ch.inputs = {"FRICTION_MULTIPLIER": 0.02, "HYDIAMETER": 2.499e-3, "Roughness": 2.0e-6, "IFRICTION": ifr, "VOID_FRACTION": 0.33, "CROSSECTION": 3.7e-4}
         ch.dict_friction_factor = {True: {"laminar": None, "turbulent": None, "total": 0.0}}
         ch.laminar_friction_factor_correlation = getattr(ch, lam)
         ch.turbulent_friction_factor_correlation = getattr(ch, turb)
-        ch.total_friction_factor_correlation = ch._eval_total_friction_factor_max
+        ch.total_friction_factor_correlation = (ch._eval_total_friction_factor_L_lim_T if ifr in (106, 120)
+                                                else ch._eval_total_friction_factor_max)      # channel.py:116-132
         ch.eval_friction_factor(re.copy(), nodal=True)
         out[f"f{ifr}_total"] = np.array(ch.dict_friction_factor[True]["total"])
+        if 102 <= ifr <= 109:
+            # the fixed-point iteration of these laws is chaotic below Re ~ 100 (it never settles; the array-wide loop of the
+            # reference ends when the wandering element happens to move by less than 1 % in the same sweep as the others):
+            # a second vector on Reynolds numbers where every element converges monotonically, i.e. where the result does not
+            # depend on the last bit of pow()
+            ch.dict_friction_factor = {True: {"laminar": None, "turbulent": None, "total": 0.0}}
+            ch.eval_friction_factor(out["re_regular"].copy(), nodal=True)
+            out[f"f{ifr}_total_regular"] = np.array(ch.dict_friction_factor[True]["total"])
     # steady-state heat transfer: Flag_htc_steady_corr 119 / 120 / 121 / 211 through Channel.eval_steady_state_htc
     pr = rng.uniform(0.5, 2.0, re.size)
     kf = rng.uniform(0.01, 0.03, re.size)

@@ -335,7 +335,7 @@ def test_stack_component_solid_on_the_device():
 
 
 @pytest.mark.parametrize("laws", [(110, 121), (111, 112), (204, 206), (205, 209), (113, 114), (115, 118), (200, 201), (202, 203),
-                                  (207, 210), (211, 113)])
+                                  (207, 210), (211, 113), (100, 101), (102, 103), (104, 105), (106, 107), (108, 109), (120, 106)])
 def test_more_friction_laws_on_the_device(laws):
     """IFRICTION 110 (Blasius), 111 (Bhatti-Shah), 112 (LHC recipe), 121 (Haaland), 204 / 205 (Katheder bundle),
     206 / 209 (Darcy-Forchheimer bundle) in K_P vs the oracle (which

@@ -108,7 +108,8 @@ def test_stack_component_homogenisation_against_the_reference():
             assert err <= 2e-12, f"{key}: {err:.3e}"
 
 
-@pytest.mark.parametrize("ifr", [110, 111, 112, 113, 114, 115, 118, 121, 200, 201, 202, 203, 204, 205, 206, 207, 209, 210, 211])
+@pytest.mark.parametrize("ifr", [100, 101, 110, 111, 112, 113, 114, 115, 118, 120, 121, 200, 201, 202, 203, 204, 205, 206, 207, 209, 210,
+                                 211])
 def test_more_friction_laws_against_the_reference_channel(ifr):
     """IFRICTION 110 / 111 / 112 / 121 and the bundle laws 204 / 205 (Katheder), 206 / 209 (Darcy-Forchheimer)
     through the reference's Channel.eval_friction_factor (laminar, turbulent
@@ -175,3 +176,28 @@ def test_magnesium_diboride_and_all_densities_against_the_reference():
         assert np.array_equal(got == 0.0, ref == 0.0)
     for mat, rho in enumerate(g["densities"]):
         assert O.fit("density", np.ones(1), p1=mat)[0] == rho, mat
+
+
+@pytest.mark.parametrize("ifr", list(range(102, 110)))
+def test_newton_hole_friction_laws_against_the_reference_channel(ifr):
+    """IFRICTION 102..109 (turbulent_friction_with_newton_hole + _eval_ft_newton, channel.py:190-222, 349-390): the
+    fixed-point iteration runs on the WHOLE Reynolds array until the largest relative change is below 1e-2, so every
+    element gets the array-wide number of iterations; 106 takes the interpolated total, the others the maximum.  Oracle
+    (array loop) and host numpy restatement against the reference's Channel.eval_friction_factor."""
+    import os
+    from helpers import GOLDEN_DIR
+    from opensc2_b200.correlations import friction_factor
+    g = np.load(os.path.join(GOLDEN_DIR, "props_stack.npz"))
+    re, dh, ref = g["re"], float(g["hydiameter"]), g[f"f{ifr}_total"]
+    # the array loop itself, on a vector with Reynolds numbers below ~100 where the iteration wanders chaotically: the
+    # oracle (same libm, same loop) lands on the reference's iteration count and values
+    got = O.fit("friction_hole_newton", re, p1=ifr, p2=dh) * 0.02
+    assert np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-300)) <= 2e-12, f"oracle IFRICTION {ifr}"
+    # where every element converges (Re >= 1e3) the result does not hang on the last bit of pow(): oracle and the host
+    # numpy restatement against the reference
+    re, ref = g["re_regular"], g[f"f{ifr}_total_regular"]
+    got = O.fit("friction_hole_newton", re, p1=ifr, p2=dh) * 0.02
+    assert np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-300)) <= 2e-12, f"oracle IFRICTION {ifr}, regular"
+    host = friction_factor(ifr, 0.02, re, dh)
+    assert np.max(np.abs(host - ref) / np.maximum(np.abs(ref), 1e-300)) <= 2e-12, f"host IFRICTION {ifr}"
+
