@@ -123,7 +123,7 @@ def reference_operating_conditions(topo, model, tab, sweep, sysvar, n_nodes, tim
 
     solids = []
     names = {0: "STR_MIX", 1: "STR_STAB", 2: "Z_JACKET"}
-    mat_name = {0: "Cu", 1: "Nb3Sn", 2: "ss", 3: "ge", 4: "Al"}
+    mat_name = {0: "Cu", 1: "Nb3Sn", 2: "ss", 3: "ge", 4: "Al", 5: "re123"}
     for l, sm in enumerate(model.solids):
         if sm.kind == 0:
             s = object.__new__(StrandMixedComponent)
@@ -133,6 +133,18 @@ def reference_operating_conditions(topo, model, tab, sweep, sysvar, n_nodes, tim
             s._StrandMixedComponent__reorganize_input()
             s._StrandMixedComponent__strand_density_flag = False
         elif sm.kind == 1:
+            if sm.materials[0] == 5:
+                # legacy STR_SC (CASE_2) restated as a single-material RE123 solid: HEAD's
+                # StrandStabilizerComponent picks its fits from module-level tables keyed by the material name; the
+                # reference's own RE123 fits are registered there under "re123" (no reference code is changed)
+                import strand_stabilizer_component as ssc
+                from properties_of_materials.rare_earth_123 import (density_re123, isobaric_specific_heat_re123,
+                                                                     thermal_conductivity_re123)
+                ssc.DENSITY_FUNC.setdefault("re123", density_re123)
+                ssc.ISOBARIC_SPECIFIC_HEAT_FUNC.setdefault("re123", isobaric_specific_heat_re123)
+                ssc.THERMAL_CONDUCTIVITY_FUNC.setdefault("re123", thermal_conductivity_re123)
+                # the resistivity is evaluated too (it only feeds the electric module, which is off): any finite array
+                ssc.ELECTRICAL_RESISTIVITY_FUNC.setdefault("re123", lambda t, *a: np.ones_like(np.asarray(t, dtype=float)))
             s = object.__new__(StrandStabilizerComponent)
             s.inputs = {"stabilizer_material": mat_name[sm.materials[0]].lower(), "RRR": sm.rrr,
                         "CROSSECTION": topo.sol_area[l], "COSTETA": topo.sol_costeta[l]}

@@ -11,7 +11,7 @@ current_sharing_temperature_nb3sn (scipy bisect) once at step 0.  Initial state 
 mesh (restatements; their pins are the golden mesh coordinates and the golden outlet pressure of CASE_3 CHAN_2).
 
 Writes tests/golden/transient_<tag>.npz: snapshots of SYSVAR every `every` steps + everything needed to rebuild the
-run on the device.  Usage:  python tests/golden/ref_transient.py case1 | case1_current | case3
+run on the device.  Usage:  python tests/golden/ref_transient.py case1 | case1_current | case2 | case3
 """
 import os
 import sys
@@ -52,6 +52,9 @@ def case_setup(tag):
         deck = load_deck(os.path.join(DECKS, "CASE_3_HTS_HVDC"), intial_override=3)
         tabs = [helium_gas_table(), build_table(N2.state, (2.0e5, 4.0e5), (90.0, 160.0), 201, 281)]
         return deck, tabs, ["helium", "nitrogen"], {}, True, 2000, 100
+    if tag == "case2":
+        deck = load_deck(os.path.join(DECKS, "CASE_2_ENEA_HTS_CICC"), intial_override=3)
+        return deck, [synthetic_helium_table()], ["helium"], {}, True, int(os.environ.get("OSC2_REF_CASE2_STEPS", 320)), 80
     raise SystemExit(f"unknown case {tag}")
 
 

@@ -1,7 +1,7 @@
 """Full transients on the device (VERDICT r1 "next" 1): the runner `opensc2_b200.runner.Transient` against
   (a) the UNMODIFIED reference functions looped in-process over the whole transient (tests/golden/ref_transient.py ->
-      transient_<tag>.npz: CASE_1 as shipped, 1000 steps; CASE_1 with field, strain and 30 kA, 300 steps; CASE_3 as
-      shipped, 2000 steps) -- snapshots every 100 steps;
+      transient_<tag>.npz: CASE_1 as shipped, 1000 steps; CASE_1 with field, strain and 30 kA, 300 steps; CASE_2 as
+      shipped, 320 steps across its heat slug; CASE_3 as shipped, 2000 steps) -- snapshots every 100 (CASE_2: 80) steps;
   (b) the CPU oracle's loop run here beside the device (CASE_2 size, d = 64).
 Tolerance (stated, FP64): drift of any field, normalised by the field's maximum, <= 1e-6 at EVERY snapshot.  The fits
 differ by 1e-15 (numpy / libm vs CUDA), each solve amplifies by cond ~ 2e8 (the per-step tolerance of DESIGN.md 6 is
@@ -29,7 +29,7 @@ def _report(tag, rows):
                 f.write(f"{tag}\t{r[0]}\t{r[1]:.3e}\t{r[2]:.3e}\n")
 
 
-@pytest.mark.parametrize("tag", ["case1", "case1_current", "case3"])
+@pytest.mark.parametrize("tag", ["case1", "case1_current", "case2", "case3"])
 def test_transient_matches_the_reference_loop(tag):
     from opensc2_b200.runner import Transient
 

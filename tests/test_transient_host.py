@@ -10,7 +10,7 @@ from helpers import GOLDEN_DIR
 from transient_common import deck_of, field_drift, legacy_of, oracle_transient, sweep_kwargs, tables_of
 
 
-@pytest.mark.parametrize("tag,n_steps", [("case1", 1000), ("case1_current", 300), ("case3", 2000)])
+@pytest.mark.parametrize("tag,n_steps", [("case1", 1000), ("case1_current", 300), ("case2", 320), ("case3", 2000)])
 def test_oracle_loop_follows_the_reference_loop(tag, n_steps):
     from opensc2_b200.runner import TransientSetup
 
