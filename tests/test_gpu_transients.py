@@ -88,7 +88,7 @@ def test_case2_transient_matches_the_oracle_loop():
         got = res.snapshots.get(k, res.sysvar)
         e = np.max([field_drift(got[b], ref[k][b], N, topo) for b in range(2)], axis=0)
         rows.append((k, e[:M].max(), e[M:].max()))
-    _report("case2", rows)
+    _report("case2_two_variants_vs_oracle_loop", rows)
     assert max(r[1] for r in rows) <= TOL_V and max(r[2] for r in rows) <= TOL_PT, rows
 
 
