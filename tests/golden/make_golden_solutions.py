@@ -20,6 +20,10 @@ def main():
             name = f[:-4]
             if name.startswith("CHAN"):
                 out[f"{tag}/{name}"] = np.stack([a[:, 0], a[:, 1], a[:, 2], a[:, 3], a[:, 4], a[:, -1]], axis=1)   # z p T rho v mdot
+                # every column, for the property checks and the local helium table of tests/transient_common.py.  Legacy
+                # layout (CASE_1 / CASE_2, 15 columns; the header's unit labels are shuffled, the order below is the real one):
+                # x p T rho v mu Gruneisen h cp cv w k Re Pr mdot; HEAD layout (CASE_3, 17 columns): see the file's header
+                out[f"{tag}/{name}/all"] = a
             else:
                 out[f"{tag}/{name}"] = a[:, :2]                                                                    # z T
     np.savez_compressed(os.path.join(HERE, "tdd_solutions.npz"), **out)

@@ -168,3 +168,25 @@ def test_solution_files_from_the_device_nodal_pass(tmp_path):
             assert a.shape == c.shape and a.shape[1] == 18
             assert np.array_equal(a[:, :17], c[:, :17])
             assert np.max(np.abs(a[:, 17] / c[:, 17] - 1.0)) <= 2e-12
+
+
+@pytest.mark.parametrize("tag", ["case1", "case2"])
+def test_helium_cases_as_shipped_against_the_shipped_golden_solutions(tag):
+    """CASE_1 and CASE_2 exactly as shipped (heat slugs included, 1000 steps each) on the device, end state against the
+    reference's own TDD_examples/CASE_*/Solution/*.tsv, tolerance 1e-5.  Helium properties: the
+    table rebuilt from the property columns of those files (tests/transient_common.helium_table_from_golden; CoolProp is
+    not available) -- exact on the end state's (p, T) line, crude on the slug's excursion, which the relaxed
+    end state no longer remembers."""
+    from opensc2_b200.runner import Transient
+    from test_transient_host import GOLDEN_TSV_TOL, max_golden_error
+    from transient_common import helium_table_from_golden
+
+    deck = deck_of(tag)
+    with Transient(deck, [helium_table_from_golden(tag)], 1, legacy_intial2=legacy_of(tag)) as tr:
+        res = tr.run()
+        N = tr.zcoord.shape[0]
+    assert np.all(res.status == 0) and len(res.time) == 1001
+    ev, ep, etf, ets = max_golden_error(res.sysvar[0].reshape(N, deck.topology.ndf), deck, tag)
+    _report(f"{tag}_vs_shipped_golden_tsv", [(1000, ev, max(ep, etf, ets))])
+    assert max(ev, ep, etf, ets) <= GOLDEN_TSV_TOL, (ev, ep, etf, ets)
+

@@ -77,3 +77,42 @@ def oracle_transient(tr, n_steps, tcs=None, snapshot_every=0):
         if (snapshot_every and k % snapshot_every == 0) or k == n_steps:
             snaps[k] = arr.sysvar.copy()
     return snaps
+
+
+def helium_table_from_golden(tag, chans=None, p_pad=2.0e3, t_pad=0.02, n_p=401, n_t=41, t_props=None):
+    """A LOCAL helium table rebuilt from the property columns of the reference's own shipped result (CoolProp outputs along
+    the end state of the case), for the comparison of a steady state with that result -- CoolProp and its helium equation
+    of state are not available here (DESIGN.md 3).  The samples of all channels lie on a line T_l(p) of the (p, T) plane;
+    every property is interpolated along that line in p and continued off it to first order in (T - T_l(p)) where
+    thermodynamics gives the slope: d rho / dT = -rho beta, dh / dT = cp, with beta = Gruneisen cp / w^2 and
+    kappa = cp / (cv rho w^2) from the columns; the other properties are taken constant across the few mK the states
+    visited here are away from the line.  Valid only within `t_pad` of the line: a transient with a heat slug leaves it."""
+    from opensc2_b200.model import (FP_BETA, FP_CP, FP_CV, FP_H, FP_K, FP_KAPPA, FP_MU, FP_PRANDTL, FP_RHO, FP_SOUND,
+                                    FluidTable)
+
+    z = np.load(os.path.join(GOLDEN_DIR, "tdd_solutions.npz"))
+    chans = chans or [k.split("/")[1] for k in z.files if k.startswith(f"{tag}/CHAN") and k.endswith("/all")]
+    rows = np.concatenate([z[f"{tag}/{c}/all"] for c in chans])
+    rows = rows[np.argsort(rows[:, 1])]
+    _, first = np.unique(rows[:, 1], return_index=True)
+    rows = rows[first]
+    if rows.shape[1] == 15:       # legacy files (CASE_1, CASE_2): x p T rho v mu Gruneisen h cp cv w k Re Pr mdot
+        p, T, rho, mu, phi, h, cp, cv, w, k, pr = (rows[:, i] for i in (1, 2, 3, 5, 6, 7, 8, 9, 10, 11, 13))
+        kappa, beta = cp / (cv * rho * w ** 2), phi * cp / w ** 2
+    else:                         # HEAD files (CASE_3): x p T rho v beta kappa Pr mu h cp cv w k Re Gruneisen mdot
+        p, T, rho, beta, kappa, pr, mu, h, cp, cv, w, k = (rows[:, i] for i in (1, 2, 3, 5, 6, 7, 8, 9, 10, 11, 12, 13))
+    pg = np.linspace(p.min() - p_pad, p.max() + p_pad, n_p)
+    tg = np.linspace(T.min() - t_pad, T.max() + t_pad, n_t)
+    on = lambda col: np.interp(pg, p, col)                        # along the line (held constant beyond its ends)
+    dT = tg[None, :] - on(T)[:, None]
+    # the density column belongs to the end state (T above); the other property columns were written from the nodal
+    # pass of the step before -- at a steady state that is the same temperature, except where the caller knows
+    # better (`t_props`: CASE_3's helium columns carry the uniform initial 30 K, not the 30 - 31.2 K of its end state)
+    dTp = dT if t_props is None else (tg[None, :] - t_props) * np.ones((n_p, 1))
+    props = np.empty((10, n_p, n_t))
+    flat = lambda col: np.repeat(on(col)[:, None], n_t, axis=1)
+    props[FP_RHO] = on(rho)[:, None] * (1.0 - on(beta)[:, None] * dT)
+    props[FP_H] = on(h)[:, None] + on(cp)[:, None] * dTp
+    for idx, col in ((FP_BETA, beta), (FP_KAPPA, kappa), (FP_PRANDTL, pr), (FP_MU, mu), (FP_CP, cp), (FP_CV, cv), (FP_SOUND, w), (FP_K, k)):
+        props[idx] = flat(col)
+    return FluidTable(p_min=float(pg[0]), p_step=float(pg[1] - pg[0]), t_min=float(tg[0]), t_step=float(tg[1] - tg[0]), props=props)
