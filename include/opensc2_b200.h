@@ -122,8 +122,8 @@ enum { OSC2_SOLID_STRAND_MIXED = 0, OSC2_SOLID_STRAND_STAB = 1, OSC2_SOLID_JACKE
 typedef struct {
     /* channels (channel.py:43-169) */
     int ch_fluid[OSC2_MAX_CHANNELS];            /* which fluid table */
-    int ch_ifriction[OSC2_MAX_CHANNELS];        /* IFRICTION: -99, 110 (Blasius), 111 (Bhatti-Shah), 112 (LHC), 121 (Haaland), 122 (Colebrook), 124,
-                                                   204 / 205 (Katheder bundle), 206 / 209 (Darcy-Forchheimer bundle) */
+    int ch_ifriction[OSC2_MAX_CHANNELS];        /* IFRICTION: -99, 100-115, 118-122, 124, 200-207, 209-211 (every law of channel.py that
+                                                   runs; 116 / 117 / 123 fail and 208 raises in the reference) */
     double ch_friction_mult[OSC2_MAX_CHANNELS]; /* FRICTION_MULTIPLIER */
     int ch_htc_corr[OSC2_MAX_CHANNELS];         /* Flag_htc_steady_corr: 1, 119, 120, 121, 211 or 212 */
     /* solids */
@@ -155,6 +155,8 @@ typedef struct {
     double ch_void_fraction[OSC2_MAX_CHANNELS]; /* Channel.inputs["VOID_FRACTION"] (bundle laws 204, 205, 206, 209) */
     double sol_c0[OSC2_MAX_SOLIDS];             /* strand inputs["c0"]: scaling constant of Jc (A T / m^2), physical definition
                                                    (strand_component.py:266-276); only read by osc2_eval_tcs */
+    double ch_lam_coef[OSC2_MAX_CHANNELS];      /* IFRICTION 119 (rectangular duct, channel.py:664-686): numerator of its laminar law,
+                                                   24 (1 - 1.3553 a + 1.9467 a^2 - 1.7012 a^3 + 0.9564 a^4 - 0.2537 a^5), a = SIDE2 / SIDE1 */
 } osc2_model;
 
 /* Swept per-conductor scalars, batch leading. */

@@ -82,6 +82,7 @@ class Osc2Model(C.Structure):
         ("ss_rad_den", C.c_double * _IF), ("ss_rad_mlt", C.c_double * _IF),
         ("ch_void_fraction", C.c_double * _CH),
         ("sol_c0", C.c_double * _SO),
+        ("ch_lam_coef", C.c_double * _CH),
     ]
 
 

@@ -17,15 +17,15 @@ writers (utility_functions/output.py).  Reference: `Channel.eval_friction_factor
 * 100 / 101                ITER spiral holes (:321-347)
 * 102-109                  hole laws by fixed-point iteration on the whole array (:190-222, 349-390); 106 interpolates
                            between laminar and turbulent (:1068-1101), the others take the maximum
-* 120                      triangular duct (:650-662, 688-698), total by interpolation
-Every total is multiplied by FRICTION_MULTIPLIER.  Not built: 116 / 117 / 119 (need the duct sides SIDE1 / SIDE2, which the
-model does not carry), 123 (fails in the reference on arrays), 208 (raises in the reference).
+* 119 / 120                rectangular (SIDE2 / SIDE1) and triangular duct (:650-698), total by interpolation
+Every total is multiplied by FRICTION_MULTIPLIER.  Not built because they do not run in the reference: 116 / 117 (`dict_coeff(flag_eval_ccc)` calls a
+dict: TypeError, channel.py:498-555), 123 (`and` on arrays, a misspelt method: :759-780), 208 (raises ValueError, :965-987).
 """
 from __future__ import annotations
 
 import numpy as np
 
-SUPPORTED_IFRICTION = (-99, 100, 101, 102, 103, 104, 105, 106, 107, 108, 109, 110, 111, 112, 113, 114, 115, 118, 120, 121, 122, 124,
+SUPPORTED_IFRICTION = (-99, 100, 101, 102, 103, 104, 105, 106, 107, 108, 109, 110, 111, 112, 113, 114, 115, 118, 119, 120, 121, 122, 124,
                        200, 201, 202, 203, 204, 205, 206, 207, 209, 210, 211)
 
 
@@ -53,14 +53,14 @@ def _haaland(re, rough, dh):
 
 
 def friction_factor(ifriction: int, multiplier: float, reynolds, dh: float, roughness: float = 0.0,
-                    void_fraction: float = 0.0, area: float = 0.0, nodal=True) -> np.ndarray:
+                    void_fraction: float = 0.0, area: float = 0.0, nodal=True, side_ratio: float = 0.0) -> np.ndarray:
     """Total friction factor (Fanning) of one channel for an array of Reynolds numbers.
 
     nodal: the reference's `nodal` argument (True: nodal pass, False: Gauss points, None: gen_flow).  It only matters
     for the interpolated totals (106, 120): `eval_friction_factor` passes it positionally into the L_lim_T parameter of
     `_eval_total_friction_factor_L_lim_T` (channel.py:1068-1138), so L_lim_T is 1, 0 or -- in gen_flow -- None, where the
     reference raises TypeError."""
-    if int(ifriction) in (106, 120) and nodal is None:
+    if int(ifriction) in (106, 119, 120) and nodal is None:
         raise TypeError(f"IFRICTION {int(ifriction)} in gen_flow: '>=' not supported between instances of 'float' and "
                         "'NoneType' (the reference compares the Reynolds number with L_lim_T = nodal = None)")
     llim = 1.0 if nodal else 0.0
@@ -125,9 +125,11 @@ def friction_factor(ifriction: int, multiplier: float, reynolds, dh: float, roug
                 turb = 2.0 / (rhpiu - 2.5 * np.log10(hd2) - 3.75) ** 2
                 err, it = np.fabs((turb - old) / turb), it + 1
         total = _total_llimt(re, _laminar(re), turb, llim) if flag == 106 else np.maximum(_laminar(re), turb)
-    elif flag == 120:
+    elif flag in (119, 120):
+        from .model import duct_laminar_coefficient
+        lamc = duct_laminar_coefficient(side_ratio) if flag == 119 else 13.33
         with np.errstate(all="ignore"):
-            total = _total_llimt(re, 13.33 / np.minimum(re, 2000), 0.00128 + 0.1143 * np.maximum(re, 4000) ** -0.311, llim)
+            total = _total_llimt(re, lamc / np.minimum(re, 2000), 0.00128 + 0.1143 * np.maximum(re, 4000) ** -0.311, llim)
     elif flag in (113, 114, 115, 118, 200, 201, 202, 203, 207, 210, 211):
         turb = np.zeros(re.shape)
         if flag == 113:
@@ -185,4 +187,5 @@ def channel_friction_factor(model, topo, j: int, reynolds, nodal=True) -> np.nda
     """`friction_factor` for channel j of a (Model, Topology) pair."""
     return friction_factor(model.ch_ifriction[j], model.ch_friction_mult[j], reynolds, topo.ch_dh[j],
                            model.ch_roughness[j] if model.ch_roughness else 0.0,
-                           model.ch_void_fraction[j] if model.ch_void_fraction else 0.0, topo.ch_area[j], nodal)
+                           model.ch_void_fraction[j] if model.ch_void_fraction else 0.0, topo.ch_area[j], nodal,
+                           model.ch_side_ratio[j] if getattr(model, "ch_side_ratio", ()) else 0.0)

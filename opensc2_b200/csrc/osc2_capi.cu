@@ -520,13 +520,13 @@ int osc2_set_model(osc2_handle h, const osc2_model *model)
         if (model->ch_fluid[j] + 1 > nf) nf = model->ch_fluid[j] + 1;
         {
             const int ifr = model->ch_ifriction[j];
-            static const int known[] = {-99, 100, 101, 102, 103, 104, 105, 106, 107, 108, 109, 110, 111, 112, 113, 114, 115, 118, 120, 121, 122, 124,
+            static const int known[] = {-99, 100, 101, 102, 103, 104, 105, 106, 107, 108, 109, 110, 111, 112, 113, 114, 115, 118, 119, 120, 121, 122, 124,
                                         200, 201, 202, 203, 204, 205, 206, 207, 209, 210, 211};
             bool ok = false;
             for (int v : known) ok = ok || (ifr == v);
             if (!ok)
-                return fail(OSC2_ERR_INVALID, "channel %d: IFRICTION %d is not implemented on the device (-99, 100-115, 118, 120, 121, 122, 124, 200-207, 209-211; "
-                            "208 raises in the reference, 123 fails there on arrays, 116 / 117 / 119 need the duct sides, which the model does not carry)", j, ifr);
+                return fail(OSC2_ERR_INVALID, "channel %d: IFRICTION %d is not implemented on the device (-99, 100-115, 118-122, 124, 200-207, 209-211; "
+                            "116 / 117 / 123 fail and 208 raises in the reference itself)", j, ifr);
         }
         {
             const int hc = model->ch_htc_corr[j];

@@ -581,7 +581,7 @@ __device__ __noinline__ double friction_more(int ifr, double re, double dh, doub
 // (Darcy-Forchheimer porous medium): channel.py:392-438, 700-717, katheder_correlation_bundle, _eval_jj_and_kk;
 // total = max(laminar, turbulent) with the general laminar correlation 16/Re (channel.py:284-299, 1104-1115);
 // for 121 the laminar slot calls the Haaland method again, which writes the turbulent array: laminar stays 0
-__device__ __noinline__ double friction_simple(int ifr, double re, double rough, double dh, double vf, double area, double llim)
+__device__ __noinline__ double friction_simple(int ifr, double re, double rough, double dh, double vf, double area, double llim, double lamc)
 {
     re = fabs(re);
     double turb = 0.0, lam = 0.0;
@@ -597,8 +597,8 @@ __device__ __noinline__ double friction_simple(int ifr, double re, double rough,
     }
     else if (ifr == 110) turb = (0.316 * pw(re, -0.25)) / 4.0;
     else if (ifr == 111) turb = 0.00128 + 0.1143 * pw(fmax(re, 4000.0), -0.311);
-    else if (ifr == 120)      // triangular duct: laminar 13.33 / min(Re, 2000) (:688-698), total by interpolation
-        return total_llimt(re, 13.33 / fmin(re, 2000.0), friction_more(ifr, re, dh, vf, area), llim);
+    else if (ifr == 119 || ifr == 120)      // rectangular (:664-686) / triangular (:688-698) duct: laminar c / min(Re, 2000), turbulent
+        return total_llimt(re, (ifr == 119 ? lamc : 13.33) / fmin(re, 2000.0), friction_more(120, re, dh, vf, area), llim);   // :650-662
     else if (ifr != 112) return fmax(friction_more(ifr, re, dh, vf, area), ifr == 211 ? 0.0 : lam);
     else {
         if (re <= 2.0e3) turb = 64 / re / 4.0;
@@ -621,7 +621,7 @@ __device__ inline double friction_total(const osc2_model *md, const osc2_topolog
         f = (ifr == 106) ? total_llimt(ra, lam, turb, llim) : fmax(lam, turb);
     }
     else if (ifr != -99 && ifr != 122)      // the closed-form laws (validated by osc2_set_model)
-        f = friction_simple(ifr, re, md->ch_roughness[j], tp->ch_dh[j], md->ch_void_fraction[j], tp->ch_area[j], llim);
+        f = friction_simple(ifr, re, md->ch_roughness[j], tp->ch_dh[j], md->ch_void_fraction[j], tp->ch_area[j], llim, md->ch_lam_coef[j]);
     else if (md->ch_ifriction[j] == 122) {
         const double rough = md->ch_roughness[j], dh = tp->ch_dh[j];
         f = haaland(fabs(re), rough, dh);

@@ -290,6 +290,8 @@ def load_deck(folder: str, conductor: int = 1, legacy_no_field: bool = True,
                   ch_htc_corr=tuple(int(_get(chans[c], "Flag_htc_steady_corr", default=1)) for c in chan_ids),
                   ch_roughness=tuple(float(_get(chans[c], "Roughness", default=0.0)) for c in chan_ids),
                   ch_void_fraction=tuple(float(_get(chans[c], "VOID_FRACTION", default=0.0)) for c in chan_ids),
+                  ch_side_ratio=tuple((float(_get(chans[c], "SIDE2", default=0.0)) / float(_get(chans[c], "SIDE1", default=1.0)))
+                                      if float(_get(chans[c], "SIDE1", default=0.0)) != 0.0 else 0.0 for c in chan_ids),
                   solids=tuple(solid_models), fs=tuple(m_fs), ff=tuple(m_ff), ss=tuple(m_ss), ss_rad=tuple(m_ss_rad),
                   es_htc=tuple(m_es))
     peri = {"ff": np.array(p_ff).T.reshape(2, len(ff)), "fs": np.array(p_fs), "ss": np.array(p_ss), "es": np.array(p_es)}

@@ -53,6 +53,7 @@ class Model:
     es_htc: Tuple[float, ...] = ()          # constant convective HTC incl. Phi_conv and multiplier
     ch_roughness: Tuple[float, ...] = ()    # Channel.inputs["Roughness"], used by IFRICTION 121, 122
     ch_void_fraction: Tuple[float, ...] = ()   # Channel.inputs["VOID_FRACTION"], used by the bundle laws 204-206, 209
+    ch_side_ratio: Tuple[float, ...] = ()      # Channel.inputs["SIDE2"] / ["SIDE1"], used by IFRICTION 119 (rectangular duct)
     ss_rad: Tuple[Tuple[float, float], ...] = ()   # per solid-solid interface: (denominator, multiplier) of choice 3
 
     def struct(self, topo) -> Osc2Model:
@@ -65,6 +66,7 @@ class Model:
             m.ch_friction_mult[j], m.ch_htc_corr[j] = self.ch_friction_mult[j], self.ch_htc_corr[j]
             m.ch_roughness[j] = self.ch_roughness[j] if self.ch_roughness else 0.0
             m.ch_void_fraction[j] = self.ch_void_fraction[j] if self.ch_void_fraction else 0.0
+            m.ch_lam_coef[j] = duct_laminar_coefficient(self.ch_side_ratio[j]) if self.ch_side_ratio else 0.0
         for l, s in enumerate(self.solids):
             m.sol_kind[l], m.sol_nmat[l] = s.kind, len(s.materials)
             for i, (mat, w) in enumerate(zip(s.materials, s.weights)):
@@ -85,6 +87,12 @@ class Model:
             den, mlt = self.ss_rad[k] if self.ss_rad else (float("inf"), 1.0)
             m.ss_rad_den[k], m.ss_rad_mlt[k] = den, mlt
         return m
+
+
+def duct_laminar_coefficient(alpha: float) -> float:
+    """Numerator of the laminar friction law of a rectangular duct, rectangular_duct_demo_common_memo_laminar_flow_hole
+    (channel.py:664-686), with the reference's own expression on Python floats (alpha = SIDE2 / SIDE1)."""
+    return 24.0 * (1.0 - 1.3553 * alpha + 1.9467 * alpha ** 2 - 1.7012 * alpha ** 3 + 0.9564 * alpha ** 4 - 0.2537 * alpha ** 5)
 
 
 @dataclass

@@ -420,7 +420,7 @@ static int newton_hole_array(const double *re, double *tot, long n, int ifr, dou
  * (channel.py:1104-1115).  110-112: laminar slot = general_laminar_correlation.  121: the laminar slot calls
  * haaland_equation again, which writes the TURBULENT array, so laminar stays 0.  112 assigns by masks that
  * leave Re = 2e3 < . , Re = 4e3 exactly at the initial 0 of the turbulent array. */
-static double friction_simple(int ifr, double re, double rough, double dh, double vf, double area, double llim)
+static double friction_simple(int ifr, double re, double rough, double dh, double vf, double area, double llim, double lamc)
 {
     re = fabs(re);
     double turb = 0.0, lam = 0.0;
@@ -455,6 +455,8 @@ static double friction_simple(int ifr, double re, double rough, double dh, doubl
         break;
     }
     /* 120: triangular duct, laminar 13.33 / min(Re, 2000) (:688-698), turbulent :650-662, total by interpolation (:1068-1101) */
+    case 119:   /* rectangular duct (:664-686): laminar lamc / min(Re, 2000), lamc = 24 (1 - 1.3553 a + ...) from the host */
+        return total_llimt(re, lamc / fmin(re, 2000.0), 0.00128 + 0.1143 * pow(fmax(re, 4000.0), -0.311), llim);
     case 120:
         return total_llimt(re, 13.33 / fmin(re, 2000.0), 0.00128 + 0.1143 * pow(fmax(re, 4000.0), -0.311), llim);
     /* hole laws 113 (memorandum_bessette_iter_cs_spiral_hole_y2015, channel.py:447-468: its closing statement
@@ -620,7 +622,7 @@ int osc2o_fit(int which, long n, const double *x, const double *y, const double 
         case 30: out[i] = cp_mgb2(x[i]); break;
         case 26: out[i] = cp_nbti(x[i], y[i], z[i], out[i]); break;   /* x = T, y = B, z = Tcs; out[] holds Tc on entry */
         case 27: out[i] = tc_nbti(x[i], p1, p2); break;                            /* x = B, p1 = Bc20m, p2 = Tc0m */
-        case 24: out[i] = friction_simple((int)p1, x[i], y[i], z[i], p2, y[i], 1.0); break;   /* nodal pass: L_lim_T = True; */   /* p1 = IFRICTION, y = roughness (IFRICTION 200: CROSSECTION), z = Dh, p2 = void fraction */
+        case 24: out[i] = friction_simple((int)p1, x[i], y[i], z[i], p2, y[i], 1.0, y[i]); break;   /* y: also the laminar numerator of 119 */   /* nodal pass: L_lim_T = True; */   /* p1 = IFRICTION, y = roughness (IFRICTION 200: CROSSECTION), z = Dh, p2 = void fraction */
         default: return -1;
         }
     }
@@ -706,7 +708,7 @@ static void one_conductor(const osc2_topology *tp, const osc2_model *md, osc2o_o
             const int ifr = md->ch_ifriction[j];
             const double ftot = ((ifr == 124) ? friction_124(re)
                                  : (ifr != -99 && ifr != 122 && !(ifr >= 102 && ifr <= 109))
-                                     ? friction_simple(ifr, re, md->ch_roughness[j], tp->ch_dh[j], md->ch_void_fraction[j], tp->ch_area[j], 0.0)
+                                     ? friction_simple(ifr, re, md->ch_roughness[j], tp->ch_dh[j], md->ch_void_fraction[j], tp->ch_area[j], 0.0, md->ch_lam_coef[j])
                                  : 1.0) * (ifr == 211 ? 1.0 : md->ch_friction_mult[j]);
             rey[e] = re;
             fg[((size_t)0 * M + j) * E + e] = v;

@@ -81,7 +81,9 @@ def main():
               211: ("hts_cl_correlation_bundle", "hts_cl_correlation_bundle"),
               100: ("general_laminar_correlation", "iter_conductor_hole"),
               101: ("general_laminar_correlation", "iter_conductor_hole"),
+              119: ("rectangular_duct_demo_common_memo_laminar_flow_hole", "duct_demo_common_memo_turbulent_flow_hole"),
               120: ("triangular_duct_demo_common_memo_laminar_flow_hole", "duct_demo_common_memo_turbulent_flow_hole")}
+    out["side_ratio"] = np.array(2.0e-3 / 5.0e-3)
     wiring.update({k: ("general_laminar_correlation", "turbulent_friction_with_newton_hole") for k in range(102, 110)})
     out["crossection"] = np.array(3.7e-4)
     out["void_fraction"] = np.array(0.33)
@@ -92,11 +94,12 @@ def main():
         for name in ("_quantities_initialization", "_eval_total_friction_factor_max", "_eval_total_friction_factor_L_lim_T",
                      "eval_friction_factor", "_eval_jj_and_kk", "_eval_correction_diameter_hole", "_eval_ft_newton", lam, turb):
             setattr(ch, name, types.MethodType(getattr(Channel, name), ch))
-        ch.inputs = {"FRICTION_MULTIPLIER": 0.02, "HYDIAMETER": 2.499e-3, "Roughness": 2.0e-6, "IFRICTION": ifr, "VOID_FRACTION": 0.33, "CROSSECTION": 3.7e-4}
+        ch.inputs = {"FRICTION_MULTIPLIER": 0.02, "HYDIAMETER": 2.499e-3, "Roughness": 2.0e-6, "IFRICTION": ifr, "VOID_FRACTION": 0.33, "CROSSECTION": 3.7e-4,
+                     "SIDE1": 5.0e-3, "SIDE2": 2.0e-3}
         ch.dict_friction_factor = {True: {"laminar": None, "turbulent": None, "total": 0.0}}
         ch.laminar_friction_factor_correlation = getattr(ch, lam)
         ch.turbulent_friction_factor_correlation = getattr(ch, turb)
-        ch.total_friction_factor_correlation = (ch._eval_total_friction_factor_L_lim_T if ifr in (106, 120)
+        ch.total_friction_factor_correlation = (ch._eval_total_friction_factor_L_lim_T if ifr in (106, 119, 120)
                                                 else ch._eval_total_friction_factor_max)      # channel.py:116-132
         ch.eval_friction_factor(re.copy(), nodal=True)
         out[f"f{ifr}_total"] = np.array(ch.dict_friction_factor[True]["total"])

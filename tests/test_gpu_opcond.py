@@ -335,7 +335,7 @@ def test_stack_component_solid_on_the_device():
 
 
 @pytest.mark.parametrize("laws", [(110, 121), (111, 112), (204, 206), (205, 209), (113, 114), (115, 118), (200, 201), (202, 203),
-                                  (207, 210), (211, 113), (100, 101), (102, 103), (104, 105), (106, 107), (108, 109), (120, 106)])
+                                  (207, 210), (211, 113), (100, 101), (102, 103), (104, 105), (106, 107), (108, 109), (120, 106), (119, 120)])
 def test_more_friction_laws_on_the_device(laws):
     """IFRICTION 110 (Blasius), 111 (Bhatti-Shah), 112 (LHC recipe), 121 (Haaland), 204 / 205 (Katheder bundle),
     206 / 209 (Darcy-Forchheimer bundle) in K_P vs the oracle (which
@@ -346,7 +346,8 @@ def test_more_friction_laws_on_the_device(laws):
 
     n, batch = 33, 21
     topo, model, tab, arr, sweep = _setup(True, n, batch)
-    model = dataclasses.replace(model, ch_ifriction=laws, ch_roughness=(2.0e-6, 2.0e-6), ch_void_fraction=(0.33, 0.36))
+    model = dataclasses.replace(model, ch_ifriction=laws, ch_roughness=(2.0e-6, 2.0e-6), ch_void_fraction=(0.33, 0.36),
+                                ch_side_ratio=(0.4, 0.7))
     with BatchedStep(topo, batch, n) as bs:
         bs.set_model(model, [tab])
         bs.upload_sweep(sweep)

@@ -108,7 +108,7 @@ def test_stack_component_homogenisation_against_the_reference():
             assert err <= 2e-12, f"{key}: {err:.3e}"
 
 
-@pytest.mark.parametrize("ifr", [100, 101, 110, 111, 112, 113, 114, 115, 118, 120, 121, 200, 201, 202, 203, 204, 205, 206, 207, 209, 210,
+@pytest.mark.parametrize("ifr", [100, 101, 110, 111, 112, 113, 114, 115, 118, 119, 120, 121, 200, 201, 202, 203, 204, 205, 206, 207, 209, 210,
                                  211])
 def test_more_friction_laws_against_the_reference_channel(ifr):
     """IFRICTION 110 / 111 / 112 / 121 and the bundle laws 204 / 205 (Katheder), 206 / 209 (Darcy-Forchheimer)
@@ -119,13 +119,17 @@ def test_more_friction_laws_against_the_reference_channel(ifr):
     from helpers import GOLDEN_DIR
     g = np.load(os.path.join(GOLDEN_DIR, "props_stack.npz"))
     re = g["re"]
-    y = float(g["crossection"]) if ifr == 200 else float(g["roughness"])        # the fit's second argument: CROSSECTION for 200
+    from opensc2_b200.model import duct_laminar_coefficient
+    y = float(g["crossection"]) if ifr == 200 else float(g["roughness"])        # the fit's second argument: CROSSECTION for 200,
+    if ifr == 119:                                                                # the laminar numerator for 119
+        y = duct_laminar_coefficient(float(g["side_ratio"]))
     got = O.fit("friction_simple", re, np.full_like(re, y), np.full_like(re, float(g["hydiameter"])), p1=ifr,
                 p2=float(g["void_fraction"])) * (1.0 if ifr == 211 else 0.02)        # 211 forces FRICTION_MULTIPLIER to 1
     ref = g[f"f{ifr}_total"]
     # the host-side numpy restatement (gen_flow, writers) against the same reference vectors
     from opensc2_b200.correlations import friction_factor
-    host = friction_factor(ifr, 0.02, re, float(g["hydiameter"]), float(g["roughness"]), float(g["void_fraction"]), float(g["crossection"]))
+    host = friction_factor(ifr, 0.02, re, float(g["hydiameter"]), float(g["roughness"]), float(g["void_fraction"]), float(g["crossection"]),
+                           side_ratio=float(g["side_ratio"]))
     assert np.max(np.abs(host - ref) / np.maximum(np.abs(ref), 1e-300)) <= 2e-12, f"host IFRICTION {ifr}"
     err = np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-300))
     assert err <= 2e-12, f"IFRICTION {ifr}: {err:.3e}"
