@@ -43,3 +43,17 @@ def test_product_arm_refuses_to_run_without_a_gpu():
     assert r.returncode != 0
     assert "no CPU fallback" in r.stderr
     assert not [l for l in r.stdout.splitlines() if l.startswith("{")], "no bench line without the CUDA path"
+
+
+def test_reference_arm_under_torchrun_prints_one_line_from_rank_zero():
+    # the driver launches both arms the same way at N > 1: rank 0 alone runs the CPU reference, the others exit 0
+    e = dict(os.environ)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29547", os.path.join(ROOT, "bench.py"),
+                        "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
+                       cwd=ROOT, env=e, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    assert j["impl"] == "reference" and j["n_gpus"] == 2 and j["value"] > 0
